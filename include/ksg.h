@@ -1,0 +1,191 @@
+/*
+ * ksg.h — C-ABI of the B200-native semantic TSDF integrator ("ksg" = Kimera-Semantics on GPU).
+ *
+ * This header is the drop-in boundary. Everything above it (the C++ classes in
+ * kimera_semantics_b200/cpp that mirror kimera::FastSemanticTsdfIntegrator /
+ * kimera::MergedSemanticTsdfIntegrator / kimera::SemanticTsdfIntegratorFactory) is a thin
+ * host shim; everything below it is hand-written sm_100a CUDA.  Signatures use plain
+ * pointers and sizes only (no torch / Eigen / voxblox types).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout, see SURVEY.md for the abbreviations):
+ *   fast.cpp   = kimera_semantics/src/semantic_tsdf_integrator_fast.cpp
+ *   merged.cpp = kimera_semantics/src/semantic_tsdf_integrator_merged.cpp
+ *   base.cpp/h = kimera_semantics/{src,include/kimera_semantics}/semantic_integrator_base.*
+ *   factory.*  = kimera_semantics/{src,include/kimera_semantics}/semantic_tsdf_integrator_factory.*
+ */
+#ifndef KSG_H_
+#define KSG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSG_ABI_VERSION 1
+
+/* status codes (the reference aborts through glog CHECK; the C++ shim turns non-zero
+ * codes back into aborts, the C-ABI itself never throws / aborts) */
+enum {
+  KSG_OK = 0,
+  KSG_ERR_INVALID_ARGUMENT = 1, /* reference: CHECK failures base.cpp:74,80,98-107; factory.cpp:61,83 */
+  KSG_ERR_CUDA = 2,
+  KSG_ERR_POOL_FULL = 3,       /* device block pool / hash table exhausted */
+  KSG_ERR_SCRATCH_FULL = 4,    /* per-frame scratch exhausted (grow max_* in the config) */
+  KSG_ERR_INDEX_RANGE = 5,     /* a voxel index left the packed-key range (|idx| >= 2^20 blocks) */
+  KSG_ERR_NO_DEVICE = 6
+};
+
+/* integrator types: factory.h:49-54 (kMerged = 0, kFast = 1) */
+enum { KSG_INTEGRATOR_MERGED = 0, KSG_INTEGRATOR_FAST = 1 };
+/* colour modes: base.h:54-58 */
+enum { KSG_COLOR_MODE_COLOR = 0, KSG_COLOR_MODE_SEMANTIC = 1, KSG_COLOR_MODE_SEMANTIC_PROBABILITY = 2 };
+/* integration order: voxblox ThreadSafeIndexFactory ("mixed" | "sorted"), fast.cpp:172-174 */
+enum { KSG_ORDER_MIXED = 0, KSG_ORDER_SORTED = 1 };
+
+/*
+ * One POD that carries vxb::TsdfIntegratorBase::Config (voxblox tsdf_integrator.h, defaults in
+ * SURVEY.md A.6), kimera::SemanticIntegratorBase::SemanticConfig (base.h:68-87), the layer
+ * geometry (vxb::Layer ctor: voxel_size, voxels_per_side; ros/src/semantic_tsdf_server.cpp:68-69)
+ * and the run-time class count that replaces the compile-time kTotalNumberOfLabels (common.h:26).
+ */
+typedef struct ksg_config {
+  int32_t abi_version;                 /* must be KSG_ABI_VERSION */
+  int32_t integrator_type;             /* KSG_INTEGRATOR_* (factory.h:49-54) */
+  /* layer geometry */
+  float voxel_size;                    /* metres */
+  int32_t voxels_per_side;             /* power of two */
+  /* vxb::TsdfIntegratorBase::Config */
+  float default_truncation_distance;
+  float max_weight;
+  int32_t voxel_carving_enabled;
+  float min_ray_length_m;
+  float max_ray_length_m;
+  int32_t use_const_weight;
+  int32_t allow_clear;
+  int32_t use_weight_dropoff;
+  int32_t use_sparsity_compensation_factor;
+  float sparsity_compensation_factor;
+  int32_t integration_order_mode;      /* KSG_ORDER_* */
+  int32_t enable_anti_grazing;         /* merged only (merged.cpp:306-313) */
+  float start_voxel_subsampling_factor;      /* fast only (fast.cpp:87-92) */
+  int32_t max_consecutive_ray_collisions;    /* fast only (fast.cpp:115-122) */
+  int32_t clear_checks_every_n_frames;       /* fast only (fast.cpp:165-170) */
+  int32_t integrator_threads;          /* CPU oracle only; the GPU path ignores it */
+  /* kimera SemanticConfig */
+  int32_t num_labels;                  /* C, 2..256 (reference: constexpr 21) */
+  float semantic_measurement_probability;    /* base.h:77 */
+  int32_t color_mode;                  /* KSG_COLOR_MODE_* */
+  uint8_t label_color[256][4];         /* SemanticLabel2Color label -> RGBA (color.cpp:84-94) */
+  uint8_t label_color_known[256];      /* 0 -> lookup miss: colour (0,0,0,0), color.cpp:92 */
+  uint8_t dynamic_label[256];          /* 1 -> label is dynamic; fast skips it (base.h:170-175) */
+  /* device side sizing (GPU path only) */
+  int32_t device;                      /* CUDA device ordinal */
+  int32_t max_blocks;                  /* block pool capacity (blocks of voxels_per_side^3) */
+  int32_t max_points;                  /* largest cloud / frame (pixels) accepted */
+  int64_t max_ray_steps;               /* scratch: upper bound on ray-step candidates per frame */
+  int64_t max_updates;                 /* scratch: upper bound on voxel updates per frame */
+  int32_t apply_mode;                  /* 0 = TMA-staged tile apply (default), 1 = direct-global apply */
+  int32_t reserved[7];
+} ksg_config;
+
+/* per-frame counters (the oracle reports the same numbers; SURVEY.md 8d: one voxel update =
+ * one {updateTsdfVoxel; updateSemanticVoxel} pair, fast.cpp:124-140 / merged.cpp:315-327) */
+typedef struct ksg_frame_stats {
+  int64_t points_in;          /* points handed to integratePointCloud */
+  int64_t points_valid;       /* passed isPointValid (+ dynamic-label filter for fast) */
+  int64_t rays_cast;          /* fast: rays surviving the start-voxel set; merged: bundles (both passes) */
+  int64_t ray_steps;          /* candidate ray steps enumerated */
+  int64_t voxel_updates;      /* executed per-voxel update bodies */
+  int64_t blocks_allocated;   /* blocks in the map after this frame */
+  int64_t blocks_touched;     /* blocks that received >= 1 update this frame */
+  int64_t tiles_touched;      /* 8^3 tiles staged by the apply kernel */
+  int64_t fixpoint_iterations;/* fast: iterations of the observed-set solver */
+  int64_t reserved[7];
+} ksg_frame_stats;
+
+typedef struct ksg_integrator ksg_integrator; /* opaque */
+
+/* Fill *cfg with the voxblox / kimera defaults (base.h:77-86) for the given
+ * geometry: truncation 4*voxel_size as voxblox_ros sets it, p = 0.9, colour mode kSemantic,
+ * label colours = grey for every label (known), no dynamic labels. */
+void ksg_default_config(ksg_config* cfg, int32_t integrator_type, float voxel_size,
+                        int32_t voxels_per_side, int32_t num_labels);
+
+/* Replaces SemanticTsdfIntegratorFactory::create (factory.h:71-93, factory.cpp:43-88) together with
+ * the Fast/Merged constructors (fast.cpp:49-55, merged.cpp:56-62) and SemanticIntegratorBase's
+ * ctor (base.cpp:57-76: layer geometry cache + setSemanticProbabilities base.cpp:93-128).
+ * The map (both layers) lives in device memory owned by the returned object. */
+int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out);
+void ksg_destroy(ksg_integrator* h);
+
+/* Human-readable description of the last non-OK status on this handle (NULL handle: global). */
+const char* ksg_last_error(const ksg_integrator* h);
+
+/* Replaces  virtual void integratePointCloud(const Transformation& T_G_C, const Pointcloud& points_C,
+ *           const Colors& colors, const bool freespace_points)       fast.h:82-86, merged.h:70-73
+ * (bodies fast.cpp:145-199, merged.cpp:65-149).
+ *   T_G_C      : 7 floats  qw qx qy qz tx ty tz  (minkindr QuatTransformation<float>)
+ *   xyz        : n*3 floats, camera frame
+ *   rgba       : n*4 bytes or NULL. When labels == NULL the label of a point is looked up from its
+ *                colour through the table set with ksg_set_color_to_label (fast.cpp:152-158).
+ *   labels     : n bytes or NULL. merged.h:82-86 label-explicit overload.
+ * Host buffers; the call copies them to the device, integrates and returns after the device
+ * finished (the reference call is synchronous, SURVEY.md 8b "Threading"). */
+int32_t ksg_integrate_points(ksg_integrator* h, const float* T_G_C, const float* xyz,
+                             const uint8_t* rgba, const uint8_t* labels, int64_t n,
+                             int32_t freespace_points, ksg_frame_stats* stats);
+
+/* Same call with DEVICE buffers, enqueued on `cuda_stream` (a cudaStream_t passed as void*); does not
+ * synchronise unless stats != NULL. Used by bench.py's device-resident leg. */
+int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T_G_C_host, const float* d_xyz,
+                                    const uint8_t* d_rgba, const uint8_t* d_labels, int64_t n,
+                                    int32_t freespace_points, void* cuda_stream, ksg_frame_stats* stats);
+
+/* Depth + label frame entry (SURVEY.md 8f NEXT-1): fuses PointCloudFromDepth::convert<float>
+ * (kimera_semantics_ros/include/kimera_semantics_ros/depth_map_to_pointcloud.h:222-266; x=(u-cx)*d*(1/fx),
+ * y=(v-cy)*d*(1/fy), z=d, non-finite depth -> dropped point as voxblox_ros convertPointcloud does)
+ * with integratePointCloud.  depth: h*w float32 metres, label: h*w uint8, K = fx fy cx cy. */
+int32_t ksg_integrate_depth(ksg_integrator* h, const float* T_G_C, const float* depth,
+                            const uint8_t* label, int32_t width, int32_t height, const float* K,
+                            ksg_frame_stats* stats);
+int32_t ksg_integrate_depth_device(ksg_integrator* h, const float* T_G_C_host, const float* d_depth,
+                                   const uint8_t* d_label, int32_t width, int32_t height,
+                                   const float* K_host, void* cuda_stream, ksg_frame_stats* stats);
+
+/* Colour -> label table: SemanticLabel2Color::getSemanticLabelFromColor (color.cpp:69-82). n entries
+ * of (r,g,b) -> label (alpha is forced to 255 by the callers fast.cpp:157, merged.cpp:87). A colour
+ * that is not in the table maps to label 0 (color.cpp:80). */
+int32_t ksg_set_color_to_label(ksg_integrator* h, const uint8_t* rgb, const uint8_t* labels, int32_t n);
+
+/* Wait for all enqueued work of this integrator; returns a deferred device-side error if any. */
+int32_t ksg_sync(ksg_integrator* h);
+
+/* Map read-back: replaces the direct host reads of Layer<TsdfVoxel> / Layer<SemanticVoxel> that
+ * callers perform after integratePointCloud returns (SURVEY.md 8b "Ownership"; base.cpp:257-265
+ * merges the blocks into the host layer).  Blocks come out sorted by (z, y, x) block index; voxels in
+ * voxblox linear order x + vps*(y + vps*z).  Any output pointer may be NULL.
+ *   block_index  nb*3 int32
+ *   tsdf_distance, tsdf_weight  nb*V float ;  tsdf_rgba nb*V*4 uint8           (vxb::TsdfVoxel)
+ *   sem_label nb*V uint8 ; sem_priors nb*V*C float ; sem_rgba nb*V*4 uint8     (semantic_voxel.h:14-27)
+ */
+int64_t ksg_num_blocks(ksg_integrator* h);
+int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index,
+                          float* tsdf_distance, float* tsdf_weight, uint8_t* tsdf_rgba,
+                          uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba);
+/* Indices (nb*3 int32, sorted as above) of the blocks updated by the most recent integrate call:
+ * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
+int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);
+
+/* Remove every block and reset the fast integrator's two approximate sets. */
+int32_t ksg_reset(ksg_integrator* h);
+
+/* Build information: "sm_100a" etc. */
+const char* ksg_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSG_H_ */

@@ -1,0 +1,325 @@
+"""ctypes binding of the C-ABI in include/ksg.h (the drop-in boundary).
+
+This is plumbing for tests and bench.py: it loads `csrc/libksg.so` (hand-written sm_100a CUDA behind
+`extern "C"` entry points) and fails loudly when the library is missing — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+KSG_ABI_VERSION = 1
+KSG_INTEGRATOR_MERGED = 0
+KSG_INTEGRATOR_FAST = 1
+KSG_COLOR_MODE_COLOR = 0
+KSG_COLOR_MODE_SEMANTIC = 1
+KSG_COLOR_MODE_SEMANTIC_PROBABILITY = 2
+KSG_ORDER_MIXED = 0
+KSG_ORDER_SORTED = 1
+
+KSG_STATUS = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "POOL_FULL", 4: "SCRATCH_FULL", 5: "INDEX_RANGE",
+              6: "NO_DEVICE"}
+
+
+class KsgConfig(C.Structure):
+    """Mirror of `struct ksg_config` (include/ksg.h)."""
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("integrator_type", C.c_int32),
+        ("voxel_size", C.c_float),
+        ("voxels_per_side", C.c_int32),
+        ("default_truncation_distance", C.c_float),
+        ("max_weight", C.c_float),
+        ("voxel_carving_enabled", C.c_int32),
+        ("min_ray_length_m", C.c_float),
+        ("max_ray_length_m", C.c_float),
+        ("use_const_weight", C.c_int32),
+        ("allow_clear", C.c_int32),
+        ("use_weight_dropoff", C.c_int32),
+        ("use_sparsity_compensation_factor", C.c_int32),
+        ("sparsity_compensation_factor", C.c_float),
+        ("integration_order_mode", C.c_int32),
+        ("enable_anti_grazing", C.c_int32),
+        ("start_voxel_subsampling_factor", C.c_float),
+        ("max_consecutive_ray_collisions", C.c_int32),
+        ("clear_checks_every_n_frames", C.c_int32),
+        ("integrator_threads", C.c_int32),
+        ("num_labels", C.c_int32),
+        ("semantic_measurement_probability", C.c_float),
+        ("color_mode", C.c_int32),
+        ("label_color", (C.c_uint8 * 4) * 256),
+        ("label_color_known", C.c_uint8 * 256),
+        ("dynamic_label", C.c_uint8 * 256),
+        ("device", C.c_int32),
+        ("max_blocks", C.c_int32),
+        ("max_points", C.c_int32),
+        ("max_ray_steps", C.c_int64),
+        ("max_updates", C.c_int64),
+        ("apply_mode", C.c_int32),
+        ("reserved", C.c_int32 * 7),
+    ]
+
+
+class KsgFrameStats(C.Structure):
+    """Mirror of `struct ksg_frame_stats` (include/ksg.h)."""
+    _fields_ = [
+        ("points_in", C.c_int64),
+        ("points_valid", C.c_int64),
+        ("rays_cast", C.c_int64),
+        ("ray_steps", C.c_int64),
+        ("voxel_updates", C.c_int64),
+        ("blocks_allocated", C.c_int64),
+        ("blocks_touched", C.c_int64),
+        ("tiles_touched", C.c_int64),
+        ("fixpoint_iterations", C.c_int64),
+        ("reserved", C.c_int64 * 7),
+    ]
+
+    def as_dict(self) -> Dict[str, int]:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+def label_palette(num_labels: int) -> np.ndarray:
+    """A deterministic label -> RGBA table (label 0 = white as color.cpp:64-66 forces)."""
+    pal = np.zeros((256, 4), dtype=np.uint8)
+    for l in range(256):
+        pal[l] = ((l * 67 + 29) % 256, (l * 131 + 71) % 256, (l * 199 + 113) % 256, 255)
+    pal[0] = (255, 255, 255, 255)
+    return pal
+
+
+def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float = 0.05, voxels_per_side: int = 16,
+                   num_labels: int = 21) -> KsgConfig:
+    """voxblox / kimera defaults (base.h:77-86, 8d "Integrator config"). Must equal
+    ksg_default_config() except for the palette / dynamic label which this helper also fills."""
+    cfg = KsgConfig()
+    cfg.abi_version = KSG_ABI_VERSION
+    cfg.integrator_type = integrator_type
+    cfg.voxel_size = voxel_size
+    cfg.voxels_per_side = voxels_per_side
+    cfg.default_truncation_distance = float(np.float32(4.0) * np.float32(voxel_size))
+    cfg.max_weight = 10000.0
+    cfg.voxel_carving_enabled = 1
+    cfg.min_ray_length_m = 0.1
+    cfg.max_ray_length_m = 5.0
+    cfg.use_const_weight = 0
+    cfg.allow_clear = 1
+    cfg.use_weight_dropoff = 1
+    cfg.use_sparsity_compensation_factor = 0
+    cfg.sparsity_compensation_factor = 1.0
+    cfg.integration_order_mode = KSG_ORDER_MIXED
+    cfg.enable_anti_grazing = 0
+    cfg.start_voxel_subsampling_factor = 2.0
+    cfg.max_consecutive_ray_collisions = 2
+    cfg.clear_checks_every_n_frames = 1
+    cfg.integrator_threads = 1
+    cfg.num_labels = num_labels
+    cfg.semantic_measurement_probability = 0.9
+    cfg.color_mode = KSG_COLOR_MODE_SEMANTIC
+    pal = label_palette(num_labels)
+    for l in range(256):
+        for k in range(4):
+            cfg.label_color[l][k] = int(pal[l, k])
+        cfg.label_color_known[l] = 1 if l < num_labels else 0
+        cfg.dynamic_label[l] = 0
+    cfg.device = 0
+    cfg.max_blocks = 8192
+    cfg.max_points = 640 * 480
+    cfg.max_ray_steps = 0   # 0 = let the library size it from max_points
+    cfg.max_updates = 0
+    cfg.apply_mode = 0
+    return cfg
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libksg.so")
+
+
+_LIB = None
+
+
+def _ptr(a: Optional[np.ndarray], ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def load_library(path: Optional[str] = None):
+    """Load libksg.so and declare every symbol of include/ksg.h. Raises if the library is missing."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or library_path()
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                           "There is no CPU fallback.")
+    lib = C.CDLL(p)
+    H = C.c_void_p
+    fp, u8p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    sp = C.POINTER(KsgFrameStats)
+    lib.ksg_default_config.argtypes = [C.POINTER(KsgConfig), C.c_int32, C.c_float, C.c_int32, C.c_int32]
+    lib.ksg_default_config.restype = None
+    lib.ksg_create.argtypes = [C.POINTER(KsgConfig), C.POINTER(H)]
+    lib.ksg_create.restype = C.c_int32
+    lib.ksg_destroy.argtypes = [H]
+    lib.ksg_destroy.restype = None
+    lib.ksg_last_error.argtypes = [H]
+    lib.ksg_last_error.restype = C.c_char_p
+    lib.ksg_integrate_points.argtypes = [H, fp, fp, u8p, u8p, C.c_int64, C.c_int32, sp]
+    lib.ksg_integrate_points.restype = C.c_int32
+    lib.ksg_integrate_points_device.argtypes = [H, fp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, sp]
+    lib.ksg_integrate_points_device.restype = C.c_int32
+    lib.ksg_integrate_depth.argtypes = [H, fp, fp, u8p, C.c_int32, C.c_int32, fp, sp]
+    lib.ksg_integrate_depth.restype = C.c_int32
+    lib.ksg_integrate_depth_device.argtypes = [H, fp, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, fp, C.c_void_p, sp]
+    lib.ksg_integrate_depth_device.restype = C.c_int32
+    lib.ksg_set_color_to_label.argtypes = [H, u8p, u8p, C.c_int32]
+    lib.ksg_set_color_to_label.restype = C.c_int32
+    lib.ksg_sync.argtypes = [H]
+    lib.ksg_sync.restype = C.c_int32
+    lib.ksg_num_blocks.argtypes = [H]
+    lib.ksg_num_blocks.restype = C.c_int64
+    lib.ksg_export_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
+    lib.ksg_export_blocks.restype = C.c_int32
+    lib.ksg_last_updated_blocks.argtypes = [H, C.c_int64, i32p]
+    lib.ksg_last_updated_blocks.restype = C.c_int64
+    lib.ksg_reset.argtypes = [H]
+    lib.ksg_reset.restype = C.c_int32
+    lib.ksg_build_info.argtypes = []
+    lib.ksg_build_info.restype = C.c_char_p
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
+               "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
+               "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks",
+               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info"]
+
+
+class KsgError(RuntimeError):
+    pass
+
+
+def export_arrays(lib, handle, prefix: str, vps: int, num_labels: int) -> Dict[str, np.ndarray]:
+    """Shared by the product binding and the oracle binding (same export signature)."""
+    nb = int(getattr(lib, prefix + "_num_blocks")(handle))
+    V = vps ** 3
+    out = {
+        "block_index": np.zeros((nb, 3), np.int32),
+        "tsdf_distance": np.zeros((nb, V), np.float32),
+        "tsdf_weight": np.zeros((nb, V), np.float32),
+        "tsdf_rgba": np.zeros((nb, V, 4), np.uint8),
+        "sem_label": np.zeros((nb, V), np.uint8),
+        "sem_priors": np.zeros((nb, V, num_labels), np.float32),
+        "sem_rgba": np.zeros((nb, V, 4), np.uint8),
+    }
+    rc = getattr(lib, prefix + "_export_blocks")(
+        handle, nb, _ptr(out["block_index"], C.c_int32), _ptr(out["tsdf_distance"], C.c_float),
+        _ptr(out["tsdf_weight"], C.c_float), _ptr(out["tsdf_rgba"], C.c_uint8), _ptr(out["sem_label"], C.c_uint8),
+        _ptr(out["sem_priors"], C.c_float), _ptr(out["sem_rgba"], C.c_uint8))
+    if rc != 0:
+        raise KsgError(f"{prefix}_export_blocks failed: {rc}")
+    return out
+
+
+class Integrator:
+    """Host-buffer view of one ksg integrator handle (numpy in, numpy out)."""
+
+    def __init__(self, cfg: KsgConfig, lib=None):
+        self.lib = lib or load_library()
+        self.cfg = cfg
+        self.handle = C.c_void_p()
+        rc = self.lib.ksg_create(C.byref(cfg), C.byref(self.handle))
+        if rc != 0:
+            msg = self.lib.ksg_last_error(None)
+            raise KsgError(f"ksg_create failed: {KSG_STATUS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self.handle:
+            self.lib.ksg_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.ksg_last_error(self.handle)
+            raise KsgError(f"{what} failed: {KSG_STATUS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def set_color_to_label(self, rgb: np.ndarray, labels: np.ndarray):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        self._check(self.lib.ksg_set_color_to_label(self.handle, _ptr(rgb, C.c_uint8), _ptr(labels, C.c_uint8), len(labels)),
+                    "ksg_set_color_to_label")
+
+    def integrate_points(self, T_G_C, xyz, rgba=None, labels=None, freespace=False) -> KsgFrameStats:
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        rgba = None if rgba is None else np.ascontiguousarray(rgba, np.uint8)
+        labels = None if labels is None else np.ascontiguousarray(labels, np.uint8)
+        st = KsgFrameStats()
+        self._check(self.lib.ksg_integrate_points(self.handle, _ptr(T, C.c_float), _ptr(xyz, C.c_float), _ptr(rgba, C.c_uint8),
+                                                  _ptr(labels, C.c_uint8), xyz.shape[0], int(freespace), C.byref(st)),
+                    "ksg_integrate_points")
+        return st
+
+    def integrate_depth(self, T_G_C, depth, label, K) -> KsgFrameStats:
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        label = np.ascontiguousarray(label, np.uint8)
+        K = np.ascontiguousarray(K, np.float32)
+        st = KsgFrameStats()
+        h, w = depth.shape
+        self._check(self.lib.ksg_integrate_depth(self.handle, _ptr(T, C.c_float), _ptr(depth, C.c_float), _ptr(label, C.c_uint8),
+                                                 w, h, _ptr(K, C.c_float), C.byref(st)), "ksg_integrate_depth")
+        return st
+
+    def integrate_depth_device(self, T_G_C, d_depth_ptr: int, d_label_ptr: int, width: int, height: int, K,
+                               stream: int = 0, want_stats: bool = False) -> Optional[KsgFrameStats]:
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        K = np.ascontiguousarray(K, np.float32)
+        st = KsgFrameStats() if want_stats else None
+        self._check(self.lib.ksg_integrate_depth_device(self.handle, _ptr(T, C.c_float), C.c_void_p(d_depth_ptr),
+                                                        C.c_void_p(d_label_ptr), width, height, _ptr(K, C.c_float),
+                                                        C.c_void_p(stream), C.byref(st) if st is not None else None),
+                    "ksg_integrate_depth_device")
+        return st
+
+    def integrate_points_device(self, T_G_C, d_xyz: int, d_rgba: int, d_labels: int, n: int, freespace=False,
+                                stream: int = 0, want_stats: bool = False) -> Optional[KsgFrameStats]:
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        st = KsgFrameStats() if want_stats else None
+        self._check(self.lib.ksg_integrate_points_device(self.handle, _ptr(T, C.c_float), C.c_void_p(d_xyz),
+                                                         C.c_void_p(d_rgba) if d_rgba else None,
+                                                         C.c_void_p(d_labels) if d_labels else None, n, int(freespace),
+                                                         C.c_void_p(stream), C.byref(st) if st is not None else None),
+                    "ksg_integrate_points_device")
+        return st
+
+    def sync(self):
+        self._check(self.lib.ksg_sync(self.handle), "ksg_sync")
+
+    def reset(self):
+        self._check(self.lib.ksg_reset(self.handle), "ksg_reset")
+
+    def num_blocks(self) -> int:
+        return int(self.lib.ksg_num_blocks(self.handle))
+
+    def export(self) -> Dict[str, np.ndarray]:
+        return export_arrays(self.lib, self.handle, "ksg", self.cfg.voxels_per_side, self.cfg.num_labels)
+
+    def last_updated_blocks(self) -> np.ndarray:
+        n = int(self.lib.ksg_last_updated_blocks(self.handle, 0, None))
+        out = np.zeros((n, 3), np.int32)
+        if n:
+            self.lib.ksg_last_updated_blocks(self.handle, n, _ptr(out, C.c_int32))
+        return out
