@@ -1,0 +1,818 @@
+// ksg_api.cu — host side of the C-ABI in include/ksg.h: owns the device-resident map (spatial block hash +
+// tile pool), the per-frame scratch, and enqueues the kernel family of ksg_kernels.cuh.
+// Compiled for sm_100a only, with -fmad=false (bit-exact index arithmetic, see ksg_device.cuh).
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ksg.h"
+#include "ksg_kernels.cuh"
+
+using namespace ksg;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define KSG_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      char buf_[512];                                                                               \
+      snprintf(buf_, sizeof(buf_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return fail(KSG_ERR_CUDA, buf_);                                                              \
+    }                                                                                               \
+  } while (0)
+
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+inline int grid_for(long long n, int block) { return (int)std::max<long long>(1, (n + block - 1) / block); }
+
+}  // namespace
+
+struct ksg_integrator {
+  ksg_config cfg{};
+  DevCfg dc{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  int deferred_status = 0;
+
+  // map
+  MapRef map{};
+  uint32_t ht_cap = 0;
+  Luts h_luts{};
+  Luts* d_luts = nullptr;
+  Counters* d_cnt = nullptr;
+  Counters* h_cnt = nullptr;  // pinned
+  int frame_stamp = 0;
+  int64_t num_blocks = 0;
+  int64_t last_blocks_touched = 0;
+
+  // per-frame scratch
+  int cap_points = 0;
+  float4 *pt_pC = nullptr, *pt_pG = nullptr;
+  uint8_t *pt_label = nullptr, *pt_flags = nullptr;
+  uint32_t* pt_color = nullptr;
+  uint64_t* pt_key = nullptr;
+  uint8_t *flags8 = nullptr, *is_last = nullptr;  // flags8: 2*cap bytes
+  int* pix_list = nullptr;
+  int* point_of_seq = nullptr;
+  uint32_t *sq_keys = nullptr, *sq_keys_out = nullptr;
+  uint32_t *iota = nullptr;
+
+  // fast
+  int *start_head = nullptr, *start_next = nullptr;
+  uint32_t *start_table = nullptr;
+  uint64_t set_offset = 0;  // both ApproxHashSets share reset times, hence one offset (fast.cpp:165-170)
+  int64_t reset_counter = 0;
+  int* cast_seq = nullptr;
+  float4* ray_param = nullptr;
+  uint8_t *ray_label = nullptr, *ray_flags = nullptr, *trunc_flag = nullptr;
+  uint32_t* ray_color = nullptr;
+  int *nsteps = nullptr, *H = nullptr, *L = nullptr;
+  RayState* ray_state = nullptr;
+  long long* ext_off = nullptr;
+  ObsBuf ob{};
+
+  // merged
+  uint64_t* ks_sorted = nullptr;
+  uint32_t* seq_sorted = nullptr;
+  int *bstart = nullptr, *bundle_f = nullptr;
+  float *hist = nullptr, *tmp = nullptr;
+  uint64_t* b_key = nullptr;
+  long long* b_base = nullptr;
+
+  // records
+  uint64_t *rec_a = nullptr, *rec_b = nullptr;
+  long long rec_cap = 0;
+  long long* tile_begin = nullptr;
+  long long tile_cap = 0;
+  void* cub_temp = nullptr;
+  size_t cub_temp_bytes = 0;
+
+  // host staging (pinned) + device input buffers for the host-buffer entry points
+  uint8_t* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+  uint8_t* d_in = nullptr;
+  size_t d_in_bytes = 0;
+
+  // export staging
+  uint8_t* d_exp = nullptr;
+  size_t d_exp_bytes = 0;
+  int* d_exp_slots = nullptr;
+  int exp_slots_cap = 0;
+
+  int apply_smem = 0;
+  int group_planes = 0;
+  bool use_tma = true;
+
+  int fail(int code, const char* msg) { err = msg; g_last_error = msg; return code; }
+};
+
+namespace {
+
+int validate(const ksg_config* c, std::string& why) {
+  if (!c) { why = "null config"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->abi_version != KSG_ABI_VERSION) { why = "abi_version mismatch"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->integrator_type != KSG_INTEGRATOR_FAST && c->integrator_type != KSG_INTEGRATOR_MERGED) {
+    why = "Unknown Semantic/TSDF integrator type (factory.cpp:83)"; return KSG_ERR_INVALID_ARGUMENT; }
+  const int v = c->voxels_per_side;
+  if (v <= 0 || (v & (v - 1)) || v > 64) { why = "voxels_per_side must be a power of two <= 64"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (!(c->voxel_size > 0.0f)) { why = "voxel_size must be positive"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->num_labels < 2 || c->num_labels > 256) { why = "num_labels must be in [2, 256]"; return KSG_ERR_INVALID_ARGUMENT; }
+  const float p = c->semantic_measurement_probability;  // base.cpp:98-107
+  if (!(p > 0.0f && p < 1.0f) || !((1.0f - p) > 0.0f) || !(std::log(p) > std::log(1.0f - p))) {
+    why = "semantic_measurement_probability must satisfy 0 < 1-p < p < 1 (base.cpp:98-107)"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->integration_order_mode != KSG_ORDER_MIXED && c->integration_order_mode != KSG_ORDER_SORTED) {
+    why = "unknown integration_order_mode"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->color_mode < 0 || c->color_mode > 2) { why = "Unknown semantic color mode (base.cpp:186-190)"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->max_points <= 0 || c->max_points > (1 << kRecOrdBits)) { why = "max_points must be in (0, 2^23]"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->max_blocks <= 0) { why = "max_blocks must be positive"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->max_consecutive_ray_collisions < 0) { why = "max_consecutive_ray_collisions < 0"; return KSG_ERR_INVALID_ARGUMENT; }
+  return KSG_OK;
+}
+
+template <typename Tp>
+cudaError_t dmalloc(Tp** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(Tp)); }
+
+void free_all(ksg_integrator* h) {
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->map.ht_keys, h->map.ht_slot, h->map.new_list, h->map.pool, h->map.slot_key, h->map.touched_stamp,
+                  h->map.touched_list, h->d_luts, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color, h->pt_key,
+                  h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota, h->start_head,
+                  h->start_next, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
+                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->ob.cand_val, h->ob.cand_order,
+                  h->ob.cand_next, h->ob.head, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
+                  h->tmp, h->b_key, h->b_base, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+}
+
+__global__ void k_iota(uint32_t* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
+__global__ void k_fill_u32(uint32_t* p, long long n, uint32_t v) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void k_fill_u64(uint64_t* p, long long n, uint64_t v) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+// "sorted" integration order (voxblox SortedThreadSafeIndex, A.3): key = squared norm of the point
+__global__ void k_sqnorm(FrameIn in, const Counters* cnt, int capacity, uint32_t* keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= capacity) return;
+  if (i >= cnt->n_points) { keys[i] = 0xFFFFFFFFu; return; }
+  F3 pC;
+  if (in.depth) {
+    const int pix = in.pix_list[i];
+    const int v = pix / in.width, u = pix - v * in.width;
+    const float d = in.depth[pix];
+    pC = f3(((float)u - in.cx) * d * in.constant_x, ((float)v - in.cy) * d * in.constant_y, d);
+  } else pC = f3(in.xyz[3 * i], in.xyz[3 * i + 1], in.xyz[3 * i + 2]);
+  keys[i] = __float_as_uint(dot3(pC, pC));
+}
+
+int reset_map(ksg_integrator* h, cudaStream_t s) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaMemsetAsync(h->map.ht_keys, 0xFF, sizeof(uint64_t) * h->ht_cap, s));
+  KSG_CUDA(cudaMemsetAsync(h->map.ht_slot, 0xFF, sizeof(int) * h->ht_cap, s));
+  KSG_CUDA(cudaMemsetAsync(h->map.touched_stamp, 0, sizeof(int) * h->ht_cap, s));
+  KSG_CUDA(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), s));
+  if (h->start_table) KSG_CUDA(cudaMemsetAsync(h->start_table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+  if (h->ob.table) KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+  h->set_offset = 0;
+  h->reset_counter = 0;
+  h->num_blocks = 0;
+  h->frame_stamp = 0;
+  h->last_blocks_touched = 0;
+  h->deferred_status = 0;
+  KSG_CUDA(cudaStreamSynchronize(s));
+  return KSG_OK;
+}
+
+struct InputDesc {
+  const float* d_xyz = nullptr;
+  const uint8_t* d_rgba = nullptr;
+  const uint8_t* d_labels = nullptr;
+  const float* d_depth = nullptr;
+  const uint8_t* d_label_img = nullptr;
+  int width = 0, height = 0;
+  float K[4] = {0, 0, 0, 0};
+  int64_t n = 0;  // points (points entry) or pixels (depth entry)
+  int freespace = 0;
+};
+
+int fetch_counters(ksg_integrator* h, cudaStream_t s) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaStreamSynchronize(s));
+  return KSG_OK;
+}
+
+const char* err_text(int e) {
+  switch (e) {
+    case 1: return "invalid argument: a semantic label >= num_labels (CHECK_LT fast.cpp:134 / merged.cpp:278)";
+    case 3: return "block pool / hash table full: raise ksg_config.max_blocks";
+    case 4: return "per-frame scratch full: raise ksg_config.max_ray_steps / max_updates";
+    case 5: return "voxel or block index outside the supported range";
+    default: return "device-side error";
+  }
+}
+
+int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaStream_t s, ksg_frame_stats* stats) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
+  if (in.n > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");
+  KSG_CUDA(cudaSetDevice(h->device));
+  const DevCfg& dc = h->dc;
+  const bool fast = h->cfg.integrator_type == KSG_INTEGRATOR_FAST;
+  const int cap = (int)in.n;  // host upper bound of the point count
+  const int B = 256;
+  Xform T{T_host[0], T_host[1], T_host[2], T_host[3], T_host[4], T_host[5], T_host[6]};
+  h->frame_stamp += 1;
+
+  if (cap == 0) {
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->blocks_allocated = h->num_blocks; }
+    if (fast) {  // the sets are still reset (fast.cpp:165-170 runs before any point is looked at)
+      if ((++h->reset_counter) >= h->cfg.clear_checks_every_n_frames) {
+        h->reset_counter = 0;
+        if (++h->set_offset >= 10000) {
+          h->set_offset = 0;
+          KSG_CUDA(cudaMemsetAsync(h->start_table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+          KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+        }
+      }
+    }
+    h->last_blocks_touched = 0;
+    return KSG_OK;
+  }
+
+  FrameIn fin{};
+  fin.xyz = in.d_xyz; fin.rgba = in.d_rgba; fin.labels = in.d_labels;
+  fin.depth = in.d_depth; fin.label_img = in.d_label_img; fin.pix_list = h->pix_list;
+  fin.point_of_seq = nullptr;
+  fin.width = in.width;
+  fin.cx = in.K[2]; fin.cy = in.K[3];
+  if (in.d_depth) {  // depth_map_to_pointcloud.h:228-230: float constant = unit_scaling / f  (double division)
+    fin.constant_x = (float)(1.0 / (double)in.K[0]);
+    fin.constant_y = (float)(1.0 / (double)in.K[1]);
+  }
+  fin.freespace = in.freespace;
+
+  k_frame_reset<<<1, 1, 0, s>>>(h->d_cnt, in.d_depth ? 0 : cap);
+  if (in.d_depth) {
+    k_depth_flags<<<grid_for(cap, B), B, 0, s>>>(in.d_depth, cap, h->flags8);
+    size_t tb = h->cub_temp_bytes;
+    KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->pix_list,
+                                        &h->d_cnt->n_points, cap, s));
+  }
+  if (h->cfg.integration_order_mode == KSG_ORDER_SORTED) {
+    k_sqnorm<<<grid_for(cap, B), B, 0, s>>>(fin, h->d_cnt, cap, h->sq_keys);
+    size_t tb = h->cub_temp_bytes;
+    KSG_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_temp, tb, h->sq_keys, h->sq_keys_out, h->iota, (uint32_t*)h->point_of_seq,
+                                             cap, 0, 32, s));
+    fin.point_of_seq = h->point_of_seq;
+  }
+
+  // ApproxHashSet resets (fast.cpp:165-170, A.4)
+  if (fast) {
+    if ((++h->reset_counter) >= h->cfg.clear_checks_every_n_frames) {
+      h->reset_counter = 0;
+      if (++h->set_offset >= 10000) {
+        h->set_offset = 0;
+        KSG_CUDA(cudaMemsetAsync(h->start_table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+        KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+      }
+    }
+  }
+
+  long long n_records = 0;
+  int iterations = 0;
+  ApplySrc src{};
+  if (fast) {
+    KSG_CUDA(cudaMemsetAsync(h->start_head, 0xFF, sizeof(int) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->ob.head, 0xFF, sizeof(int) * kSetSize, s));
+    k_classify<true><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, h->set_offset, cap, h->d_cnt, h->pt_pC, h->pt_pG,
+                                                    h->pt_label, h->pt_flags, h->pt_color, h->pt_key);
+    k_start_push<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next);
+    k_start_eval<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next, h->start_table, h->flags8,
+                                                h->is_last, cap);
+    k_start_commit<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->is_last, h->start_table);
+    {
+      size_t tb = h->cub_temp_bytes;
+      KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->cast_seq,
+                                          &h->d_cnt->n_cast, cap, s));
+    }
+    k_ray_setup<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->cast_seq, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color,
+                                                   h->set_offset, h->ob, h->ray_param, h->ray_label, h->ray_flags, h->ray_color,
+                                                   h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->trunc_flag);
+    // observed-set fixpoint
+    int n_cast = cap;
+    for (;;) {
+      k_iter_reset<<<1, 1, 0, s>>>(h->d_cnt);
+      k_eval<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, h->d_cnt, h->ob, h->nsteps, h->H, h->L, h->ext_off, h->trunc_flag);
+      ++iterations;
+      int rc = fetch_counters(h, s);
+      if (rc) return rc;
+      n_cast = std::max(1, h->h_cnt->n_cast);
+      if (h->h_cnt->err) break;
+      if (h->h_cnt->changed) continue;
+      if (h->h_cnt->n_truncated > 0) {
+        k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state,
+                                                       h->ext_off, h->trunc_flag);
+        continue;
+      }
+      break;
+    }
+    if (!h->h_cnt->err) {
+      n_records = (long long)h->h_cnt->sum_updates;
+      if (n_records > h->rec_cap) { h->deferred_status = KSG_ERR_SCRATCH_FULL; return fail(KSG_ERR_SCRATCH_FULL, err_text(4)); }
+      k_obs_commit<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->ob, h->L, h->ext_off);
+      k_emit_fast<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->L, h->rec_a,
+                                                        h->rec_cap);
+    }
+    src.param = h->ray_param; src.label = h->ray_label; src.color = h->ray_color; src.tmp = nullptr;
+  } else {
+    k_classify<false><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, 0ull, cap, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label,
+                                                     h->pt_flags, h->pt_color, h->pt_key);
+    {
+      size_t tb = h->cub_temp_bytes;
+      KSG_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_temp, tb, h->pt_key, h->ks_sorted, h->iota, h->seq_sorted, cap, 0, 64, s));
+    }
+    KSG_CUDA(cudaMemsetAsync(h->flags8, 0, 2 * (size_t)cap, s));
+    k_bundle_heads<<<grid_for(cap, B), B, 0, s>>>(h->ks_sorted, h->seq_sorted, cap, h->flags8, h->bstart);
+    {
+      size_t tb = h->cub_temp_bytes;
+      KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->bundle_f,
+                                          &h->d_cnt->n_cast, 2 * cap, s));
+    }
+    k_bundle_merge<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, h->seq_sorted, cap,
+                                                      h->pt_pC, h->pt_label, h->hist, h->ray_param, h->ray_flags, h->b_key,
+                                                      h->nsteps, h->b_base, h->rec_cap);
+    int rc = fetch_counters(h, s);
+    if (rc) return rc;
+    if (!h->h_cnt->err) {
+      const int nb = std::max(1, h->h_cnt->n_cast);
+      n_records = (long long)h->h_cnt->n_records;
+      k_bundle_loglik<<<grid_for((long long)nb * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp);
+      k_emit_merged<<<grid_for(nb, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps,
+                                                      h->b_base, h->ks_sorted, cap, h->rec_a);
+    }
+    src.param = h->ray_param; src.label = nullptr; src.color = nullptr; src.tmp = h->tmp;
+  }
+
+  int dev_err = h->h_cnt->err;
+  if (!dev_err && n_records > 0) {
+    // order the update records by (tile, voxel, order): per-voxel application order = reference order
+    size_t tb = h->cub_temp_bytes;
+    KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, 0, 64, s));
+    k_block_assign<<<grid_for(h->map.new_cap, B), B, 0, s>>>(h->d_cnt, h->map);
+    k_block_init<<<h->sm_count * 4, 256, 0, s>>>(dc, h->d_cnt, h->map);
+    k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
+                                                      h->tile_cap);
+    const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem))));
+    const int grid = h->sm_count * ctas_per_sm;
+    if (h->use_tma)
+      k_tile_apply<true><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
+                                                                     h->tile_begin, src, h->group_planes);
+    else
+      k_tile_apply<false><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
+                                                                      h->tile_begin, src, h->group_planes);
+  }
+  k_frame_finish<<<1, 1, 0, s>>>(h->d_cnt, h->map);
+  KSG_CUDA(cudaGetLastError());
+  int rc = fetch_counters(h, s);
+  if (rc) return rc;
+  dev_err = h->h_cnt->err;
+  h->num_blocks = h->h_cnt->pool_count;
+  h->last_blocks_touched = h->h_cnt->n_blocks_touched;
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->points_in = h->h_cnt->n_points;
+    stats->points_valid = h->h_cnt->n_valid;
+    stats->rays_cast = h->h_cnt->n_cast;
+    stats->ray_steps = (int64_t)h->h_cnt->ray_steps;
+    stats->voxel_updates = n_records;
+    stats->blocks_allocated = h->num_blocks;
+    stats->blocks_touched = h->h_cnt->n_blocks_touched;
+    stats->tiles_touched = h->h_cnt->n_tiles;
+    stats->fixpoint_iterations = iterations;
+  }
+  if (dev_err) {
+    h->deferred_status = dev_err;  // the map may be inconsistent from here on
+    return fail(dev_err, err_text(dev_err));
+  }
+  return KSG_OK;
+}
+
+int ensure_input(ksg_integrator* h, size_t bytes) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (bytes > h->h_stage_bytes) {
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr;
+    KSG_CUDA(cudaMallocHost((void**)&h->h_stage, bytes));
+    h->h_stage_bytes = bytes;
+  }
+  if (bytes > h->d_in_bytes) {
+    if (h->d_in) cudaFree(h->d_in);
+    h->d_in = nullptr;
+    KSG_CUDA(cudaMalloc((void**)&h->d_in, bytes));
+    h->d_in_bytes = bytes;
+  }
+  return KSG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size, int32_t voxels_per_side, int32_t num_labels) {
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = KSG_ABI_VERSION;
+  c->integrator_type = integrator_type;
+  c->voxel_size = voxel_size;
+  c->voxels_per_side = voxels_per_side;
+  c->default_truncation_distance = 4.0f * voxel_size;  // voxblox_ros: truncation_distance = 4 * voxel_size
+  c->max_weight = 10000.0f;
+  c->voxel_carving_enabled = 1;
+  c->min_ray_length_m = 0.1f;
+  c->max_ray_length_m = 5.0f;
+  c->use_const_weight = 0;
+  c->allow_clear = 1;
+  c->use_weight_dropoff = 1;
+  c->use_sparsity_compensation_factor = 0;
+  c->sparsity_compensation_factor = 1.0f;
+  c->integration_order_mode = KSG_ORDER_MIXED;
+  c->enable_anti_grazing = 0;
+  c->start_voxel_subsampling_factor = 2.0f;
+  c->max_consecutive_ray_collisions = 2;
+  c->clear_checks_every_n_frames = 1;
+  c->integrator_threads = 1;
+  c->num_labels = num_labels;
+  c->semantic_measurement_probability = 0.9f;  // base.h:77
+  c->color_mode = KSG_COLOR_MODE_SEMANTIC;     // base.h:80
+  for (int l = 0; l < 256; ++l) {
+    c->label_color[l][0] = 127; c->label_color[l][1] = 127; c->label_color[l][2] = 127; c->label_color[l][3] = 255;
+    c->label_color_known[l] = 1;
+    c->dynamic_label[l] = 0;
+  }
+  c->device = 0;
+  c->max_blocks = 8192;
+  c->max_points = 640 * 480;
+  c->max_ray_steps = 0;
+  c->max_updates = 0;
+  c->apply_mode = 0;
+}
+
+#define KSG_STR_(x) #x
+#define KSG_STR(x) KSG_STR_(x)
+const char* ksg_build_info(void) { return "ksg abi " KSG_STR(KSG_ABI_VERSION) " sm_100a nvcc " KSG_STR(__CUDACC_VER_MAJOR__) "." KSG_STR(__CUDACC_VER_MINOR__) " built " __DATE__; }
+
+const char* ksg_last_error(const ksg_integrator* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
+  if (!out) return KSG_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  std::string why;
+  int rc = validate(cfg, why);
+  if (rc) { g_last_error = why; return rc; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) {
+    g_last_error = "no CUDA device (the integrator has no CPU fallback)";
+    cudaGetLastError();
+    return KSG_ERR_NO_DEVICE;
+  }
+  ksg_integrator* h = new ksg_integrator();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  auto fail = [&](int c, const char* m) { g_last_error = m; free_all(h); delete h; return c; };
+  KSG_CUDA(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  KSG_CUDA(cudaGetDeviceProperties(&prop, h->device));
+  h->sm_count = prop.multiProcessorCount;
+  KSG_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+
+  // ---- geometry (voxblox Layer: inverses are 1.0 / x in double, stored as float; A.1, base.cpp:84-89)
+  DevCfg& dc = h->dc;
+  dc.voxel_size = cfg->voxel_size;
+  dc.vsi = (float)(1.0 / cfg->voxel_size);
+  dc.vps = cfg->voxels_per_side;
+  dc.vps_inv = (float)(1.0f / (float)cfg->voxels_per_side);
+  dc.tile_side = std::min(cfg->voxels_per_side, kTileSideMax);
+  dc.tile_side_log2 = ilog2(dc.tile_side);
+  dc.tiles_per_side = dc.vps / dc.tile_side;
+  dc.tiles_per_block = dc.tiles_per_side * dc.tiles_per_side * dc.tiles_per_side;
+  dc.tile_voxels = dc.tile_side * dc.tile_side * dc.tile_side;
+  dc.plane_f32 = round_up(4u * dc.tile_voxels, 16);
+  dc.plane_u8 = round_up((uint32_t)dc.tile_voxels, 16);
+  dc.head_bytes = 4 * dc.plane_f32 + dc.plane_u8;
+  dc.C = cfg->num_labels;
+  dc.tile_stride = round_up(dc.head_bytes + (uint32_t)dc.C * dc.plane_f32, 128);
+  dc.block_stride = (uint64_t)dc.tile_stride * dc.tiles_per_block;
+  dc.tp.voxel_size = cfg->voxel_size;
+  dc.tp.trunc = cfg->default_truncation_distance;
+  dc.tp.max_weight = cfg->max_weight;
+  dc.tp.sparsity_factor = cfg->sparsity_compensation_factor;
+  dc.tp.use_weight_dropoff = cfg->use_weight_dropoff;
+  dc.tp.use_sparsity = cfg->use_sparsity_compensation_factor;
+  dc.min_ray = cfg->min_ray_length_m;
+  dc.max_ray = cfg->max_ray_length_m;
+  dc.start_inv = cfg->start_voxel_subsampling_factor * dc.vsi;  // fast.cpp:89
+  dc.carving = cfg->voxel_carving_enabled;
+  dc.const_weight = cfg->use_const_weight;
+  dc.allow_clear = cfg->allow_clear;
+  dc.maxc = cfg->max_consecutive_ray_collisions;
+  dc.anti_grazing = cfg->enable_anti_grazing;
+  // setSemanticProbabilities (base.cpp:93-128): std::log on float, on the host (same libm as the reference)
+  dc.lm = std::log(cfg->semantic_measurement_probability);
+  dc.ln = std::log(1.0f - cfg->semantic_measurement_probability);
+  dc.color_mode = cfg->color_mode;
+  dc.type = cfg->integrator_type;
+
+  // ---- look-up tables
+  for (int l = 0; l < 256; ++l) {
+    const uint8_t* c = cfg->label_color[l];
+    h->h_luts.label_rgba[l] = cfg->label_color_known[l] ? ((uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24)) : 0u;
+    h->h_luts.dynamic_label[l] = cfg->dynamic_label[l];
+  }
+  for (int i = 0; i < 1024; ++i) { h->h_luts.c2l_keys[i] = 0xFFFFFFFFu; h->h_luts.c2l_vals[i] = 0; }
+  KSG_CUDA(dmalloc(&h->d_luts, 1));
+  KSG_CUDA(cudaMemcpy(h->d_luts, &h->h_luts, sizeof(Luts), cudaMemcpyHostToDevice));
+
+  // ---- map
+  h->ht_cap = 1024;
+  while (h->ht_cap < 2u * (uint32_t)cfg->max_blocks) h->ht_cap <<= 1;
+  if ((unsigned long long)h->ht_cap * dc.tiles_per_block >= (1ull << 32)) return fail(KSG_ERR_INVALID_ARGUMENT, "max_blocks too large");
+  h->map.ht_mask = h->ht_cap - 1;
+  h->map.max_blocks = cfg->max_blocks;
+  h->map.new_cap = cfg->max_blocks;
+  KSG_CUDA(dmalloc(&h->map.ht_keys, h->ht_cap));
+  KSG_CUDA(dmalloc(&h->map.ht_slot, h->ht_cap));
+  KSG_CUDA(dmalloc(&h->map.touched_stamp, h->ht_cap));
+  KSG_CUDA(dmalloc(&h->map.touched_list, h->ht_cap));
+  KSG_CUDA(dmalloc(&h->map.new_list, (size_t)cfg->max_blocks));
+  KSG_CUDA(dmalloc(&h->map.slot_key, (size_t)cfg->max_blocks));
+  KSG_CUDA(cudaMalloc((void**)&h->map.pool, (size_t)dc.block_stride * (size_t)cfg->max_blocks));
+  KSG_CUDA(dmalloc(&h->d_cnt, 1));
+  KSG_CUDA(cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)));
+  std::memset(h->h_cnt, 0, sizeof(Counters));
+
+  // ---- frame scratch
+  const size_t N = (size_t)cfg->max_points;
+  h->cap_points = cfg->max_points;
+  const bool fast = cfg->integrator_type == KSG_INTEGRATOR_FAST;
+  KSG_CUDA(dmalloc(&h->pt_pC, N)); KSG_CUDA(dmalloc(&h->pt_pG, N));
+  KSG_CUDA(dmalloc(&h->pt_label, N)); KSG_CUDA(dmalloc(&h->pt_flags, N));
+  KSG_CUDA(dmalloc(&h->pt_color, N)); KSG_CUDA(dmalloc(&h->pt_key, N));
+  KSG_CUDA(dmalloc(&h->flags8, 2 * N)); KSG_CUDA(dmalloc(&h->is_last, N));
+  KSG_CUDA(dmalloc(&h->pix_list, N));
+  KSG_CUDA(dmalloc(&h->iota, N));
+  k_iota<<<grid_for((long long)N, 256), 256>>>(h->iota, (int)N);
+  if (cfg->integration_order_mode == KSG_ORDER_SORTED) {
+    KSG_CUDA(dmalloc(&h->point_of_seq, N)); KSG_CUDA(dmalloc(&h->sq_keys, N)); KSG_CUDA(dmalloc(&h->sq_keys_out, N));
+  }
+  KSG_CUDA(dmalloc(&h->ray_param, N)); KSG_CUDA(dmalloc(&h->ray_flags, N)); KSG_CUDA(dmalloc(&h->nsteps, N));
+  long long rec_cap = cfg->max_updates > 0 ? cfg->max_updates : (fast ? std::max<long long>(4ll << 20, 64ll * (long long)N) : (64ll << 20));
+  if (fast) {
+    KSG_CUDA(dmalloc(&h->start_head, kSetSize)); KSG_CUDA(dmalloc(&h->start_next, N)); KSG_CUDA(dmalloc(&h->start_table, kSetSize));
+    KSG_CUDA(dmalloc(&h->cast_seq, N));
+    KSG_CUDA(dmalloc(&h->ray_label, N)); KSG_CUDA(dmalloc(&h->ray_color, N)); KSG_CUDA(dmalloc(&h->trunc_flag, N));
+    KSG_CUDA(dmalloc(&h->H, N)); KSG_CUDA(dmalloc(&h->L, N)); KSG_CUDA(dmalloc(&h->ray_state, N)); KSG_CUDA(dmalloc(&h->ext_off, N));
+    long long ext = cfg->max_ray_steps > 0 ? cfg->max_ray_steps : std::max<long long>(16ll << 20, 64ll * (long long)N);
+    h->ob.ext_base = (long long)N * kH0;
+    h->ob.cand_cap = h->ob.ext_base + ext;
+    if (h->ob.cand_cap >= 0x7FFFFFFFll) { h->ob.cand_cap = 0x7FFFFFFEll; }
+    KSG_CUDA(dmalloc(&h->ob.cand_val, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_order, (size_t)h->ob.cand_cap));
+    KSG_CUDA(dmalloc(&h->ob.cand_next, (size_t)h->ob.cand_cap));
+    KSG_CUDA(dmalloc(&h->ob.head, kSetSize)); KSG_CUDA(dmalloc(&h->ob.table, kSetSize));
+  } else {
+    KSG_CUDA(dmalloc(&h->ks_sorted, N)); KSG_CUDA(dmalloc(&h->seq_sorted, N));
+    KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
+    KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, N * dc.C));
+    KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
+  }
+  h->rec_cap = rec_cap;
+  KSG_CUDA(dmalloc(&h->rec_a, (size_t)rec_cap)); KSG_CUDA(dmalloc(&h->rec_b, (size_t)rec_cap));
+  h->tile_cap = (long long)std::min<unsigned long long>((unsigned long long)cfg->max_blocks * dc.tiles_per_block, (unsigned long long)rec_cap);
+  KSG_CUDA(dmalloc(&h->tile_begin, (size_t)h->tile_cap));
+
+  // ---- CUB temp storage: the largest of every call made per frame
+  {
+    size_t need = 0, t = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t, h->rec_a, h->rec_b, rec_cap, 0, 64); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, h->pt_key, h->pt_key, h->iota, h->iota, (int)N, 0, 64); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairs(nullptr, t, h->iota, h->iota, h->iota, h->iota, (int)N, 0, 32); need = std::max(need, t);
+    cub::DeviceSelect::Flagged(nullptr, t, cub::CountingInputIterator<int>(0), h->flags8, h->pix_list, (int*)nullptr, (int)(2 * N));
+    need = std::max(need, t);
+    h->cub_temp_bytes = need + 256;
+    KSG_CUDA(cudaMalloc(&h->cub_temp, h->cub_temp_bytes));
+  }
+
+  // ---- tile-apply launch configuration: stage as many class planes as fit ~100 KB (2 CTAs / SM)
+  {
+    const int V = dc.tile_voxels;
+    const size_t aux = (size_t)V * 16 + 64;
+    const size_t budget = 100 * 1024;
+    int g = (int)((budget - dc.head_bytes - aux) / dc.plane_f32);
+    g = std::max(1, std::min(g, dc.C));
+    h->group_planes = g;
+    h->apply_smem = (int)(dc.head_bytes + (size_t)g * dc.plane_f32 + aux);
+    h->use_tma = cfg->apply_mode == 0;
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+  }
+  KSG_CUDA(cudaDeviceSynchronize());
+  {
+    int r2 = reset_map(h, h->own_stream);
+    if (r2) { std::string m = h->err; return fail(r2, m.c_str()); }
+  }
+  *out = h;
+  return KSG_OK;
+}
+
+void ksg_destroy(ksg_integrator* h) {
+  if (!h) return;
+  free_all(h);
+  delete h;
+}
+
+int32_t ksg_set_color_to_label(ksg_integrator* h, const uint8_t* rgb, const uint8_t* labels, int32_t n) {
+  if (!h || n < 0 || n > 512 || (n > 0 && (!rgb || !labels))) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  for (int i = 0; i < 1024; ++i) { h->h_luts.c2l_keys[i] = 0xFFFFFFFFu; h->h_luts.c2l_vals[i] = 0; }
+  for (int i = 0; i < n; ++i) {
+    const uint32_t key = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16);
+    uint32_t p = (key * 2654435761u) >> 22;
+    while (h->h_luts.c2l_keys[p] != 0xFFFFFFFFu && h->h_luts.c2l_keys[p] != key) p = (p + 1) & 1023;
+    h->h_luts.c2l_keys[p] = key;
+    h->h_luts.c2l_vals[p] = labels[i];  // later rows overwrite earlier ones (color.cpp:58-59)
+  }
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaMemcpy(h->d_luts, &h->h_luts, sizeof(Luts), cudaMemcpyHostToDevice));
+  return KSG_OK;
+}
+
+int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T, const float* d_xyz, const uint8_t* d_rgba,
+                                    const uint8_t* d_labels, int64_t n, int32_t freespace, void* stream, ksg_frame_stats* stats) {
+  if (!h || !T || n < 0 || (n > 0 && !d_xyz)) return KSG_ERR_INVALID_ARGUMENT;
+  InputDesc in; in.d_xyz = d_xyz; in.d_rgba = d_rgba; in.d_labels = d_labels; in.n = n; in.freespace = freespace;
+  return integrate(h, in, T, stream ? (cudaStream_t)stream : h->own_stream, stats);
+}
+
+int32_t ksg_integrate_depth_device(ksg_integrator* h, const float* T, const float* d_depth, const uint8_t* d_label, int32_t width,
+                                   int32_t height, const float* K, void* stream, ksg_frame_stats* stats) {
+  if (!h || !T || !K || width <= 0 || height <= 0 || !d_depth || !d_label) return KSG_ERR_INVALID_ARGUMENT;
+  InputDesc in; in.d_depth = d_depth; in.d_label_img = d_label; in.width = width; in.height = height;
+  in.n = (int64_t)width * height; std::memcpy(in.K, K, sizeof(in.K));
+  return integrate(h, in, T, stream ? (cudaStream_t)stream : h->own_stream, stats);
+}
+
+int32_t ksg_integrate_points(ksg_integrator* h, const float* T, const float* xyz, const uint8_t* rgba, const uint8_t* labels,
+                             int64_t n, int32_t freespace, ksg_frame_stats* stats) {
+  if (!h || !T || n < 0 || (n > 0 && !xyz)) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  const size_t b_xyz = (size_t)n * 12, b_rgba = rgba ? (size_t)n * 4 : 0, b_lab = labels ? (size_t)n : 0;
+  const size_t o_rgba = round_up((uint32_t)b_xyz, 256), o_lab = o_rgba + round_up((uint32_t)b_rgba, 256);
+  const size_t total = o_lab + round_up((uint32_t)b_lab, 256) + 256;
+  int rc = ensure_input(h, total);
+  if (rc) return rc;
+  if (n > 0) {
+    std::memcpy(h->h_stage, xyz, b_xyz);
+    if (rgba) std::memcpy(h->h_stage + o_rgba, rgba, b_rgba);
+    if (labels) std::memcpy(h->h_stage + o_lab, labels, b_lab);
+    KSG_CUDA(cudaMemcpyAsync(h->d_in, h->h_stage, total, cudaMemcpyHostToDevice, h->own_stream));
+  }
+  InputDesc in; in.d_xyz = (const float*)h->d_in; in.d_rgba = rgba ? h->d_in + o_rgba : nullptr;
+  in.d_labels = labels ? h->d_in + o_lab : nullptr; in.n = n; in.freespace = freespace;
+  ksg_frame_stats local;
+  return integrate(h, in, T, h->own_stream, stats ? stats : &local);
+}
+
+int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* depth, const uint8_t* label, int32_t width,
+                            int32_t height, const float* K, ksg_frame_stats* stats) {
+  if (!h || !T || !K || width <= 0 || height <= 0 || !depth || !label) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  const size_t P = (size_t)width * height;
+  const size_t o_lab = round_up((uint32_t)(P * 4), 256);
+  const size_t total = o_lab + round_up((uint32_t)P, 256);
+  int rc = ensure_input(h, total);
+  if (rc) return rc;
+  std::memcpy(h->h_stage, depth, P * 4);
+  std::memcpy(h->h_stage + o_lab, label, P);
+  KSG_CUDA(cudaMemcpyAsync(h->d_in, h->h_stage, total, cudaMemcpyHostToDevice, h->own_stream));
+  InputDesc in; in.d_depth = (const float*)h->d_in; in.d_label_img = h->d_in + o_lab; in.width = width; in.height = height;
+  in.n = (int64_t)P; std::memcpy(in.K, K, sizeof(in.K));
+  ksg_frame_stats local;
+  return integrate(h, in, T, h->own_stream, stats ? stats : &local);
+}
+
+int32_t ksg_sync(ksg_integrator* h) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
+  return KSG_OK;
+}
+
+int64_t ksg_num_blocks(ksg_integrator* h) { return h ? h->num_blocks : 0; }
+
+static bool key_less_zyx(uint64_t a, uint64_t b) { return a < b; }  // packed as z:y:x, biased -> numeric order = (z, y, x)
+
+int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index, float* tsdf_distance,
+                          float* tsdf_weight, uint8_t* tsdf_rgba, uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  const int64_t nb = h->num_blocks;
+  if (nb > capacity_blocks) return fail(KSG_ERR_INVALID_ARGUMENT, "export capacity too small");
+  if (nb == 0) return KSG_OK;
+  std::vector<uint64_t> keys((size_t)nb);
+  KSG_CUDA(cudaMemcpy(keys.data(), h->map.slot_key, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost));
+  std::vector<int> order((size_t)nb);
+  for (int64_t i = 0; i < nb; ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key_less_zyx(keys[a], keys[b]); });
+  if (block_index)
+    for (int64_t i = 0; i < nb; ++i) {
+      const I3 b = unpack_key(keys[order[i]]);
+      block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
+    }
+  if (!tsdf_distance && !tsdf_weight && !tsdf_rgba && !sem_label && !sem_priors && !sem_rgba) return KSG_OK;
+  const DevCfg& dc = h->dc;
+  const size_t VB = (size_t)dc.vps * dc.vps * dc.vps;
+  const size_t per_block = VB * (4 + 4 + 4 + 1 + 4 + 4 * (size_t)dc.C) + 64;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)((256ull << 20) / per_block)));
+  if (h->exp_slots_cap < batch) {
+    if (h->d_exp_slots) cudaFree(h->d_exp_slots);
+    h->d_exp_slots = nullptr;
+    KSG_CUDA(dmalloc(&h->d_exp_slots, (size_t)batch));
+    h->exp_slots_cap = (int)batch;
+  }
+  const size_t need = (size_t)batch * per_block;
+  if (h->d_exp_bytes < need) {
+    if (h->d_exp) cudaFree(h->d_exp);
+    h->d_exp = nullptr;
+    KSG_CUDA(cudaMalloc((void**)&h->d_exp, need));
+    h->d_exp_bytes = need;
+  }
+  for (int64_t b0 = 0; b0 < nb; b0 += batch) {
+    const int64_t cnt = std::min(batch, nb - b0);
+    KSG_CUDA(cudaMemcpy(h->d_exp_slots, order.data() + b0, sizeof(int) * cnt, cudaMemcpyHostToDevice));
+    uint8_t* p = h->d_exp;
+    float* o_dist = (float*)p; p += cnt * VB * 4;
+    float* o_wgt = (float*)p; p += cnt * VB * 4;
+    uint32_t* o_rgba = (uint32_t*)p; p += cnt * VB * 4;
+    uint32_t* o_srgba = (uint32_t*)p; p += cnt * VB * 4;
+    float* o_prior = (float*)p; p += cnt * VB * 4 * dc.C;
+    uint8_t* o_label = p;
+    k_export<<<h->sm_count * 4, 256, 0, h->own_stream>>>(dc, h->map, h->d_exp_slots, (int)cnt, tsdf_distance ? o_dist : nullptr,
+                                                         tsdf_weight ? o_wgt : nullptr, tsdf_rgba ? o_rgba : nullptr,
+                                                         sem_label ? o_label : nullptr, sem_priors ? o_prior : nullptr,
+                                                         sem_rgba ? o_srgba : nullptr);
+    KSG_CUDA(cudaStreamSynchronize(h->own_stream));
+    if (tsdf_distance) KSG_CUDA(cudaMemcpy(tsdf_distance + b0 * VB, o_dist, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (tsdf_weight) KSG_CUDA(cudaMemcpy(tsdf_weight + b0 * VB, o_wgt, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (tsdf_rgba) KSG_CUDA(cudaMemcpy(tsdf_rgba + b0 * VB * 4, o_rgba, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (sem_rgba) KSG_CUDA(cudaMemcpy(sem_rgba + b0 * VB * 4, o_srgba, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (sem_label) KSG_CUDA(cudaMemcpy(sem_label + b0 * VB, o_label, cnt * VB, cudaMemcpyDeviceToHost));
+    if (sem_priors) KSG_CUDA(cudaMemcpy(sem_priors + b0 * VB * dc.C, o_prior, cnt * VB * 4 * dc.C, cudaMemcpyDeviceToHost));
+  }
+  return KSG_OK;
+}
+
+int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index) {
+  if (!h) return 0;
+  const int64_t n = h->last_blocks_touched;
+  if (!block_index || capacity_blocks < n || n == 0) return n;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  std::vector<int> pos((size_t)n);
+  if (cudaMemcpy(pos.data(), h->map.touched_list, sizeof(int) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  std::vector<uint64_t> all((size_t)h->ht_cap);
+  if (cudaMemcpy(all.data(), h->map.ht_keys, sizeof(uint64_t) * h->ht_cap, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  std::vector<uint64_t> keys((size_t)n);
+  for (int64_t i = 0; i < n; ++i) keys[i] = all[pos[i]];
+  std::sort(keys.begin(), keys.end());
+  for (int64_t i = 0; i < n; ++i) {
+    const I3 b = unpack_key(keys[i]);
+    block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
+  }
+  return n;
+}
+
+int32_t ksg_reset(ksg_integrator* h) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  return reset_map(h, h->own_stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,853 @@
+// ksg_kernels.cuh — hand-written sm_100a kernels of the semantic TSDF integrator.
+//
+// Kernel family (SURVEY.md §7.4 numbering in brackets):
+//   k_depth_flags / k_classify      [K1]  back-projection, validity, dynamic-label filter, T_G_C * p
+//   k_start_push/eval/commit        [K3]  exact emulation of fast's start_voxel_approx_set_
+//   k_ray_setup / k_extend / k_eval / k_obs_commit   [K4] exact emulation of voxel_observed_approx_set_
+//                                         (asynchronous fixpoint over per-slot visit lists)
+//   k_bundle_heads / k_bundle_merge / k_bundle_loglik [K2] merged: bundleRays + integrateVoxel merge loop
+//   k_emit_fast / k_emit_merged     [K4]  ray cast -> update records + block-hash insertion [K5]
+//   k_block_assign / k_block_init   [K5]  pool allocation of new voxel blocks
+//   k_tile_heads / k_tile_apply     [K6]  per-tile ordered TSDF + semantic update, TMA-staged
+//   k_export                        [K8]  tiles -> voxblox block layout
+#pragma once
+#include "ksg_device.cuh"
+
+namespace ksg {
+
+struct DevCfg {
+  float voxel_size, vsi, vps_inv;
+  int vps;
+  int tile_side, tile_side_log2, tiles_per_side, tiles_per_block, tile_voxels;
+  uint32_t plane_f32, plane_u8;  // bytes of one float / byte plane of a tile (16 B multiples)
+  uint32_t head_bytes;           // dist | weight | rgba | sem_rgba | label
+  uint32_t tile_stride;          // bytes
+  uint64_t block_stride;         // bytes
+  TsdfParams tp;
+  float min_ray, max_ray, start_inv;
+  int carving, const_weight, allow_clear, maxc, anti_grazing;
+  int C;
+  float lm, ln;
+  int color_mode;
+  int type;
+};
+
+struct Luts {
+  uint32_t label_rgba[256];   // 0 when unknown (color.cpp:92)
+  uint8_t dynamic_label[256];
+  uint32_t c2l_keys[1024];    // colour -> label open addressing table, 0xFFFFFFFF = empty
+  uint8_t c2l_vals[1024];
+};
+
+struct Counters {
+  int n_points;
+  int n_valid;
+  int n_cast;        // fast: cast rays R; merged: bundles B
+  int changed;
+  int n_truncated;
+  int n_new_blocks;
+  int n_tiles;
+  int err;
+  int n_blocks_touched;
+  int pool_count;    // blocks allocated in the pool (persistent across frames)
+  unsigned long long n_records;
+  unsigned long long sum_updates;
+  unsigned long long n_cand_ext;
+  unsigned long long ray_steps;
+};
+
+static constexpr int kH0 = 16;           // ray steps materialised before the first observed-set sweep
+static constexpr int kOrderStepBits = 16;
+static constexpr int kRecVoxBits = 9, kRecOrdBits = 23;
+
+__device__ __forceinline__ void set_err(Counters* c, int e) { atomicCAS(&c->err, 0, e); }
+
+// ---------------------------------------------------------------------------------------------
+// frame set-up
+// ---------------------------------------------------------------------------------------------
+__global__ void k_frame_reset(Counters* c, int n_points) {
+  c->n_points = n_points; c->n_valid = 0; c->n_cast = 0; c->changed = 0; c->n_truncated = 0;
+  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0;
+  c->n_records = 0; c->sum_updates = 0; c->n_cand_ext = 0; c->ray_steps = 0;
+}
+__global__ void k_iter_reset(Counters* c) { c->changed = 0; c->n_truncated = 0; c->sum_updates = 0; }
+
+// depth_map_to_pointcloud.h:259: DepthTraits<float>::valid = isfinite
+__global__ void k_depth_flags(const float* __restrict__ depth, int n, uint8_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = isfinite(depth[i]) ? 1 : 0;
+}
+
+__device__ __forceinline__ int mixed_index(int seq, int n) {  // voxblox MixedThreadSafeIndex (A.3)
+  const int groups = n / 1024;
+  if (groups * 1024 <= seq) return seq;
+  return (seq % groups) * 1024 + seq / groups;
+}
+
+struct FrameIn {
+  const float* xyz;         // n*3 or NULL
+  const uint8_t* rgba;      // n*4 or NULL
+  const uint8_t* labels;    // n or NULL
+  const float* depth;       // image or NULL
+  const uint8_t* label_img; // image or NULL
+  const int* pix_list;      // finite pixels (depth entry)
+  const int* point_of_seq;  // "sorted" order mode, else NULL
+  int width;
+  float cx, cy, constant_x, constant_y;
+  int freespace;
+};
+
+// One thread per sequence position (the order in which the reference's ThreadSafeIndex hands out points).
+// Replaces fast.cpp:152-158 (colour->label), :75-81 (validity, dynamic filter, transform), :87-89 (start cell)
+// and bundleRays' per-point part (A.5).
+template <bool FAST>
+__global__ void k_classify(DevCfg cfg, Xform T, FrameIn in, const Luts* __restrict__ luts, uint64_t start_offset,
+                           int capacity, Counters* cnt, float4* __restrict__ pt_pC, float4* __restrict__ pt_pG,
+                           uint8_t* __restrict__ pt_label, uint8_t* __restrict__ pt_flags, uint32_t* __restrict__ pt_color,
+                           uint64_t* __restrict__ pt_key) {
+  const int seq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= capacity) return;
+  const int n = cnt->n_points;
+  if (seq >= n) { pt_key[seq] = ~0ull; pt_flags[seq] = 0; return; }
+  const int i = in.point_of_seq ? in.point_of_seq[seq] : mixed_index(seq, n);
+  F3 pC;
+  uint8_t label;
+  uint32_t color;
+  if (in.depth) {
+    const int pix = in.pix_list[i];
+    const int v = pix / in.width, u = pix - v * in.width;
+    const float d = in.depth[pix];
+    pC = f3(((float)u - in.cx) * d * in.constant_x, ((float)v - in.cy) * d * in.constant_y, d);
+    label = in.label_img[pix];
+    color = luts->label_rgba[label];
+  } else {
+    pC = f3(in.xyz[3 * i], in.xyz[3 * i + 1], in.xyz[3 * i + 2]);
+    if (in.rgba) color = (uint32_t)in.rgba[4 * i] | ((uint32_t)in.rgba[4 * i + 1] << 8) | ((uint32_t)in.rgba[4 * i + 2] << 16) | ((uint32_t)in.rgba[4 * i + 3] << 24);
+    else color = 0;
+    if (in.labels) label = in.labels[i];
+    else if (in.rgba) {  // SemanticLabel2Color::getSemanticLabelFromColor (color.cpp:69-82), alpha forced to 255
+      const uint32_t rgb = color & 0x00FFFFFFu;
+      uint32_t h = (rgb * 2654435761u) >> 22;
+      label = 0;
+      for (int p = 0; p < 1024; ++p) {
+        const uint32_t k = luts->c2l_keys[h];
+        if (k == rgb) { label = luts->c2l_vals[h]; break; }
+        if (k == 0xFFFFFFFFu) break;
+        h = (h + 1) & 1023;
+      }
+    } else label = 0;
+    if (!in.rgba) color = luts->label_rgba[label];
+  }
+  if ((int)label >= cfg.C) { set_err(cnt, 1 /*KSG_ERR_INVALID_ARGUMENT: CHECK_LT fast.cpp:134*/); label = 0; }
+  // isPointValid (A.6)
+  const float ray_distance = norm3(pC);
+  bool valid = true, clearing = false;
+  if (ray_distance < cfg.min_ray) valid = false;
+  else if (ray_distance > cfg.max_ray) {
+    if (cfg.allow_clear || in.freespace) clearing = true; else valid = false;
+  } else clearing = in.freespace != 0;
+  if (!(ray_distance == ray_distance)) valid = false;  // NaN points never pass the comparisons upstream either way
+  if (FAST && luts->dynamic_label[label]) valid = false;  // isSemanticLabelValid (base.h:170-175), fast only
+  // getVoxelWeight (A.6)
+  float w;
+  if (cfg.const_weight) w = 1.0f;
+  else { const float z = fabsf(pC.z); w = (z > kEps) ? 1.0f / (z * z) : 0.0f; }
+  const F3 pG = xform_apply(T, pC);
+  pt_pC[seq] = make_float4(pC.x, pC.y, pC.z, w);
+  pt_pG[seq] = make_float4(pG.x, pG.y, pG.z, w);
+  pt_label[seq] = label;
+  pt_color[seq] = color;
+  pt_flags[seq] = (valid ? 1 : 0) | (clearing ? 2 : 0);
+  uint64_t key = ~0ull;
+  if (valid) {
+    if (FAST) {
+      const F3 sc = mul(pG, cfg.start_inv);
+      if (!index_in_range(sc)) set_err(cnt, 5);
+      const I3 g = grid_index(pG, cfg.start_inv);   // fast.cpp:88-89
+      key = (uint64_t)index_hash(g) + start_offset;  // ApproxHashSet value = hash + offset_
+    } else {
+      const I3 g = grid_index(pG, cfg.vsi);          // bundleRays (A.5)
+      if (!key_in_range(g) || !index_in_range(mul(pG, cfg.vsi))) { set_err(cnt, 5); }
+      else key = pack_key(g) | (clearing ? (1ull << 63) : 0ull);
+    }
+    atomicAdd(&cnt->n_valid, 1);
+  }
+  pt_key[seq] = key;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast: start_voxel_approx_set_ (fast.cpp:87-92, A.4).  The set's state is "value of the last
+// replaceHash on the slot", so a point is skipped iff the previous visitor of its slot (in sequence
+// order; before the first visitor: the persistent table) carried the same value.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_start_push(const Counters* cnt, const uint64_t* __restrict__ key, int* head, int* next) {
+  const int seq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= cnt->n_points) return;
+  const uint64_t v = key[seq];
+  if (v == ~0ull) return;
+  next[seq] = atomicExch(&head[(uint32_t)v & kSetMask], seq);
+}
+__global__ void k_start_eval(const Counters* cnt, const uint64_t* __restrict__ key, const int* __restrict__ head,
+                             const int* __restrict__ next, const uint32_t* __restrict__ table, uint8_t* __restrict__ cast_flag,
+                             uint8_t* __restrict__ is_last, int capacity) {
+  const int seq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= capacity) return;
+  uint8_t cast = 0, last = 0;
+  if (seq < cnt->n_points) {
+    const uint64_t v = key[seq];
+    if (v != ~0ull) {
+      const uint32_t slot = (uint32_t)v & kSetMask;
+      int best = -1;
+      bool later = false;
+      for (int e = head[slot]; e >= 0; e = next[e]) {
+        if (e < seq && e > best) best = e;
+        if (e > seq) later = true;
+      }
+      if (best >= 0) cast = key[best] != v;
+      else cast = table[slot] != (uint32_t)(v >> kSetBits);
+      last = !later;
+    }
+  }
+  cast_flag[seq] = cast;
+  is_last[seq] = last;
+}
+__global__ void k_start_commit(const Counters* cnt, const uint64_t* __restrict__ key, const uint8_t* __restrict__ is_last,
+                               uint32_t* table) {
+  const int seq = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seq >= cnt->n_points || !is_last[seq]) return;
+  const uint64_t v = key[seq];
+  table[(uint32_t)v & kSetMask] = (uint32_t)(v >> kSetBits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast: voxel_observed_approx_set_ (fast.cpp:110-122, A.4) solved as a fixpoint.
+//   candidates  = ray steps materialised so far (the first kH0 of every cast ray, all remaining steps of
+//                 a ray once it is found to survive that far),
+//   U[r]        = number of voxels ray r updates (= index of the step at which it breaks),
+//   a candidate (r,s) "collides" iff the latest PERFORMED candidate (s' < U[r']) that precedes it in
+//   (rank, step) order on the same slot carries the same value (none: the persistent table decides).
+// The dependency is triangular in rank order, so the fixpoint is unique; k_eval is swept until no U
+// changes (in-place / asynchronous updates only accelerate convergence).
+// ---------------------------------------------------------------------------------------------
+struct RayState {      // saved DDA state after the materialised steps
+  int cx, cy, cz, sg;  // sg: 2 bits per axis (0,1,2 = -1,0,+1)
+  float tn0, tn1, tn2, ts0, ts1, ts2;
+};
+__device__ __forceinline__ void save_state(RayState& s, const Dda& d) {
+  s.cx = d.cur.x; s.cy = d.cur.y; s.cz = d.cur.z;
+  s.sg = (d.sg[0] + 1) | ((d.sg[1] + 1) << 2) | ((d.sg[2] + 1) << 4);
+  s.tn0 = d.tn[0]; s.tn1 = d.tn[1]; s.tn2 = d.tn[2]; s.ts0 = d.ts[0]; s.ts1 = d.ts[1]; s.ts2 = d.ts[2];
+}
+__device__ __forceinline__ void load_state(Dda& d, const RayState& s) {
+  d.cur.x = s.cx; d.cur.y = s.cy; d.cur.z = s.cz;
+  d.sg[0] = (s.sg & 3) - 1; d.sg[1] = ((s.sg >> 2) & 3) - 1; d.sg[2] = ((s.sg >> 4) & 3) - 1;
+  d.tn[0] = s.tn0; d.tn[1] = s.tn1; d.tn[2] = s.tn2; d.ts[0] = s.ts0; d.ts[1] = s.ts1; d.ts[2] = s.ts2;
+}
+
+struct ObsBuf {
+  uint64_t* cand_val;    // value = hash + offset of the visited voxel
+  uint64_t* cand_order;  // (rank << 16) | step
+  int* cand_next;        // per-slot list link
+  int* head;             // 2^20 list heads
+  uint32_t* table;       // persistent compact table: value >> 20, kSetNever = matches nothing
+  long long ext_base;    // first extension candidate index (= capacity_rays * kH0)
+  long long cand_cap;    // total candidate capacity
+};
+__device__ __forceinline__ long long cand_index(const ObsBuf& o, const long long* ext_off, int r, int s) {
+  return (s < kH0) ? (long long)r * kH0 + s : o.ext_base + ext_off[r] + (s - kH0);
+}
+
+__global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __restrict__ cast_seq,
+                            const float4* __restrict__ pt_pG, const uint8_t* __restrict__ pt_label,
+                            const uint8_t* __restrict__ pt_flags, const uint32_t* __restrict__ pt_color, uint64_t obs_offset,
+                            ObsBuf ob, float4* __restrict__ ray_param, uint8_t* __restrict__ ray_label,
+                            uint8_t* __restrict__ ray_flags, uint32_t* __restrict__ ray_color, int* __restrict__ nsteps,
+                            int* __restrict__ H, int* L, RayState* __restrict__ state, long long* __restrict__ ext_off,
+                            uint8_t* __restrict__ trunc_flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cnt->n_cast) return;
+  const int seq = cast_seq[r];
+  const float4 p = pt_pG[seq];
+  const uint8_t fl = pt_flags[seq];
+  ray_param[r] = p;
+  ray_label[r] = pt_label[seq];
+  ray_flags[r] = fl;
+  ray_color[r] = pt_color[seq];
+  Dda d;
+  raycaster_init(d, f3(T.tx, T.ty, T.tz), f3(p.x, p.y, p.z), (fl & 2) != 0, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc,
+                 /*cast_from_origin=*/false);
+  int n = d.length_in_steps + 1;
+  if (!d.in_range || n >= (1 << kOrderStepBits)) { set_err(cnt, 5); n = 0; }
+  nsteps[r] = n;
+  const int h = n < kH0 ? n : kH0;
+  for (int s = 0; s < h; ++s) {
+    const I3 g = dda_next(d);
+    const uint64_t v = (uint64_t)index_hash(g) + obs_offset;
+    const long long ci = (long long)r * kH0 + s;
+    ob.cand_val[ci] = v;
+    ob.cand_order[ci] = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+    ob.cand_next[ci] = atomicExch(&ob.head[(uint32_t)v & kSetMask], (int)ci);
+  }
+  RayState st; save_state(st, d); state[r] = st;
+  H[r] = h;
+  L[r] = h;
+  ext_off[r] = -1;
+  trunc_flag[r] = 0;
+  atomicAdd(&cnt->ray_steps, (unsigned long long)h);
+}
+
+// Materialise the remaining steps of the rays that performed every step they had (trunc_flag set).
+__global__ void k_extend(Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
+                         int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cnt->n_cast) return;
+  if (!trunc_flag[r]) return;
+  trunc_flag[r] = 0;
+  const int n = nsteps[r], h = H[r];
+  if (h >= n) return;
+  const long long need = n - h;
+  const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need);
+  if (ob.ext_base + off + need > ob.cand_cap || ob.ext_base + off + need >= 0x7FFFFFFFll) { set_err(cnt, 4); return; }
+  ext_off[r] = off;
+  Dda d; load_state(d, state[r]);
+  for (int s = h; s < n; ++s) {
+    const I3 g = dda_next(d);
+    const uint64_t v = (uint64_t)index_hash(g) + obs_offset;
+    const long long ci = ob.ext_base + off + (s - kH0);
+    ob.cand_val[ci] = v;
+    ob.cand_order[ci] = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+    ob.cand_next[ci] = atomicExch(&ob.head[(uint32_t)v & kSetMask], (int)ci);
+  }
+  H[r] = n;
+  L[r] = n;  // optimistic: everything performed until the next sweep says otherwise
+  atomicAdd(&cnt->ray_steps, (unsigned long long)need);
+  cnt->changed = 1;
+}
+
+__global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restrict__ nsteps, const int* __restrict__ H, int* L,
+                       const long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int U = 0;
+  if (r < cnt->n_cast) {
+    const int h = H[r];
+    const int old = L[r];
+    int coll_run = 0;
+    U = -1;
+    for (int s = 0; s < h; ++s) {
+      const long long ci = cand_index(ob, ext_off, r, s);
+      const uint64_t v = ob.cand_val[ci];
+      const uint32_t slot = (uint32_t)v & kSetMask;
+      const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+      long long best_order = -1;
+      uint64_t best_val = 0;
+      for (int e = ob.head[slot]; e >= 0; e = ob.cand_next[e]) {
+        const uint64_t eo = ob.cand_order[e];
+        if (eo < my_order && (long long)eo > best_order) {
+          const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
+          const bool performed = (er == r) ? true : (es < ((volatile int*)L)[er]);
+          if (performed) { best_order = (long long)eo; best_val = ob.cand_val[e]; }
+        }
+      }
+      const bool coll = (best_order >= 0) ? (best_val == v) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
+      if (coll) ++coll_run; else coll_run = 0;          // fast.cpp:115-119
+      if (coll_run > cfg.maxc) { U = s; break; }        // fast.cpp:120-122
+    }
+    bool truncated = false;
+    if (U < 0) { U = h; truncated = h < nsteps[r]; }
+    trunc_flag[r] = truncated ? 1 : 0;
+    if (truncated) atomicAdd(&cnt->n_truncated, 1);
+    if (U != old) { L[r] = U; cnt->changed = 1; }
+  }
+  // warp-aggregated sum of U
+  unsigned long long u = (unsigned long long)U;
+  for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
+  if ((threadIdx.x & 31) == 0 && u) atomicAdd(&cnt->sum_updates, u);
+}
+
+// After convergence: the last performed visit of every slot becomes the persistent table entry.
+__global__ void k_obs_commit(Counters* cnt, ObsBuf ob, const int* __restrict__ L, const long long* __restrict__ ext_off) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cnt->n_cast) return;
+  const int U = L[r];
+  for (int s = 0; s < U; ++s) {
+    const long long ci = cand_index(ob, ext_off, r, s);
+    const uint64_t v = ob.cand_val[ci];
+    const uint32_t slot = (uint32_t)v & kSetMask;
+    const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+    bool later = false;
+    for (int e = ob.head[slot]; e >= 0 && !later; e = ob.cand_next[e]) {
+      const uint64_t eo = ob.cand_order[e];
+      if (eo > my_order) {
+        const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
+        if (es < L[er]) later = true;
+      }
+    }
+    if (!later) ob.table[slot] = (uint32_t)(v >> kSetBits);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spatial block hash (Layer<>::BlockHashMap replacement): open addressing, 64-bit packed keys
+// ---------------------------------------------------------------------------------------------
+struct MapRef {
+  uint64_t* ht_keys;
+  int* ht_slot;          // pool slot of the entry, -1 until k_block_assign ran
+  uint32_t ht_mask;
+  int* new_list;         // hash positions inserted this frame
+  int new_cap;
+  uint8_t* pool;
+  uint64_t* slot_key;    // block key of every pool slot
+  int max_blocks;
+  int* touched_stamp;    // per hash position: frame stamp of the last touch
+  int* touched_list;
+};
+
+__device__ __forceinline__ int ht_find_or_insert(const MapRef& m, uint64_t key, Counters* cnt) {
+  uint32_t pos = mix64(key) & m.ht_mask;
+  for (uint32_t probe = 0; probe <= m.ht_mask; ++probe) {
+    const uint64_t k = ((volatile uint64_t*)m.ht_keys)[pos];
+    if (k == key) return (int)pos;
+    if (k == kEmptyKey) {
+      const uint64_t old = atomicCAS((unsigned long long*)&m.ht_keys[pos], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey) {
+        const int i = atomicAdd(&cnt->n_new_blocks, 1);
+        if (i < m.new_cap) m.new_list[i] = (int)pos; else set_err(cnt, 3);
+        return (int)pos;
+      }
+      if (old == key) return (int)pos;
+    }
+    pos = (pos + 1) & m.ht_mask;
+  }
+  set_err(cnt, 3);
+  return -1;
+}
+
+// update record: [hash position * tiles_per_block + tile : 32][voxel in tile : 9][order : 23]
+__device__ __forceinline__ uint64_t make_record(const DevCfg& cfg, int htpos, I3 g, uint32_t order) {
+  const int m = cfg.vps - 1;
+  const int lx = g.x & m, ly = g.y & m, lz = g.z & m;  // getLocalFromGlobalVoxelIndex (A.2)
+  const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+  const int tile = (lx >> ts) + cfg.tiles_per_side * ((ly >> ts) + cfg.tiles_per_side * (lz >> ts));
+  const int vox = (lx & tm) + cfg.tile_side * ((ly & tm) + cfg.tile_side * (lz & tm));
+  const uint64_t tk = (uint64_t)htpos * (uint64_t)cfg.tiles_per_block + (uint64_t)tile;
+  return (tk << 32) | ((uint64_t)vox << kRecOrdBits) | (uint64_t)order;
+}
+
+// fast.cpp:110-141 for the steps that survived the observed-set logic: allocate + emit update records.
+__global__ void k_emit_fast(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const float4* __restrict__ ray_param,
+                            const uint8_t* __restrict__ ray_flags, const int* __restrict__ L, uint64_t* __restrict__ records,
+                            long long rec_cap) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cnt->n_cast) return;
+  const int U = L[r];
+  if (U <= 0) return;
+  const long long base = (long long)atomicAdd(&cnt->n_records, (unsigned long long)U);
+  if (base + U > rec_cap) { set_err(cnt, 4); return; }
+  const float4 p = ray_param[r];
+  Dda d;
+  raycaster_init(d, f3(T.tx, T.ty, T.tz), f3(p.x, p.y, p.z), (ray_flags[r] & 2) != 0, cfg.carving != 0, cfg.max_ray, cfg.vsi,
+                 cfg.tp.trunc, false);
+  I3 last_b; last_b.x = last_b.y = last_b.z = 0x7fffffff;
+  int htpos = -1;
+  for (int s = 0; s < U; ++s) {
+    const I3 g = dda_next(d);
+    const I3 b = block_of_voxel(g, cfg.vps_inv);
+    if (b.x != last_b.x || b.y != last_b.y || b.z != last_b.z) {
+      last_b = b;
+      if (!key_in_range(b)) { set_err(cnt, 5); htpos = -1; }
+      else htpos = ht_find_or_insert(map, pack_key(b), cnt);
+    }
+    records[base + s] = (htpos >= 0) ? make_record(cfg, htpos, g, (uint32_t)r) : ~0ull;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merged: bundles (A.5 bundleRays + merged.cpp:235-294)
+// ---------------------------------------------------------------------------------------------
+// sorted (key, seq) pairs: a bundle = run of equal keys; its points are in sequence order (stable sort of a
+// sequence-ordered array); its rank = first sequence position (canonical first-insertion order).
+__global__ void k_bundle_heads(const uint64_t* __restrict__ ks, const uint32_t* __restrict__ seq_sorted, int capacity,
+                               uint8_t* __restrict__ bflag, int* __restrict__ bstart) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= capacity) return;
+  const uint64_t k = ks[i];
+  if (k == ~0ull) return;
+  if (i > 0 && ks[i - 1] == k) return;
+  const size_t f = (size_t)(k >> 63) * (size_t)capacity + seq_sorted[i];  // non-clearing pass first (merged.cpp:126-144)
+  bflag[f] = 1;
+  bstart[f] = i;
+}
+
+__global__ void k_bundle_merge(DevCfg cfg, Xform T, Counters* cnt, const int* __restrict__ bundle_f, const int* __restrict__ bstart,
+                               const uint64_t* __restrict__ ks, const uint32_t* __restrict__ seq_sorted, int capacity,
+                               const float4* __restrict__ pt_pC, const uint8_t* __restrict__ pt_label, float* __restrict__ hist,
+                               float4* __restrict__ b_param, uint8_t* __restrict__ b_flags, uint64_t* __restrict__ b_key,
+                               int* __restrict__ b_nsteps, long long* __restrict__ b_base, long long rec_cap) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= cnt->n_cast) return;
+  const int f = bundle_f[b];
+  const int i0 = bstart[f];
+  const uint64_t key = ks[i0];
+  const bool clearing = (key >> 63) != 0;
+  float* h = hist + (size_t)b * cfg.C;
+  for (int c = 0; c < cfg.C; ++c) h[c] = 0.0f;
+  F3 mp = f3(0.0f, 0.0f, 0.0f);
+  float mw = 0.0f;
+  for (int i = i0; i < capacity && ks[i] == key; ++i) {   // merged.cpp:263-285
+    const uint32_t seq = seq_sorted[i];
+    const float4 pc = pt_pC[seq];
+    const float pw = pc.w;
+    if (pw < kEps) continue;
+    const float tot = mw + pw;
+    mp = f3((mp.x * mw + pc.x * pw) / tot, (mp.y * mw + pc.y * pw) / tot, (mp.z * mw + pc.z * pw) / tot);
+    mw += pw;
+    h[pt_label[seq]] += 1.0f;
+    if (clearing) break;
+  }
+  const F3 pG = xform_apply(T, mp);
+  b_param[b] = make_float4(pG.x, pG.y, pG.z, mw);
+  b_flags[b] = clearing ? 2 : 0;
+  b_key[b] = key & ~(1ull << 63);
+  Dda d;
+  raycaster_init(d, f3(T.tx, T.ty, T.tz), pG, clearing, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc, true);
+  int n = d.length_in_steps + 1;
+  if (!d.in_range) { set_err(cnt, 5); n = 0; }
+  b_nsteps[b] = n;
+  const long long base = (long long)atomicAdd(&cnt->n_records, (unsigned long long)n);
+  if (base + n > rec_cap) { set_err(cnt, 4); b_nsteps[b] = 0; }
+  b_base[b] = base;
+  atomicAdd(&cnt->ray_steps, (unsigned long long)n);
+}
+
+// tmp[b][i] = sum_j L[i][j] * freq[j]  (base.cpp:306-307) with L[i][j] = log_match on the diagonal, log_non_match
+// elsewhere, column 0 zero (base.cpp:108-127); summation fixed as j ascending, one multiply + one add per term (A.9).
+__global__ void k_bundle_loglik(DevCfg cfg, const Counters* cnt, const float* __restrict__ hist, float* __restrict__ tmp) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)cnt->n_cast * cfg.C;
+  if (t >= total) return;
+  const int i = (int)(t % cfg.C);
+  const float* h = hist + (t - i);
+  float acc = 0.0f;
+  for (int j = 1; j < cfg.C; ++j) acc = acc + ((i == j) ? cfg.lm : cfg.ln) * h[j];
+  tmp[t] = acc;
+}
+
+__global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const float4* __restrict__ b_param,
+                              const uint8_t* __restrict__ b_flags, const uint64_t* __restrict__ b_key,
+                              const int* __restrict__ b_nsteps, const long long* __restrict__ b_base,
+                              const uint64_t* __restrict__ ks, int capacity, uint64_t* __restrict__ records) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= cnt->n_cast) return;
+  const int n = b_nsteps[b];
+  if (n <= 0) return;
+  const float4 p = b_param[b];
+  const bool clearing = (b_flags[b] & 2) != 0;
+  Dda d;
+  raycaster_init(d, f3(T.tx, T.ty, T.tz), f3(p.x, p.y, p.z), clearing, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc, true);
+  const long long base = b_base[b];
+  I3 last_b; last_b.x = last_b.y = last_b.z = 0x7fffffff;
+  int htpos = -1;
+  const uint64_t own = b_key[b];
+  for (int s = 0; s < n; ++s) {
+    const I3 g = dda_next(d);
+    bool skip = false;
+    if (cfg.anti_grazing) {  // merged.cpp:306-313: skip voxels that are some bundle's end voxel
+      if (!key_in_range(g)) skip = false;
+      else {
+        const uint64_t gk = pack_key(g);
+        if (clearing || gk != own) {
+          int lo = 0, hi = capacity;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] < gk) lo = mid + 1; else hi = mid; }
+          skip = (lo < capacity && ks[lo] == gk);
+        }
+      }
+    }
+    if (skip) { records[base + s] = ~0ull; continue; }
+    const I3 bi = block_of_voxel(g, cfg.vps_inv);
+    if (bi.x != last_b.x || bi.y != last_b.y || bi.z != last_b.z) {
+      last_b = bi;
+      if (!key_in_range(bi)) { set_err(cnt, 5); htpos = -1; }
+      else htpos = ht_find_or_insert(map, pack_key(bi), cnt);
+    }
+    records[base + s] = (htpos >= 0) ? make_record(cfg, htpos, g, (uint32_t)b) : ~0ull;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// block pool
+// ---------------------------------------------------------------------------------------------
+__global__ void k_block_assign(Counters* cnt, MapRef map) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_new = cnt->n_new_blocks < map.new_cap ? cnt->n_new_blocks : map.new_cap;
+  if (i >= n_new) return;
+  const int slot = cnt->pool_count + i;
+  const int pos = map.new_list[i];
+  if (slot >= map.max_blocks) { set_err(cnt, 3); return; }
+  map.ht_slot[pos] = slot;
+  map.slot_key[slot] = map.ht_keys[pos];
+}
+// SemanticVoxel / TsdfVoxel default construction (semantic_voxel.h:14-27; TsdfVoxel A.0)
+__global__ void k_block_init(DevCfg cfg, const Counters* cnt, MapRef map) {
+  const int n_new = cnt->n_new_blocks < map.new_cap ? cnt->n_new_blocks : map.new_cap;
+  const int per_block = cfg.tiles_per_block;
+  for (long long w = blockIdx.x; w < (long long)n_new * per_block; w += gridDim.x) {
+    const int i = (int)(w / per_block), tile = (int)(w % per_block);
+    const int slot = cnt->pool_count + i;
+    if (slot >= map.max_blocks) continue;
+    uint8_t* chunk = map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
+    float* dist = (float*)chunk;
+    float* wgt = (float*)(chunk + cfg.plane_f32);
+    uint32_t* rgba = (uint32_t*)(chunk + 2 * cfg.plane_f32);
+    uint32_t* srgba = (uint32_t*)(chunk + 3 * cfg.plane_f32);
+    uint8_t* label = chunk + 4 * cfg.plane_f32;
+    float* prior = (float*)(chunk + cfg.head_bytes);
+    const int V = cfg.tile_voxels;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      dist[v] = 0.0f; wgt[v] = 0.0f; rgba[v] = 0u; srgba[v] = 0xFF7F7F7Fu; label[v] = 0;
+    }
+    const int pf = cfg.plane_f32 / 4;
+    for (int t = threadIdx.x; t < cfg.C * V; t += blockDim.x) prior[(t / V) * pf + (t % V)] = (float)-0.60205999132;
+  }
+}
+__global__ void k_frame_finish(Counters* cnt, MapRef map) {
+  int n_new = cnt->n_new_blocks < map.new_cap ? cnt->n_new_blocks : map.new_cap;
+  if (cnt->pool_count + n_new > map.max_blocks) n_new = map.max_blocks - cnt->pool_count;
+  cnt->pool_count += n_new;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile apply
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64_t* __restrict__ rec, long long n, int stamp,
+                             long long* __restrict__ tile_begin, long long tile_cap) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = rec[i];
+  if (k == ~0ull) return;
+  const uint32_t tk = (uint32_t)(k >> 32);
+  if (i > 0 && (uint32_t)(rec[i - 1] >> 32) == tk) return;
+  const int j = atomicAdd(&cnt->n_tiles, 1);
+  if (j < tile_cap) tile_begin[j] = i; else set_err(cnt, 4);
+  const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
+  const int old = atomicExch(&map.touched_stamp[pos], stamp);
+  if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// TMA 1-D bulk copies (cp.async.bulk -> SASS UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct ApplySrc {
+  const float4* param;   // per order id: (point_G xyz, weight)
+  const uint8_t* label;  // fast: measured label (one-hot frequencies, fast.cpp:132-135); NULL for merged
+  const uint32_t* color; // fast: point colour; NULL -> (0,0,0,0) (merged.cpp:70 unfilled hash_colors)
+  const float* tmp;      // merged: C floats per bundle = L * freq; NULL for fast
+};
+
+static constexpr int kApplyThreads = 256;
+
+// One CTA per touched tile (persistent grid).  The tile's voxel planes are staged in shared memory with
+// TMA bulk copies (or a cooperative copy when USE_TMA == false), every voxel's update records (sorted by
+// (voxel, order)) are applied sequentially in the reference's order — updateTsdfVoxel (A.6) and
+// updateSemanticVoxel (base.cpp:136-194) — and the tile is written back once.
+template <bool USE_TMA>
+__global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
+                                                               const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
+                                                               long long n_rec, const long long* __restrict__ tile_begin,
+                                                               ApplySrc src, int group_planes) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int V = cfg.tile_voxels;
+  float* s_dist = (float*)smem;
+  float* s_wgt = (float*)(smem + cfg.plane_f32);
+  uint32_t* s_rgba = (uint32_t*)(smem + 2 * cfg.plane_f32);
+  uint32_t* s_srgba = (uint32_t*)(smem + 3 * cfg.plane_f32);
+  uint8_t* s_label = smem + 4 * cfg.plane_f32;
+  float* s_prior = (float*)(smem + cfg.head_bytes);
+  uint8_t* aux = smem + cfg.head_bytes + (size_t)group_planes * cfg.plane_f32;
+  int* s_seg_lo = (int*)aux;                 // [V]
+  int* s_seg_hi = s_seg_lo + V;              // [V]
+  float* s_best = (float*)(s_seg_hi + V);    // [V] running arg-max across class groups
+  int* s_best_lab = (int*)(s_best + V);      // [V]
+  uint64_t* s_bar = (uint64_t*)(s_best_lab + V);
+  __shared__ long long s_begin, s_end;
+  __shared__ uint8_t* s_chunk;
+  __shared__ int s_g0x, s_g0y, s_g0z;
+
+  const int tid = threadIdx.x;
+  const int pf = cfg.plane_f32 / 4;
+  uint32_t phase = 0;
+  if (USE_TMA && tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  const int n_tiles = cnt->n_tiles;
+  const int ngroups = (cfg.C + group_planes - 1) / group_planes;
+  const F3 origin = f3(T.tx, T.ty, T.tz);
+
+  for (int j = blockIdx.x; j < n_tiles; j += gridDim.x) {
+    if (tid == 0) {
+      const long long b = tile_begin[j];
+      const uint32_t tk = (uint32_t)(rec[b] >> 32);
+      long long lo = b, hi = n_rec;  // first record whose tile key is greater
+      while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((uint32_t)(rec[mid] >> 32) <= tk) lo = mid + 1; else hi = mid; }
+      s_begin = b; s_end = lo;
+      const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block), tile = (int)(tk % (uint32_t)cfg.tiles_per_block);
+      const int slot = map.ht_slot[pos];
+      s_chunk = (slot >= 0 && slot < map.max_blocks) ? map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride : nullptr;
+      const I3 bi = unpack_key(map.ht_keys[pos]);
+      const int tps = cfg.tiles_per_side;
+      const int tx = tile % tps, ty = (tile / tps) % tps, tz = tile / (tps * tps);
+      s_g0x = bi.x * cfg.vps + tx * cfg.tile_side;
+      s_g0y = bi.y * cfg.vps + ty * cfg.tile_side;
+      s_g0z = bi.z * cfg.vps + tz * cfg.tile_side;
+    }
+    for (int v = tid; v < V; v += kApplyThreads) { s_seg_lo[v] = 0; s_seg_hi[v] = 0; }
+    __syncthreads();
+    uint8_t* chunk = s_chunk;
+    if (chunk == nullptr) { __syncthreads(); continue; }  // pool overflow already flagged
+    const long long begin = s_begin, end = s_end;
+    // per-voxel record segments
+    for (long long i = begin + tid; i < end; i += kApplyThreads) {
+      const int vx = (int)((rec[i] >> kRecOrdBits) & ((1u << kRecVoxBits) - 1));
+      if (i == begin || (int)((rec[i - 1] >> kRecOrdBits) & ((1u << kRecVoxBits) - 1)) != vx) s_seg_lo[vx] = (int)(i - begin);
+      if (i + 1 == end || (int)((rec[i + 1] >> kRecOrdBits) & ((1u << kRecVoxBits) - 1)) != vx) s_seg_hi[vx] = (int)(i + 1 - begin);
+    }
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const int c0 = grp * group_planes;
+      const int gc = (cfg.C - c0) < group_planes ? (cfg.C - c0) : group_planes;
+      const uint32_t prior_bytes = (uint32_t)gc * cfg.plane_f32;
+      // ---- stage in
+      if (USE_TMA) {
+        if (tid == 0) {
+          mbar_expect_tx(s_bar, prior_bytes + (grp == 0 ? cfg.head_bytes : 0u));
+          if (grp == 0) tma_load_1d(smem, chunk, cfg.head_bytes, s_bar);
+          tma_load_1d(s_prior, chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32, prior_bytes, s_bar);
+        }
+        mbar_wait(s_bar, phase);
+        phase ^= 1;
+      } else {
+        if (grp == 0) for (uint32_t t = tid; t < cfg.head_bytes / 16; t += kApplyThreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
+        const uint4* gp = (const uint4*)(chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32);
+        for (uint32_t t = tid; t < prior_bytes / 16; t += kApplyThreads) ((uint4*)s_prior)[t] = gp[t];
+      }
+      __syncthreads();
+      // ---- ordered per-voxel updates
+      for (int v = tid; v < V; v += kApplyThreads) {
+        const int lo = s_seg_lo[v], hi = s_seg_hi[v];
+        if (lo >= hi) continue;
+        if (grp == 0) {  // TSDF chain (A.6)
+          const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+          I3 g; g.x = s_g0x + (v & tm); g.y = s_g0y + ((v >> ts) & tm); g.z = s_g0z + (v >> (2 * ts));
+          const F3 center = voxel_center(g, cfg.voxel_size);
+          float dist = s_dist[v], wgt = s_wgt[v];
+          uint32_t rgba = s_rgba[v];
+          for (int k = lo; k < hi; ++k) {
+            const uint32_t ord = (uint32_t)(rec[begin + k] & ((1u << kRecOrdBits) - 1));
+            const float4 p = src.param[ord];
+            const uint32_t col = src.color ? src.color[ord] : 0u;
+            tsdf_update(cfg.tp, origin, f3(p.x, p.y, p.z), center, col, p.w, dist, wgt, rgba);
+          }
+          s_dist[v] = dist; s_wgt[v] = wgt; s_rgba[v] = rgba;
+        }
+        // semantic log-probabilities (base.cpp:283-314), classes [c0, c0+gc)
+        for (int k = lo; k < hi; ++k) {
+          const uint32_t ord = (uint32_t)(rec[begin + k] & ((1u << kRecOrdBits) - 1));
+          if (src.label) {
+            const int l = src.label[ord];
+            if (l != 0) for (int c = 0; c < gc; ++c) s_prior[c * pf + v] += ((c0 + c) == l) ? cfg.lm : cfg.ln;
+          } else {
+            const float* t = src.tmp + (size_t)ord * cfg.C + c0;
+            for (int c = 0; c < gc; ++c) s_prior[c * pf + v] += t[c];
+          }
+        }
+        // arg-max, first maximum wins (base.cpp:352-367)
+        float best = (grp == 0) ? s_prior[v] : s_best[v];
+        int lab = (grp == 0) ? 0 : s_best_lab[v];
+        for (int c = (grp == 0 ? 1 : 0); c < gc; ++c) { const float x = s_prior[c * pf + v]; if (x > best) { best = x; lab = c0 + c; } }
+        s_best[v] = best; s_best_lab[v] = lab;
+        if (grp == ngroups - 1) {
+          s_label[v] = (uint8_t)lab;
+          const uint32_t sc = luts->label_rgba[lab];       // base.cpp:370-380
+          s_srgba[v] = sc;
+          if (cfg.color_mode == 1) s_rgba[v] = sc;         // kSemantic (base.cpp:177-180)
+          else if (cfg.color_mode == 2) s_rgba[v] = rainbow_color_map((double)expf(best));  // base.cpp:181-185
+        }
+      }
+      // ---- stage out
+      if (USE_TMA) {
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          tma_store_1d(chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32, s_prior, prior_bytes);
+          if (grp == ngroups - 1) tma_store_1d(chunk, smem, cfg.head_bytes);
+          tma_store_commit_wait();
+        }
+        __syncthreads();
+      } else {
+        __syncthreads();
+        uint4* gp = (uint4*)(chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32);
+        for (uint32_t t = tid; t < prior_bytes / 16; t += kApplyThreads) gp[t] = ((const uint4*)s_prior)[t];
+        if (grp == ngroups - 1) for (uint32_t t = tid; t < cfg.head_bytes / 16; t += kApplyThreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// export: tiles -> voxblox block layout (linear index x + vps*(y + vps*z))
+// ---------------------------------------------------------------------------------------------
+__global__ void k_export(DevCfg cfg, MapRef map, const int* __restrict__ slots, int nb, float* __restrict__ o_dist,
+                         float* __restrict__ o_wgt, uint32_t* __restrict__ o_rgba, uint8_t* __restrict__ o_label,
+                         float* __restrict__ o_prior, uint32_t* __restrict__ o_srgba) {
+  const int per_block = cfg.tiles_per_block;
+  const int V = cfg.tile_voxels;
+  const size_t VB = (size_t)cfg.vps * cfg.vps * cfg.vps;
+  const int pf = cfg.plane_f32 / 4;
+  for (long long w = blockIdx.x; w < (long long)nb * per_block; w += gridDim.x) {
+    const int bi = (int)(w / per_block), tile = (int)(w % per_block);
+    const uint8_t* chunk = map.pool + (uint64_t)slots[bi] * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
+    const float* dist = (const float*)chunk;
+    const float* wgt = (const float*)(chunk + cfg.plane_f32);
+    const uint32_t* rgba = (const uint32_t*)(chunk + 2 * cfg.plane_f32);
+    const uint32_t* srgba = (const uint32_t*)(chunk + 3 * cfg.plane_f32);
+    const uint8_t* label = chunk + 4 * cfg.plane_f32;
+    const float* prior = (const float*)(chunk + cfg.head_bytes);
+    const int tps = cfg.tiles_per_side, ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+    const int tx = tile % tps, ty = (tile / tps) % tps, tz = tile / (tps * tps);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const int lx = tx * cfg.tile_side + (v & tm), ly = ty * cfg.tile_side + ((v >> ts) & tm), lz = tz * cfg.tile_side + (v >> (2 * ts));
+      const size_t lin = (size_t)bi * VB + (size_t)lx + (size_t)cfg.vps * ((size_t)ly + (size_t)cfg.vps * lz);
+      if (o_dist) o_dist[lin] = dist[v];
+      if (o_wgt) o_wgt[lin] = wgt[v];
+      if (o_rgba) o_rgba[lin] = rgba[v];
+      if (o_srgba) o_srgba[lin] = srgba[v];
+      if (o_label) o_label[lin] = label[v];
+      if (o_prior) for (int c = 0; c < cfg.C; ++c) o_prior[lin * cfg.C + c] = prior[c * pf + v];
+    }
+  }
+}
+
+}  // namespace ksg

@@ -326,7 +326,9 @@ struct Integrator {
   std::vector<BIdx> last_updated;
   std::atomic<int64_t> n_updates{0}, n_rays{0}, n_steps{0}, n_valid{0};
   std::string error;
-  double last_integrate_seconds = 0.0;  // span of the reference timers integrate/fast + inserting_missed_blocks
+  double last_integrate_seconds = 0.0;
+  bool trace_fast = false;  // debug: record (point index, #updates) of every cast ray
+  std::vector<int64_t> trace_point, trace_updates;  // span of the reference timers integrate/fast + inserting_missed_blocks
 
   explicit Integrator(const ksg_config& c, bool canonical) : cfg(c), canonical_merged(canonical) {
     C = c.num_labels;
@@ -486,6 +488,7 @@ struct Integrator {
       GIdx global_voxel_idx = getGridIndexFromPoint(point_G, cfg.start_voxel_subsampling_factor * voxel_size_inv);
       if (!start_voxel_approx_set.replaceHash(global_voxel_idx)) continue;
       ++rays;
+      const int64_t updates_before = updates;
       RayCaster ray_caster(origin, point_G, is_clearing, cfg.voxel_carving_enabled, cfg.max_ray_length_m,
                            voxel_size_inv, cfg.default_truncation_distance, /*cast_from_origin=*/false);
       int64_t consecutive_ray_collisions = 0;
@@ -504,6 +507,7 @@ struct Integrator {
         updateSemanticVoxel(global_voxel_idx, freq.data(), b, lin, lock);
         ++updates;
       }
+      if (trace_fast) { trace_point.push_back((int64_t)point_idx); trace_updates.push_back(updates - updates_before); }
     }
     n_updates += updates; n_rays += rays; n_valid += valid;
   }
@@ -517,6 +521,7 @@ struct Integrator {
       voxel_observed_approx_set.resetApproxSet();
     }
     ThreadSafeIndex index_getter(cfg.integration_order_mode, pts);
+    trace_point.clear(); trace_updates.clear();
     const int threads = std::max(1, cfg.integrator_threads);
     if (threads == 1) {
       integrateSemanticFunction(T, pts, colors, labels, freespace, &index_getter, false);
@@ -707,8 +712,10 @@ int kso_integrate_points(void* hh, const float* T_G_C, const float* xyz, const u
     if (rgba) { colors[i].r = rgba[4 * i]; colors[i].g = rgba[4 * i + 1]; colors[i].b = rgba[4 * i + 2]; colors[i].a = rgba[4 * i + 3]; }
     else {  // depth+label entry: the point colour is the label's colour (the semantic image pixel)
       const uint8_t l = labels[i];
-      colors[i].r = h->cfg.label_color[l][0]; colors[i].g = h->cfg.label_color[l][1];
-      colors[i].b = h->cfg.label_color[l][2]; colors[i].a = h->cfg.label_color[l][3];
+      if (h->cfg.label_color_known[l]) {
+        colors[i].r = h->cfg.label_color[l][0]; colors[i].g = h->cfg.label_color[l][1];
+        colors[i].b = h->cfg.label_color[l][2]; colors[i].a = h->cfg.label_color[l][3];
+      }
     }
     if (labels[i] >= h->C) return KSG_ERR_INVALID_ARGUMENT;  // CHECK_LT fast.cpp:134
   }
@@ -872,6 +879,25 @@ void kso_blend(const uint8_t* c1, float w1, const uint8_t* c2, float w2, uint8_t
   out[0] = o.r; out[1] = o.g; out[2] = o.b; out[3] = o.a;
 }
 void kso_rainbow(double h, uint8_t* out) { const Color c = rainbowColorMap(h); out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a; }
+
+// debug hooks used by tests/ to validate the parallel observed-set solver against the sequential sets
+void kso_trace_fast(void* hh, int enable) { ((Integrator*)hh)->trace_fast = enable != 0; }
+int64_t kso_get_fast_trace(void* hh, int64_t capacity, int64_t* point_idx, int64_t* updates) {
+  Integrator* h = (Integrator*)hh;
+  const int64_t n = (int64_t)h->trace_point.size();
+  if (point_idx && updates && n <= capacity) {
+    std::memcpy(point_idx, h->trace_point.data(), n * sizeof(int64_t));
+    std::memcpy(updates, h->trace_updates.data(), n * sizeof(int64_t));
+  }
+  return n;
+}
+// which: 0 = start_voxel_approx_set_, 1 = voxel_observed_approx_set_. out has 2^20 entries.
+uint64_t kso_get_approx_set(void* hh, int which, uint64_t* out) {
+  Integrator* h = (Integrator*)hh;
+  ApproxHashSet& s = which ? h->voxel_observed_approx_set : h->start_voxel_approx_set;
+  if (out) for (size_t i = 0; i < ApproxHashSet::kSize; ++i) out[i] = (uint64_t)s.table[i].load();
+  return (uint64_t)s.offset;
+}
 
 // wall-clock of the last integrate call (timed span = fast.cpp:160-198 / merged.cpp:106-148: the
 // colour->label loop and input marshalling are outside), for bench.py's CPU legs
