@@ -182,6 +182,15 @@ int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int3
 /* Remove every block and reset the fast integrator's two approximate sets. */
 int32_t ksg_reset(ksg_integrator* h);
 
+/* Optional per-phase device timing (CUDA events on the launching stream) and kernel-launch counting.
+ * Phases: 0 classify+start-set, 1 observed-set fixpoint (fast) / bundling (merged), 2 ray emit,
+ * 3 record sort, 4 block alloc + tile heads, 5 tile apply, 6 whole frame.  ksg_get_profile returns the
+ * accumulated milliseconds per phase since the last ksg_set_profiling call and the number of frames. */
+#define KSG_NUM_PHASES 7
+int32_t ksg_set_profiling(ksg_integrator* h, int32_t enable);
+int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms /* KSG_NUM_PHASES */, int64_t* frames,
+                        int64_t* kernel_launches /* own kernels */, int64_t* library_calls /* CUB sort/select calls */);
+
 /* Build information: "sm_100a" etc. */
 const char* ksg_build_info(void);
 

@@ -188,6 +188,10 @@ def load_library(path: Optional[str] = None):
     lib.ksg_last_updated_blocks.restype = C.c_int64
     lib.ksg_reset.argtypes = [H]
     lib.ksg_reset.restype = C.c_int32
+    lib.ksg_set_profiling.argtypes = [H, C.c_int32]
+    lib.ksg_set_profiling.restype = C.c_int32
+    lib.ksg_get_profile.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ksg_get_profile.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -198,7 +202,7 @@ def load_library(path: Optional[str] = None):
 KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks",
-               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info"]
+               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile"]
 
 
 class KsgError(RuntimeError):
@@ -304,6 +308,21 @@ class Integrator:
                                                          C.c_void_p(stream), C.byref(st) if st is not None else None),
                     "ksg_integrate_points_device")
         return st
+
+    PHASES = ("classify+start_set", "fixpoint|bundling", "ray_emit", "record_sort", "alloc+tile_heads", "tile_apply", "frame")
+
+    def set_profiling(self, enable: bool):
+        self._check(self.lib.ksg_set_profiling(self.handle, int(enable)), "ksg_set_profiling")
+
+    def get_profile(self) -> Dict[str, float]:
+        ms = (C.c_double * 7)()
+        frames, launches, libcalls = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.ksg_get_profile(self.handle, ms, C.byref(frames), C.byref(launches), C.byref(libcalls)), "ksg_get_profile")
+        out = {n: float(ms[i]) for i, n in enumerate(self.PHASES)}
+        out["frames"] = int(frames.value)
+        out["kernel_launches"] = int(launches.value)
+        out["library_calls"] = int(libcalls.value)
+        return out
 
     def sync(self):
         self._check(self.lib.ksg_sync(self.handle), "ksg_sync")

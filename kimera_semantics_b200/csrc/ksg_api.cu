@@ -114,6 +114,13 @@ struct ksg_integrator {
   int group_planes = 0;
   bool use_tma = true;
 
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[KSG_NUM_PHASES + 1] = {};
+  double phase_ms[KSG_NUM_PHASES] = {};
+  int64_t prof_frames = 0;
+  int64_t n_launches = 0, n_libcalls = 0;
+
   int fail(int code, const char* msg) { err = msg; g_last_error = msg; return code; }
 };
 
@@ -155,6 +162,7 @@ void free_all(ksg_integrator* h) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -264,16 +272,22 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   }
   fin.freespace = in.freespace;
 
+  if (h->profiling) cudaEventRecord(h->ev[0], s);
+  ++h->n_launches;
   k_frame_reset<<<1, 1, 0, s>>>(h->d_cnt, in.d_depth ? 0 : cap);
   if (in.d_depth) {
+    ++h->n_launches;
     k_depth_flags<<<grid_for(cap, B), B, 0, s>>>(in.d_depth, cap, h->flags8);
     size_t tb = h->cub_temp_bytes;
+    ++h->n_libcalls;
     KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->pix_list,
                                         &h->d_cnt->n_points, cap, s));
   }
   if (h->cfg.integration_order_mode == KSG_ORDER_SORTED) {
+    ++h->n_launches;
     k_sqnorm<<<grid_for(cap, B), B, 0, s>>>(fin, h->d_cnt, cap, h->sq_keys);
     size_t tb = h->cub_temp_bytes;
+    ++h->n_libcalls;
     KSG_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_temp, tb, h->sq_keys, h->sq_keys_out, h->iota, (uint32_t*)h->point_of_seq,
                                              cap, 0, 32, s));
     fin.point_of_seq = h->point_of_seq;
@@ -297,24 +311,33 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   if (fast) {
     KSG_CUDA(cudaMemsetAsync(h->start_head, 0xFF, sizeof(int) * kSetSize, s));
     KSG_CUDA(cudaMemsetAsync(h->ob.head, 0xFF, sizeof(int) * kSetSize, s));
+    ++h->n_launches;
     k_classify<true><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, h->set_offset, cap, h->d_cnt, h->pt_pC, h->pt_pG,
                                                     h->pt_label, h->pt_flags, h->pt_color, h->pt_key);
+    ++h->n_launches;
     k_start_push<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next);
+    ++h->n_launches;
     k_start_eval<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next, h->start_table, h->flags8,
                                                 h->is_last, cap);
+    ++h->n_launches;
     k_start_commit<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->is_last, h->start_table);
     {
       size_t tb = h->cub_temp_bytes;
+      ++h->n_libcalls;
       KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->cast_seq,
                                           &h->d_cnt->n_cast, cap, s));
     }
+    ++h->n_launches;
     k_ray_setup<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->cast_seq, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color,
                                                    h->set_offset, h->ob, h->ray_param, h->ray_label, h->ray_flags, h->ray_color,
                                                    h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->trunc_flag);
+    if (h->profiling) cudaEventRecord(h->ev[1], s);
     // observed-set fixpoint
     int n_cast = cap;
     for (;;) {
+      ++h->n_launches;
       k_iter_reset<<<1, 1, 0, s>>>(h->d_cnt);
+      ++h->n_launches;
       k_eval<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, h->d_cnt, h->ob, h->nsteps, h->H, h->L, h->ext_off, h->trunc_flag);
       ++iterations;
       int rc = fetch_counters(h, s);
@@ -323,60 +346,83 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       if (h->h_cnt->err) break;
       if (h->h_cnt->changed) continue;
       if (h->h_cnt->n_truncated > 0) {
+        ++h->n_launches;
         k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state,
                                                        h->ext_off, h->trunc_flag);
         continue;
       }
       break;
     }
+    if (h->profiling) cudaEventRecord(h->ev[2], s);
     if (!h->h_cnt->err) {
       n_records = (long long)h->h_cnt->sum_updates;
       if (n_records > h->rec_cap) { h->deferred_status = KSG_ERR_SCRATCH_FULL; return fail(KSG_ERR_SCRATCH_FULL, err_text(4)); }
+      ++h->n_launches;
       k_obs_commit<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->ob, h->L, h->ext_off);
+      ++h->n_launches;
       k_emit_fast<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->L, h->rec_a,
                                                         h->rec_cap);
     }
     src.param = h->ray_param; src.label = h->ray_label; src.color = h->ray_color; src.tmp = nullptr;
   } else {
+    ++h->n_launches;
     k_classify<false><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, 0ull, cap, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label,
                                                      h->pt_flags, h->pt_color, h->pt_key);
+    if (h->profiling) cudaEventRecord(h->ev[1], s);
     {
       size_t tb = h->cub_temp_bytes;
+      ++h->n_libcalls;
       KSG_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_temp, tb, h->pt_key, h->ks_sorted, h->iota, h->seq_sorted, cap, 0, 64, s));
     }
     KSG_CUDA(cudaMemsetAsync(h->flags8, 0, 2 * (size_t)cap, s));
+    ++h->n_launches;
     k_bundle_heads<<<grid_for(cap, B), B, 0, s>>>(h->ks_sorted, h->seq_sorted, cap, h->flags8, h->bstart);
     {
       size_t tb = h->cub_temp_bytes;
+      ++h->n_libcalls;
       KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->bundle_f,
                                           &h->d_cnt->n_cast, 2 * cap, s));
     }
+    ++h->n_launches;
     k_bundle_merge<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, h->seq_sorted, cap,
                                                       h->pt_pC, h->pt_label, h->hist, h->ray_param, h->ray_flags, h->b_key,
                                                       h->nsteps, h->b_base, h->rec_cap);
     int rc = fetch_counters(h, s);
     if (rc) return rc;
+    if (h->profiling) cudaEventRecord(h->ev[2], s);
     if (!h->h_cnt->err) {
       const int nb = std::max(1, h->h_cnt->n_cast);
       n_records = (long long)h->h_cnt->n_records;
+      ++h->n_launches;
       k_bundle_loglik<<<grid_for((long long)nb * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp);
+      ++h->n_launches;
       k_emit_merged<<<grid_for(nb, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps,
                                                       h->b_base, h->ks_sorted, cap, h->rec_a);
     }
     src.param = h->ray_param; src.label = nullptr; src.color = nullptr; src.tmp = h->tmp;
   }
 
+  if (h->profiling) cudaEventRecord(h->ev[3], s);
   int dev_err = h->h_cnt->err;
+  bool did_apply = false;
   if (!dev_err && n_records > 0) {
     // order the update records by (tile, voxel, order): per-voxel application order = reference order
     size_t tb = h->cub_temp_bytes;
+    ++h->n_libcalls;
     KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, 0, 64, s));
+    if (h->profiling) cudaEventRecord(h->ev[4], s);
+    ++h->n_launches;
     k_block_assign<<<grid_for(h->map.new_cap, B), B, 0, s>>>(h->d_cnt, h->map);
+    ++h->n_launches;
     k_block_init<<<h->sm_count * 4, 256, 0, s>>>(dc, h->d_cnt, h->map);
+    ++h->n_launches;
     k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
                                                       h->tile_cap);
+    if (h->profiling) cudaEventRecord(h->ev[5], s);
+    did_apply = true;
     const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem))));
     const int grid = h->sm_count * ctas_per_sm;
+    ++h->n_launches;
     if (h->use_tma)
       k_tile_apply<true><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
                                                                      h->tile_begin, src, h->group_planes);
@@ -384,10 +430,19 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       k_tile_apply<false><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
                                                                       h->tile_begin, src, h->group_planes);
   }
+  if (h->profiling) { if (!did_apply) { cudaEventRecord(h->ev[4], s); cudaEventRecord(h->ev[5], s); } cudaEventRecord(h->ev[6], s); }
+  ++h->n_launches;
   k_frame_finish<<<1, 1, 0, s>>>(h->d_cnt, h->map);
   KSG_CUDA(cudaGetLastError());
   int rc = fetch_counters(h, s);
   if (rc) return rc;
+  if (h->profiling) {
+    cudaEventRecord(h->ev[7], s);
+    cudaEventSynchronize(h->ev[7]);
+    for (int p = 0; p < 6; ++p) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[p], h->ev[p + 1]) == cudaSuccess) h->phase_ms[p] += ms; }
+    { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[7]) == cudaSuccess) h->phase_ms[6] += ms; }
+    h->prof_frames += 1;
+  }
   dev_err = h->h_cnt->err;
   h->num_blocks = h->h_cnt->pool_count;
   h->last_blocks_touched = h->h_cnt->n_blocks_touched;
@@ -806,6 +861,24 @@ int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int3
     block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
   }
   return n;
+}
+
+int32_t ksg_set_profiling(ksg_integrator* h, int32_t enable) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  if (enable && !h->ev[0]) for (auto& e : h->ev) cudaEventCreate(&e);
+  h->profiling = enable != 0;
+  for (double& m : h->phase_ms) m = 0.0;
+  h->prof_frames = 0; h->n_launches = 0; h->n_libcalls = 0;
+  return KSG_OK;
+}
+int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms, int64_t* frames, int64_t* kernel_launches, int64_t* library_calls) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  if (phase_ms) for (int p = 0; p < KSG_NUM_PHASES; ++p) phase_ms[p] = h->phase_ms[p];
+  if (frames) *frames = h->prof_frames;
+  if (kernel_launches) *kernel_launches = h->n_launches;
+  if (library_calls) *library_calls = h->n_libcalls;
+  return KSG_OK;
 }
 
 int32_t ksg_reset(ksg_integrator* h) {

@@ -694,7 +694,12 @@ static void fillStats(Integrator* h, int64_t n, ksg_frame_stats* s, int64_t u0, 
   s->rays_cast = h->n_rays - r0;
   s->voxel_updates = h->n_updates - u0;
   s->blocks_allocated = (int64_t)h->layer.size();
-  s->blocks_touched = (int64_t)h->last_updated.size();
+  {
+    std::vector<BIdx> v = h->last_updated;  // merged appends per pass: count unique blocks
+    std::sort(v.begin(), v.end(), [](const BIdx& a, const BIdx& b) { return a.z != b.z ? a.z < b.z : (a.y != b.y ? a.y < b.y : a.x < b.x); });
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    s->blocks_touched = (int64_t)v.size();
+  }
 }
 
 int kso_integrate_points(void* hh, const float* T_G_C, const float* xyz, const uint8_t* rgba,
