@@ -80,6 +80,8 @@ struct ksg_integrator {
   int *nsteps = nullptr, *H = nullptr, *L = nullptr;
   RayState* ray_state = nullptr;
   long long* ext_off = nullptr;
+  int* eval_sweep = nullptr;
+  int sweep_counter = 0;
   ObsBuf ob{};
 
   // merged
@@ -111,7 +113,7 @@ struct ksg_integrator {
   int exp_slots_cap = 0;
 
   int apply_smem = 0;
-  int group_planes = 0;
+  int apply_nch = 1;
   bool use_tma = true;
 
   // profiling
@@ -156,7 +158,7 @@ void free_all(ksg_integrator* h) {
                   h->map.touched_list, h->d_luts, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color, h->pt_key,
                   h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota, h->start_head,
                   h->start_next, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
-                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->ob.cand_val, h->ob.cand_order,
+                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.head, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -193,6 +195,8 @@ int reset_map(ksg_integrator* h, cudaStream_t s) {
   KSG_CUDA(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), s));
   if (h->start_table) KSG_CUDA(cudaMemsetAsync(h->start_table, 0xFF, sizeof(uint32_t) * kSetSize, s));
   if (h->ob.table) KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+  if (h->ob.slot_stamp) KSG_CUDA(cudaMemsetAsync(h->ob.slot_stamp, 0, sizeof(int) * kSetSize, s));
+  h->sweep_counter = 0;
   h->set_offset = 0;
   h->reset_counter = 0;
   h->num_blocks = 0;
@@ -330,36 +334,39 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     ++h->n_launches;
     k_ray_setup<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->cast_seq, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color,
                                                    h->set_offset, h->ob, h->ray_param, h->ray_label, h->ray_flags, h->ray_color,
-                                                   h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->trunc_flag);
+                                                   h->nsteps, h->H, h->L, h->ray_state, h->eval_sweep, h->trunc_flag);
     if (h->profiling) cudaEventRecord(h->ev[1], s);
-    // observed-set fixpoint
+    // observed-set fixpoint: sweeps until no ray changes; two sweeps per host read-back
     int n_cast = cap;
+    if (h->sweep_counter > 0x3FFFFFFF) {  // keep sweep ids monotonic: restart the stamps long before int overflow
+      KSG_CUDA(cudaMemsetAsync(h->ob.slot_stamp, 0, sizeof(int) * kSetSize, s));
+      h->sweep_counter = 0;
+    }
+    h->sweep_counter = (h->sweep_counter + 4) & ~3;  // counters of the first sweep (index 1) were zeroed by k_frame_reset
     for (;;) {
-      ++h->n_launches;
-      k_iter_reset<<<1, 1, 0, s>>>(h->d_cnt);
-      ++h->n_launches;
-      k_eval<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, h->d_cnt, h->ob, h->nsteps, h->H, h->L, h->ext_off, h->trunc_flag);
-      ++iterations;
+      int sweep = 0;
+      for (int rep = 0; rep < 2; ++rep) {
+        sweep = ++h->sweep_counter;
+        h->n_launches += 2;
+        k_eval<<<grid_for((long long)n_cast * kEvalGroup, 128), 128, 0, s>>>(dc, h->d_cnt, h->ob, h->nsteps, h->H, h->L, h->ext_off,
+                                                                            h->trunc_flag, h->eval_sweep, sweep);
+        k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state,
+                                                       h->ext_off, h->trunc_flag, h->eval_sweep, sweep);
+        ++iterations;
+      }
       int rc = fetch_counters(h, s);
       if (rc) return rc;
       n_cast = std::max(1, h->h_cnt->n_cast);
       if (h->h_cnt->err) break;
-      if (h->h_cnt->changed) continue;
-      if (h->h_cnt->n_truncated > 0) {
-        ++h->n_launches;
-        k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state,
-                                                       h->ext_off, h->trunc_flag);
-        continue;
-      }
+      if (h->h_cnt->changed[sweep & 3] || h->h_cnt->n_truncated[sweep & 3]) continue;
+      n_records = (long long)h->h_cnt->sum_updates[sweep & 3];
       break;
     }
     if (h->profiling) cudaEventRecord(h->ev[2], s);
     if (!h->h_cnt->err) {
-      n_records = (long long)h->h_cnt->sum_updates;
       if (n_records > h->rec_cap) { h->deferred_status = KSG_ERR_SCRATCH_FULL; return fail(KSG_ERR_SCRATCH_FULL, err_text(4)); }
-      ++h->n_launches;
+      h->n_launches += 2;
       k_obs_commit<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->ob, h->L, h->ext_off);
-      ++h->n_launches;
       k_emit_fast<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->L, h->rec_a,
                                                         h->rec_cap);
     }
@@ -420,15 +427,20 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
                                                       h->tile_cap);
     if (h->profiling) cudaEventRecord(h->ev[5], s);
     did_apply = true;
-    const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem))));
+    const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem + 1024))));
     const int grid = h->sm_count * ctas_per_sm;
     ++h->n_launches;
-    if (h->use_tma)
-      k_tile_apply<true><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
-                                                                     h->tile_begin, src, h->group_planes);
-    else
-      k_tile_apply<false><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
-                                                                      h->tile_begin, src, h->group_planes);
+#define KSG_LAUNCH_APPLY(TMA, NCH)                                                                                   \
+    k_tile_apply<TMA, NCH><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
+                                                                      n_records, h->tile_begin, src)
+    if (h->use_tma) {
+      switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(true, 1); break; case 2: KSG_LAUNCH_APPLY(true, 2); break;
+                              case 4: KSG_LAUNCH_APPLY(true, 4); break; default: KSG_LAUNCH_APPLY(true, 8); break; }
+    } else {
+      switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(false, 1); break; case 2: KSG_LAUNCH_APPLY(false, 2); break;
+                              case 4: KSG_LAUNCH_APPLY(false, 4); break; default: KSG_LAUNCH_APPLY(false, 8); break; }
+    }
+#undef KSG_LAUNCH_APPLY
   }
   if (h->profiling) { if (!did_apply) { cudaEventRecord(h->ev[4], s); cudaEventRecord(h->ev[5], s); } cudaEventRecord(h->ev[6], s); }
   ++h->n_launches;
@@ -452,7 +464,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     stats->points_valid = h->h_cnt->n_valid;
     stats->rays_cast = h->h_cnt->n_cast;
     stats->ray_steps = (int64_t)h->h_cnt->ray_steps;
-    stats->voxel_updates = n_records;
+    stats->voxel_updates = n_records - (int64_t)h->h_cnt->n_skipped;
     stats->blocks_allocated = h->num_blocks;
     stats->blocks_touched = h->h_cnt->n_blocks_touched;
     stats->tiles_touched = h->h_cnt->n_tiles;
@@ -567,7 +579,9 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   dc.plane_u8 = round_up((uint32_t)dc.tile_voxels, 16);
   dc.head_bytes = 4 * dc.plane_f32 + dc.plane_u8;
   dc.C = cfg->num_labels;
-  dc.tile_stride = round_up(dc.head_bytes + (uint32_t)dc.C * dc.plane_f32, 128);
+  dc.prior_bytes = round_up(4u * (uint32_t)dc.tile_voxels * (uint32_t)dc.C, 16);
+  dc.tile_stride = round_up(dc.head_bytes + dc.prior_bytes, 128);
+  dc.full_stage = (dc.head_bytes + dc.prior_bytes + 8u * dc.tile_voxels + 64u) <= 110u * 1024u ? 1 : 0;
   dc.block_stride = (uint64_t)dc.tile_stride * dc.tiles_per_block;
   dc.tp.voxel_size = cfg->voxel_size;
   dc.tp.trunc = cfg->default_truncation_distance;
@@ -637,7 +651,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->start_head, kSetSize)); KSG_CUDA(dmalloc(&h->start_next, N)); KSG_CUDA(dmalloc(&h->start_table, kSetSize));
     KSG_CUDA(dmalloc(&h->cast_seq, N));
     KSG_CUDA(dmalloc(&h->ray_label, N)); KSG_CUDA(dmalloc(&h->ray_color, N)); KSG_CUDA(dmalloc(&h->trunc_flag, N));
-    KSG_CUDA(dmalloc(&h->H, N)); KSG_CUDA(dmalloc(&h->L, N)); KSG_CUDA(dmalloc(&h->ray_state, N)); KSG_CUDA(dmalloc(&h->ext_off, N));
+    KSG_CUDA(dmalloc(&h->H, N)); KSG_CUDA(dmalloc(&h->L, N)); KSG_CUDA(dmalloc(&h->ray_state, N)); KSG_CUDA(dmalloc(&h->ext_off, N * kExtSegs));
+    KSG_CUDA(dmalloc(&h->eval_sweep, N)); KSG_CUDA(dmalloc(&h->ob.slot_stamp, kSetSize));
     long long ext = cfg->max_ray_steps > 0 ? cfg->max_ray_steps : std::max<long long>(16ll << 20, 64ll * (long long)N);
     h->ob.ext_base = (long long)N * kH0;
     h->ob.cand_cap = h->ob.ext_base + ext;
@@ -668,18 +683,21 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(cudaMalloc(&h->cub_temp, h->cub_temp_bytes));
   }
 
-  // ---- tile-apply launch configuration: stage as many class planes as fit ~100 KB (2 CTAs / SM)
+  // ---- tile-apply launch configuration
   {
     const int V = dc.tile_voxels;
-    const size_t aux = (size_t)V * 16 + 64;
-    const size_t budget = 100 * 1024;
-    int g = (int)((budget - dc.head_bytes - aux) / dc.plane_f32);
-    g = std::max(1, std::min(g, dc.C));
-    h->group_planes = g;
-    h->apply_smem = (int)(dc.head_bytes + (size_t)g * dc.plane_f32 + aux);
+    const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
+    h->apply_smem = (int)(stage + (size_t)V * 8 + 64);
+    h->apply_nch = dc.C <= 32 ? 1 : (dc.C <= 64 ? 2 : (dc.C <= 128 ? 4 : 8));
     h->use_tma = cfg->apply_mode == 0;
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
   }
   KSG_CUDA(cudaDeviceSynchronize());
   {

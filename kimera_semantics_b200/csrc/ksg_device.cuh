@@ -191,6 +191,35 @@ __host__ __device__ __forceinline__ void tsdf_update(const TsdfParams& P, F3 ori
   weight = fminf(P.max_weight, new_weight);
 }
 
+// The two halves of updateTsdfVoxel, split so that the measurement part (independent of the voxel state) can be
+// evaluated for many records in parallel while the state recurrence runs in the reference's order.
+__host__ __device__ __forceinline__ void tsdf_measure(const TsdfParams& P, F3 origin, F3 point_G, F3 center, float w,
+                                                      float& sdf, float& uw) {
+  const F3 v_voxel_origin = sub(center, origin);
+  const F3 v_point_origin = sub(point_G, origin);
+  const float dist_G = norm3(v_point_origin);
+  const float dist_G_V = dot3(v_voxel_origin, v_point_origin) / dist_G;
+  sdf = dist_G - dist_G_V;
+  uw = w;
+  const float dropoff_epsilon = P.voxel_size;
+  if (P.use_weight_dropoff && sdf < -dropoff_epsilon) {
+    uw = w * (P.trunc + sdf) / (P.trunc - dropoff_epsilon);
+    uw = fmaxf(uw, 0.0f);
+  }
+  if (P.use_sparsity) {
+    if (fabsf(sdf) < P.trunc) uw *= P.sparsity_factor;
+  }
+}
+__host__ __device__ __forceinline__ void tsdf_chain_step(const TsdfParams& P, float sdf, float uw, uint32_t color, bool blend,
+                                                         float& dist, float& weight, uint32_t& rgba) {
+  const float new_weight = weight + uw;
+  if (new_weight < kEps) return;
+  const float new_sdf = (sdf * uw + dist * weight) / new_weight;
+  if (blend && fabsf(sdf) < P.trunc) rgba = blend_two_colors(rgba, weight, color, uw);
+  dist = (new_sdf > 0.0f) ? fminf(P.trunc, new_sdf) : fmaxf(-P.trunc, new_sdf);
+  weight = fminf(P.max_weight, new_weight);
+}
+
 __host__ __device__ __forceinline__ F3 voxel_center(I3 g, float voxel_size) {
   return f3(((float)g.x + 0.5f) * voxel_size, ((float)g.y + 0.5f) * voxel_size, ((float)g.z + 0.5f) * voxel_size);
 }

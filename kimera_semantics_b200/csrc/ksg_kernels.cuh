@@ -21,7 +21,9 @@ struct DevCfg {
   int tile_side, tile_side_log2, tiles_per_side, tiles_per_block, tile_voxels;
   uint32_t plane_f32, plane_u8;  // bytes of one float / byte plane of a tile (16 B multiples)
   uint32_t head_bytes;           // dist | weight | rgba | sem_rgba | label
+  uint32_t prior_bytes;          // V * C floats, voxel-major rows (16 B multiple)
   uint32_t tile_stride;          // bytes
+  int full_stage;                // 1: the whole tile chunk is staged in shared memory, 0: head only
   uint64_t block_stride;         // bytes
   TsdfParams tp;
   float min_ray, max_ray, start_inv;
@@ -43,20 +45,26 @@ struct Counters {
   int n_points;
   int n_valid;
   int n_cast;        // fast: cast rays R; merged: bundles B
-  int changed;
-  int n_truncated;
   int n_new_blocks;
   int n_tiles;
   int err;
   int n_blocks_touched;
   int pool_count;    // blocks allocated in the pool (persistent across frames)
+  int tile_cursor;   // dynamic tile queue of k_tile_apply
+  int pad0;
+  // observed-set solver, indexed by (sweep & 3)
+  int changed[4];
+  int n_truncated[4];
+  unsigned long long sum_updates[4];
   unsigned long long n_records;
-  unsigned long long sum_updates;
+  unsigned long long n_skipped;   // merged anti-grazing: ray steps that emit no update
   unsigned long long n_cand_ext;
   unsigned long long ray_steps;
 };
 
 static constexpr int kH0 = 16;           // ray steps materialised before the first observed-set sweep
+static constexpr int kExtSegs = 12;      // horizon doubles per extension: 16, 32, ..., 65536
+static constexpr int kEvalGroup = 8;     // lanes cooperating on one ray in k_eval
 static constexpr int kOrderStepBits = 16;
 static constexpr int kRecVoxBits = 9, kRecOrdBits = 23;
 
@@ -66,11 +74,11 @@ __device__ __forceinline__ void set_err(Counters* c, int e) { atomicCAS(&c->err,
 // frame set-up
 // ---------------------------------------------------------------------------------------------
 __global__ void k_frame_reset(Counters* c, int n_points) {
-  c->n_points = n_points; c->n_valid = 0; c->n_cast = 0; c->changed = 0; c->n_truncated = 0;
-  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0;
-  c->n_records = 0; c->sum_updates = 0; c->n_cand_ext = 0; c->ray_steps = 0;
+  c->n_points = n_points; c->n_valid = 0; c->n_cast = 0;
+  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0; c->tile_cursor = 0;
+  for (int i = 0; i < 4; ++i) { c->changed[i] = 0; c->n_truncated[i] = 0; c->sum_updates[i] = 0; }
+  c->n_records = 0; c->n_skipped = 0; c->n_cand_ext = 0; c->ray_steps = 0;
 }
-__global__ void k_iter_reset(Counters* c) { c->changed = 0; c->n_truncated = 0; c->sum_updates = 0; }
 
 // depth_map_to_pointcloud.h:259: DepthTraits<float>::valid = isfinite
 __global__ void k_depth_flags(const float* __restrict__ depth, int n, uint8_t* __restrict__ flags) {
@@ -249,12 +257,16 @@ struct ObsBuf {
   uint64_t* cand_order;  // (rank << 16) | step
   int* cand_next;        // per-slot list link
   int* head;             // 2^20 list heads
+  int* slot_stamp;       // 2^20: sweep in which a candidate of the slot last toggled "performed"
   uint32_t* table;       // persistent compact table: value >> 20, kSetNever = matches nothing
   long long ext_base;    // first extension candidate index (= capacity_rays * kH0)
   long long cand_cap;    // total candidate capacity
 };
+// candidate (r, s): the first kH0 steps live at r*kH0 + s, steps [16<<k, 32<<k) in extension segment k
 __device__ __forceinline__ long long cand_index(const ObsBuf& o, const long long* ext_off, int r, int s) {
-  return (s < kH0) ? (long long)r * kH0 + s : o.ext_base + ext_off[r] + (s - kH0);
+  if (s < kH0) return (long long)r * kH0 + s;
+  const int k = 31 - __clz(s >> 4);
+  return o.ext_base + ext_off[(size_t)r * kExtSegs + k] + (s - (kH0 << k));
 }
 
 __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __restrict__ cast_seq,
@@ -262,7 +274,7 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
                             const uint8_t* __restrict__ pt_flags, const uint32_t* __restrict__ pt_color, uint64_t obs_offset,
                             ObsBuf ob, float4* __restrict__ ray_param, uint8_t* __restrict__ ray_label,
                             uint8_t* __restrict__ ray_flags, uint32_t* __restrict__ ray_color, int* __restrict__ nsteps,
-                            int* __restrict__ H, int* L, RayState* __restrict__ state, long long* __restrict__ ext_off,
+                            int* __restrict__ H, int* L, RayState* __restrict__ state, int* __restrict__ eval_sweep,
                             uint8_t* __restrict__ trunc_flag) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= cnt->n_cast) return;
@@ -290,78 +302,128 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
   }
   RayState st; save_state(st, d); state[r] = st;
   H[r] = h;
-  L[r] = h;
-  ext_off[r] = -1;
+  L[r] = h;          // optimistic start: every materialised step performed
+  eval_sweep[r] = 0; // never evaluated
   trunc_flag[r] = 0;
   atomicAdd(&cnt->ray_steps, (unsigned long long)h);
 }
 
-// Materialise the remaining steps of the rays that performed every step they had (trunc_flag set).
+// Rays that performed every step they had (trunc_flag) double their horizon. Runs after sweep `sweep`.
 __global__ void k_extend(Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
-                         int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag) {
+                         int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag,
+                         int* __restrict__ eval_sweep, int sweep) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0) { const int nx = (sweep + 1) & 3; cnt->changed[nx] = 0; cnt->n_truncated[nx] = 0; cnt->sum_updates[nx] = 0; }
   if (r >= cnt->n_cast) return;
   if (!trunc_flag[r]) return;
   trunc_flag[r] = 0;
   const int n = nsteps[r], h = H[r];
   if (h >= n) return;
-  const long long need = n - h;
+  const int nh = (2 * h < n) ? 2 * h : n;
+  const int k = 31 - __clz(h >> 4);      // h = 16 << k
+  const long long need = nh - h;
   const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need);
-  if (ob.ext_base + off + need > ob.cand_cap || ob.ext_base + off + need >= 0x7FFFFFFFll) { set_err(cnt, 4); return; }
-  ext_off[r] = off;
+  if (ob.ext_base + off + need > ob.cand_cap) { set_err(cnt, 4); return; }
+  ext_off[(size_t)r * kExtSegs + k] = off;
   Dda d; load_state(d, state[r]);
-  for (int s = h; s < n; ++s) {
+  for (int s = h; s < nh; ++s) {
     const I3 g = dda_next(d);
     const uint64_t v = (uint64_t)index_hash(g) + obs_offset;
-    const long long ci = ob.ext_base + off + (s - kH0);
+    const uint32_t slot = (uint32_t)v & kSetMask;
+    const long long ci = ob.ext_base + off + (s - h);
     ob.cand_val[ci] = v;
     ob.cand_order[ci] = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
-    ob.cand_next[ci] = atomicExch(&ob.head[(uint32_t)v & kSetMask], (int)ci);
+    ob.cand_next[ci] = atomicExch(&ob.head[slot], (int)ci);
+    atomicMax(&ob.slot_stamp[slot], sweep);   // new performed visits: dependants must re-evaluate
   }
-  H[r] = n;
-  L[r] = n;  // optimistic: everything performed until the next sweep says otherwise
+  RayState st; save_state(st, d); state[r] = st;
+  H[r] = nh;
+  L[r] = nh;          // optimistic until the next sweep says otherwise
+  eval_sweep[r] = 0;
   atomicAdd(&cnt->ray_steps, (unsigned long long)need);
-  cnt->changed = 1;
+  cnt->changed[sweep & 3] = 1;
 }
 
+// One sweep of the solver: kEvalGroup lanes per ray, one ray step per lane and chunk.
+// A ray is re-evaluated only if a candidate on one of the slots it depends on toggled since its last evaluation.
 __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restrict__ nsteps, const int* __restrict__ H, int* L,
-                       const long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+                       const long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag, int* __restrict__ eval_sweep,
+                       int sweep) {
+  constexpr int G = kEvalGroup;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = tid / G;
+  const int gl = threadIdx.x % G;                               // lane in group
+  const int wl = threadIdx.x & 31;
+  const unsigned gmask = ((1u << G) - 1u) << (wl - gl);         // the group's lanes inside the warp
+  const int gshift = wl - gl;
+  const int n_cast = cnt->n_cast;
   int U = 0;
-  if (r < cnt->n_cast) {
+  if (r < n_cast) {
     const int h = H[r];
-    const int old = L[r];
-    int coll_run = 0;
-    U = -1;
-    for (int s = 0; s < h; ++s) {
-      const long long ci = cand_index(ob, ext_off, r, s);
-      const uint64_t v = ob.cand_val[ci];
-      const uint32_t slot = (uint32_t)v & kSetMask;
-      const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
-      long long best_order = -1;
-      uint64_t best_val = 0;
-      for (int e = ob.head[slot]; e >= 0; e = ob.cand_next[e]) {
-        const uint64_t eo = ob.cand_order[e];
-        if (eo < my_order && (long long)eo > best_order) {
-          const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
-          const bool performed = (er == r) ? true : (es < ((volatile int*)L)[er]);
-          if (performed) { best_order = (long long)eo; best_val = ob.cand_val[e]; }
+    const int old = ((volatile int*)L)[r];
+    const int last = eval_sweep[r];
+    bool need = last == 0;
+    if (!need) {
+      const int upto = (old < h - 1) ? old : h - 1;             // steps 0..upto were examined last time
+      bool dirty = false;
+      for (int s = gl; s <= upto; s += G) {
+        const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
+        if (ob.slot_stamp[(uint32_t)v & kSetMask] >= last) dirty = true;
+      }
+      need = __ballot_sync(gmask, dirty) != 0u;
+    }
+    U = old;
+    if (need) {
+      int run = 0;
+      U = -1;
+      for (int s0 = 0; s0 < h && U < 0; s0 += G) {
+        const int s = s0 + gl;
+        bool coll = false;
+        if (s < h) {
+          const long long ci = cand_index(ob, ext_off, r, s);
+          const uint64_t v = ob.cand_val[ci];
+          const uint32_t slot = (uint32_t)v & kSetMask;
+          const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+          long long best_order = -1;
+          uint64_t best_val = 0;
+          for (int e = ob.head[slot]; e >= 0; e = ob.cand_next[e]) {
+            const uint64_t eo = ob.cand_order[e];
+            if (eo < my_order && (long long)eo > best_order) {
+              const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
+              // own earlier steps are performed whenever this step is reached
+              const bool performed = (er == r) ? true : (es < ((volatile int*)L)[er]);
+              if (performed) { best_order = (long long)eo; best_val = ob.cand_val[e]; }
+            }
+          }
+          coll = (best_order >= 0) ? (best_val == v) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
+        }
+        const unsigned bits = (__ballot_sync(gmask, coll) & gmask) >> gshift;
+        for (int j = 0; j < G && s0 + j < h; ++j) {
+          if ((bits >> j) & 1u) ++run; else run = 0;            // fast.cpp:115-119
+          if (run > cfg.maxc) { U = s0 + j; break; }            // fast.cpp:120-122
         }
       }
-      const bool coll = (best_order >= 0) ? (best_val == v) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
-      if (coll) ++coll_run; else coll_run = 0;          // fast.cpp:115-119
-      if (coll_run > cfg.maxc) { U = s; break; }        // fast.cpp:120-122
+      bool truncated = false;
+      if (U < 0) { U = h; truncated = h < nsteps[r]; }
+      if (U != old) {   // candidates [min, max) toggled: stamp their slots
+        const int lo = U < old ? U : old, hi = U < old ? old : U;
+        for (int s = lo + gl; s < hi; s += G) {
+          const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
+          atomicMax(&ob.slot_stamp[(uint32_t)v & kSetMask], sweep);
+        }
+      }
+      if (gl == 0) {
+        trunc_flag[r] = truncated ? 1 : 0;
+        if (U != old) { L[r] = U; cnt->changed[sweep & 3] = 1; }
+        eval_sweep[r] = sweep;
+      }
     }
-    bool truncated = false;
-    if (U < 0) { U = h; truncated = h < nsteps[r]; }
-    trunc_flag[r] = truncated ? 1 : 0;
-    if (truncated) atomicAdd(&cnt->n_truncated, 1);
-    if (U != old) { L[r] = U; cnt->changed = 1; }
+    if (gl == 0 && trunc_flag[r]) atomicAdd(&cnt->n_truncated[sweep & 3], 1);
   }
-  // warp-aggregated sum of U
-  unsigned long long u = (unsigned long long)U;
+  __syncwarp();
+  unsigned long long u = (gl == 0 && r < n_cast) ? (unsigned long long)U : 0ull;
   for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
-  if ((threadIdx.x & 31) == 0 && u) atomicAdd(&cnt->sum_updates, u);
+  if (wl == 0 && u) atomicAdd(&cnt->sum_updates[sweep & 3], u);
 }
 
 // After convergence: the last performed visit of every slot becomes the persistent table entry.
@@ -562,7 +624,7 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
         }
       }
     }
-    if (skip) { records[base + s] = ~0ull; continue; }
+    if (skip) { records[base + s] = ~0ull; atomicAdd(&cnt->n_skipped, 1ull); continue; }
     const I3 bi = block_of_voxel(g, cfg.vps_inv);
     if (bi.x != last_b.x || bi.y != last_b.y || bi.z != last_b.z) {
       last_b = bi;
@@ -605,8 +667,7 @@ __global__ void k_block_init(DevCfg cfg, const Counters* cnt, MapRef map) {
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
       dist[v] = 0.0f; wgt[v] = 0.0f; rgba[v] = 0u; srgba[v] = 0xFF7F7F7Fu; label[v] = 0;
     }
-    const int pf = cfg.plane_f32 / 4;
-    for (int t = threadIdx.x; t < cfg.C * V; t += blockDim.x) prior[(t / V) * pf + (t % V)] = (float)-0.60205999132;
+    for (int t = threadIdx.x; t < cfg.C * V; t += blockDim.x) prior[t] = (float)-0.60205999132;
   }
 }
 __global__ void k_frame_finish(Counters* cnt, MapRef map) {
@@ -670,43 +731,52 @@ struct ApplySrc {
 
 static constexpr int kApplyThreads = 256;
 
-// One CTA per touched tile (persistent grid).  The tile's voxel planes are staged in shared memory with
-// TMA bulk copies (or a cooperative copy when USE_TMA == false), every voxel's update records (sorted by
-// (voxel, order)) are applied sequentially in the reference's order — updateTsdfVoxel (A.6) and
-// updateSemanticVoxel (base.cpp:136-194) — and the tile is written back once.
-template <bool USE_TMA>
+// One CTA per touched tile, tiles handed out through a device-side queue.  The tile's voxel planes (and, when
+// they fit, its log-probability rows) are staged in shared memory with ONE TMA bulk copy (cooperative copy when
+// USE_TMA == false) that overlaps the record-segment scan.  Each warp then takes voxels from a CTA-local queue;
+// a voxel's update records (sorted by (voxel, order)) are applied in the reference's order:
+//   * lanes = records : the state-independent half of updateTsdfVoxel (sdf, weight drop-off; A.6) for 32 records
+//   * all lanes       : the (distance, weight, colour) recurrence, one record after the other
+//   * lanes = classes : semantic log-probability rows, prior[c] += (L * freq)[c]  (base.cpp:283-314)
+// followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
+// written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
+template <bool USE_TMA, int NCH>
 __global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
-                                                               ApplySrc src, int group_planes) {
+                                                               ApplySrc src) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int V = cfg.tile_voxels;
+  const int C = cfg.C;
   float* s_dist = (float*)smem;
   float* s_wgt = (float*)(smem + cfg.plane_f32);
   uint32_t* s_rgba = (uint32_t*)(smem + 2 * cfg.plane_f32);
   uint32_t* s_srgba = (uint32_t*)(smem + 3 * cfg.plane_f32);
   uint8_t* s_label = smem + 4 * cfg.plane_f32;
-  float* s_prior = (float*)(smem + cfg.head_bytes);
-  uint8_t* aux = smem + cfg.head_bytes + (size_t)group_planes * cfg.plane_f32;
+  float* s_prior = (float*)(smem + cfg.head_bytes);             // only when cfg.full_stage
+  const uint32_t stage_bytes = cfg.head_bytes + (cfg.full_stage ? cfg.prior_bytes : 0u);
+  uint8_t* aux = smem + stage_bytes;
   int* s_seg_lo = (int*)aux;                 // [V]
   int* s_seg_hi = s_seg_lo + V;              // [V]
-  float* s_best = (float*)(s_seg_hi + V);    // [V] running arg-max across class groups
-  int* s_best_lab = (int*)(s_best + V);      // [V]
-  uint64_t* s_bar = (uint64_t*)(s_best_lab + V);
+  uint64_t* s_bar = (uint64_t*)(s_seg_hi + V + (V & 1));
   __shared__ long long s_begin, s_end;
   __shared__ uint8_t* s_chunk;
-  __shared__ int s_g0x, s_g0y, s_g0z;
+  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor;
 
-  const int tid = threadIdx.x;
-  const int pf = cfg.plane_f32 / 4;
+  const int tid = threadIdx.x, lane = tid & 31;
   uint32_t phase = 0;
   if (USE_TMA && tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   const int n_tiles = cnt->n_tiles;
-  const int ngroups = (cfg.C + group_planes - 1) / group_planes;
   const F3 origin = f3(T.tx, T.ty, T.tz);
+  const bool keep_blend = cfg.color_mode == 0;  // kColor: the blended colour survives; otherwise base.cpp:177-185 overwrites it
+  const uint32_t ord_mask = (1u << kRecOrdBits) - 1u, vox_mask = (1u << kRecVoxBits) - 1u;
 
-  for (int j = blockIdx.x; j < n_tiles; j += gridDim.x) {
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(&cnt->tile_cursor, 1);
+    __syncthreads();
+    const int j = s_tile;
+    if (j >= n_tiles) break;
     if (tid == 0) {
       const long long b = tile_begin[j];
       const uint32_t tk = (uint32_t)(rec[b] >> 32);
@@ -715,104 +785,123 @@ __global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform 
       s_begin = b; s_end = lo;
       const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block), tile = (int)(tk % (uint32_t)cfg.tiles_per_block);
       const int slot = map.ht_slot[pos];
-      s_chunk = (slot >= 0 && slot < map.max_blocks) ? map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride : nullptr;
+      uint8_t* chunk = (slot >= 0 && slot < map.max_blocks) ? map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride : nullptr;
+      s_chunk = chunk;
       const I3 bi = unpack_key(map.ht_keys[pos]);
       const int tps = cfg.tiles_per_side;
       const int tx = tile % tps, ty = (tile / tps) % tps, tz = tile / (tps * tps);
       s_g0x = bi.x * cfg.vps + tx * cfg.tile_side;
       s_g0y = bi.y * cfg.vps + ty * cfg.tile_side;
       s_g0z = bi.z * cfg.vps + tz * cfg.tile_side;
+      s_vox_cursor = 0;
+      if (USE_TMA && chunk) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
     }
     for (int v = tid; v < V; v += kApplyThreads) { s_seg_lo[v] = 0; s_seg_hi[v] = 0; }
     __syncthreads();
     uint8_t* chunk = s_chunk;
-    if (chunk == nullptr) { __syncthreads(); continue; }  // pool overflow already flagged
+    if (chunk == nullptr) continue;  // pool overflow already flagged; the loop-top barrier keeps the CTA in step
     const long long begin = s_begin, end = s_end;
-    // per-voxel record segments
+    // per-voxel record segments (overlaps the bulk load)
     for (long long i = begin + tid; i < end; i += kApplyThreads) {
-      const int vx = (int)((rec[i] >> kRecOrdBits) & ((1u << kRecVoxBits) - 1));
-      if (i == begin || (int)((rec[i - 1] >> kRecOrdBits) & ((1u << kRecVoxBits) - 1)) != vx) s_seg_lo[vx] = (int)(i - begin);
-      if (i + 1 == end || (int)((rec[i + 1] >> kRecOrdBits) & ((1u << kRecVoxBits) - 1)) != vx) s_seg_hi[vx] = (int)(i + 1 - begin);
+      const int vx = (int)((rec[i] >> kRecOrdBits) & vox_mask);
+      if (i == begin || (int)((rec[i - 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_lo[vx] = (int)(i - begin);
+      if (i + 1 == end || (int)((rec[i + 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_hi[vx] = (int)(i + 1 - begin);
     }
-    for (int grp = 0; grp < ngroups; ++grp) {
-      const int c0 = grp * group_planes;
-      const int gc = (cfg.C - c0) < group_planes ? (cfg.C - c0) : group_planes;
-      const uint32_t prior_bytes = (uint32_t)gc * cfg.plane_f32;
-      // ---- stage in
-      if (USE_TMA) {
-        if (tid == 0) {
-          mbar_expect_tx(s_bar, prior_bytes + (grp == 0 ? cfg.head_bytes : 0u));
-          if (grp == 0) tma_load_1d(smem, chunk, cfg.head_bytes, s_bar);
-          tma_load_1d(s_prior, chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32, prior_bytes, s_bar);
+    if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
+    else for (uint32_t t = tid; t < stage_bytes / 16; t += kApplyThreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
+    __syncthreads();
+    float* g_prior = (float*)(chunk + cfg.head_bytes);
+
+    for (;;) {
+      int v = 0;
+      if (lane == 0) v = atomicAdd(&s_vox_cursor, 1);
+      v = __shfl_sync(0xffffffffu, v, 0);
+      if (v >= V) break;
+      const int lo = s_seg_lo[v], hi = s_seg_hi[v];
+      if (lo >= hi) continue;
+      const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+      I3 g; g.x = s_g0x + (v & tm); g.y = s_g0y + ((v >> ts) & tm); g.z = s_g0z + (v >> (2 * ts));
+      const F3 center = voxel_center(g, cfg.voxel_size);
+      float dist = s_dist[v], wgt = s_wgt[v];
+      uint32_t rgba = s_rgba[v];
+      float* prow = (cfg.full_stage ? s_prior : g_prior) + (size_t)v * C;
+      float p[NCH];
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
+
+      for (int base = lo; base < hi; base += 32) {
+        const int k = base + lane;
+        uint32_t ord = 0, col = 0;
+        int lab = 0;
+        float sdf = 0.0f, uw = 0.0f;
+        if (k < hi) {
+          ord = (uint32_t)(rec[begin + k]) & ord_mask;
+          const float4 pr = src.param[ord];
+          tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), center, pr.w, sdf, uw);
+          if (src.color && keep_blend) col = src.color[ord];
+          if (src.label) lab = src.label[ord];
         }
-        mbar_wait(s_bar, phase);
-        phase ^= 1;
-      } else {
-        if (grp == 0) for (uint32_t t = tid; t < cfg.head_bytes / 16; t += kApplyThreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
-        const uint4* gp = (const uint4*)(chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32);
-        for (uint32_t t = tid; t < prior_bytes / 16; t += kApplyThreads) ((uint4*)s_prior)[t] = gp[t];
+        const int nb = (hi - base) < 32 ? (hi - base) : 32;
+        // semantic rows: lanes = classes
+        if (src.label) {
+          for (int jj = 0; jj < nb; ++jj) {
+            const int l = __shfl_sync(0xffffffffu, lab, jj);
+            if (l != 0) {   // label 0: column 0 of the likelihood is zero (base.cpp:127)
+#pragma unroll
+              for (int q = 0; q < NCH; ++q) p[q] += ((q * 32 + lane) == l) ? cfg.lm : cfg.ln;
+            }
+          }
+        } else {
+#pragma unroll 4
+          for (int jj = 0; jj < nb; ++jj) {
+            const uint32_t o = __shfl_sync(0xffffffffu, ord, jj);
+            const float* row = src.tmp + (size_t)o * C;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) p[q] += row[c]; }
+          }
+        }
+        // TSDF recurrence in record order (every lane carries the same state)
+        for (int jj = 0; jj < nb; ++jj) {
+          const float sj = __shfl_sync(0xffffffffu, sdf, jj);
+          const float uj = __shfl_sync(0xffffffffu, uw, jj);
+          const uint32_t cj = keep_blend ? __shfl_sync(0xffffffffu, col, jj) : 0u;
+          tsdf_chain_step(cfg.tp, sj, uj, cj, keep_blend, dist, wgt, rgba);
+        }
       }
+      // arg-max, first maximum wins (base.cpp:352-367)
+      float best = -3.402823466e38f;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C && (p[q] > best || bi == 0x7fffffff)) { best = p[q]; bi = c; } }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+      }
+      best = __shfl_sync(0xffffffffu, best, 0);
+      bi = __shfl_sync(0xffffffffu, bi, 0);
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) prow[c] = p[q]; }
+      if (lane == 0) {
+        s_dist[v] = dist; s_wgt[v] = wgt;
+        s_label[v] = (uint8_t)bi;
+        const uint32_t sc = luts->label_rgba[bi];          // base.cpp:370-380
+        s_srgba[v] = sc;
+        if (cfg.color_mode == 1) rgba = sc;                 // kSemantic (base.cpp:177-180)
+        else if (cfg.color_mode == 2) rgba = rainbow_color_map((double)expf(best));  // base.cpp:181-185
+        s_rgba[v] = rgba;
+      }
+    }
+    // ---- write the tile back
+    if (USE_TMA) {
+      fence_proxy_async();
       __syncthreads();
-      // ---- ordered per-voxel updates
-      for (int v = tid; v < V; v += kApplyThreads) {
-        const int lo = s_seg_lo[v], hi = s_seg_hi[v];
-        if (lo >= hi) continue;
-        if (grp == 0) {  // TSDF chain (A.6)
-          const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
-          I3 g; g.x = s_g0x + (v & tm); g.y = s_g0y + ((v >> ts) & tm); g.z = s_g0z + (v >> (2 * ts));
-          const F3 center = voxel_center(g, cfg.voxel_size);
-          float dist = s_dist[v], wgt = s_wgt[v];
-          uint32_t rgba = s_rgba[v];
-          for (int k = lo; k < hi; ++k) {
-            const uint32_t ord = (uint32_t)(rec[begin + k] & ((1u << kRecOrdBits) - 1));
-            const float4 p = src.param[ord];
-            const uint32_t col = src.color ? src.color[ord] : 0u;
-            tsdf_update(cfg.tp, origin, f3(p.x, p.y, p.z), center, col, p.w, dist, wgt, rgba);
-          }
-          s_dist[v] = dist; s_wgt[v] = wgt; s_rgba[v] = rgba;
-        }
-        // semantic log-probabilities (base.cpp:283-314), classes [c0, c0+gc)
-        for (int k = lo; k < hi; ++k) {
-          const uint32_t ord = (uint32_t)(rec[begin + k] & ((1u << kRecOrdBits) - 1));
-          if (src.label) {
-            const int l = src.label[ord];
-            if (l != 0) for (int c = 0; c < gc; ++c) s_prior[c * pf + v] += ((c0 + c) == l) ? cfg.lm : cfg.ln;
-          } else {
-            const float* t = src.tmp + (size_t)ord * cfg.C + c0;
-            for (int c = 0; c < gc; ++c) s_prior[c * pf + v] += t[c];
-          }
-        }
-        // arg-max, first maximum wins (base.cpp:352-367)
-        float best = (grp == 0) ? s_prior[v] : s_best[v];
-        int lab = (grp == 0) ? 0 : s_best_lab[v];
-        for (int c = (grp == 0 ? 1 : 0); c < gc; ++c) { const float x = s_prior[c * pf + v]; if (x > best) { best = x; lab = c0 + c; } }
-        s_best[v] = best; s_best_lab[v] = lab;
-        if (grp == ngroups - 1) {
-          s_label[v] = (uint8_t)lab;
-          const uint32_t sc = luts->label_rgba[lab];       // base.cpp:370-380
-          s_srgba[v] = sc;
-          if (cfg.color_mode == 1) s_rgba[v] = sc;         // kSemantic (base.cpp:177-180)
-          else if (cfg.color_mode == 2) s_rgba[v] = rainbow_color_map((double)expf(best));  // base.cpp:181-185
-        }
-      }
-      // ---- stage out
-      if (USE_TMA) {
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-          tma_store_1d(chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32, s_prior, prior_bytes);
-          if (grp == ngroups - 1) tma_store_1d(chunk, smem, cfg.head_bytes);
-          tma_store_commit_wait();
-        }
-        __syncthreads();
-      } else {
-        __syncthreads();
-        uint4* gp = (uint4*)(chunk + cfg.head_bytes + (size_t)c0 * cfg.plane_f32);
-        for (uint32_t t = tid; t < prior_bytes / 16; t += kApplyThreads) gp[t] = ((const uint4*)s_prior)[t];
-        if (grp == ngroups - 1) for (uint32_t t = tid; t < cfg.head_bytes / 16; t += kApplyThreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
-        __syncthreads();
-      }
+      if (tid == 0) { tma_store_1d(chunk, smem, stage_bytes); tma_store_commit_wait(); }
+    } else {
+      __syncthreads();
+      for (uint32_t t = tid; t < stage_bytes / 16; t += kApplyThreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
     }
+    // the loop-top barrier orders the store's completion before the next tile's load
   }
 }
 
@@ -825,7 +914,6 @@ __global__ void k_export(DevCfg cfg, MapRef map, const int* __restrict__ slots, 
   const int per_block = cfg.tiles_per_block;
   const int V = cfg.tile_voxels;
   const size_t VB = (size_t)cfg.vps * cfg.vps * cfg.vps;
-  const int pf = cfg.plane_f32 / 4;
   for (long long w = blockIdx.x; w < (long long)nb * per_block; w += gridDim.x) {
     const int bi = (int)(w / per_block), tile = (int)(w % per_block);
     const uint8_t* chunk = map.pool + (uint64_t)slots[bi] * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
@@ -845,7 +933,7 @@ __global__ void k_export(DevCfg cfg, MapRef map, const int* __restrict__ slots, 
       if (o_rgba) o_rgba[lin] = rgba[v];
       if (o_srgba) o_srgba[lin] = srgba[v];
       if (o_label) o_label[lin] = label[v];
-      if (o_prior) for (int c = 0; c < cfg.C; ++c) o_prior[lin * cfg.C + c] = prior[c * pf + v];
+      if (o_prior) for (int c = 0; c < cfg.C; ++c) o_prior[lin * cfg.C + c] = prior[(size_t)v * cfg.C + c];
     }
   }
 }
