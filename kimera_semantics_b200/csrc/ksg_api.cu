@@ -158,7 +158,7 @@ void free_all(ksg_integrator* h) {
                   h->map.touched_list, h->d_luts, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color, h->pt_key,
                   h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota, h->start_head,
                   h->start_next, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
-                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_val, h->ob.cand_order,
+                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.slot_cnt, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.head, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -315,6 +315,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   if (fast) {
     KSG_CUDA(cudaMemsetAsync(h->start_head, 0xFF, sizeof(int) * kSetSize, s));
     KSG_CUDA(cudaMemsetAsync(h->ob.head, 0xFF, sizeof(int) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->ob.slot_cnt, 0, sizeof(int) * kSetSize, s));
     ++h->n_launches;
     k_classify<true><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, h->set_offset, cap, h->d_cnt, h->pt_pC, h->pt_pG,
                                                     h->pt_label, h->pt_flags, h->pt_color, h->pt_key);
@@ -350,7 +351,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
         h->n_launches += 2;
         k_eval<<<grid_for((long long)n_cast * kEvalGroup, 128), 128, 0, s>>>(dc, h->d_cnt, h->ob, h->nsteps, h->H, h->L, h->ext_off,
                                                                             h->trunc_flag, h->eval_sweep, sweep);
-        k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state,
+        k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->ray_state,
                                                        h->ext_off, h->trunc_flag, h->eval_sweep, sweep);
         ++iterations;
       }
@@ -366,7 +367,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     if (!h->h_cnt->err) {
       if (n_records > h->rec_cap) { h->deferred_status = KSG_ERR_SCRATCH_FULL; return fail(KSG_ERR_SCRATCH_FULL, err_text(4)); }
       h->n_launches += 2;
-      k_obs_commit<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->ob, h->L, h->ext_off);
+      k_obs_commit<<<grid_for((long long)n_cast * kEvalGroup, 128), 128, 0, s>>>(h->d_cnt, h->ob, h->L, h->ext_off);
       k_emit_fast<<<grid_for(n_cast, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->L, h->rec_a,
                                                         h->rec_cap);
     }
@@ -429,9 +430,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     did_apply = true;
     const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem + 1024))));
     const int grid = h->sm_count * ctas_per_sm;
+    const int apply_threads = fast ? 512 : 256;  // fast: few records per voxel, latency bound -> more warps per tile
     ++h->n_launches;
 #define KSG_LAUNCH_APPLY(TMA, NCH)                                                                                   \
-    k_tile_apply<TMA, NCH><<<grid, kApplyThreads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
+    k_tile_apply<TMA, NCH><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
                                                                       n_records, h->tile_begin, src)
     if (h->use_tma) {
       switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(true, 1); break; case 2: KSG_LAUNCH_APPLY(true, 2); break;
@@ -658,7 +660,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     h->ob.cand_cap = h->ob.ext_base + ext;
     if (h->ob.cand_cap >= 0x7FFFFFFFll) { h->ob.cand_cap = 0x7FFFFFFEll; }
     KSG_CUDA(dmalloc(&h->ob.cand_val, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_order, (size_t)h->ob.cand_cap));
-    KSG_CUDA(dmalloc(&h->ob.cand_next, (size_t)h->ob.cand_cap));
+    KSG_CUDA(dmalloc(&h->ob.cand_next, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_pos, (size_t)h->ob.cand_cap));
+    KSG_CUDA(dmalloc(&h->ob.slot_cnt, kSetSize)); KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));
     KSG_CUDA(dmalloc(&h->ob.head, kSetSize)); KSG_CUDA(dmalloc(&h->ob.table, kSetSize));
   } else {
     KSG_CUDA(dmalloc(&h->ks_sorted, N)); KSG_CUDA(dmalloc(&h->seq_sorted, N));

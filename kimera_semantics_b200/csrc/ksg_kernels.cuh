@@ -252,11 +252,18 @@ __device__ __forceinline__ void load_state(Dda& d, const RayState& s) {
   d.tn[0] = s.tn0; d.tn[1] = s.tn1; d.tn[2] = s.tn2; d.ts[0] = s.ts0; d.ts[1] = s.ts1; d.ts[2] = s.ts2;
 }
 
+static constexpr int kBktK = 16;  // bucket entries per approximate-set slot (128 B), overflow goes to a linked list
+static constexpr uint64_t kEntPerf = 1ull << 63;
+static constexpr int kEntOrderBits = 23 + kOrderStepBits;  // rank < 2^23, step < 2^16
+
 struct ObsBuf {
   uint64_t* cand_val;    // value = hash + offset of the visited voxel
   uint64_t* cand_order;  // (rank << 16) | step
-  int* cand_next;        // per-slot list link
-  int* head;             // 2^20 list heads
+  int* cand_next;        // overflow list link
+  int* cand_pos;         // bucket entry index of the candidate, -1: overflow list
+  int* slot_cnt;         // 2^20: candidates inserted per slot this frame
+  uint64_t* bkt;         // 2^20 * kBktK entries: [performed:1][order:39][value >> 20 : 13]
+  int* head;             // 2^20 overflow list heads
   int* slot_stamp;       // 2^20: sweep in which a candidate of the slot last toggled "performed"
   uint32_t* table;       // persistent compact table: value >> 20, kSetNever = matches nothing
   long long ext_base;    // first extension candidate index (= capacity_rays * kH0)
@@ -267,6 +274,50 @@ __device__ __forceinline__ long long cand_index(const ObsBuf& o, const long long
   if (s < kH0) return (long long)r * kH0 + s;
   const int k = 31 - __clz(s >> 4);
   return o.ext_base + ext_off[(size_t)r * kExtSegs + k] + (s - (kH0 << k));
+}
+__device__ __forceinline__ void cand_insert(const ObsBuf& ob, long long ci, uint64_t v, uint64_t order, bool performed) {
+  const uint32_t slot = (uint32_t)v & kSetMask;
+  ob.cand_val[ci] = v;
+  ob.cand_order[ci] = order;
+  const int idx = atomicAdd(&ob.slot_cnt[slot], 1);
+  if (idx < kBktK) {
+    const int pos = (int)slot * kBktK + idx;
+    ob.bkt[pos] = (performed ? kEntPerf : 0ull) | (order << 13) | (v >> kSetBits);
+    ob.cand_pos[ci] = pos;
+  } else {
+    ob.cand_pos[ci] = -1;
+    ob.cand_next[ci] = atomicExch(&ob.head[slot], (int)ci);
+  }
+}
+// latest performed visit of `slot` that precedes `my_order`; returns its (value >> 20) or -1
+__device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const int* L, uint32_t slot, uint64_t my_order, int r) {
+  const int total = ob.slot_cnt[slot];
+  const int n = total < kBktK ? total : kBktK;
+  long long best = -1;
+  int best_hi = -1;
+  const uint64_t* b = ob.bkt + (size_t)slot * kBktK;
+  for (int j = 0; j < n; ++j) {
+    const uint64_t e = b[j];
+    const uint64_t eo = (e >> 13) & ((1ull << kEntOrderBits) - 1);
+    if (eo < my_order && (long long)eo > best) {
+      const bool performed = ((int)(eo >> kOrderStepBits) == r) || (e & kEntPerf);   // own earlier steps always count
+      if (performed) { best = (long long)eo; best_hi = (int)(e & 0x1FFF); }
+    }
+  }
+  if (total > kBktK) {
+    for (int e = ob.head[slot]; e >= 0; e = ob.cand_next[e]) {
+      const uint64_t eo = ob.cand_order[e];
+      if (eo < my_order && (long long)eo > best) {
+        const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
+        if (er == r || es < ((volatile const int*)L)[er]) { best = (long long)eo; best_hi = (int)(ob.cand_val[e] >> kSetBits); }
+      }
+    }
+  }
+  return best_hi;
+}
+__device__ __forceinline__ void set_performed(const ObsBuf& ob, long long ci, bool on) {
+  const int pos = ob.cand_pos[ci];
+  if (pos >= 0) { const uint64_t e = ob.bkt[pos]; ob.bkt[pos] = on ? (e | kEntPerf) : (e & ~kEntPerf); }   // single writer: the owning ray
 }
 
 __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __restrict__ cast_seq,
@@ -292,17 +343,15 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
   if (!d.in_range || n >= (1 << kOrderStepBits)) { set_err(cnt, 5); n = 0; }
   nsteps[r] = n;
   const int h = n < kH0 ? n : kH0;
+  // a ray cannot break before `maxc` consecutive collisions: its first maxc steps are always performed
+  const int l0 = h < cfg.maxc ? h : cfg.maxc;
   for (int s = 0; s < h; ++s) {
     const I3 g = dda_next(d);
-    const uint64_t v = (uint64_t)index_hash(g) + obs_offset;
-    const long long ci = (long long)r * kH0 + s;
-    ob.cand_val[ci] = v;
-    ob.cand_order[ci] = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
-    ob.cand_next[ci] = atomicExch(&ob.head[(uint32_t)v & kSetMask], (int)ci);
+    cand_insert(ob, (long long)r * kH0 + s, (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, s < l0);
   }
   RayState st; save_state(st, d); state[r] = st;
   H[r] = h;
-  L[r] = h;          // optimistic start: every materialised step performed
+  L[r] = l0;
   eval_sweep[r] = 0; // never evaluated
   trunc_flag[r] = 0;
   atomicAdd(&cnt->ray_steps, (unsigned long long)h);
@@ -310,7 +359,7 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
 
 // Rays that performed every step they had (trunc_flag) double their horizon. Runs after sweep `sweep`.
 __global__ void k_extend(Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
-                         int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag,
+                         RayState* __restrict__ state, long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag,
                          int* __restrict__ eval_sweep, int sweep) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r == 0) { const int nx = (sweep + 1) & 3; cnt->changed[nx] = 0; cnt->n_truncated[nx] = 0; cnt->sum_updates[nx] = 0; }
@@ -328,18 +377,11 @@ __global__ void k_extend(Counters* cnt, uint64_t obs_offset, ObsBuf ob, const in
   Dda d; load_state(d, state[r]);
   for (int s = h; s < nh; ++s) {
     const I3 g = dda_next(d);
-    const uint64_t v = (uint64_t)index_hash(g) + obs_offset;
-    const uint32_t slot = (uint32_t)v & kSetMask;
-    const long long ci = ob.ext_base + off + (s - h);
-    ob.cand_val[ci] = v;
-    ob.cand_order[ci] = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
-    ob.cand_next[ci] = atomicExch(&ob.head[slot], (int)ci);
-    atomicMax(&ob.slot_stamp[slot], sweep);   // new performed visits: dependants must re-evaluate
+    cand_insert(ob, ob.ext_base + off + (s - h), (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, false);
   }
   RayState st; save_state(st, d); state[r] = st;
-  H[r] = nh;
-  L[r] = nh;          // optimistic until the next sweep says otherwise
-  eval_sweep[r] = 0;
+  H[r] = nh;          // U stays h: the new steps are not performed until the next sweep says so
+  eval_sweep[r] = 0;  // force re-evaluation
   atomicAdd(&cnt->ray_steps, (unsigned long long)need);
   cnt->changed[sweep & 3] = 1;
 }
@@ -380,22 +422,10 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
         const int s = s0 + gl;
         bool coll = false;
         if (s < h) {
-          const long long ci = cand_index(ob, ext_off, r, s);
-          const uint64_t v = ob.cand_val[ci];
+          const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
           const uint32_t slot = (uint32_t)v & kSetMask;
-          const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
-          long long best_order = -1;
-          uint64_t best_val = 0;
-          for (int e = ob.head[slot]; e >= 0; e = ob.cand_next[e]) {
-            const uint64_t eo = ob.cand_order[e];
-            if (eo < my_order && (long long)eo > best_order) {
-              const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
-              // own earlier steps are performed whenever this step is reached
-              const bool performed = (er == r) ? true : (es < ((volatile int*)L)[er]);
-              if (performed) { best_order = (long long)eo; best_val = ob.cand_val[e]; }
-            }
-          }
-          coll = (best_order >= 0) ? (best_val == v) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
+          const int hi = latest_performed_before(ob, L, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, r);
+          coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
         }
         const unsigned bits = (__ballot_sync(gmask, coll) & gmask) >> gshift;
         for (int j = 0; j < G && s0 + j < h; ++j) {
@@ -405,11 +435,12 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
       }
       bool truncated = false;
       if (U < 0) { U = h; truncated = h < nsteps[r]; }
-      if (U != old) {   // candidates [min, max) toggled: stamp their slots
+      if (U != old) {   // candidates [min, max) toggle: flip their performed bits, stamp their slots
         const int lo = U < old ? U : old, hi = U < old ? old : U;
         for (int s = lo + gl; s < hi; s += G) {
-          const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
-          atomicMax(&ob.slot_stamp[(uint32_t)v & kSetMask], sweep);
+          const long long ci = cand_index(ob, ext_off, r, s);
+          set_performed(ob, ci, U > old);
+          atomicMax(&ob.slot_stamp[(uint32_t)ob.cand_val[ci] & kSetMask], sweep);
         }
       }
       if (gl == 0) {
@@ -428,22 +459,28 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
 
 // After convergence: the last performed visit of every slot becomes the persistent table entry.
 __global__ void k_obs_commit(Counters* cnt, ObsBuf ob, const int* __restrict__ L, const long long* __restrict__ ext_off) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int G = kEvalGroup;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = tid / G, gl = threadIdx.x % G;
   if (r >= cnt->n_cast) return;
   const int U = L[r];
-  for (int s = 0; s < U; ++s) {
-    const long long ci = cand_index(ob, ext_off, r, s);
-    const uint64_t v = ob.cand_val[ci];
+  for (int s = gl; s < U; s += G) {
+    const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
     const uint32_t slot = (uint32_t)v & kSetMask;
     const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+    const int total = ob.slot_cnt[slot];
+    const int n = total < kBktK ? total : kBktK;
+    const uint64_t* b = ob.bkt + (size_t)slot * kBktK;
     bool later = false;
-    for (int e = ob.head[slot]; e >= 0 && !later; e = ob.cand_next[e]) {
-      const uint64_t eo = ob.cand_order[e];
-      if (eo > my_order) {
-        const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
-        if (es < L[er]) later = true;
-      }
+    for (int j = 0; j < n; ++j) {
+      const uint64_t e = b[j];
+      if ((e & kEntPerf) && ((e >> 13) & ((1ull << kEntOrderBits) - 1)) > my_order) later = true;
     }
+    if (total > kBktK)
+      for (int e = ob.head[slot]; e >= 0 && !later; e = ob.cand_next[e]) {
+        const uint64_t eo = ob.cand_order[e];
+        if (eo > my_order && (int)(eo & ((1u << kOrderStepBits) - 1)) < L[(int)(eo >> kOrderStepBits)]) later = true;
+      }
     if (!later) ob.table[slot] = (uint32_t)(v >> kSetBits);
   }
 }
@@ -741,7 +778,7 @@ static constexpr int kApplyThreads = 256;
 // followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
 // written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
 template <bool USE_TMA, int NCH>
-__global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
+__global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
                                                                ApplySrc src) {
@@ -764,6 +801,7 @@ __global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform 
   __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor;
 
   const int tid = threadIdx.x, lane = tid & 31;
+  const int nthreads = blockDim.x;
   uint32_t phase = 0;
   if (USE_TMA && tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
@@ -796,19 +834,19 @@ __global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform 
       s_vox_cursor = 0;
       if (USE_TMA && chunk) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
     }
-    for (int v = tid; v < V; v += kApplyThreads) { s_seg_lo[v] = 0; s_seg_hi[v] = 0; }
+    for (int v = tid; v < V; v += nthreads) { s_seg_lo[v] = 0; s_seg_hi[v] = 0; }
     __syncthreads();
     uint8_t* chunk = s_chunk;
     if (chunk == nullptr) continue;  // pool overflow already flagged; the loop-top barrier keeps the CTA in step
     const long long begin = s_begin, end = s_end;
     // per-voxel record segments (overlaps the bulk load)
-    for (long long i = begin + tid; i < end; i += kApplyThreads) {
+    for (long long i = begin + tid; i < end; i += nthreads) {
       const int vx = (int)((rec[i] >> kRecOrdBits) & vox_mask);
       if (i == begin || (int)((rec[i - 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_lo[vx] = (int)(i - begin);
       if (i + 1 == end || (int)((rec[i + 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_hi[vx] = (int)(i + 1 - begin);
     }
     if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
-    else for (uint32_t t = tid; t < stage_bytes / 16; t += kApplyThreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
+    else for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
     __syncthreads();
     float* g_prior = (float*)(chunk + cfg.head_bytes);
 
@@ -899,7 +937,7 @@ __global__ void __launch_bounds__(kApplyThreads) k_tile_apply(DevCfg cfg, Xform 
       if (tid == 0) { tma_store_1d(chunk, smem, stage_bytes); tma_store_commit_wait(); }
     } else {
       __syncthreads();
-      for (uint32_t t = tid; t < stage_bytes / 16; t += kApplyThreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
+      for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
     }
     // the loop-top barrier orders the store's completion before the next tile's load
   }
