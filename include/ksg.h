@@ -175,6 +175,12 @@ int64_t ksg_num_blocks(ksg_integrator* h);
 int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index,
                           float* tsdf_distance, float* tsdf_weight, uint8_t* tsdf_rgba,
                           uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba);
+/* Same outputs for an explicit list of n block indices (n*3 int32), in list order; found[i] = 0 and the
+ * outputs of block i are left untouched when the block is not allocated.  Used by the C++ shim to refresh
+ * only the blocks an integrate call updated (SURVEY.md 8f NEXT-3). */
+int32_t ksg_export_blocks_by_index(ksg_integrator* h, int64_t n, const int32_t* block_index, uint8_t* found,
+                                   float* tsdf_distance, float* tsdf_weight, uint8_t* tsdf_rgba,
+                                   uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba);
 /* Indices (nb*3 int32, sorted as above) of the blocks updated by the most recent integrate call:
  * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);

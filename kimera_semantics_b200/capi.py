@@ -184,6 +184,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_num_blocks.restype = C.c_int64
     lib.ksg_export_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
     lib.ksg_export_blocks.restype = C.c_int32
+    lib.ksg_export_blocks_by_index.argtypes = [H, C.c_int64, i32p, u8p, fp, fp, u8p, u8p, fp, u8p]
+    lib.ksg_export_blocks_by_index.restype = C.c_int32
     lib.ksg_last_updated_blocks.argtypes = [H, C.c_int64, i32p]
     lib.ksg_last_updated_blocks.restype = C.c_int64
     lib.ksg_reset.argtypes = [H]
@@ -201,7 +203,7 @@ def load_library(path: Optional[str] = None):
 
 KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
-               "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks",
+               "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile"]
 
 

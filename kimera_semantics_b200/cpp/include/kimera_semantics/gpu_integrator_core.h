@@ -1,0 +1,38 @@
+// Shared implementation of the two drop-in integrators: owns the ksg handle (include/ksg.h) and keeps the host
+// Layer<TsdfVoxel> / Layer<SemanticVoxel> in step with the device-resident map.
+#pragma once
+#include <vector>
+#include "kimera_semantics/semantic_integrator_base.h"
+struct ksg_integrator;
+namespace kimera {
+// How the host layers follow the device map after integratePointCloud returns (SURVEY.md 8b "Ownership"):
+//  kEager (default, reference semantics): every block the call updated is copied back before the call returns;
+//  kLazy : nothing is copied until syncLayers() is called (mesher / ESDF / save should call it first).
+enum class LayerSyncMode : int { kEager = 0, kLazy = 1 };
+
+class GpuIntegratorCore {
+ public:
+  GpuIntegratorCore(int integrator_type, const vxb::TsdfIntegratorBase::Config& config,
+                    const SemanticIntegratorBase::SemanticConfig& semantic_config, vxb::Layer<vxb::TsdfVoxel>* tsdf_layer,
+                    vxb::Layer<SemanticVoxel>* semantic_layer);
+  ~GpuIntegratorCore();
+  GpuIntegratorCore(const GpuIntegratorCore&) = delete;
+  GpuIntegratorCore& operator=(const GpuIntegratorCore&) = delete;
+
+  void integrate(const vxb::Transformation& T_G_C, const vxb::Pointcloud& points_C, const vxb::Color* colors,
+                 const SemanticLabel* labels, bool freespace_points);
+  void setLayerSyncMode(LayerSyncMode m) { sync_mode_ = m; }
+  void syncLayers();           // copy every device block into the host layers
+  void syncUpdatedBlocks();    // copy the blocks of the last integrate call
+  int64_t lastVoxelUpdates() const { return last_voxel_updates_; }
+  ksg_integrator* handle() { return handle_; }
+
+ private:
+  void copyBlocks(const std::vector<int32_t>& idx);
+  ksg_integrator* handle_ = nullptr;
+  vxb::Layer<vxb::TsdfVoxel>* tsdf_layer_;
+  vxb::Layer<SemanticVoxel>* semantic_layer_;
+  LayerSyncMode sync_mode_ = LayerSyncMode::kEager;
+  int64_t last_voxel_updates_ = 0;
+};
+}  // namespace kimera

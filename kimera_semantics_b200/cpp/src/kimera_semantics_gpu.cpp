@@ -1,0 +1,288 @@
+// Host shim: the reference's C++ integrator API (SemanticTsdfIntegratorFactory, Fast/MergedSemanticTsdfIntegrator,
+// SemanticIntegratorBase, SemanticLabel2Color) implemented on top of the C-ABI of include/ksg.h.  No CUDA, Eigen, glog
+// or ROS here; errors follow the reference's convention (abort with a message).  There is no CPU fallback: when the
+// device library reports an error (including "no CUDA device") construction aborts.
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+
+#include "../../../include/ksg.h"
+#include "kimera_semantics/semantic_tsdf_integrator_factory.h"
+#include "kimera_semantics/semantic_tsdf_integrator_fast.h"
+#include "kimera_semantics/semantic_tsdf_integrator_merged.h"
+
+namespace kimera {
+
+// ------------------------------------------------------------------------------------------------
+// SemanticLabel2Color (color.cpp:42-94)
+// ------------------------------------------------------------------------------------------------
+SemanticLabel2Color::SemanticLabel2Color(const std::string& filename) {
+  std::ifstream file(filename.c_str());
+  KSG_CHECK(file.good()) << "Couldn't open file: " << filename;
+  std::string line;
+  size_t row_number = 1;
+  while (std::getline(file, line)) {  // CSVIterator: one row per line, comma separated (csv_iterator.cpp:22-38)
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    std::vector<std::string> cells;
+    std::stringstream ss(line);
+    std::string cell;
+    while (std::getline(ss, cell, ',')) cells.push_back(cell);
+    if (!line.empty() && line.back() == ',') cells.push_back("");
+    KSG_CHECK(cells.size() == 6u) << "Row " << row_number << " is invalid.";
+    // the header row parses to (0,0,0,0) -> 0 exactly as std::atoi does in the reference (color.cpp:52-56)
+    const uint8_t r = std::atoi(cells[1].c_str()), g = std::atoi(cells[2].c_str()), b = std::atoi(cells[3].c_str());
+    const uint8_t a = std::atoi(cells[4].c_str()), id = std::atoi(cells[5].c_str());
+    const HashableColor rgba(r, g, b, a);
+    semantic_label_to_color_map_[id] = rgba;
+    color_to_semantic_label_[rgba] = id;
+    row_number++;
+  }
+  semantic_label_to_color_map_[kUnknownSemanticLabelId] = HashableColor(vxb::Color::White());  // color.cpp:64-66
+  color_to_semantic_label_[HashableColor(vxb::Color::White())] = kUnknownSemanticLabelId;
+}
+SemanticLabel2Color::SemanticLabel2Color(const SemanticLabelToColorMap& label_to_color) : semantic_label_to_color_map_(label_to_color) {
+  for (const auto& kv : label_to_color) color_to_semantic_label_[kv.second] = kv.first;
+}
+SemanticLabel SemanticLabel2Color::getSemanticLabelFromColor(const HashableColor& color) const {
+  const auto it = color_to_semantic_label_.find(color);
+  return it != color_to_semantic_label_.end() ? it->second : kUnknownSemanticLabelId;  // color.cpp:74-81 (LOG(ERROR) dropped)
+}
+HashableColor SemanticLabel2Color::getColorFromSemanticLabel(const SemanticLabel& semantic_label) const {
+  const auto it = semantic_label_to_color_map_.find(semantic_label);
+  return it != semantic_label_to_color_map_.end() ? it->second : HashableColor();  // color.cpp:88-93
+}
+
+// ------------------------------------------------------------------------------------------------
+// SemanticIntegratorBase (base.cpp:57-128, 352-380)
+// ------------------------------------------------------------------------------------------------
+SemanticIntegratorBase::SemanticIntegratorBase(const SemanticConfig& semantic_config, vxb::Layer<SemanticVoxel>* semantic_layer)
+    : semantic_config_(semantic_config), semantic_layer_(nullptr) {
+  setSemanticLayer(semantic_layer);
+  KSG_CHECK(semantic_layer_ != nullptr);
+  setSemanticProbabilities();
+}
+void SemanticIntegratorBase::setSemanticLayer(vxb::Layer<SemanticVoxel>* semantic_layer) {
+  KSG_CHECK(semantic_layer != nullptr);
+  semantic_layer_ = semantic_layer;
+  semantic_voxel_size_ = semantic_layer_->voxel_size();
+  semantic_block_size_ = semantic_layer_->block_size();
+  semantic_voxels_per_side_ = semantic_layer_->voxels_per_side();
+  semantic_voxel_size_inv_ = 1.0 / semantic_voxel_size_;
+  semantic_block_size_inv_ = 1.0 / semantic_block_size_;
+  semantic_voxels_per_side_inv_ = 1.0 / semantic_voxels_per_side_;
+}
+void SemanticIntegratorBase::setSemanticProbabilities() {
+  const SemanticProbability match_probability = semantic_config_.semantic_measurement_probability_;
+  const SemanticProbability non_match_probability = 1.0f - semantic_config_.semantic_measurement_probability_;
+  KSG_CHECK(match_probability > 0.0);
+  KSG_CHECK(non_match_probability > 0.0);
+  KSG_CHECK(match_probability < 1.0);
+  KSG_CHECK(non_match_probability < 1.0);
+  log_match_probability_ = std::log(match_probability);
+  log_non_match_probability_ = std::log(non_match_probability);
+  KSG_CHECK(log_match_probability_ > log_non_match_probability_) << "Your probabilities do not make sense...";
+  for (size_t i = 0; i < kTotalNumberOfLabels; ++i)
+    for (size_t j = 0; j < kTotalNumberOfLabels; ++j)
+      semantic_log_likelihood_(i, j) = (i == j) ? log_match_probability_ : log_non_match_probability_;
+  for (size_t i = 0; i < kTotalNumberOfLabels; ++i) semantic_log_likelihood_(i, kUnknownSemanticLabelId) = 0.0f;  // base.cpp:127
+}
+void SemanticIntegratorBase::calculateMaximumLikelihoodLabel(const SemanticProbabilities& semantic_posterior,
+                                                             SemanticLabel* semantic_label) const {
+  KSG_CHECK(semantic_label != nullptr);
+  semantic_posterior.maxCoeff(semantic_label);
+}
+void SemanticIntegratorBase::updateSemanticVoxelColor(const SemanticLabel& semantic_label, HashableColor* semantic_voxel_color) const {
+  KSG_CHECK(semantic_voxel_color != nullptr);
+  *semantic_voxel_color = semantic_config_.semantic_label_to_color_->getColorFromSemanticLabel(semantic_label);
+}
+bool SemanticIntegratorBase::isSemanticLabelValid(const SemanticLabel& semantic_label) const {
+  return std::find(semantic_config_.dynamic_labels_.begin(), semantic_config_.dynamic_labels_.end(), semantic_label) ==
+         semantic_config_.dynamic_labels_.end();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GpuIntegratorCore
+// ------------------------------------------------------------------------------------------------
+GpuIntegratorCore::GpuIntegratorCore(int integrator_type, const vxb::TsdfIntegratorBase::Config& config,
+                                     const SemanticIntegratorBase::SemanticConfig& sc, vxb::Layer<vxb::TsdfVoxel>* tsdf_layer,
+                                     vxb::Layer<SemanticVoxel>* semantic_layer)
+    : tsdf_layer_(tsdf_layer), semantic_layer_(semantic_layer) {
+  KSG_CHECK(tsdf_layer != nullptr);
+  KSG_CHECK(semantic_layer != nullptr);
+  KSG_CHECK(tsdf_layer->voxels_per_side() == semantic_layer->voxels_per_side());
+  KSG_CHECK(tsdf_layer->voxel_size() == semantic_layer->voxel_size());
+  KSG_CHECK(sc.semantic_label_to_color_ != nullptr);  // CHECK(semantic_config_.semantic_label_to_color_) fast.cpp:154
+  ksg_config c;
+  ksg_default_config(&c, integrator_type, tsdf_layer->voxel_size(), (int)tsdf_layer->voxels_per_side(), (int)kTotalNumberOfLabels);
+  c.default_truncation_distance = config.default_truncation_distance;
+  c.max_weight = config.max_weight;
+  c.voxel_carving_enabled = config.voxel_carving_enabled;
+  c.min_ray_length_m = config.min_ray_length_m;
+  c.max_ray_length_m = config.max_ray_length_m;
+  c.use_const_weight = config.use_const_weight;
+  c.allow_clear = config.allow_clear;
+  c.use_weight_dropoff = config.use_weight_dropoff;
+  c.use_sparsity_compensation_factor = config.use_sparsity_compensation_factor;
+  c.sparsity_compensation_factor = config.sparsity_compensation_factor;
+  if (config.integration_order_mode == "mixed") c.integration_order_mode = KSG_ORDER_MIXED;
+  else if (config.integration_order_mode == "sorted") c.integration_order_mode = KSG_ORDER_SORTED;
+  else KSG_LOG_FATAL << "Unknown integration order mode: '" << config.integration_order_mode << "'!";  // ThreadSafeIndexFactory
+  c.enable_anti_grazing = config.enable_anti_grazing;
+  c.start_voxel_subsampling_factor = config.start_voxel_subsampling_factor;
+  c.max_consecutive_ray_collisions = config.max_consecutive_ray_collisions;
+  c.clear_checks_every_n_frames = config.clear_checks_every_n_frames;
+  c.integrator_threads = (int)config.integrator_threads;
+  c.semantic_measurement_probability = sc.semantic_measurement_probability_;
+  c.color_mode = static_cast<int>(sc.color_mode);
+  for (int l = 0; l < 256; ++l) {
+    const auto it = sc.semantic_label_to_color_->semantic_label_to_color_map_.find((SemanticLabel)l);
+    const bool known = it != sc.semantic_label_to_color_->semantic_label_to_color_map_.end();
+    c.label_color_known[l] = known ? 1 : 0;
+    c.label_color[l][0] = known ? it->second.r : 0; c.label_color[l][1] = known ? it->second.g : 0;
+    c.label_color[l][2] = known ? it->second.b : 0; c.label_color[l][3] = known ? it->second.a : 0;
+    c.dynamic_label[l] = 0;
+  }
+  for (const SemanticLabel l : sc.dynamic_labels_) c.dynamic_label[l] = 1;
+  if (const char* e = std::getenv("KSG_MAX_POINTS")) c.max_points = std::atoi(e); else c.max_points = 1 << 20;
+  if (const char* e = std::getenv("KSG_MAX_BLOCKS")) c.max_blocks = std::atoi(e);
+  if (const char* e = std::getenv("KSG_MAX_UPDATES")) c.max_updates = std::atoll(e);
+  if (const char* e = std::getenv("KSG_DEVICE")) c.device = std::atoi(e);
+  const int rc = ksg_create(&c, &handle_);
+  KSG_CHECK(rc == KSG_OK) << "ksg_create failed (" << rc << "): " << ksg_last_error(nullptr);
+  // colour -> label table (color.cpp:69-82); alpha is forced to 255 by the callers
+  std::vector<uint8_t> rgb, lab;
+  for (const auto& kv : sc.semantic_label_to_color_->color_to_semantic_label_) {
+    if (kv.first.a != 255) continue;  // can never match a lookup made with alpha 255
+    rgb.push_back(kv.first.r); rgb.push_back(kv.first.g); rgb.push_back(kv.first.b);
+    lab.push_back(kv.second);
+  }
+  KSG_CHECK(ksg_set_color_to_label(handle_, rgb.data(), lab.data(), (int)lab.size()) == KSG_OK) << ksg_last_error(handle_);
+}
+GpuIntegratorCore::~GpuIntegratorCore() { ksg_destroy(handle_); }
+
+void GpuIntegratorCore::integrate(const vxb::Transformation& T_G_C, const vxb::Pointcloud& points_C, const vxb::Color* colors,
+                                  const SemanticLabel* labels, bool freespace_points) {
+  static_assert(sizeof(vxb::Point) == 12, "Point must be 3 packed floats");
+  static_assert(sizeof(vxb::Color) == 4, "Color must be 4 packed bytes");
+  const vxb::FloatingPoint* q = T_G_C.getRotationWxyz();
+  const vxb::Point& t = T_G_C.getPosition();
+  const float T[7] = {q[0], q[1], q[2], q[3], t.x(), t.y(), t.z()};
+  ksg_frame_stats st;
+  const int rc = ksg_integrate_points(handle_, T, points_C.empty() ? nullptr : &points_C[0].v[0], reinterpret_cast<const uint8_t*>(colors),
+                                      labels, (int64_t)points_C.size(), freespace_points ? 1 : 0, &st);
+  KSG_CHECK(rc == KSG_OK) << "ksg_integrate_points failed (" << rc << "): " << ksg_last_error(handle_);
+  last_voxel_updates_ = st.voxel_updates;
+  if (sync_mode_ == LayerSyncMode::kEager) syncUpdatedBlocks();
+}
+
+void GpuIntegratorCore::copyBlocks(const std::vector<int32_t>& idx) {
+  const size_t nb = idx.size() / 3;
+  if (nb == 0) return;
+  const size_t vps = tsdf_layer_->voxels_per_side(), V = vps * vps * vps, C = kTotalNumberOfLabels;
+  std::vector<float> dist(nb * V), wgt(nb * V), priors(nb * V * C);
+  std::vector<uint8_t> rgba(nb * V * 4), srgba(nb * V * 4), label(nb * V), found(nb);
+  const int rc = ksg_export_blocks_by_index(handle_, (int64_t)nb, idx.data(), found.data(), dist.data(), wgt.data(), rgba.data(),
+                                            label.data(), priors.data(), srgba.data());
+  KSG_CHECK(rc == KSG_OK) << "ksg_export_blocks_by_index failed: " << ksg_last_error(handle_);
+  for (size_t b = 0; b < nb; ++b) {
+    if (!found[b]) continue;
+    const vxb::BlockIndex bi(idx[3 * b], idx[3 * b + 1], idx[3 * b + 2]);
+    // base.cpp:257-265 / voxblox updateLayerWithStoredBlocks: blocks appear in both layers
+    vxb::Block<vxb::TsdfVoxel>::Ptr tb = tsdf_layer_->allocateBlockPtrByIndex(bi);
+    vxb::Block<SemanticVoxel>::Ptr sb = semantic_layer_->allocateBlockPtrByIndex(bi);
+    for (size_t v = 0; v < V; ++v) {
+      vxb::TsdfVoxel& tv = tb->getVoxelByLinearIndex(v);
+      tv.distance = dist[b * V + v];
+      tv.weight = wgt[b * V + v];
+      const uint8_t* c = &rgba[(b * V + v) * 4];
+      tv.color = vxb::Color(c[0], c[1], c[2], c[3]);
+      SemanticVoxel& sv = sb->getVoxelByLinearIndex(v);
+      sv.semantic_label = label[b * V + v];
+      std::memcpy(sv.semantic_priors.data(), &priors[(b * V + v) * C], C * sizeof(float));
+      const uint8_t* s = &srgba[(b * V + v) * 4];
+      sv.color = HashableColor(s[0], s[1], s[2], s[3]);
+    }
+    tb->updated() = true;  // base.cpp:248
+    sb->updated() = true;
+    tb->has_data() = true;
+    sb->has_data() = true;
+  }
+}
+void GpuIntegratorCore::syncUpdatedBlocks() {
+  const int64_t n = ksg_last_updated_blocks(handle_, 0, nullptr);
+  std::vector<int32_t> idx((size_t)n * 3);
+  if (n) ksg_last_updated_blocks(handle_, n, idx.data());
+  copyBlocks(idx);
+}
+void GpuIntegratorCore::syncLayers() {
+  const int64_t n = ksg_num_blocks(handle_);
+  std::vector<int32_t> idx((size_t)n * 3);
+  if (n) KSG_CHECK(ksg_export_blocks(handle_, n, idx.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) == KSG_OK);
+  copyBlocks(idx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the two integrators + factory
+// ------------------------------------------------------------------------------------------------
+FastSemanticTsdfIntegrator::FastSemanticTsdfIntegrator(const Config& config, const SemanticConfig& semantic_config,
+                                                       vxb::Layer<vxb::TsdfVoxel>* tsdf_layer, vxb::Layer<SemanticVoxel>* semantic_layer)
+    : TsdfIntegratorBase(config, tsdf_layer), SemanticIntegratorBase(semantic_config, semantic_layer),
+      core_(KSG_INTEGRATOR_FAST, config, semantic_config, tsdf_layer, semantic_layer) {}
+
+void FastSemanticTsdfIntegrator::integratePointCloud(const vxb::Transformation& T_G_C, const vxb::Pointcloud& points_C,
+                                                     const vxb::Colors& colors, const bool freespace_points) {
+  KSG_CHECK(points_C.size() == colors.size());  // CHECK_EQ fast.cpp:161
+  core_.integrate(T_G_C, points_C, colors.data(), nullptr, freespace_points);
+}
+
+MergedSemanticTsdfIntegrator::MergedSemanticTsdfIntegrator(const Config& config, const SemanticConfig& semantic_config,
+                                                           vxb::Layer<vxb::TsdfVoxel>* tsdf_layer, vxb::Layer<SemanticVoxel>* semantic_layer)
+    : MergedTsdfIntegrator(config, tsdf_layer), SemanticIntegratorBase(semantic_config, semantic_layer),
+      core_(KSG_INTEGRATOR_MERGED, config, semantic_config, tsdf_layer, semantic_layer) {}
+
+void MergedSemanticTsdfIntegrator::integratePointCloud(const vxb::Transformation& T_G_C, const vxb::Pointcloud& points_C,
+                                                       const vxb::Colors& colors, const bool freespace_points) {
+  KSG_CHECK(points_C.size() == colors.size());
+  core_.integrate(T_G_C, points_C, colors.data(), nullptr, freespace_points);
+}
+void MergedSemanticTsdfIntegrator::integratePointCloud(const vxb::Transformation& T_G_C, const vxb::Pointcloud& points_C,
+                                                       const HashableColors& colors, const SemanticLabels& semantic_labels,
+                                                       const bool freespace_points) {
+  KSG_CHECK(points_C.size() == colors.size());            // merged.cpp:103-105
+  KSG_CHECK(points_C.size() == semantic_labels.size());
+  for (const SemanticLabel l : semantic_labels) KSG_CHECK(l < kTotalNumberOfLabels);  // CHECK_LT merged.cpp:278
+  core_.integrate(T_G_C, points_C, nullptr, semantic_labels.data(), freespace_points);
+}
+
+std::unique_ptr<vxb::TsdfIntegratorBase> SemanticTsdfIntegratorFactory::create(
+    const std::string& integrator_type_name, const vxb::TsdfIntegratorBase::Config& config,
+    const SemanticIntegratorBase::SemanticConfig& semantic_config, vxb::Layer<vxb::TsdfVoxel>* tsdf_layer,
+    vxb::Layer<SemanticVoxel>* semantic_layer) {
+  KSG_CHECK(!integrator_type_name.empty());
+  int integrator_type = 0;
+  for (const std::string& valid : kSemanticTsdfIntegratorTypeNames) {
+    if (integrator_type_name == valid)
+      return create(static_cast<SemanticTsdfIntegratorType>(integrator_type), config, semantic_config, tsdf_layer, semantic_layer);
+    ++integrator_type;
+  }
+  KSG_LOG_FATAL << "Unknown TSDF integrator type: " << integrator_type_name;  // factory.cpp:61
+  return nullptr;
+}
+std::unique_ptr<vxb::TsdfIntegratorBase> SemanticTsdfIntegratorFactory::create(
+    const SemanticTsdfIntegratorType& integrator_type, const vxb::TsdfIntegratorBase::Config& config,
+    const SemanticIntegratorBase::SemanticConfig& semantic_config, vxb::Layer<vxb::TsdfVoxel>* tsdf_layer,
+    vxb::Layer<SemanticVoxel>* semantic_layer) {
+  KSG_CHECK(tsdf_layer != nullptr);
+  switch (integrator_type) {
+    case SemanticTsdfIntegratorType::kFast:
+      return kimera::make_unique<FastSemanticTsdfIntegrator>(config, semantic_config, tsdf_layer, semantic_layer);
+    case SemanticTsdfIntegratorType::kMerged:
+      return kimera::make_unique<MergedSemanticTsdfIntegrator>(config, semantic_config, tsdf_layer, semantic_layer);
+    default:
+      KSG_LOG_FATAL << "Unknown Semantic/TSDF integrator type: " << static_cast<int>(integrator_type);  // factory.cpp:83
+  }
+  return nullptr;
+}
+
+}  // namespace kimera

@@ -1,0 +1,83 @@
+// Drives the drop-in C++ API exactly the way SemanticTsdfServer does (kimera_semantics_ros/src/semantic_tsdf_server.cpp:58-79):
+// build both layers, SemanticTsdfIntegratorFactory::create(method, ...), then integratePointCloud per frame.
+//   shim_demo <fast|merged|bogus> <frames.bin> <out.bin> [lazy]
+// frames.bin : int32 n_frames, float voxel_size, int32 vps, int32 n_palette, palette n*(r,g,b,a,id), int32 n_dynamic, ids...,
+//              then per frame: int32 n, float T[7], float xyz[3n], uint8 rgba[4n]
+// out.bin    : int32 n_blocks, then per block (sorted z,y,x): int32 idx[3], per voxel: float d, float w, u8 rgba[4], u8 label,
+//              float priors[C], u8 sem_rgba[4]
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include "kimera_semantics/semantic_tsdf_integrator_factory.h"
+#include "kimera_semantics/semantic_tsdf_integrator_fast.h"
+#include "kimera_semantics/semantic_tsdf_integrator_merged.h"
+
+using namespace kimera;
+template <typename T> static T rd(std::ifstream& f) { T v; f.read(reinterpret_cast<char*>(&v), sizeof(T)); return v; }
+
+int main(int argc, char** argv) {
+  if (argc < 4) { std::fprintf(stderr, "usage: shim_demo <fast|merged> frames.bin out.bin [lazy]\n"); return 2; }
+  std::ifstream f(argv[2], std::ios::binary);
+  KSG_CHECK(f.good()) << "cannot open " << argv[2];
+  const int n_frames = rd<int32_t>(f);
+  const float voxel_size = rd<float>(f);
+  const int vps = rd<int32_t>(f);
+  SemanticLabelToColorMap pal;
+  const int n_pal = rd<int32_t>(f);
+  for (int i = 0; i < n_pal; ++i) { uint8_t e[5]; f.read(reinterpret_cast<char*>(e), 5); pal[e[4]] = HashableColor(e[0], e[1], e[2], e[3]); }
+  SemanticIntegratorBase::SemanticConfig sc;
+  sc.semantic_label_to_color_ = std::make_shared<SemanticLabel2Color>(pal);
+  const int n_dyn = rd<int32_t>(f);
+  for (int i = 0; i < n_dyn; ++i) sc.dynamic_labels_.push_back(rd<uint8_t>(f));
+  vxb::TsdfIntegratorBase::Config config;
+  config.default_truncation_distance = 4.0f * voxel_size;  // voxblox_ros
+  vxb::Layer<vxb::TsdfVoxel> tsdf_layer(voxel_size, vps);
+  vxb::Layer<SemanticVoxel> semantic_layer(voxel_size, vps);
+  std::unique_ptr<vxb::TsdfIntegratorBase> integrator =
+      SemanticTsdfIntegratorFactory::create(std::string(argv[1]), config, sc, &tsdf_layer, &semantic_layer);
+  const bool lazy = argc > 4 && std::strcmp(argv[4], "lazy") == 0;
+  GpuIntegratorCore* core = nullptr;
+  if (auto* p = dynamic_cast<FastSemanticTsdfIntegrator*>(integrator.get())) core = &p->gpu();
+  if (auto* p = dynamic_cast<MergedSemanticTsdfIntegrator*>(integrator.get())) core = &p->gpu();
+  if (lazy) core->setLayerSyncMode(LayerSyncMode::kLazy);
+  for (int fr = 0; fr < n_frames; ++fr) {
+    const int n = rd<int32_t>(f);
+    float T[7]; f.read(reinterpret_cast<char*>(T), sizeof(T));
+    vxb::Pointcloud pts(n); vxb::Colors cols(n);
+    f.read(reinterpret_cast<char*>(pts.data()), sizeof(float) * 3 * n);
+    f.read(reinterpret_cast<char*>(cols.data()), 4 * (size_t)n);
+    integrator->integratePointCloud(vxb::Transformation(T[0], T[1], T[2], T[3], vxb::Point(T[4], T[5], T[6])), pts, cols, false);
+    std::printf("frame %d: %d points, %lld voxel updates, %zu blocks in the host layer\n", fr, n, (long long)core->lastVoxelUpdates(),
+                tsdf_layer.getNumberOfAllocatedBlocks());
+  }
+  if (lazy) core->syncLayers();
+  vxb::BlockIndexList blocks;
+  tsdf_layer.getAllAllocatedBlocks(&blocks);
+  std::sort(blocks.begin(), blocks.end(), [](const vxb::BlockIndex& a, const vxb::BlockIndex& b) {
+    return a.z() != b.z() ? a.z() < b.z() : (a.y() != b.y() ? a.y() < b.y() : a.x() < b.x()); });
+  std::ofstream o(argv[3], std::ios::binary);
+  const int32_t nb = (int32_t)blocks.size();
+  o.write(reinterpret_cast<const char*>(&nb), 4);
+  for (const auto& bi : blocks) {
+    const int32_t idx[3] = {bi.x(), bi.y(), bi.z()};
+    o.write(reinterpret_cast<const char*>(idx), 12);
+    auto tb = tsdf_layer.getBlockPtrByIndex(bi);
+    auto sb = semantic_layer.getBlockPtrByIndex(bi);
+    KSG_CHECK(sb != nullptr) << "semantic layer misses a block of the TSDF layer";
+    for (size_t v = 0; v < tb->num_voxels(); ++v) {
+      const vxb::TsdfVoxel& tv = tb->getVoxelByLinearIndex(v);
+      const SemanticVoxel& sv = sb->getVoxelByLinearIndex(v);
+      o.write(reinterpret_cast<const char*>(&tv.distance), 4);
+      o.write(reinterpret_cast<const char*>(&tv.weight), 4);
+      const uint8_t c[4] = {tv.color.r, tv.color.g, tv.color.b, tv.color.a};
+      o.write(reinterpret_cast<const char*>(c), 4);
+      o.write(reinterpret_cast<const char*>(&sv.semantic_label), 1);
+      o.write(reinterpret_cast<const char*>(sv.semantic_priors.v.data()), 4 * kTotalNumberOfLabels);
+      const uint8_t s[4] = {sv.color.r, sv.color.g, sv.color.b, sv.color.a};
+      o.write(reinterpret_cast<const char*>(s), 4);
+    }
+  }
+  std::printf("wrote %d blocks\n", nb);
+  return 0;
+}

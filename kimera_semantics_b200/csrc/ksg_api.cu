@@ -802,6 +802,53 @@ int64_t ksg_num_blocks(ksg_integrator* h) { return h ? h->num_blocks : 0; }
 
 static bool key_less_zyx(uint64_t a, uint64_t b) { return a < b; }  // packed as z:y:x, biased -> numeric order = (z, y, x)
 
+static int export_slots(ksg_integrator* h, const std::vector<int>& slots, float* tsdf_distance, float* tsdf_weight,
+                        uint8_t* tsdf_rgba, uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  const int64_t nb = (int64_t)slots.size();
+  if (nb == 0) return KSG_OK;
+  const DevCfg& dc = h->dc;
+  const size_t VB = (size_t)dc.vps * dc.vps * dc.vps;
+  const size_t per_block = VB * (4 + 4 + 4 + 1 + 4 + 4 * (size_t)dc.C) + 64;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)((256ull << 20) / per_block)));
+  if (h->exp_slots_cap < batch) {
+    if (h->d_exp_slots) cudaFree(h->d_exp_slots);
+    h->d_exp_slots = nullptr;
+    KSG_CUDA(dmalloc(&h->d_exp_slots, (size_t)batch));
+    h->exp_slots_cap = (int)batch;
+  }
+  const size_t need = (size_t)batch * per_block;
+  if (h->d_exp_bytes < need) {
+    if (h->d_exp) cudaFree(h->d_exp);
+    h->d_exp = nullptr;
+    KSG_CUDA(cudaMalloc((void**)&h->d_exp, need));
+    h->d_exp_bytes = need;
+  }
+  for (int64_t b0 = 0; b0 < nb; b0 += batch) {
+    const int64_t cnt = std::min(batch, nb - b0);
+    KSG_CUDA(cudaMemcpy(h->d_exp_slots, slots.data() + b0, sizeof(int) * cnt, cudaMemcpyHostToDevice));
+    uint8_t* p = h->d_exp;
+    float* o_dist = (float*)p; p += cnt * VB * 4;
+    float* o_wgt = (float*)p; p += cnt * VB * 4;
+    uint32_t* o_rgba = (uint32_t*)p; p += cnt * VB * 4;
+    uint32_t* o_srgba = (uint32_t*)p; p += cnt * VB * 4;
+    float* o_prior = (float*)p; p += cnt * VB * 4 * dc.C;
+    uint8_t* o_label = p;
+    k_export<<<h->sm_count * 4, 256, 0, h->own_stream>>>(dc, h->map, h->d_exp_slots, (int)cnt, tsdf_distance ? o_dist : nullptr,
+                                                         tsdf_weight ? o_wgt : nullptr, tsdf_rgba ? o_rgba : nullptr,
+                                                         sem_label ? o_label : nullptr, sem_priors ? o_prior : nullptr,
+                                                         sem_rgba ? o_srgba : nullptr);
+    KSG_CUDA(cudaStreamSynchronize(h->own_stream));
+    if (tsdf_distance) KSG_CUDA(cudaMemcpy(tsdf_distance + b0 * VB, o_dist, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (tsdf_weight) KSG_CUDA(cudaMemcpy(tsdf_weight + b0 * VB, o_wgt, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (tsdf_rgba) KSG_CUDA(cudaMemcpy(tsdf_rgba + b0 * VB * 4, o_rgba, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (sem_rgba) KSG_CUDA(cudaMemcpy(sem_rgba + b0 * VB * 4, o_srgba, cnt * VB * 4, cudaMemcpyDeviceToHost));
+    if (sem_label) KSG_CUDA(cudaMemcpy(sem_label + b0 * VB, o_label, cnt * VB, cudaMemcpyDeviceToHost));
+    if (sem_priors) KSG_CUDA(cudaMemcpy(sem_priors + b0 * VB * dc.C, o_prior, cnt * VB * 4 * dc.C, cudaMemcpyDeviceToHost));
+  }
+  return KSG_OK;
+}
+
 int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index, float* tsdf_distance,
                           float* tsdf_weight, uint8_t* tsdf_rgba, uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba) {
   if (!h) return KSG_ERR_INVALID_ARGUMENT;
@@ -822,44 +869,58 @@ int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* b
       block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
     }
   if (!tsdf_distance && !tsdf_weight && !tsdf_rgba && !sem_label && !sem_priors && !sem_rgba) return KSG_OK;
-  const DevCfg& dc = h->dc;
-  const size_t VB = (size_t)dc.vps * dc.vps * dc.vps;
-  const size_t per_block = VB * (4 + 4 + 4 + 1 + 4 + 4 * (size_t)dc.C) + 64;
-  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)((256ull << 20) / per_block)));
-  if (h->exp_slots_cap < batch) {
-    if (h->d_exp_slots) cudaFree(h->d_exp_slots);
-    h->d_exp_slots = nullptr;
-    KSG_CUDA(dmalloc(&h->d_exp_slots, (size_t)batch));
-    h->exp_slots_cap = (int)batch;
+  return export_slots(h, order, tsdf_distance, tsdf_weight, tsdf_rgba, sem_label, sem_priors, sem_rgba);
+}
+
+int32_t ksg_export_blocks_by_index(ksg_integrator* h, int64_t n, const int32_t* block_index, uint8_t* found, float* tsdf_distance,
+                                   float* tsdf_weight, uint8_t* tsdf_rgba, uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba) {
+  if (!h || n < 0 || (n > 0 && !block_index)) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (n == 0) return KSG_OK;
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  // host copy of the hash table: look the keys up exactly as the device does
+  std::vector<uint64_t> keys((size_t)h->ht_cap);
+  std::vector<int> slot_of((size_t)h->ht_cap);
+  KSG_CUDA(cudaMemcpy(keys.data(), h->map.ht_keys, sizeof(uint64_t) * h->ht_cap, cudaMemcpyDeviceToHost));
+  KSG_CUDA(cudaMemcpy(slot_of.data(), h->map.ht_slot, sizeof(int) * h->ht_cap, cudaMemcpyDeviceToHost));
+  std::vector<int> slots;
+  std::vector<int64_t> where;
+  for (int64_t i = 0; i < n; ++i) {
+    I3 b; b.x = block_index[3 * i]; b.y = block_index[3 * i + 1]; b.z = block_index[3 * i + 2];
+    int slot = -1;
+    if (key_in_range(b)) {
+      const uint64_t key = pack_key(b);
+      uint32_t pos = mix64(key) & h->map.ht_mask;
+      for (uint32_t probe = 0; probe <= h->map.ht_mask; ++probe) {
+        if (keys[pos] == key) { slot = slot_of[pos]; break; }
+        if (keys[pos] == kEmptyKey) break;
+        pos = (pos + 1) & h->map.ht_mask;
+      }
+    }
+    if (found) found[i] = slot >= 0 ? 1 : 0;
+    if (slot >= 0) { slots.push_back(slot); where.push_back(i); }
   }
-  const size_t need = (size_t)batch * per_block;
-  if (h->d_exp_bytes < need) {
-    if (h->d_exp) cudaFree(h->d_exp);
-    h->d_exp = nullptr;
-    KSG_CUDA(cudaMalloc((void**)&h->d_exp, need));
-    h->d_exp_bytes = need;
-  }
-  for (int64_t b0 = 0; b0 < nb; b0 += batch) {
-    const int64_t cnt = std::min(batch, nb - b0);
-    KSG_CUDA(cudaMemcpy(h->d_exp_slots, order.data() + b0, sizeof(int) * cnt, cudaMemcpyHostToDevice));
-    uint8_t* p = h->d_exp;
-    float* o_dist = (float*)p; p += cnt * VB * 4;
-    float* o_wgt = (float*)p; p += cnt * VB * 4;
-    uint32_t* o_rgba = (uint32_t*)p; p += cnt * VB * 4;
-    uint32_t* o_srgba = (uint32_t*)p; p += cnt * VB * 4;
-    float* o_prior = (float*)p; p += cnt * VB * 4 * dc.C;
-    uint8_t* o_label = p;
-    k_export<<<h->sm_count * 4, 256, 0, h->own_stream>>>(dc, h->map, h->d_exp_slots, (int)cnt, tsdf_distance ? o_dist : nullptr,
-                                                         tsdf_weight ? o_wgt : nullptr, tsdf_rgba ? o_rgba : nullptr,
-                                                         sem_label ? o_label : nullptr, sem_priors ? o_prior : nullptr,
-                                                         sem_rgba ? o_srgba : nullptr);
-    KSG_CUDA(cudaStreamSynchronize(h->own_stream));
-    if (tsdf_distance) KSG_CUDA(cudaMemcpy(tsdf_distance + b0 * VB, o_dist, cnt * VB * 4, cudaMemcpyDeviceToHost));
-    if (tsdf_weight) KSG_CUDA(cudaMemcpy(tsdf_weight + b0 * VB, o_wgt, cnt * VB * 4, cudaMemcpyDeviceToHost));
-    if (tsdf_rgba) KSG_CUDA(cudaMemcpy(tsdf_rgba + b0 * VB * 4, o_rgba, cnt * VB * 4, cudaMemcpyDeviceToHost));
-    if (sem_rgba) KSG_CUDA(cudaMemcpy(sem_rgba + b0 * VB * 4, o_srgba, cnt * VB * 4, cudaMemcpyDeviceToHost));
-    if (sem_label) KSG_CUDA(cudaMemcpy(sem_label + b0 * VB, o_label, cnt * VB, cudaMemcpyDeviceToHost));
-    if (sem_priors) KSG_CUDA(cudaMemcpy(sem_priors + b0 * VB * dc.C, o_prior, cnt * VB * 4 * dc.C, cudaMemcpyDeviceToHost));
+  if (slots.empty()) return KSG_OK;
+  const size_t VB = (size_t)h->dc.vps * h->dc.vps * h->dc.vps;
+  const size_t C = (size_t)h->dc.C;
+  const bool dense = (int64_t)slots.size() == n;
+  if (dense) return export_slots(h, slots, tsdf_distance, tsdf_weight, tsdf_rgba, sem_label, sem_priors, sem_rgba);
+  // sparse hit list: export compactly, then scatter to the callers positions
+  const size_t m = slots.size();
+  std::vector<float> d(tsdf_distance ? m * VB : 0), w(tsdf_weight ? m * VB : 0), pr(sem_priors ? m * VB * C : 0);
+  std::vector<uint8_t> c1(tsdf_rgba ? m * VB * 4 : 0), c2(sem_rgba ? m * VB * 4 : 0), lb(sem_label ? m * VB : 0);
+  int rc = export_slots(h, slots, tsdf_distance ? d.data() : nullptr, tsdf_weight ? w.data() : nullptr, tsdf_rgba ? c1.data() : nullptr,
+                        sem_label ? lb.data() : nullptr, sem_priors ? pr.data() : nullptr, sem_rgba ? c2.data() : nullptr);
+  if (rc) return rc;
+  for (size_t k = 0; k < m; ++k) {
+    const size_t i = (size_t)where[k];
+    if (tsdf_distance) std::memcpy(tsdf_distance + i * VB, d.data() + k * VB, VB * 4);
+    if (tsdf_weight) std::memcpy(tsdf_weight + i * VB, w.data() + k * VB, VB * 4);
+    if (tsdf_rgba) std::memcpy(tsdf_rgba + i * VB * 4, c1.data() + k * VB * 4, VB * 4);
+    if (sem_rgba) std::memcpy(sem_rgba + i * VB * 4, c2.data() + k * VB * 4, VB * 4);
+    if (sem_label) std::memcpy(sem_label + i * VB, lb.data() + k * VB, VB);
+    if (sem_priors) std::memcpy(sem_priors + i * VB * C, pr.data() + k * VB * C, VB * C * 4);
   }
   return KSG_OK;
 }

@@ -64,7 +64,7 @@ struct Counters {
 
 static constexpr int kH0 = 16;           // ray steps materialised before the first observed-set sweep
 static constexpr int kExtSegs = 12;      // horizon doubles per extension: 16, 32, ..., 65536
-static constexpr int kEvalGroup = 8;     // lanes cooperating on one ray in k_eval
+static constexpr int kEvalGroup = 32;    // lanes cooperating on one ray in k_eval (a full warp: long rays set the critical path)
 static constexpr int kOrderStepBits = 16;
 static constexpr int kRecVoxBits = 9, kRecOrdBits = 23;
 
@@ -396,7 +396,7 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
   const int r = tid / G;
   const int gl = threadIdx.x % G;                               // lane in group
   const int wl = threadIdx.x & 31;
-  const unsigned gmask = ((1u << G) - 1u) << (wl - gl);         // the group's lanes inside the warp
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (wl - gl));  // the group's lanes inside the warp
   const int gshift = wl - gl;
   const int n_cast = cnt->n_cast;
   int U = 0;

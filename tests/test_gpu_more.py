@@ -1,0 +1,148 @@
+"""More GPU tests: golden fixtures without the oracle in the loop, the C++ drop-in shim end to end, BASELINE.json
+full-size configurations (direct oracle comparison where the oracle finishes in seconds, size-independent properties
+beyond that)."""
+import importlib.util
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from kimera_semantics_b200 import synth
+from kimera_semantics_b200.capi import Integrator, KSG_INTEGRATOR_FAST, KSG_INTEGRATOR_MERGED
+from oracle.oracle_py import OracleIntegrator
+from parity_utils import assert_parity, compare_maps, frames, make_config, stats_equal
+from test_shim_cpu import CPP, demo, write_frames  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "oracle_golden.json")))
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_cuda_path_matches_committed_golden_digests(name):
+    got = make_golden.run_case(name, Integrator)
+    assert got["stats"] == GOLDEN[name]["stats"]
+    assert got["digest"] == GOLDEN[name]["digest"]      # bit-exact map, no oracle involved at run time
+
+
+def read_shim_output(path, vps, C):
+    V = vps ** 3
+    rec = np.dtype([("d", "<f4"), ("w", "<f4"), ("rgba", "u1", 4), ("label", "u1"), ("priors", "<f4", C), ("srgba", "u1", 4)])
+    raw = open(path, "rb").read()
+    nb = int(np.frombuffer(raw, "<i4", 1)[0])
+    off = 4
+    out = {"block_index": np.zeros((nb, 3), np.int32), "tsdf_distance": np.zeros((nb, V), np.float32), "tsdf_weight": np.zeros((nb, V), np.float32),
+           "tsdf_rgba": np.zeros((nb, V, 4), np.uint8), "sem_label": np.zeros((nb, V), np.uint8), "sem_priors": np.zeros((nb, V, C), np.float32),
+           "sem_rgba": np.zeros((nb, V, 4), np.uint8)}
+    for b in range(nb):
+        out["block_index"][b] = np.frombuffer(raw, "<i4", 3, off); off += 12
+        a = np.frombuffer(raw, rec, V, off); off += V * rec.itemsize
+        out["tsdf_distance"][b], out["tsdf_weight"][b], out["tsdf_rgba"][b] = a["d"], a["w"], a["rgba"]
+        out["sem_label"][b], out["sem_priors"][b], out["sem_rgba"][b] = a["label"], a["priors"], a["srgba"]
+    return out
+
+
+@pytest.mark.parametrize("method,mode", [("fast", "eager"), ("merged", "eager"), ("fast", "lazy")])
+def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mode):
+    """SemanticTsdfIntegratorFactory::create(method, ...) + integratePointCloud(T_G_C, points_C, colors) through the C++ shim
+    fill the host Layer<TsdfVoxel> / Layer<SemanticVoxel> exactly as the oracle's layers."""
+    C, w, h, vs = 21, 320, 240, 0.10
+    itype = KSG_INTEGRATOR_FAST if method == "fast" else KSG_INTEGRATOR_MERGED
+    cfg = make_config(itype, vs, C, max_points=w * h)
+    pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(C)], np.uint8)
+    ora = OracleIntegrator(cfg)
+    ora.set_color_to_label(pal[:, :3], np.arange(C, dtype=np.uint8))
+    fr = []
+    for cam, depth, label, T in frames(w, h, C, 2):
+        xyz, pix = synth.backproject(depth, cam)
+        rgba = pal[label.reshape(-1)[pix]].copy()
+        rgba[::53] = (9, 8, 7, 255)                      # unknown colour -> label 0
+        fr.append((T, xyz, rgba))
+        ora.integrate_points(T, xyz, rgba=rgba)
+    fpath, opath = tmp_path / "frames.bin", tmp_path / "out.bin"
+    write_frames(fpath, fr, vs, 16, pal, [C - 1])
+    env = dict(os.environ, KSG_MAX_POINTS=str(w * h), KSG_MAX_UPDATES=str(8 << 20))
+    args = [demo, method, str(fpath), str(opath)] + (["lazy"] if mode == "lazy" else [])
+    r = subprocess.run(args, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    got = read_shim_output(opath, 16, C)
+    assert_parity(compare_maps(got, ora.export()))
+
+
+# ---- BASELINE.json full-size configurations -------------------------------------------------------------------------
+def test_fullsize_config1_fast_640x480_5cm_c21_ten_frames():
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.05, 21)
+    gpu, ora = Integrator(cfg), OracleIntegrator(cfg)
+    for i, (cam, depth, label, T) in enumerate(frames(640, 480, 21, 10)):
+        sg, so = gpu.integrate_depth(T, depth, label, cam.K), ora.integrate_depth(T, depth, label, cam.K)
+        ok, why = stats_equal(sg, so)
+        assert ok, f"frame {i}: {why}"
+    assert_parity(compare_maps(gpu.export(), ora.export()))
+
+
+def test_fullsize_config2_merged_640x480_2cm_c21_one_frame_vs_oracle():
+    cfg = make_config(KSG_INTEGRATOR_MERGED, 0.02, 21, max_updates=48 << 20, max_blocks=4096)
+    gpu, ora = Integrator(cfg), OracleIntegrator(cfg)
+    cam, depth, label, T = next(frames(640, 480, 21, 1))
+    sg, so = gpu.integrate_depth(T, depth, label, cam.K), ora.integrate_depth(T, depth, label, cam.K)   # ~10 s of CPU
+    ok, why = stats_equal(sg, so)
+    assert ok, why
+    assert sg.voxel_updates > 25_000_000
+    assert_parity(compare_maps(gpu.export(), ora.export()))
+
+
+def _invariants(cfg, e):
+    C = cfg.num_labels
+    trunc = np.float32(cfg.default_truncation_distance)
+    assert np.isfinite(e["tsdf_distance"]).all() and (np.abs(e["tsdf_distance"]) <= trunc).all()
+    assert (e["tsdf_weight"] >= 0).all() and (e["tsdf_weight"] <= cfg.max_weight).all()
+    assert (e["sem_priors"] <= np.float32(-0.60205999132)).all()      # every log-likelihood increment is <= 0
+    assert (e["sem_label"] < C).all()
+    lut = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(256)], np.uint8)
+    touched = (e["sem_priors"] < np.float32(-0.60205999132)).any(axis=-1)
+    assert np.array_equal(e["sem_rgba"][touched], lut[e["sem_label"][touched]])     # base.cpp:370-380
+    assert np.array_equal(e["tsdf_rgba"][touched], e["sem_rgba"][touched])          # kSemantic hand-off base.cpp:177-180
+    best = e["sem_priors"].max(axis=-1)
+    first = (e["sem_priors"] == best[..., None]).argmax(axis=-1)
+    assert np.array_equal(first.astype(np.uint8), e["sem_label"])                   # label = first arg-max of the priors
+
+
+def test_fullsize_fast_weight_checksum_property_40_frames():
+    """Size-independent property: with constant weights and no drop-off every update adds exactly 1.0 to its voxel, so the
+    sum of all voxel weights equals the number of voxel updates (a checksum over the whole stream, no oracle needed)."""
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.05, 21, use_const_weight=1, use_weight_dropoff=0)
+    gpu = Integrator(cfg)
+    total = 0
+    for cam, depth, label, T in frames(640, 480, 21, 40):
+        total += gpu.integrate_depth(T, depth, label, cam.K).voxel_updates
+    e = gpu.export()
+    assert e["tsdf_weight"].max() < cfg.max_weight
+    assert int(e["tsdf_weight"].astype(np.float64).sum()) == total
+    assert (e["tsdf_weight"] == np.round(e["tsdf_weight"])).all()
+    _invariants(cfg, e)
+
+
+def test_fullsize_merged_2cm_invariants_three_frames():
+    cfg = make_config(KSG_INTEGRATOR_MERGED, 0.02, 21, max_updates=48 << 20, max_blocks=4096)
+    gpu = Integrator(cfg)
+    for cam, depth, label, T in frames(640, 480, 21, 3):
+        st = gpu.integrate_depth(T, depth, label, cam.K)
+        assert st.voxel_updates == st.ray_steps > 25_000_000
+    _invariants(cfg, gpu.export())
+
+
+# BASELINE.json configs[3] geometry on one GPU: 1280x720, 5 cm, 150 classes (one frame of the 8-frame batch)
+def test_config3_1280x720_5cm_c150_one_frame():
+    for itype in (KSG_INTEGRATOR_FAST,):
+        cfg = make_config(itype, 0.05, 150, max_points=1280 * 720, max_blocks=2048)
+        gpu, ora = Integrator(cfg), OracleIntegrator(cfg)
+        for cam, depth, label, T in frames(1280, 720, 150, 2):
+            sg, so = gpu.integrate_depth(T, depth, label, cam.K), ora.integrate_depth(T, depth, label, cam.K)
+            ok, why = stats_equal(sg, so)
+            assert ok, why
+        assert_parity(compare_maps(gpu.export(), ora.export()))
