@@ -114,6 +114,7 @@ struct ksg_integrator {
 
   int apply_smem = 0;
   int apply_nch = 1;
+  int rows_per_sub = 32;
   bool use_tma = true;
 
   // profiling
@@ -426,6 +427,8 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     ++h->n_launches;
     k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
                                                       h->tile_cap);
+    ++h->n_launches;
+    k_tile_queue_reset<<<1, 1, 0, s>>>(h->d_cnt);
     if (h->profiling) cudaEventRecord(h->ev[5], s);
     did_apply = true;
     const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem + 1024))));
@@ -434,7 +437,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     ++h->n_launches;
 #define KSG_LAUNCH_APPLY(TMA, NCH)                                                                                   \
     k_tile_apply<TMA, NCH><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
-                                                                      n_records, h->tile_begin, src)
+                                                                      n_records, h->tile_begin, h->tile_cap, src, h->rows_per_sub)
     if (h->use_tma) {
       switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(true, 1); break; case 2: KSG_LAUNCH_APPLY(true, 2); break;
                               case 4: KSG_LAUNCH_APPLY(true, 4); break; default: KSG_LAUNCH_APPLY(true, 8); break; }
@@ -583,7 +586,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   dc.C = cfg->num_labels;
   dc.prior_bytes = round_up(4u * (uint32_t)dc.tile_voxels * (uint32_t)dc.C, 16);
   dc.tile_stride = round_up(dc.head_bytes + dc.prior_bytes, 128);
-  dc.full_stage = (dc.head_bytes + dc.prior_bytes + 8u * dc.tile_voxels + 64u) <= 110u * 1024u ? 1 : 0;
+  dc.full_stage = (dc.head_bytes + dc.prior_bytes + 8u * dc.tile_voxels + 64u) <= 72u * 1024u ? 1 : 0;
   dc.block_stride = (uint64_t)dc.tile_stride * dc.tiles_per_block;
   dc.tp.voxel_size = cfg->voxel_size;
   dc.tp.trunc = cfg->default_truncation_distance;
@@ -690,7 +693,9 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   {
     const int V = dc.tile_voxels;
     const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
-    h->apply_smem = (int)(stage + (size_t)V * 8 + 64);
+    const bool fast_cfg = cfg->integrator_type == KSG_INTEGRATOR_FAST;
+    h->rows_per_sub = std::max(1, std::min(32, kRowBufFloats / dc.C));
+    h->apply_smem = (int)(stage + (size_t)V * 8 + 64 + (fast_cfg ? 0 : (size_t)(256 / 32) * kRowBufFloats * 4));
     h->apply_nch = dc.C <= 32 ? 1 : (dc.C <= 64 ? 2 : (dc.C <= 128 ? 4 : 8));
     h->use_tma = cfg->apply_mode == 0;
     KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));

@@ -51,7 +51,7 @@ struct Counters {
   int n_blocks_touched;
   int pool_count;    // blocks allocated in the pool (persistent across frames)
   int tile_cursor;   // dynamic tile queue of k_tile_apply
-  int pad0;
+  int n_big_tiles;   // tiles with many records are queued first (front of tile_begin; the others fill it from the back)
   // observed-set solver, indexed by (sweep & 3)
   int changed[4];
   int n_truncated[4];
@@ -75,7 +75,7 @@ __device__ __forceinline__ void set_err(Counters* c, int e) { atomicCAS(&c->err,
 // ---------------------------------------------------------------------------------------------
 __global__ void k_frame_reset(Counters* c, int n_points) {
   c->n_points = n_points; c->n_valid = 0; c->n_cast = 0;
-  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0; c->tile_cursor = 0;
+  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0; c->tile_cursor = 0; c->n_big_tiles = 0;
   for (int i = 0; i < 4; ++i) { c->changed[i] = 0; c->n_truncated[i] = 0; c->sum_updates[i] = 0; }
   c->n_records = 0; c->n_skipped = 0; c->n_cand_ext = 0; c->ray_steps = 0;
 }
@@ -716,6 +716,7 @@ __global__ void k_frame_finish(Counters* cnt, MapRef map) {
 // ---------------------------------------------------------------------------------------------
 // tile apply
 // ---------------------------------------------------------------------------------------------
+static constexpr int kBigTileRecords = 8192;
 __global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64_t* __restrict__ rec, long long n, int stamp,
                              long long* __restrict__ tile_begin, long long tile_cap) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -724,12 +725,21 @@ __global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64
   if (k == ~0ull) return;
   const uint32_t tk = (uint32_t)(k >> 32);
   if (i > 0 && (uint32_t)(rec[i - 1] >> 32) == tk) return;
-  const int j = atomicAdd(&cnt->n_tiles, 1);
-  if (j < tile_cap) tile_begin[j] = i; else set_err(cnt, 4);
+  // does the tile hold more than kBigTileRecords records? (longest-processing-time-first scheduling)
+  const long long probe = i + kBigTileRecords;
+  const bool big = probe < n && (uint32_t)(rec[probe] >> 32) == tk;
+  atomicAdd(&cnt->n_tiles, 1);
+  if (big) { const int j = atomicAdd(&cnt->n_big_tiles, 1); if (j < tile_cap) tile_begin[j] = i; }
+  else {
+    const int j = atomicAdd(&cnt->tile_cursor, 1);   // borrowed as the small-tile counter; reset by k_tile_queue_reset
+    if (j < tile_cap) tile_begin[tile_cap - 1 - j] = i;
+  }
+  if (cnt->n_tiles > tile_cap) set_err(cnt, 4);
   const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
   const int old = atomicExch(&map.touched_stamp[pos], stamp);
   if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
 }
+__global__ void k_tile_queue_reset(Counters* cnt) { cnt->tile_cursor = 0; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -767,6 +777,7 @@ struct ApplySrc {
 };
 
 static constexpr int kApplyThreads = 256;
+static constexpr int kRowBufFloats = 1024;   // per-warp row staging buffer (4 KB)
 
 // One CTA per touched tile, tiles handed out through a device-side queue.  The tile's voxel planes (and, when
 // they fit, its log-probability rows) are staged in shared memory with ONE TMA bulk copy (cooperative copy when
@@ -781,7 +792,7 @@ template <bool USE_TMA, int NCH>
 __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
-                                                               ApplySrc src) {
+                                                               long long tile_cap, ApplySrc src, int rows_per_sub) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int V = cfg.tile_voxels;
   const int C = cfg.C;
@@ -796,6 +807,7 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
   int* s_seg_lo = (int*)aux;                 // [V]
   int* s_seg_hi = s_seg_lo + V;              // [V]
   uint64_t* s_bar = (uint64_t*)(s_seg_hi + V + (V & 1));
+  float* s_rows = (float*)(s_bar + 2) + (size_t)(threadIdx.x >> 5) * kRowBufFloats;   // per-warp staging of L*freq rows (merged)
   __shared__ long long s_begin, s_end;
   __shared__ uint8_t* s_chunk;
   __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor;
@@ -805,7 +817,7 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
   uint32_t phase = 0;
   if (USE_TMA && tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  const int n_tiles = cnt->n_tiles;
+  const int n_tiles = cnt->n_tiles, n_big = cnt->n_big_tiles;
   const F3 origin = f3(T.tx, T.ty, T.tz);
   const bool keep_blend = cfg.color_mode == 0;  // kColor: the blended colour survives; otherwise base.cpp:177-185 overwrites it
   const uint32_t ord_mask = (1u << kRecOrdBits) - 1u, vox_mask = (1u << kRecVoxBits) - 1u;
@@ -816,7 +828,7 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
     const int j = s_tile;
     if (j >= n_tiles) break;
     if (tid == 0) {
-      const long long b = tile_begin[j];
+      const long long b = (j < n_big) ? tile_begin[j] : tile_begin[tile_cap - 1 - (j - n_big)];
       const uint32_t tk = (uint32_t)(rec[b] >> 32);
       long long lo = b, hi = n_rec;  // first record whose tile key is greater
       while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((uint32_t)(rec[mid] >> 32) <= tk) lo = mid + 1; else hi = mid; }
@@ -890,20 +902,73 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
             }
           }
         } else {
-#pragma unroll 4
-          for (int jj = 0; jj < nb; ++jj) {
-            const uint32_t o = __shfl_sync(0xffffffffu, ord, jj);
-            const float* row = src.tmp + (size_t)o * C;
+          // the (L * freq) rows of up to rows_per_sub records are gathered with independent coalesced loads into the
+          // warp's shared-memory buffer, then every class lane adds its column in record order
+          for (int j0 = 0; j0 < nb; j0 += rows_per_sub) {
+            const int nr = (nb - j0) < rows_per_sub ? (nb - j0) : rows_per_sub;
+            const int total = nr * C;
+            for (int f0 = 0; f0 < total; f0 += 32) {
+              const int f = f0 + lane;
+              const int jj = (f < total) ? f / C : 0;
+              const uint32_t o = __shfl_sync(0xffffffffu, ord, j0 + jj);
+              if (f < total) s_rows[f] = src.tmp[(size_t)o * C + (f - jj * C)];
+            }
+            __syncwarp();
+            for (int jj = 0; jj < nr; ++jj) {
 #pragma unroll
-            for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) p[q] += row[c]; }
+              for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) p[q] += s_rows[jj * C + c]; }
+            }
+            __syncwarp();
           }
         }
-        // TSDF recurrence in record order (every lane carries the same state)
-        for (int jj = 0; jj < nb; ++jj) {
-          const float sj = __shfl_sync(0xffffffffu, sdf, jj);
-          const float uj = __shfl_sync(0xffffffffu, uw, jj);
-          const uint32_t cj = keep_blend ? __shfl_sync(0xffffffffu, col, jj) : 0u;
-          tsdf_chain_step(cfg.tp, sj, uj, cj, keep_blend, dist, wgt, rgba);
+        // TSDF recurrence in record order (A.6).  The weight chain does not depend on the distance, so it runs first
+        // (uniform over the lanes, each lane keeps the weight seen by ITS record); then every lane evaluates its
+        // record under the assumption that the distance did not change before it.  Free-space voxels stay pinned at
+        // +truncation, so whole batches commit without a sequential pass; the first record that moves the distance
+        // ends the speculation and the remainder of the batch is replayed in order.
+        {
+          float w_before = 0.0f, wc = wgt;
+          for (int jj = 0; jj < nb; ++jj) {
+            const float uj = __shfl_sync(0xffffffffu, uw, jj);
+            if (jj == lane) w_before = wc;
+            const float nw = wc + uj;
+            if (!(nw < kEps)) wc = fminf(cfg.tp.max_weight, nw);
+          }
+          bool applies = false;
+          float dn = dist;
+          if (lane < nb) {
+            const float nw = w_before + uw;
+            if (!(nw < kEps)) {
+              applies = true;
+              const float nd = (sdf * uw + dist * w_before) / nw;
+              dn = (nd > 0.0f) ? fminf(cfg.tp.trunc, nd) : fmaxf(-cfg.tp.trunc, nd);
+            }
+          }
+          if (keep_blend) {   // colour blending only near the surface, in record order (needs only the weight chain)
+            unsigned m = __ballot_sync(0xffffffffu, applies && fabsf(sdf) < cfg.tp.trunc);
+            while (m) {
+              const int jj = __ffs(m) - 1;
+              m &= m - 1;
+              rgba = blend_two_colors(rgba, __shfl_sync(0xffffffffu, w_before, jj), __shfl_sync(0xffffffffu, col, jj),
+                                      __shfl_sync(0xffffffffu, uw, jj));
+            }
+          }
+          const unsigned moved = __ballot_sync(0xffffffffu, applies && (__float_as_uint(dn) != __float_as_uint(dist)));
+          if (moved) {
+            const int f = __ffs(moved) - 1;
+            dist = __shfl_sync(0xffffffffu, dn, f);
+            for (int jj = f + 1; jj < nb; ++jj) {
+              const float sj = __shfl_sync(0xffffffffu, sdf, jj);
+              const float uj = __shfl_sync(0xffffffffu, uw, jj);
+              const float wb = __shfl_sync(0xffffffffu, w_before, jj);
+              const float nw = wb + uj;
+              if (!(nw < kEps)) {
+                const float nd = (sj * uj + dist * wb) / nw;
+                dist = (nd > 0.0f) ? fminf(cfg.tp.trunc, nd) : fmaxf(-cfg.tp.trunc, nd);
+              }
+            }
+          }
+          wgt = wc;
         }
       }
       // arg-max, first maximum wins (base.cpp:352-367)
