@@ -197,6 +197,10 @@ int32_t ksg_set_profiling(ksg_integrator* h, int32_t enable);
 int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms /* KSG_NUM_PHASES */, int64_t* frames,
                         int64_t* kernel_launches /* own kernels */, int64_t* library_calls /* CUB sort/select calls */);
 
+/* Debug aid: enable = 1 makes the tile kernel record (records, SM cycles) per processed tile; the call returns the
+ * number of tiles of the last frame and copies 2 int64 per tile when records_and_cycles has room. */
+int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity, int64_t* records_and_cycles);
+
 /* Build information: "sm_100a" etc. */
 const char* ksg_build_info(void);
 

@@ -194,6 +194,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_set_profiling.restype = C.c_int32
     lib.ksg_get_profile.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.ksg_get_profile.restype = C.c_int32
+    lib.ksg_debug_tile_times.argtypes = [H, C.c_int32, C.c_int64, C.POINTER(C.c_int64)]
+    lib.ksg_debug_tile_times.restype = C.c_int64
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -204,7 +206,7 @@ def load_library(path: Optional[str] = None):
 KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index",
-               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile"]
+               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times"]
 
 
 class KsgError(RuntimeError):

@@ -112,6 +112,7 @@ struct ksg_integrator {
   int* d_exp_slots = nullptr;
   int exp_slots_cap = 0;
 
+  long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
   int apply_smem = 0;
   int apply_nch = 1;
   int rows_per_sub = 32;
@@ -161,7 +162,7 @@ void free_all(ksg_integrator* h) {
                   h->start_next, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.slot_cnt, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.head, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
-                  h->tmp, h->b_key, h->b_base, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tmp, h->b_key, h->b_base, h->tile_debug, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -437,7 +438,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     ++h->n_launches;
 #define KSG_LAUNCH_APPLY(TMA, NCH)                                                                                   \
     k_tile_apply<TMA, NCH><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
-                                                                      n_records, h->tile_begin, h->tile_cap, src, h->rows_per_sub)
+                                                                      n_records, h->tile_begin, h->tile_cap, src, h->rows_per_sub, h->tile_debug)
     if (h->use_tma) {
       switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(true, 1); break; case 2: KSG_LAUNCH_APPLY(true, 2); break;
                               case 4: KSG_LAUNCH_APPLY(true, 4); break; default: KSG_LAUNCH_APPLY(true, 8); break; }
@@ -966,6 +967,20 @@ int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms, int64_t* frames, in
   if (kernel_launches) *kernel_launches = h->n_launches;
   if (library_calls) *library_calls = h->n_libcalls;
   return KSG_OK;
+}
+
+int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity, int64_t* records_and_cycles) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (enable && !h->tile_debug) {
+    if (cudaMalloc((void**)&h->tile_debug, sizeof(long long) * 2 * (size_t)h->tile_cap) != cudaSuccess) { h->tile_debug = nullptr; return 0; }
+  }
+  const int64_t n = std::min<int64_t>(h->h_cnt->n_tiles, h->tile_cap);
+  if (h->tile_debug && records_and_cycles && capacity >= n && n > 0)
+    cudaMemcpy(records_and_cycles, h->tile_debug, sizeof(long long) * 2 * n, cudaMemcpyDeviceToHost);
+  if (!enable && h->tile_debug) { cudaFree(h->tile_debug); h->tile_debug = nullptr; }
+  return n;
 }
 
 int32_t ksg_reset(ksg_integrator* h) {

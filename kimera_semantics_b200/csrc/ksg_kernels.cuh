@@ -275,49 +275,61 @@ __device__ __forceinline__ long long cand_index(const ObsBuf& o, const long long
   const int k = 31 - __clz(s >> 4);
   return o.ext_base + ext_off[(size_t)r * kExtSegs + k] + (s - (kH0 << k));
 }
-__device__ __forceinline__ void cand_insert(const ObsBuf& ob, long long ci, uint64_t v, uint64_t order, bool performed) {
-  const uint32_t slot = (uint32_t)v & kSetMask;
+// Slot structures hold only candidates that have been PERFORMED at some point of the solve (others cannot influence any
+// other ray): a candidate is inserted the first time it turns performed; afterwards only its bit flips.
+__device__ __forceinline__ void cand_store(const ObsBuf& ob, long long ci, uint64_t v, uint64_t order) {
   ob.cand_val[ci] = v;
   ob.cand_order[ci] = order;
+  ob.cand_pos[ci] = -2;   // not in any slot structure yet
+}
+__device__ __forceinline__ void cand_insert_performed(const ObsBuf& ob, long long ci) {
+  const uint64_t v = ob.cand_val[ci];
+  const uint32_t slot = (uint32_t)v & kSetMask;
   const int idx = atomicAdd(&ob.slot_cnt[slot], 1);
   if (idx < kBktK) {
     const int pos = (int)slot * kBktK + idx;
-    ob.bkt[pos] = (performed ? kEntPerf : 0ull) | (order << 13) | (v >> kSetBits);
+    ob.bkt[pos] = kEntPerf | (ob.cand_order[ci] << 13) | (v >> kSetBits);
     ob.cand_pos[ci] = pos;
-  } else {
+  } else {   // lock-free push that concurrent readers can always follow
     ob.cand_pos[ci] = -1;
-    ob.cand_next[ci] = atomicExch(&ob.head[slot], (int)ci);
+    int old = ((volatile int*)ob.head)[slot];
+    for (;;) {
+      ob.cand_next[ci] = old;
+      __threadfence();
+      const int seen = atomicCAS(&ob.head[slot], old, (int)ci);
+      if (seen == old) break;
+      old = seen;
+    }
   }
 }
 // latest performed visit of `slot` that precedes `my_order`; returns its (value >> 20) or -1
-__device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const int* L, uint32_t slot, uint64_t my_order, int r) {
-  const int total = ob.slot_cnt[slot];
+__device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const int* L, uint32_t slot, uint64_t my_order) {
+  const int total = ((volatile const int*)ob.slot_cnt)[slot];
   const int n = total < kBktK ? total : kBktK;
   long long best = -1;
   int best_hi = -1;
-  const uint64_t* b = ob.bkt + (size_t)slot * kBktK;
+  const volatile uint64_t* b = ob.bkt + (size_t)slot * kBktK;
   for (int j = 0; j < n; ++j) {
     const uint64_t e = b[j];
     const uint64_t eo = (e >> 13) & ((1ull << kEntOrderBits) - 1);
-    if (eo < my_order && (long long)eo > best) {
-      const bool performed = ((int)(eo >> kOrderStepBits) == r) || (e & kEntPerf);   // own earlier steps always count
-      if (performed) { best = (long long)eo; best_hi = (int)(e & 0x1FFF); }
-    }
+    if ((e & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)(e & 0x1FFF); }
   }
   if (total > kBktK) {
-    for (int e = ob.head[slot]; e >= 0; e = ob.cand_next[e]) {
+    for (int e = ((volatile const int*)ob.head)[slot]; e >= 0; e = ob.cand_next[e]) {
       const uint64_t eo = ob.cand_order[e];
       if (eo < my_order && (long long)eo > best) {
         const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
-        if (er == r || es < ((volatile const int*)L)[er]) { best = (long long)eo; best_hi = (int)(ob.cand_val[e] >> kSetBits); }
+        if (es < ((volatile const int*)L)[er]) { best = (long long)eo; best_hi = (int)(ob.cand_val[e] >> kSetBits); }
       }
     }
   }
   return best_hi;
 }
+// single writer per candidate: the warp that owns the ray
 __device__ __forceinline__ void set_performed(const ObsBuf& ob, long long ci, bool on) {
   const int pos = ob.cand_pos[ci];
-  if (pos >= 0) { const uint64_t e = ob.bkt[pos]; ob.bkt[pos] = on ? (e | kEntPerf) : (e & ~kEntPerf); }   // single writer: the owning ray
+  if (pos >= 0) { const uint64_t e = ob.bkt[pos]; ob.bkt[pos] = on ? (e | kEntPerf) : (e & ~kEntPerf); }
+  else if (pos == -2 && on) cand_insert_performed(ob, ci);
 }
 
 __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __restrict__ cast_seq,
@@ -347,7 +359,9 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
   const int l0 = h < cfg.maxc ? h : cfg.maxc;
   for (int s = 0; s < h; ++s) {
     const I3 g = dda_next(d);
-    cand_insert(ob, (long long)r * kH0 + s, (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, s < l0);
+    const long long ci = (long long)r * kH0 + s;
+    cand_store(ob, ci, (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
+    if (s < l0) cand_insert_performed(ob, ci);
   }
   RayState st; save_state(st, d); state[r] = st;
   H[r] = h;
@@ -377,7 +391,7 @@ __global__ void k_extend(Counters* cnt, uint64_t obs_offset, ObsBuf ob, const in
   Dda d; load_state(d, state[r]);
   for (int s = h; s < nh; ++s) {
     const I3 g = dda_next(d);
-    cand_insert(ob, ob.ext_base + off + (s - h), (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, false);
+    cand_store(ob, ob.ext_base + off + (s - h), (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
   }
   RayState st; save_state(st, d); state[r] = st;
   H[r] = nh;          // U stays h: the new steps are not performed until the next sweep says so
@@ -424,7 +438,7 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
         if (s < h) {
           const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
           const uint32_t slot = (uint32_t)v & kSetMask;
-          const int hi = latest_performed_before(ob, L, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, r);
+          const int hi = latest_performed_before(ob, L, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
           coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
         }
         const unsigned bits = (__ballot_sync(gmask, coll) & gmask) >> gshift;
@@ -440,6 +454,7 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
         for (int s = lo + gl; s < hi; s += G) {
           const long long ci = cand_index(ob, ext_off, r, s);
           set_performed(ob, ci, U > old);
+          __threadfence();
           atomicMax(&ob.slot_stamp[(uint32_t)ob.cand_val[ci] & kSetMask], sweep);
         }
       }
@@ -792,7 +807,8 @@ template <bool USE_TMA, int NCH>
 __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
-                                                               long long tile_cap, ApplySrc src, int rows_per_sub) {
+                                                               long long tile_cap, ApplySrc src, int rows_per_sub,
+                                                               long long* __restrict__ tile_debug) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int V = cfg.tile_voxels;
   const int C = cfg.C;
@@ -827,6 +843,7 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
     __syncthreads();
     const int j = s_tile;
     if (j >= n_tiles) break;
+    const long long t_start = tile_debug ? clock64() : 0;
     if (tid == 0) {
       const long long b = (j < n_big) ? tile_begin[j] : tile_begin[tile_cap - 1 - (j - n_big)];
       const uint32_t tk = (uint32_t)(rec[b] >> 32);
@@ -1004,6 +1021,7 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
       __syncthreads();
       for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
     }
+    if (tile_debug && tid == 0) { tile_debug[2 * j] = end - begin; tile_debug[2 * j + 1] = clock64() - t_start; }
     // the loop-top barrier orders the store's completion before the next tile's load
   }
 }
