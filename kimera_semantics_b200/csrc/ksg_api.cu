@@ -361,6 +361,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       if (rc) return rc;
       n_cast = std::max(1, h->h_cnt->n_cast);
       if (h->h_cnt->err) break;
+      if (iterations > 4096) {  // theory: <= rays + 1 sweeps, practice ~10; never hang the caller
+        h->deferred_status = KSG_ERR_CUDA;
+        return fail(KSG_ERR_CUDA, "observed-set solver did not converge within 4096 sweeps");
+      }
       if (h->h_cnt->changed[sweep & 3] || h->h_cnt->n_truncated[sweep & 3]) continue;
       n_records = (long long)h->h_cnt->sum_updates[sweep & 3];
       break;

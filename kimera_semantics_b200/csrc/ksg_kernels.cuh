@@ -430,30 +430,44 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
     }
     U = old;
     if (need) {
+      // Steps are evaluated 32 at a time against the slot structures; the steps a chunk proves performed are entered /
+      // flagged at once, so that the ray's own earlier steps are always visible to its later chunks.  (No two steps of
+      // one ray within 70 DDA steps can share a slot: the shortest alias vector of the 2^20-slot hash is longer.)
       int run = 0;
       U = -1;
       for (int s0 = 0; s0 < h && U < 0; s0 += G) {
         const int s = s0 + gl;
         bool coll = false;
+        long long ci = 0;
+        uint32_t slot = 0;
         if (s < h) {
-          const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
-          const uint32_t slot = (uint32_t)v & kSetMask;
+          ci = cand_index(ob, ext_off, r, s);
+          const uint64_t v = ob.cand_val[ci];
+          slot = (uint32_t)v & kSetMask;
           const int hi = latest_performed_before(ob, L, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
           coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
         }
         const unsigned bits = (__ballot_sync(gmask, coll) & gmask) >> gshift;
+        int brk = -1;
         for (int j = 0; j < G && s0 + j < h; ++j) {
           if ((bits >> j) & 1u) ++run; else run = 0;            // fast.cpp:115-119
-          if (run > cfg.maxc) { U = s0 + j; break; }            // fast.cpp:120-122
+          if (run > cfg.maxc) { brk = s0 + j; break; }          // fast.cpp:120-122
         }
+        const int perf_end = (brk >= 0) ? brk : ((s0 + G < h) ? s0 + G : h);
+        if (s < perf_end && s >= old) {                          // newly performed steps of this chunk
+          set_performed(ob, ci, true);
+          __threadfence();
+          atomicMax(&ob.slot_stamp[slot], sweep);
+        }
+        __syncwarp(gmask);
+        if (brk >= 0) U = brk;
       }
       bool truncated = false;
       if (U < 0) { U = h; truncated = h < nsteps[r]; }
-      if (U != old) {   // candidates [min, max) toggle: flip their performed bits, stamp their slots
-        const int lo = U < old ? U : old, hi = U < old ? old : U;
-        for (int s = lo + gl; s < hi; s += G) {
+      if (U < old) {   // steps [U, old) are no longer performed
+        for (int s = U + gl; s < old; s += G) {
           const long long ci = cand_index(ob, ext_off, r, s);
-          set_performed(ob, ci, U > old);
+          set_performed(ob, ci, false);
           __threadfence();
           atomicMax(&ob.slot_stamp[(uint32_t)ob.cand_val[ci] & kSetMask], sweep);
         }
