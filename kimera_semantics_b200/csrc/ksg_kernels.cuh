@@ -315,7 +315,10 @@ __device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const i
     if ((e & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)(e & 0x1FFF); }
   }
   if (total > kBktK) {
-    for (int e = ((volatile const int*)ob.head)[slot]; e >= 0; e = ob.cand_next[e]) {
+    // overflow list: pushes may run concurrently (k_eval), so links are read through L2 (__ldcg; L1 may hold a stale
+    // line) and the walk is bounded by the number of overflow entries
+    int guard = total - kBktK + 8;
+    for (int e = __ldcg(&ob.head[slot]); e >= 0 && guard-- > 0; e = __ldcg(&ob.cand_next[e])) {
       const uint64_t eo = ob.cand_order[e];
       if (eo < my_order && (long long)eo > best) {
         const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
@@ -505,8 +508,9 @@ __global__ void k_obs_commit(Counters* cnt, ObsBuf ob, const int* __restrict__ L
       const uint64_t e = b[j];
       if ((e & kEntPerf) && ((e >> 13) & ((1ull << kEntOrderBits) - 1)) > my_order) later = true;
     }
+    int guard = total - kBktK + 8;
     if (total > kBktK)
-      for (int e = ob.head[slot]; e >= 0 && !later; e = ob.cand_next[e]) {
+      for (int e = ob.head[slot]; e >= 0 && !later && guard-- > 0; e = ob.cand_next[e]) {
         const uint64_t eo = ob.cand_order[e];
         if (eo > my_order && (int)(eo & ((1u << kOrderStepBits) - 1)) < L[(int)(eo >> kOrderStepBits)]) later = true;
       }
