@@ -423,7 +423,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     // order the update records by (tile, voxel, order): per-voxel application order = reference order
     size_t tb = h->cub_temp_bytes;
     ++h->n_libcalls;
-    KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, 0, 64, s));
+    // significant key bits: [order 23][voxel 9][tile key < ht_cap * tiles_per_block]
+    int end_bit = 32;
+    while (end_bit < 64 && (1ull << (end_bit - 32)) < (unsigned long long)h->ht_cap * (unsigned long long)dc.tiles_per_block) ++end_bit;
+    KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, 0, end_bit, s));
     if (h->profiling) cudaEventRecord(h->ev[4], s);
     ++h->n_launches;
     k_block_assign<<<grid_for(h->map.new_cap, B), B, 0, s>>>(h->d_cnt, h->map);
@@ -700,7 +703,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
     const bool fast_cfg = cfg->integrator_type == KSG_INTEGRATOR_FAST;
     h->rows_per_sub = std::max(1, std::min(32, kRowBufFloats / dc.C));
-    h->apply_smem = (int)(stage + (size_t)V * 8 + 64 + (fast_cfg ? 0 : (size_t)(256 / 32) * kRowBufFloats * 4));
+    h->apply_smem = (int)(stage + (size_t)V * 8 + 64);
+    (void)fast_cfg;
     h->apply_nch = dc.C <= 32 ? 1 : (dc.C <= 64 ? 2 : (dc.C <= 128 ? 4 : 8));
     h->use_tma = cfg->apply_mode == 0;
     KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));

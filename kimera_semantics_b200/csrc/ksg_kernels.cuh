@@ -302,21 +302,38 @@ __device__ __forceinline__ void cand_insert_performed(const ObsBuf& ob, long lon
     }
   }
 }
-// latest performed visit of `slot` that precedes `my_order`; returns its (value >> 20) or -1
+// latest performed visit of `slot` that precedes `my_order`; returns its (value >> 20) or -1.
+// The slot's counter, the first half of its bucket and (by the caller) the persistent table entry are independent loads:
+// one L2 round trip.  __ldcg: the structures change while the sweep runs, L1 must not serve stale lines.
+__device__ __forceinline__ void scan_entries(const ulonglong2 v, int base, int n, uint64_t my_order, long long& best, int& best_hi) {
+  const uint64_t e2[2] = {v.x, v.y};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint64_t e = e2[k];
+    const uint64_t eo = (e >> 13) & ((1ull << kEntOrderBits) - 1);
+    if (base + k < n && (e & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)(e & 0x1FFF); }
+  }
+}
 __device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const int* L, uint32_t slot, uint64_t my_order) {
-  const int total = ((volatile const int*)ob.slot_cnt)[slot];
+  const ulonglong2* b = (const ulonglong2*)(ob.bkt + (size_t)slot * kBktK);
+  const int total = __ldcg(&ob.slot_cnt[slot]);
+  const ulonglong2 v0 = __ldcg(b + 0), v1 = __ldcg(b + 1), v2 = __ldcg(b + 2), v3 = __ldcg(b + 3);
   const int n = total < kBktK ? total : kBktK;
   long long best = -1;
   int best_hi = -1;
-  const volatile uint64_t* b = ob.bkt + (size_t)slot * kBktK;
-  for (int j = 0; j < n; ++j) {
-    const uint64_t e = b[j];
-    const uint64_t eo = (e >> 13) & ((1ull << kEntOrderBits) - 1);
-    if ((e & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)(e & 0x1FFF); }
+  scan_entries(v0, 0, n, my_order, best, best_hi);
+  scan_entries(v1, 2, n, my_order, best, best_hi);
+  scan_entries(v2, 4, n, my_order, best, best_hi);
+  scan_entries(v3, 6, n, my_order, best, best_hi);
+  if (n > 8) {
+    const ulonglong2 v4 = __ldcg(b + 4), v5 = __ldcg(b + 5), v6 = __ldcg(b + 6), v7 = __ldcg(b + 7);
+    scan_entries(v4, 8, n, my_order, best, best_hi);
+    scan_entries(v5, 10, n, my_order, best, best_hi);
+    scan_entries(v6, 12, n, my_order, best, best_hi);
+    scan_entries(v7, 14, n, my_order, best, best_hi);
   }
   if (total > kBktK) {
-    // overflow list: pushes may run concurrently (k_eval), so links are read through L2 (__ldcg; L1 may hold a stale
-    // line) and the walk is bounded by the number of overflow entries
+    // overflow list: pushes may run concurrently (k_eval), so links are read through L2 and the walk is bounded
     int guard = total - kBktK + 8;
     for (int e = __ldcg(&ob.head[slot]); e >= 0 && guard-- > 0; e = __ldcg(&ob.cand_next[e])) {
       const uint64_t eo = ob.cand_order[e];
@@ -447,8 +464,9 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restri
           ci = cand_index(ob, ext_off, r, s);
           const uint64_t v = ob.cand_val[ci];
           slot = (uint32_t)v & kSetMask;
+          const uint32_t stale = ob.table[slot];   // issued together with the bucket loads
           const int hi = latest_performed_before(ob, L, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
-          coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (ob.table[slot] == (uint32_t)(v >> kSetBits));
+          coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (stale == (uint32_t)(v >> kSetBits));
         }
         const unsigned bits = (__ballot_sync(gmask, coll) & gmask) >> gshift;
         int brk = -1;
@@ -822,7 +840,7 @@ static constexpr int kRowBufFloats = 1024;   // per-warp row staging buffer (4 K
 // followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
 // written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
 template <bool USE_TMA, int NCH>
-__global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
+__global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
                                                                long long tile_cap, ApplySrc src, int rows_per_sub,
@@ -937,23 +955,23 @@ __global__ void __launch_bounds__(512) k_tile_apply(DevCfg cfg, Xform T, Counter
             }
           }
         } else {
-          // the (L * freq) rows of up to rows_per_sub records are gathered with independent coalesced loads into the
-          // warp's shared-memory buffer, then every class lane adds its column in record order
-          for (int j0 = 0; j0 < nb; j0 += rows_per_sub) {
-            const int nr = (nb - j0) < rows_per_sub ? (nb - j0) : rows_per_sub;
-            const int total = nr * C;
-            for (int f0 = 0; f0 < total; f0 += 32) {
-              const int f = f0 + lane;
-              const int jj = (f < total) ? f / C : 0;
-              const uint32_t o = __shfl_sync(0xffffffffu, ord, j0 + jj);
-              if (f < total) s_rows[f] = src.tmp[(size_t)o * C + (f - jj * C)];
-            }
-            __syncwarp();
-            for (int jj = 0; jj < nr; ++jj) {
+          // (L * freq) rows: lane c adds column c of the records' rows in record order; kRowUnroll rows are loaded
+          // (coalesced, independent) before the first add so that the L2 latency is paid once per group
+          constexpr int kRowUnroll = (NCH <= 2) ? 16 / NCH : 2;
+          for (int j0 = 0; j0 < nb; j0 += kRowUnroll) {
+            float rv[kRowUnroll][NCH];
 #pragma unroll
-              for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) p[q] += s_rows[jj * C + c]; }
+            for (int u = 0; u < kRowUnroll; ++u) {
+              const uint32_t o = __shfl_sync(0xffffffffu, ord, (j0 + u) & 31);
+              const float* row = src.tmp + (size_t)o * C;
+#pragma unroll
+              for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; rv[u][q] = (j0 + u < nb && c < C) ? __ldg(row + c) : 0.0f; }
             }
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+              for (int q = 0; q < NCH; ++q) p[q] += rv[u][q];   // + 0.0f is exact for the padded tail
+            }
           }
         }
         // TSDF recurrence in record order (A.6).  The weight chain does not depend on the distance, so it runs first
