@@ -113,6 +113,7 @@ struct ksg_integrator {
   int exp_slots_cap = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
+  int sweeps_per_sync = 2;
   int apply_smem = 0;
   int apply_nch = 1;
   int rows_per_sub = 32;
@@ -337,7 +338,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     ++h->n_launches;
     k_ray_setup<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->cast_seq, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color,
                                                    h->set_offset, h->ob, h->ray_param, h->ray_label, h->ray_flags, h->ray_color,
-                                                   h->nsteps, h->H, h->L, h->ray_state, h->eval_sweep, h->trunc_flag);
+                                                   h->nsteps, h->H, h->L, h->ray_state, h->eval_sweep);
     if (h->profiling) cudaEventRecord(h->ev[1], s);
     // observed-set fixpoint: sweeps until no ray changes; two sweeps per host read-back
     int n_cast = cap;
@@ -348,13 +349,11 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     h->sweep_counter = (h->sweep_counter + 4) & ~3;  // counters of the first sweep (index 1) were zeroed by k_frame_reset
     for (;;) {
       int sweep = 0;
-      for (int rep = 0; rep < 2; ++rep) {
+      for (int rep = 0; rep < h->sweeps_per_sync; ++rep) {
         sweep = ++h->sweep_counter;
-        h->n_launches += 2;
-        k_eval<<<grid_for((long long)n_cast * kEvalGroup, 128), 128, 0, s>>>(dc, h->d_cnt, h->ob, h->nsteps, h->H, h->L, h->ext_off,
-                                                                            h->trunc_flag, h->eval_sweep, sweep);
-        k_extend<<<grid_for(n_cast, 128), 128, 0, s>>>(h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->ray_state,
-                                                       h->ext_off, h->trunc_flag, h->eval_sweep, sweep);
+        h->n_launches += 1;
+        k_eval<<<h->sm_count * 8, 256, 0, s>>>(dc, h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state, h->ext_off,
+                                               h->eval_sweep, sweep);
         ++iterations;
       }
       int rc = fetch_counters(h, s);
@@ -365,7 +364,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
         h->deferred_status = KSG_ERR_CUDA;
         return fail(KSG_ERR_CUDA, "observed-set solver did not converge within 4096 sweeps");
       }
-      if (h->h_cnt->changed[sweep & 3] || h->h_cnt->n_truncated[sweep & 3]) continue;
+      if (h->h_cnt->changed[sweep & 3]) continue;
       n_records = (long long)h->h_cnt->sum_updates[sweep & 3];
       break;
     }
@@ -716,6 +715,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
     KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
   }
+  if (const char* e = std::getenv("KSG_SWEEPS_PER_SYNC")) h->sweeps_per_sync = std::max(1, std::min(3, std::atoi(e)));
   KSG_CUDA(cudaDeviceSynchronize());
   {
     int r2 = reset_map(h, h->own_stream);

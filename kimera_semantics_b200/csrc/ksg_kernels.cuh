@@ -3,7 +3,7 @@
 // Kernel family (SURVEY.md §7.4 numbering in brackets):
 //   k_depth_flags / k_classify      [K1]  back-projection, validity, dynamic-label filter, T_G_C * p
 //   k_start_push/eval/commit        [K3]  exact emulation of fast's start_voxel_approx_set_
-//   k_ray_setup / k_extend / k_eval / k_obs_commit   [K4] exact emulation of voxel_observed_approx_set_
+//   k_ray_setup / k_eval / k_obs_commit              [K4] exact emulation of voxel_observed_approx_set_
 //                                         (asynchronous fixpoint over per-slot visit lists)
 //   k_bundle_heads / k_bundle_merge / k_bundle_loglik [K2] merged: bundleRays + integrateVoxel merge loop
 //   k_emit_fast / k_emit_merged     [K4]  ray cast -> update records + block-hash insertion [K5]
@@ -273,7 +273,7 @@ struct ObsBuf {
 __device__ __forceinline__ long long cand_index(const ObsBuf& o, const long long* ext_off, int r, int s) {
   if (s < kH0) return (long long)r * kH0 + s;
   const int k = 31 - __clz(s >> 4);
-  return o.ext_base + ext_off[(size_t)r * kExtSegs + k] + (s - (kH0 << k));
+  return o.ext_base + __ldcg(&ext_off[(size_t)r * kExtSegs + k]) + (s - (kH0 << k));   // written inside k_eval: read through L2
 }
 // Slot structures hold only candidates that have been PERFORMED at some point of the solve (others cannot influence any
 // other ray): a candidate is inserted the first time it turns performed; afterwards only its bit flips.
@@ -283,12 +283,12 @@ __device__ __forceinline__ void cand_store(const ObsBuf& ob, long long ci, uint6
   ob.cand_pos[ci] = -2;   // not in any slot structure yet
 }
 __device__ __forceinline__ void cand_insert_performed(const ObsBuf& ob, long long ci) {
-  const uint64_t v = ob.cand_val[ci];
+  const uint64_t v = __ldcg(&ob.cand_val[ci]);
   const uint32_t slot = (uint32_t)v & kSetMask;
   const int idx = atomicAdd(&ob.slot_cnt[slot], 1);
   if (idx < kBktK) {
     const int pos = (int)slot * kBktK + idx;
-    ob.bkt[pos] = kEntPerf | (ob.cand_order[ci] << 13) | (v >> kSetBits);
+    ob.bkt[pos] = kEntPerf | (__ldcg(&ob.cand_order[ci]) << 13) | (v >> kSetBits);
     ob.cand_pos[ci] = pos;
   } else {   // lock-free push that concurrent readers can always follow
     ob.cand_pos[ci] = -1;
@@ -347,8 +347,8 @@ __device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const i
 }
 // single writer per candidate: the warp that owns the ray
 __device__ __forceinline__ void set_performed(const ObsBuf& ob, long long ci, bool on) {
-  const int pos = ob.cand_pos[ci];
-  if (pos >= 0) { const uint64_t e = ob.bkt[pos]; ob.bkt[pos] = on ? (e | kEntPerf) : (e & ~kEntPerf); }
+  const int pos = __ldcg(&ob.cand_pos[ci]);
+  if (pos >= 0) { const uint64_t e = __ldcg(&ob.bkt[pos]); ob.bkt[pos] = on ? (e | kEntPerf) : (e & ~kEntPerf); }
   else if (pos == -2 && on) cand_insert_performed(ob, ci);
 }
 
@@ -357,8 +357,7 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
                             const uint8_t* __restrict__ pt_flags, const uint32_t* __restrict__ pt_color, uint64_t obs_offset,
                             ObsBuf ob, float4* __restrict__ ray_param, uint8_t* __restrict__ ray_label,
                             uint8_t* __restrict__ ray_flags, uint32_t* __restrict__ ray_color, int* __restrict__ nsteps,
-                            int* __restrict__ H, int* L, RayState* __restrict__ state, int* __restrict__ eval_sweep,
-                            uint8_t* __restrict__ trunc_flag) {
+                            int* __restrict__ H, int* L, RayState* __restrict__ state, int* __restrict__ eval_sweep) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= cnt->n_cast) return;
   const int seq = cast_seq[r];
@@ -387,124 +386,113 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
   H[r] = h;
   L[r] = l0;
   eval_sweep[r] = 0; // never evaluated
-  trunc_flag[r] = 0;
   atomicAdd(&cnt->ray_steps, (unsigned long long)h);
 }
 
-// Rays that performed every step they had (trunc_flag) double their horizon. Runs after sweep `sweep`.
-__global__ void k_extend(Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
-                         RayState* __restrict__ state, long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag,
-                         int* __restrict__ eval_sweep, int sweep) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r == 0) { const int nx = (sweep + 1) & 3; cnt->changed[nx] = 0; cnt->n_truncated[nx] = 0; cnt->sum_updates[nx] = 0; }
-  if (r >= cnt->n_cast) return;
-  if (!trunc_flag[r]) return;
-  trunc_flag[r] = 0;
-  const int n = nsteps[r], h = H[r];
-  if (h >= n) return;
-  const int nh = (2 * h < n) ? 2 * h : n;
-  const int k = 31 - __clz(h >> 4);      // h = 16 << k
-  const long long need = nh - h;
-  const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need);
-  if (ob.ext_base + off + need > ob.cand_cap) { set_err(cnt, 4); return; }
-  ext_off[(size_t)r * kExtSegs + k] = off;
-  Dda d; load_state(d, state[r]);
-  for (int s = h; s < nh; ++s) {
-    const I3 g = dda_next(d);
-    cand_store(ob, ob.ext_base + off + (s - h), (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
-  }
-  RayState st; save_state(st, d); state[r] = st;
-  H[r] = nh;          // U stays h: the new steps are not performed until the next sweep says so
-  eval_sweep[r] = 0;  // force re-evaluation
-  atomicAdd(&cnt->ray_steps, (unsigned long long)need);
-  cnt->changed[sweep & 3] = 1;
-}
-
-// One sweep of the solver: kEvalGroup lanes per ray, one ray step per lane and chunk.
+// One sweep of the solver.  One warp per ray (grid-stride), one ray step per lane and chunk; chunks are steps
+// [0,16), [16,32), then 32 at a time, aligned with the geometric storage segments.  A ray is evaluated to completion:
+// when it survives everything materialised so far, lane 0 continues the DDA for the next chunk on the spot.
 // A ray is re-evaluated only if a candidate on one of the slots it depends on toggled since its last evaluation.
-__global__ void k_eval(DevCfg cfg, Counters* cnt, ObsBuf ob, const int* __restrict__ nsteps, const int* __restrict__ H, int* L,
-                       const long long* __restrict__ ext_off, uint8_t* __restrict__ trunc_flag, int* __restrict__ eval_sweep,
-                       int sweep) {
-  constexpr int G = kEvalGroup;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = tid / G;
-  const int gl = threadIdx.x % G;                               // lane in group
-  const int wl = threadIdx.x & 31;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (wl - gl));  // the group's lanes inside the warp
-  const int gshift = wl - gl;
+__global__ void k_eval(DevCfg cfg, Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
+                       int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, int* __restrict__ eval_sweep, int sweep) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_cast = cnt->n_cast;
-  int U = 0;
-  if (r < n_cast) {
-    const int h = H[r];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { const int nx = (sweep + 1) & 3; cnt->changed[nx] = 0; cnt->sum_updates[nx] = 0; }
+  unsigned long long usum = 0;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_cast; r += warps_total) {
+    int h = H[r];
+    const int n = nsteps[r];
     const int old = ((volatile int*)L)[r];
     const int last = eval_sweep[r];
     bool need = last == 0;
     if (!need) {
       const int upto = (old < h - 1) ? old : h - 1;             // steps 0..upto were examined last time
       bool dirty = false;
-      for (int s = gl; s <= upto; s += G) {
-        const uint64_t v = ob.cand_val[cand_index(ob, ext_off, r, s)];
-        if (ob.slot_stamp[(uint32_t)v & kSetMask] >= last) dirty = true;
+      for (int s = lane; s <= upto; s += 32) {
+        const uint64_t v = __ldcg(&ob.cand_val[cand_index(ob, ext_off, r, s)]);
+        if (__ldcg(&ob.slot_stamp[(uint32_t)v & kSetMask]) >= last) dirty = true;
       }
-      need = __ballot_sync(gmask, dirty) != 0u;
+      need = __ballot_sync(0xffffffffu, dirty) != 0u;
     }
-    U = old;
+    int U = old;
     if (need) {
-      // Steps are evaluated 32 at a time against the slot structures; the steps a chunk proves performed are entered /
-      // flagged at once, so that the ray's own earlier steps are always visible to its later chunks.  (No two steps of
-      // one ray within 70 DDA steps can share a slot: the shortest alias vector of the 2^20-slot hash is longer.)
       int run = 0;
       U = -1;
-      for (int s0 = 0; s0 < h && U < 0; s0 += G) {
-        const int s = s0 + gl;
+      for (int s0 = 0; s0 < n && U < 0;) {
+        const int len = (s0 < 32) ? kH0 : 32;
+        const int cend = (s0 + len < n) ? s0 + len : n;
+        if (s0 >= h) {   // materialise the next chunk: lane 0 continues the ray's DDA (A.7) from the saved state
+          if (lane == 0) {
+            bool ok = true;
+            if ((s0 & (s0 - 1)) == 0) {   // s0 = 16 << k: first chunk of storage segment k
+              const int k = 31 - __clz(s0 >> 4);
+              const long long need_c = s0;   // segment k holds steps [16<<k, 32<<k)
+              const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need_c);
+              if (ob.ext_base + off + need_c > ob.cand_cap) { set_err(cnt, 4); ok = false; }
+              else ext_off[(size_t)r * kExtSegs + k] = off;
+            }
+            if (ok) {
+              Dda d; load_state(d, state[r]);
+              for (int s = s0; s < cend; ++s) {
+                const I3 g = dda_next(d);
+                cand_store(ob, cand_index(ob, ext_off, r, s), (uint64_t)index_hash(g) + obs_offset, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
+              }
+              RayState st; save_state(st, d); state[r] = st;
+              H[r] = cend;
+              atomicAdd(&cnt->ray_steps, (unsigned long long)(cend - s0));
+            }
+            h = ok ? cend : -1;
+          }
+          h = __shfl_sync(0xffffffffu, h, 0);
+          if (h < 0) { U = s0; break; }   // scratch exhausted (flagged): stop here
+          __syncwarp();
+        }
+        const int s = s0 + lane;
         bool coll = false;
         long long ci = 0;
         uint32_t slot = 0;
-        if (s < h) {
+        if (s < cend) {
           ci = cand_index(ob, ext_off, r, s);
-          const uint64_t v = ob.cand_val[ci];
+          const uint64_t v = __ldcg(&ob.cand_val[ci]);
           slot = (uint32_t)v & kSetMask;
           const uint32_t stale = ob.table[slot];   // issued together with the bucket loads
           const int hi = latest_performed_before(ob, L, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
           coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (stale == (uint32_t)(v >> kSetBits));
         }
-        const unsigned bits = (__ballot_sync(gmask, coll) & gmask) >> gshift;
+        const unsigned bits = __ballot_sync(0xffffffffu, coll);
         int brk = -1;
-        for (int j = 0; j < G && s0 + j < h; ++j) {
+        for (int j = 0; s0 + j < cend; ++j) {
           if ((bits >> j) & 1u) ++run; else run = 0;            // fast.cpp:115-119
           if (run > cfg.maxc) { brk = s0 + j; break; }          // fast.cpp:120-122
         }
-        const int perf_end = (brk >= 0) ? brk : ((s0 + G < h) ? s0 + G : h);
+        const int perf_end = (brk >= 0) ? brk : cend;
         if (s < perf_end && s >= old) {                          // newly performed steps of this chunk
           set_performed(ob, ci, true);
           __threadfence();
           atomicMax(&ob.slot_stamp[slot], sweep);
         }
-        __syncwarp(gmask);
+        __syncwarp();
         if (brk >= 0) U = brk;
+        s0 = cend;
       }
-      bool truncated = false;
-      if (U < 0) { U = h; truncated = h < nsteps[r]; }
-      if (U < old) {   // steps [U, old) are no longer performed
-        for (int s = U + gl; s < old; s += G) {
+      if (U < 0) U = n;   // the ray ran its full length
+      if (U < old) {      // steps [U, old) are no longer performed
+        for (int s = U + lane; s < old; s += 32) {
           const long long ci = cand_index(ob, ext_off, r, s);
           set_performed(ob, ci, false);
           __threadfence();
-          atomicMax(&ob.slot_stamp[(uint32_t)ob.cand_val[ci] & kSetMask], sweep);
+          atomicMax(&ob.slot_stamp[(uint32_t)__ldcg(&ob.cand_val[ci]) & kSetMask], sweep);
         }
       }
-      if (gl == 0) {
-        trunc_flag[r] = truncated ? 1 : 0;
+      if (lane == 0) {
         if (U != old) { L[r] = U; cnt->changed[sweep & 3] = 1; }
         eval_sweep[r] = sweep;
       }
     }
-    if (gl == 0 && trunc_flag[r]) atomicAdd(&cnt->n_truncated[sweep & 3], 1);
+    if (lane == 0) usum += (unsigned long long)U;
   }
-  __syncwarp();
-  unsigned long long u = (gl == 0 && r < n_cast) ? (unsigned long long)U : 0ull;
-  for (int o = 16; o > 0; o >>= 1) u += __shfl_down_sync(0xffffffffu, u, o);
-  if (wl == 0 && u) atomicAdd(&cnt->sum_updates[sweep & 3], u);
+  if (lane == 0 && usum) atomicAdd(&cnt->sum_updates[sweep & 3], usum);
 }
 
 // After convergence: the last performed visit of every slot becomes the persistent table entry.
