@@ -489,6 +489,12 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   return KSG_OK;
 }
 
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int ensure_input(ksg_integrator* h, size_t bytes) {
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   if (bytes > h->h_stage_bytes) {
@@ -794,9 +800,14 @@ int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* dept
   const size_t total = o_lab + round_up((uint32_t)P, 256);
   int rc = ensure_input(h, total);
   if (rc) return rc;
-  std::memcpy(h->h_stage, depth, P * 4);
-  std::memcpy(h->h_stage + o_lab, label, P);
-  KSG_CUDA(cudaMemcpyAsync(h->d_in, h->h_stage, total, cudaMemcpyHostToDevice, h->own_stream));
+  if (is_pinned_host(depth) && is_pinned_host(label)) {   // caller's buffers are page-locked: copy straight from them
+    KSG_CUDA(cudaMemcpyAsync(h->d_in, depth, P * 4, cudaMemcpyHostToDevice, h->own_stream));
+    KSG_CUDA(cudaMemcpyAsync(h->d_in + o_lab, label, P, cudaMemcpyHostToDevice, h->own_stream));
+  } else {
+    std::memcpy(h->h_stage, depth, P * 4);
+    std::memcpy(h->h_stage + o_lab, label, P);
+    KSG_CUDA(cudaMemcpyAsync(h->d_in, h->h_stage, total, cudaMemcpyHostToDevice, h->own_stream));
+  }
   InputDesc in; in.d_depth = (const float*)h->d_in; in.d_label_img = h->d_in + o_lab; in.width = width; in.height = height;
   in.n = (int64_t)P; std::memcpy(in.K, K, sizeof(in.K));
   ksg_frame_stats local;

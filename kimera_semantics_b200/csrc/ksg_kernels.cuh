@@ -70,6 +70,26 @@ static constexpr int kRecVoxBits = 9, kRecOrdBits = 23;
 
 __device__ __forceinline__ void set_err(Counters* c, int e) { atomicCAS(&c->err, 0, e); }
 
+// Warp-aggregated bump allocation: every lane of a converged warp asks for `n` items (0 allowed) and receives its base;
+// one atomic per warp instead of 32 atomics on one address (same-address atomics serialise in L2).
+__device__ __forceinline__ unsigned long long warp_alloc(unsigned long long* counter, unsigned long long n) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long incl = n;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 0 && total) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + incl - n;
+}
+__device__ __forceinline__ void warp_add(unsigned long long* counter, unsigned long long n) {
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
+}
+
 // ---------------------------------------------------------------------------------------------
 // frame set-up
 // ---------------------------------------------------------------------------------------------
@@ -178,9 +198,13 @@ __global__ void k_classify(DevCfg cfg, Xform T, FrameIn in, const Luts* __restri
       if (!key_in_range(g) || !index_in_range(mul(pG, cfg.vsi))) { set_err(cnt, 5); }
       else key = pack_key(g) | (clearing ? (1ull << 63) : 0ull);
     }
-    atomicAdd(&cnt->n_valid, 1);
   }
   pt_key[seq] = key;
+  {  // count valid points: one atomic per warp
+    const unsigned am = __activemask();
+    const unsigned m = __ballot_sync(am, valid);
+    if (m && (int)(threadIdx.x & 31) == (__ffs(am) - 1)) atomicAdd(&cnt->n_valid, __popc(m));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -359,7 +383,8 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
                             uint8_t* __restrict__ ray_flags, uint32_t* __restrict__ ray_color, int* __restrict__ nsteps,
                             int* __restrict__ H, int* L, RayState* __restrict__ state, int* __restrict__ eval_sweep) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= cnt->n_cast) return;
+  int h = 0;
+  if (r < cnt->n_cast) {
   const int seq = cast_seq[r];
   const float4 p = pt_pG[seq];
   const uint8_t fl = pt_flags[seq];
@@ -373,7 +398,7 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
   int n = d.length_in_steps + 1;
   if (!d.in_range || n >= (1 << kOrderStepBits)) { set_err(cnt, 5); n = 0; }
   nsteps[r] = n;
-  const int h = n < kH0 ? n : kH0;
+  h = n < kH0 ? n : kH0;
   // a ray cannot break before `maxc` consecutive collisions: its first maxc steps are always performed
   const int l0 = h < cfg.maxc ? h : cfg.maxc;
   for (int s = 0; s < h; ++s) {
@@ -386,7 +411,8 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
   H[r] = h;
   L[r] = l0;
   eval_sweep[r] = 0; // never evaluated
-  atomicAdd(&cnt->ray_steps, (unsigned long long)h);
+  }
+  warp_add(&cnt->ray_steps, (unsigned long long)h);   // every lane of the warp arrives here
 }
 
 // One sweep of the solver.  One warp per ray (grid-stride), one ray step per lane and chunk; chunks are steps
@@ -492,7 +518,15 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, uint64_t obs_offset, ObsBuf ob
     }
     if (lane == 0) usum += (unsigned long long)U;
   }
-  if (lane == 0 && usum) atomicAdd(&cnt->sum_updates[sweep & 3], usum);
+  // one atomic per block (instead of per warp) on the sweep's counter
+  __shared__ unsigned long long s_part[8];
+  if (lane == 0) s_part[(threadIdx.x >> 5) & 7] = usum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+    if (t) atomicAdd(&cnt->sum_updates[sweep & 3], t);
+  }
 }
 
 // After convergence: the last performed visit of every slot becomes the persistent table entry.
@@ -576,10 +610,9 @@ __global__ void k_emit_fast(DevCfg cfg, Xform T, Counters* cnt, MapRef map, cons
                             const uint8_t* __restrict__ ray_flags, const int* __restrict__ L, uint64_t* __restrict__ records,
                             long long rec_cap) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= cnt->n_cast) return;
-  const int U = L[r];
+  const int U = (r < cnt->n_cast) ? L[r] : 0;
+  const long long base = (long long)warp_alloc(&cnt->n_records, (unsigned long long)(U > 0 ? U : 0));
   if (U <= 0) return;
-  const long long base = (long long)atomicAdd(&cnt->n_records, (unsigned long long)U);
   if (base + U > rec_cap) { set_err(cnt, 4); return; }
   const float4 p = ray_param[r];
   Dda d;
@@ -622,7 +655,9 @@ __global__ void k_bundle_merge(DevCfg cfg, Xform T, Counters* cnt, const int* __
                                float4* __restrict__ b_param, uint8_t* __restrict__ b_flags, uint64_t* __restrict__ b_key,
                                int* __restrict__ b_nsteps, long long* __restrict__ b_base, long long rec_cap) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= cnt->n_cast) return;
+  const bool live = b < cnt->n_cast;
+  int n = 0;
+  if (live) {
   const int f = bundle_f[b];
   const int i0 = bstart[f];
   const uint64_t key = ks[i0];
@@ -648,13 +683,16 @@ __global__ void k_bundle_merge(DevCfg cfg, Xform T, Counters* cnt, const int* __
   b_key[b] = key & ~(1ull << 63);
   Dda d;
   raycaster_init(d, f3(T.tx, T.ty, T.tz), pG, clearing, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc, true);
-  int n = d.length_in_steps + 1;
+  n = d.length_in_steps + 1;
   if (!d.in_range) { set_err(cnt, 5); n = 0; }
   b_nsteps[b] = n;
-  const long long base = (long long)atomicAdd(&cnt->n_records, (unsigned long long)n);
-  if (base + n > rec_cap) { set_err(cnt, 4); b_nsteps[b] = 0; }
-  b_base[b] = base;
-  atomicAdd(&cnt->ray_steps, (unsigned long long)n);
+  }
+  const long long base = (long long)warp_alloc(&cnt->n_records, (unsigned long long)n);   // every lane arrives here
+  warp_add(&cnt->ray_steps, (unsigned long long)n);
+  if (live) {
+    if (base + n > rec_cap) { set_err(cnt, 4); b_nsteps[b] = 0; }
+    b_base[b] = base;
+  }
 }
 
 // tmp[b][i] = sum_j L[i][j] * freq[j]  (base.cpp:306-307) with L[i][j] = log_match on the diagonal, log_non_match
