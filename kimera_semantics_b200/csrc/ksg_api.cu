@@ -442,9 +442,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     const int grid = h->sm_count * ctas_per_sm;
     const int apply_threads = fast ? 512 : 256;  // fast: few records per voxel, latency bound -> more warps per tile
     ++h->n_launches;
-#define KSG_LAUNCH_APPLY(TMA, NCH)                                                                                   \
-    k_tile_apply<TMA, NCH><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
+#define KSG_LAUNCH_APPLY_(TMA, NCH, MRG)                                                                                 \
+    k_tile_apply<TMA, NCH, MRG><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
                                                                       n_records, h->tile_begin, h->tile_cap, src, h->rows_per_sub, h->tile_debug)
+#define KSG_LAUNCH_APPLY(TMA, NCH) do { if (fast) { KSG_LAUNCH_APPLY_(TMA, NCH, false); } else { KSG_LAUNCH_APPLY_(TMA, NCH, true); } } while (0)
     if (h->use_tma) {
       switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(true, 1); break; case 2: KSG_LAUNCH_APPLY(true, 2); break;
                               case 4: KSG_LAUNCH_APPLY(true, 4); break; default: KSG_LAUNCH_APPLY(true, 8); break; }
@@ -452,6 +453,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(false, 1); break; case 2: KSG_LAUNCH_APPLY(false, 2); break;
                               case 4: KSG_LAUNCH_APPLY(false, 4); break; default: KSG_LAUNCH_APPLY(false, 8); break; }
     }
+#undef KSG_LAUNCH_APPLY_
 #undef KSG_LAUNCH_APPLY
   }
   if (h->profiling) { if (!did_apply) { cudaEventRecord(h->ev[4], s); cudaEventRecord(h->ev[5], s); } cudaEventRecord(h->ev[6], s); }
@@ -712,14 +714,12 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     (void)fast_cfg;
     h->apply_nch = dc.C <= 32 ? 1 : (dc.C <= 64 ? 2 : (dc.C <= 128 ? 4 : 8));
     h->use_tma = cfg->apply_mode == 0;
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
-    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
+#define KSG_ATTR(TMA, NCH) \
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<TMA, NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem)); \
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<TMA, NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem))
+    KSG_ATTR(true, 1); KSG_ATTR(true, 2); KSG_ATTR(true, 4); KSG_ATTR(true, 8);
+    KSG_ATTR(false, 1); KSG_ATTR(false, 2); KSG_ATTR(false, 4); KSG_ATTR(false, 8);
+#undef KSG_ATTR
   }
   if (const char* e = std::getenv("KSG_SWEEPS_PER_SYNC")) h->sweeps_per_sync = std::max(1, std::min(3, std::atoi(e)));
   KSG_CUDA(cudaDeviceSynchronize());

@@ -856,6 +856,62 @@ struct ApplySrc {
 static constexpr int kApplyThreads = 256;
 static constexpr int kRowBufFloats = 1024;   // per-warp row staging buffer (4 KB)
 
+
+// TSDF recurrence of one batch (<= 32 records, lane j holds record j's sdf / weight / colour) in record order (A.6).
+// The weight chain does not depend on the distance, so it runs first (uniform over the lanes, each lane keeps the weight
+// seen by ITS record; skipped when the voxel already sits at max_weight: min(max_weight, max_weight + uw) = max_weight for
+// uw >= 0); then every lane evaluates its record assuming the distance did not change before it.  Free-space voxels stay
+// pinned at +truncation, so whole batches commit without a sequential pass; the first record that moves the distance ends
+// the speculation and the rest of the batch is replayed in order.
+__device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int nb, float sdf, float uw, uint32_t col, bool keep_blend,
+                                           float& dist, float& wgt, uint32_t& rgba) {
+  float w_before = wgt, wc = wgt;
+  const bool saturated = (wgt == tp.max_weight) && (__ballot_sync(0xffffffffu, lane < nb && !(uw >= 0.0f)) == 0u);
+  if (!saturated) {
+    for (int jj = 0; jj < nb; ++jj) {
+      const float uj = __shfl_sync(0xffffffffu, uw, jj);
+      if (jj == lane) w_before = wc;
+      const float nw = wc + uj;
+      if (!(nw < kEps)) wc = fminf(tp.max_weight, nw);
+    }
+  }
+  bool applies = false;
+  float dn = dist;
+  if (lane < nb) {
+    const float nw = w_before + uw;
+    if (!(nw < kEps)) {
+      applies = true;
+      const float nd = (sdf * uw + dist * w_before) / nw;
+      dn = (nd > 0.0f) ? fminf(tp.trunc, nd) : fmaxf(-tp.trunc, nd);
+    }
+  }
+  if (keep_blend) {   // colour blending only near the surface, in record order (needs only the weight chain)
+    unsigned m = __ballot_sync(0xffffffffu, applies && fabsf(sdf) < tp.trunc);
+    while (m) {
+      const int jj = __ffs(m) - 1;
+      m &= m - 1;
+      rgba = blend_two_colors(rgba, __shfl_sync(0xffffffffu, w_before, jj), __shfl_sync(0xffffffffu, col, jj),
+                              __shfl_sync(0xffffffffu, uw, jj));
+    }
+  }
+  const unsigned moved = __ballot_sync(0xffffffffu, applies && (__float_as_uint(dn) != __float_as_uint(dist)));
+  if (moved) {
+    const int f = __ffs(moved) - 1;
+    dist = __shfl_sync(0xffffffffu, dn, f);
+    for (int jj = f + 1; jj < nb; ++jj) {
+      const float sj = __shfl_sync(0xffffffffu, sdf, jj);
+      const float uj = __shfl_sync(0xffffffffu, uw, jj);
+      const float wb = __shfl_sync(0xffffffffu, w_before, jj);
+      const float nw = wb + uj;
+      if (!(nw < kEps)) {
+        const float nd = (sj * uj + dist * wb) / nw;
+        dist = (nd > 0.0f) ? fminf(tp.trunc, nd) : fmaxf(-tp.trunc, nd);
+      }
+    }
+  }
+  wgt = wc;
+}
+
 // One CTA per touched tile, tiles handed out through a device-side queue.  The tile's voxel planes (and, when
 // they fit, its log-probability rows) are staged in shared memory with ONE TMA bulk copy (cooperative copy when
 // USE_TMA == false) that overlaps the record-segment scan.  Each warp then takes voxels from a CTA-local queue;
@@ -865,7 +921,7 @@ static constexpr int kRowBufFloats = 1024;   // per-warp row staging buffer (4 K
 //   * lanes = classes : semantic log-probability rows, prior[c] += (L * freq)[c]  (base.cpp:283-314)
 // followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
 // written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
-template <bool USE_TMA, int NCH>
+template <bool USE_TMA, int NCH, bool MERGED>
 __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
@@ -958,6 +1014,45 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
 #pragma unroll
       for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
 
+      if (MERGED && NCH == 1) {
+        // software pipeline over batches of 32 records: record keys are fetched two batches ahead, the parameters and the
+        // 32 (L * freq) row values of the next batch one batch ahead, so that the recurrences below never wait on L2
+        const int c = lane;
+        const int nbatches = (hi - lo + 31) >> 5;
+        uint32_t ord_a = (lo + lane < hi) ? ((uint32_t)rec[begin + lo + lane] & ord_mask) : 0u;
+        uint32_t ord_b = (lo + 32 + lane < hi) ? ((uint32_t)rec[begin + lo + 32 + lane] & ord_mask) : 0u;
+        float4 pr_a = (lo + lane < hi) ? src.param[ord_a] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float rv_a[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const uint32_t o = __shfl_sync(0xffffffffu, ord_a, u);
+          rv_a[u] = (lo + u < hi && c < C) ? __ldg(src.tmp + (size_t)o * C + c) : 0.0f;
+        }
+        for (int bi = 0; bi < nbatches; ++bi) {
+          const int base = lo + (bi << 5);
+          const int nb = (hi - base) < 32 ? (hi - base) : 32;
+          // ---- issue the loads of the following batches
+          const uint32_t ord_c = (base + 64 + lane < hi) ? ((uint32_t)rec[begin + base + 64 + lane] & ord_mask) : 0u;
+          const float4 pr_b = (base + 32 + lane < hi) ? src.param[ord_b] : make_float4(0.f, 0.f, 0.f, 0.f);
+          float rv_b[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const uint32_t o = __shfl_sync(0xffffffffu, ord_b, u);
+            rv_b[u] = (base + 32 + u < hi && c < C) ? __ldg(src.tmp + (size_t)o * C + c) : 0.0f;
+          }
+          // ---- this batch
+          float sdf = 0.0f, uw = 0.0f;
+          if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), center, pr_a.w, sdf, uw);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) p[0] += rv_a[u];   // padded tail adds +0.0f (exact)
+          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
+          // ---- rotate
+          pr_a = pr_b;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) rv_a[u] = rv_b[u];
+          ord_b = ord_c;
+        }
+      } else {
       for (int base = lo; base < hi; base += 32) {
         const int k = base + lane;
         uint32_t ord = 0, col = 0;
@@ -972,7 +1067,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
         }
         const int nb = (hi - base) < 32 ? (hi - base) : 32;
         // semantic rows: lanes = classes
-        if (src.label) {
+        if (!MERGED) {
           for (int jj = 0; jj < nb; ++jj) {
             const int l = __shfl_sync(0xffffffffu, lab, jj);
             if (l != 0) {   // label 0: column 0 of the likelihood is zero (base.cpp:127)
@@ -991,7 +1086,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
               const uint32_t o = __shfl_sync(0xffffffffu, ord, (j0 + u) & 31);
               const float* row = src.tmp + (size_t)o * C;
 #pragma unroll
-              for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; rv[u][q] = (j0 + u < nb && c < C) ? __ldg(row + c) : 0.0f; }
+              for (int q = 0; q < NCH; ++q) { const int cc = q * 32 + lane; rv[u][q] = (j0 + u < nb && cc < C) ? __ldg(row + cc) : 0.0f; }
             }
 #pragma unroll
             for (int u = 0; u < kRowUnroll; ++u) {
@@ -1000,55 +1095,8 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
             }
           }
         }
-        // TSDF recurrence in record order (A.6).  The weight chain does not depend on the distance, so it runs first
-        // (uniform over the lanes, each lane keeps the weight seen by ITS record); then every lane evaluates its
-        // record under the assumption that the distance did not change before it.  Free-space voxels stay pinned at
-        // +truncation, so whole batches commit without a sequential pass; the first record that moves the distance
-        // ends the speculation and the remainder of the batch is replayed in order.
-        {
-          float w_before = 0.0f, wc = wgt;
-          for (int jj = 0; jj < nb; ++jj) {
-            const float uj = __shfl_sync(0xffffffffu, uw, jj);
-            if (jj == lane) w_before = wc;
-            const float nw = wc + uj;
-            if (!(nw < kEps)) wc = fminf(cfg.tp.max_weight, nw);
-          }
-          bool applies = false;
-          float dn = dist;
-          if (lane < nb) {
-            const float nw = w_before + uw;
-            if (!(nw < kEps)) {
-              applies = true;
-              const float nd = (sdf * uw + dist * w_before) / nw;
-              dn = (nd > 0.0f) ? fminf(cfg.tp.trunc, nd) : fmaxf(-cfg.tp.trunc, nd);
-            }
-          }
-          if (keep_blend) {   // colour blending only near the surface, in record order (needs only the weight chain)
-            unsigned m = __ballot_sync(0xffffffffu, applies && fabsf(sdf) < cfg.tp.trunc);
-            while (m) {
-              const int jj = __ffs(m) - 1;
-              m &= m - 1;
-              rgba = blend_two_colors(rgba, __shfl_sync(0xffffffffu, w_before, jj), __shfl_sync(0xffffffffu, col, jj),
-                                      __shfl_sync(0xffffffffu, uw, jj));
-            }
-          }
-          const unsigned moved = __ballot_sync(0xffffffffu, applies && (__float_as_uint(dn) != __float_as_uint(dist)));
-          if (moved) {
-            const int f = __ffs(moved) - 1;
-            dist = __shfl_sync(0xffffffffu, dn, f);
-            for (int jj = f + 1; jj < nb; ++jj) {
-              const float sj = __shfl_sync(0xffffffffu, sdf, jj);
-              const float uj = __shfl_sync(0xffffffffu, uw, jj);
-              const float wb = __shfl_sync(0xffffffffu, w_before, jj);
-              const float nw = wb + uj;
-              if (!(nw < kEps)) {
-                const float nd = (sj * uj + dist * wb) / nw;
-                dist = (nd > 0.0f) ? fminf(cfg.tp.trunc, nd) : fmaxf(-cfg.tp.trunc, nd);
-              }
-            }
-          }
-          wgt = wc;
-        }
+        tsdf_batch(cfg.tp, lane, nb, sdf, uw, col, keep_blend, dist, wgt, rgba);
+      }
       }
       // arg-max, first maximum wins (base.cpp:352-367)
       float best = -3.402823466e38f;
