@@ -921,6 +921,8 @@ __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int n
 //   * lanes = classes : semantic log-probability rows, prior[c] += (L * freq)[c]  (base.cpp:283-314)
 // followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
 // written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
+static constexpr int kBigParts = 16;   // a big tile is processed as 16 voxel ranges by different CTAs (no staging)
+
 template <bool USE_TMA, int NCH, bool MERGED>
 __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
@@ -930,21 +932,14 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   extern __shared__ __align__(128) uint8_t smem[];
   const int V = cfg.tile_voxels;
   const int C = cfg.C;
-  float* s_dist = (float*)smem;
-  float* s_wgt = (float*)(smem + cfg.plane_f32);
-  uint32_t* s_rgba = (uint32_t*)(smem + 2 * cfg.plane_f32);
-  uint32_t* s_srgba = (uint32_t*)(smem + 3 * cfg.plane_f32);
-  uint8_t* s_label = smem + 4 * cfg.plane_f32;
-  float* s_prior = (float*)(smem + cfg.head_bytes);             // only when cfg.full_stage
   const uint32_t stage_bytes = cfg.head_bytes + (cfg.full_stage ? cfg.prior_bytes : 0u);
   uint8_t* aux = smem + stage_bytes;
   int* s_seg_lo = (int*)aux;                 // [V]
   int* s_seg_hi = s_seg_lo + V;              // [V]
   uint64_t* s_bar = (uint64_t*)(s_seg_hi + V + (V & 1));
-  float* s_rows = (float*)(s_bar + 2) + (size_t)(threadIdx.x >> 5) * kRowBufFloats;   // per-warp staging of L*freq rows (merged)
   __shared__ long long s_begin, s_end;
   __shared__ uint8_t* s_chunk;
-  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor;
+  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor, s_vox_end, s_direct;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int nthreads = blockDim.x;
@@ -952,6 +947,9 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   if (USE_TMA && tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   const int n_tiles = cnt->n_tiles, n_big = cnt->n_big_tiles;
+  const int n_small = n_tiles - n_big;
+  const int parts = (V >= 64 * kBigParts / 2) ? kBigParts : 1;   // 512-voxel tiles: 16 parts of 32 voxels
+  const int n_items = n_big * parts + n_small;
   const F3 origin = f3(T.tx, T.ty, T.tz);
   const bool keep_blend = cfg.color_mode == 0;  // kColor: the blended colour survives; otherwise base.cpp:177-185 overwrites it
   const uint32_t ord_mask = (1u << kRecOrdBits) - 1u, vox_mask = (1u << kRecVoxBits) - 1u;
@@ -959,15 +957,29 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   for (;;) {
     if (tid == 0) s_tile = atomicAdd(&cnt->tile_cursor, 1);
     __syncthreads();
-    const int j = s_tile;
-    if (j >= n_tiles) break;
+    const int item = s_tile;
+    if (item >= n_items) break;
     const long long t_start = tile_debug ? clock64() : 0;
     if (tid == 0) {
-      const long long b = (j < n_big) ? tile_begin[j] : tile_begin[tile_cap - 1 - (j - n_big)];
+      const bool big = item < n_big * parts;
+      const int j = big ? item / parts : (item - n_big * parts);
+      const int part = big ? item % parts : 0;
+      const long long b = big ? tile_begin[j] : tile_begin[tile_cap - 1 - j];
       const uint32_t tk = (uint32_t)(rec[b] >> 32);
       long long lo = b, hi = n_rec;  // first record whose tile key is greater
       while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((uint32_t)(rec[mid] >> 32) <= tk) lo = mid + 1; else hi = mid; }
-      s_begin = b; s_end = lo;
+      long long rb = b, re = lo;
+      int v0 = 0, v1 = V;
+      if (big && parts > 1) {   // restrict to the records of voxels [v0, v1)
+        v0 = part * (V / parts); v1 = v0 + V / parts;
+        const uint64_t k0 = ((uint64_t)tk << 32) | ((uint64_t)v0 << kRecOrdBits), k1 = ((uint64_t)tk << 32) | ((uint64_t)v1 << kRecOrdBits);
+        long long l2 = b, h2 = lo;
+        while (l2 < h2) { const long long mid = (l2 + h2) >> 1; if (rec[mid] < k0) l2 = mid + 1; else h2 = mid; }
+        rb = l2; h2 = lo;
+        while (l2 < h2) { const long long mid = (l2 + h2) >> 1; if (rec[mid] < k1) l2 = mid + 1; else h2 = mid; }
+        re = l2;
+      }
+      s_begin = rb; s_end = re;
       const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block), tile = (int)(tk % (uint32_t)cfg.tiles_per_block);
       const int slot = map.ht_slot[pos];
       uint8_t* chunk = (slot >= 0 && slot < map.max_blocks) ? map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride : nullptr;
@@ -978,30 +990,43 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
       s_g0x = bi.x * cfg.vps + tx * cfg.tile_side;
       s_g0y = bi.y * cfg.vps + ty * cfg.tile_side;
       s_g0z = bi.z * cfg.vps + tz * cfg.tile_side;
-      s_vox_cursor = 0;
-      if (USE_TMA && chunk) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
+      s_vox_cursor = v0; s_vox_end = v1;
+      s_direct = (big && parts > 1) ? 1 : 0;
+      if (USE_TMA && chunk && !s_direct) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
     }
     for (int v = tid; v < V; v += nthreads) { s_seg_lo[v] = 0; s_seg_hi[v] = 0; }
     __syncthreads();
     uint8_t* chunk = s_chunk;
     if (chunk == nullptr) continue;  // pool overflow already flagged; the loop-top barrier keeps the CTA in step
     const long long begin = s_begin, end = s_end;
+    const bool direct = s_direct != 0;
+    const int vox_end = s_vox_end;
     // per-voxel record segments (overlaps the bulk load)
     for (long long i = begin + tid; i < end; i += nthreads) {
       const int vx = (int)((rec[i] >> kRecOrdBits) & vox_mask);
       if (i == begin || (int)((rec[i - 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_lo[vx] = (int)(i - begin);
       if (i + 1 == end || (int)((rec[i + 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_hi[vx] = (int)(i + 1 - begin);
     }
-    if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
-    else for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
+    if (!direct) {
+      if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
+      else for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
+    }
     __syncthreads();
+    // voxel planes: shared memory (staged tile) or the tile chunk itself (parts of a big tile)
+    uint8_t* pb = direct ? chunk : smem;
+    float* s_dist = (float*)pb;
+    float* s_wgt = (float*)(pb + cfg.plane_f32);
+    uint32_t* s_rgba = (uint32_t*)(pb + 2 * cfg.plane_f32);
+    uint32_t* s_srgba = (uint32_t*)(pb + 3 * cfg.plane_f32);
+    uint8_t* s_label = pb + 4 * cfg.plane_f32;
+    float* s_prior = (float*)(smem + cfg.head_bytes);             // only when cfg.full_stage and not direct
     float* g_prior = (float*)(chunk + cfg.head_bytes);
 
     for (;;) {
       int v = 0;
       if (lane == 0) v = atomicAdd(&s_vox_cursor, 1);
       v = __shfl_sync(0xffffffffu, v, 0);
-      if (v >= V) break;
+      if (v >= vox_end) break;
       const int lo = s_seg_lo[v], hi = s_seg_hi[v];
       if (lo >= hi) continue;
       const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
@@ -1009,7 +1034,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
       const F3 center = voxel_center(g, cfg.voxel_size);
       float dist = s_dist[v], wgt = s_wgt[v];
       uint32_t rgba = s_rgba[v];
-      float* prow = (cfg.full_stage ? s_prior : g_prior) + (size_t)v * C;
+      float* prow = ((cfg.full_stage && !direct) ? s_prior : g_prior) + (size_t)v * C;
       float p[NCH];
 #pragma unroll
       for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
@@ -1122,16 +1147,18 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
         s_rgba[v] = rgba;
       }
     }
-    // ---- write the tile back
-    if (USE_TMA) {
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) { tma_store_1d(chunk, smem, stage_bytes); tma_store_commit_wait(); }
-    } else {
-      __syncthreads();
-      for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
+    // ---- write the tile back (parts of big tiles already wrote their voxels in place)
+    if (!direct) {
+      if (USE_TMA) {
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { tma_store_1d(chunk, smem, stage_bytes); tma_store_commit_wait(); }
+      } else {
+        __syncthreads();
+        for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
+      }
     }
-    if (tile_debug && tid == 0) { tile_debug[2 * j] = end - begin; tile_debug[2 * j + 1] = clock64() - t_start; }
+    if (tile_debug && tid == 0 && item < tile_cap) { tile_debug[2 * item] = end - begin; tile_debug[2 * item + 1] = clock64() - t_start; }
     // the loop-top barrier orders the store's completion before the next tile's load
   }
 }
