@@ -407,7 +407,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       const int nb = std::max(1, h->h_cnt->n_cast);
       n_records = (long long)h->h_cnt->n_records;
       ++h->n_launches;
-      k_bundle_loglik<<<grid_for((long long)nb * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp);
+      k_bundle_loglik<<<grid_for((long long)(nb + 1) * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp);
       ++h->n_launches;
       k_emit_merged<<<grid_for(nb, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps,
                                                       h->b_base, h->ks_sorted, cap, h->rec_a);
@@ -684,7 +684,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   } else {
     KSG_CUDA(dmalloc(&h->ks_sorted, N)); KSG_CUDA(dmalloc(&h->seq_sorted, N));
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
-    KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, N * dc.C));
+    KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
   }
   h->rec_cap = rec_cap;

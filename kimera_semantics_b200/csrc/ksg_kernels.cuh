@@ -700,7 +700,7 @@ __global__ void k_bundle_merge(DevCfg cfg, Xform T, Counters* cnt, const int* __
 __global__ void k_bundle_loglik(DevCfg cfg, const Counters* cnt, const float* __restrict__ hist, float* __restrict__ tmp) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)cnt->n_cast * cfg.C;
-  if (t >= total) return;
+  if (t >= total) { if (t < total + cfg.C) tmp[t] = 0.0f; return; }   // row n_cast = zeros: target of padded row loads
   const int i = (int)(t % cfg.C);
   const float* h = hist + (t - i);
   float acc = 0.0f;
@@ -921,8 +921,6 @@ __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int n
 //   * lanes = classes : semantic log-probability rows, prior[c] += (L * freq)[c]  (base.cpp:283-314)
 // followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
 // written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
-static constexpr int kBigParts = 16;   // a big tile is processed as 16 voxel ranges by different CTAs (no staging)
-
 template <bool USE_TMA, int NCH, bool MERGED>
 __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
@@ -932,14 +930,21 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   extern __shared__ __align__(128) uint8_t smem[];
   const int V = cfg.tile_voxels;
   const int C = cfg.C;
+  float* s_dist = (float*)smem;
+  float* s_wgt = (float*)(smem + cfg.plane_f32);
+  uint32_t* s_rgba = (uint32_t*)(smem + 2 * cfg.plane_f32);
+  uint32_t* s_srgba = (uint32_t*)(smem + 3 * cfg.plane_f32);
+  uint8_t* s_label = smem + 4 * cfg.plane_f32;
+  float* s_prior = (float*)(smem + cfg.head_bytes);             // only when cfg.full_stage
   const uint32_t stage_bytes = cfg.head_bytes + (cfg.full_stage ? cfg.prior_bytes : 0u);
   uint8_t* aux = smem + stage_bytes;
   int* s_seg_lo = (int*)aux;                 // [V]
   int* s_seg_hi = s_seg_lo + V;              // [V]
   uint64_t* s_bar = (uint64_t*)(s_seg_hi + V + (V & 1));
+  float* s_rows = (float*)(s_bar + 2) + (size_t)(threadIdx.x >> 5) * kRowBufFloats;   // per-warp staging of L*freq rows (merged)
   __shared__ long long s_begin, s_end;
   __shared__ uint8_t* s_chunk;
-  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor, s_vox_end, s_direct;
+  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int nthreads = blockDim.x;
@@ -947,9 +952,6 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   if (USE_TMA && tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   const int n_tiles = cnt->n_tiles, n_big = cnt->n_big_tiles;
-  const int n_small = n_tiles - n_big;
-  const int parts = (V >= 64 * kBigParts / 2) ? kBigParts : 1;   // 512-voxel tiles: 16 parts of 32 voxels
-  const int n_items = n_big * parts + n_small;
   const F3 origin = f3(T.tx, T.ty, T.tz);
   const bool keep_blend = cfg.color_mode == 0;  // kColor: the blended colour survives; otherwise base.cpp:177-185 overwrites it
   const uint32_t ord_mask = (1u << kRecOrdBits) - 1u, vox_mask = (1u << kRecVoxBits) - 1u;
@@ -957,29 +959,15 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   for (;;) {
     if (tid == 0) s_tile = atomicAdd(&cnt->tile_cursor, 1);
     __syncthreads();
-    const int item = s_tile;
-    if (item >= n_items) break;
+    const int j = s_tile;
+    if (j >= n_tiles) break;
     const long long t_start = tile_debug ? clock64() : 0;
     if (tid == 0) {
-      const bool big = item < n_big * parts;
-      const int j = big ? item / parts : (item - n_big * parts);
-      const int part = big ? item % parts : 0;
-      const long long b = big ? tile_begin[j] : tile_begin[tile_cap - 1 - j];
+      const long long b = (j < n_big) ? tile_begin[j] : tile_begin[tile_cap - 1 - (j - n_big)];
       const uint32_t tk = (uint32_t)(rec[b] >> 32);
       long long lo = b, hi = n_rec;  // first record whose tile key is greater
       while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((uint32_t)(rec[mid] >> 32) <= tk) lo = mid + 1; else hi = mid; }
-      long long rb = b, re = lo;
-      int v0 = 0, v1 = V;
-      if (big && parts > 1) {   // restrict to the records of voxels [v0, v1)
-        v0 = part * (V / parts); v1 = v0 + V / parts;
-        const uint64_t k0 = ((uint64_t)tk << 32) | ((uint64_t)v0 << kRecOrdBits), k1 = ((uint64_t)tk << 32) | ((uint64_t)v1 << kRecOrdBits);
-        long long l2 = b, h2 = lo;
-        while (l2 < h2) { const long long mid = (l2 + h2) >> 1; if (rec[mid] < k0) l2 = mid + 1; else h2 = mid; }
-        rb = l2; h2 = lo;
-        while (l2 < h2) { const long long mid = (l2 + h2) >> 1; if (rec[mid] < k1) l2 = mid + 1; else h2 = mid; }
-        re = l2;
-      }
-      s_begin = rb; s_end = re;
+      s_begin = b; s_end = lo;
       const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block), tile = (int)(tk % (uint32_t)cfg.tiles_per_block);
       const int slot = map.ht_slot[pos];
       uint8_t* chunk = (slot >= 0 && slot < map.max_blocks) ? map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride : nullptr;
@@ -990,93 +978,96 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
       s_g0x = bi.x * cfg.vps + tx * cfg.tile_side;
       s_g0y = bi.y * cfg.vps + ty * cfg.tile_side;
       s_g0z = bi.z * cfg.vps + tz * cfg.tile_side;
-      s_vox_cursor = v0; s_vox_end = v1;
-      s_direct = (big && parts > 1) ? 1 : 0;
-      if (USE_TMA && chunk && !s_direct) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
+      s_vox_cursor = 0;
+      if (USE_TMA && chunk) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
     }
     for (int v = tid; v < V; v += nthreads) { s_seg_lo[v] = 0; s_seg_hi[v] = 0; }
     __syncthreads();
     uint8_t* chunk = s_chunk;
     if (chunk == nullptr) continue;  // pool overflow already flagged; the loop-top barrier keeps the CTA in step
     const long long begin = s_begin, end = s_end;
-    const bool direct = s_direct != 0;
-    const int vox_end = s_vox_end;
     // per-voxel record segments (overlaps the bulk load)
     for (long long i = begin + tid; i < end; i += nthreads) {
       const int vx = (int)((rec[i] >> kRecOrdBits) & vox_mask);
       if (i == begin || (int)((rec[i - 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_lo[vx] = (int)(i - begin);
       if (i + 1 == end || (int)((rec[i + 1] >> kRecOrdBits) & vox_mask) != vx) s_seg_hi[vx] = (int)(i + 1 - begin);
     }
-    if (!direct) {
-      if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
-      else for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
-    }
+    if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
+    else for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
     __syncthreads();
-    // voxel planes: shared memory (staged tile) or the tile chunk itself (parts of a big tile)
-    uint8_t* pb = direct ? chunk : smem;
-    float* s_dist = (float*)pb;
-    float* s_wgt = (float*)(pb + cfg.plane_f32);
-    uint32_t* s_rgba = (uint32_t*)(pb + 2 * cfg.plane_f32);
-    uint32_t* s_srgba = (uint32_t*)(pb + 3 * cfg.plane_f32);
-    uint8_t* s_label = pb + 4 * cfg.plane_f32;
-    float* s_prior = (float*)(smem + cfg.head_bytes);             // only when cfg.full_stage and not direct
     float* g_prior = (float*)(chunk + cfg.head_bytes);
 
+    // Work items of the CTA's warps: (voxel, role).  A voxel's TSDF recurrence and its semantic recurrences are
+    // independent, so long segments are handled by two warps, one per role, with lean loops; short
+    // segments by one warp doing both.
+    constexpr int kSplitLen = 96;
     for (;;) {
-      int v = 0;
-      if (lane == 0) v = atomicAdd(&s_vox_cursor, 1);
-      v = __shfl_sync(0xffffffffu, v, 0);
-      if (v >= vox_end) break;
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&s_vox_cursor, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= 2 * V) break;
+      const int v = item >> 1;
       const int lo = s_seg_lo[v], hi = s_seg_hi[v];
       if (lo >= hi) continue;
+      const bool split = MERGED && NCH == 1 && (hi - lo) >= kSplitLen;
+      const int role = item & 1;                 // 0: TSDF (+ everything for short segments), 1: semantic half of a split voxel
+      if (role == 1 && !split) continue;
+      const bool do_tsdf = !split || role == 0;
+      const bool do_sem = !split || role == 1;
       const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
       I3 g; g.x = s_g0x + (v & tm); g.y = s_g0y + ((v >> ts) & tm); g.z = s_g0z + (v >> (2 * ts));
       const F3 center = voxel_center(g, cfg.voxel_size);
       float dist = s_dist[v], wgt = s_wgt[v];
       uint32_t rgba = s_rgba[v];
-      float* prow = ((cfg.full_stage && !direct) ? s_prior : g_prior) + (size_t)v * C;
+      float* prow = (cfg.full_stage ? s_prior : g_prior) + (size_t)v * C;
       float p[NCH];
 #pragma unroll
       for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
 
       if (MERGED && NCH == 1) {
         // software pipeline over batches of 32 records: record keys are fetched two batches ahead, the parameters and the
-        // 32 (L * freq) row values of the next batch one batch ahead, so that the recurrences below never wait on L2
-        const int c = lane;
+        // 32 (L * freq) row values of the next batch one batch ahead, so that the recurrences below never wait on L2.
+        // Padded lanes / rows point at the all-zero row behind the last bundle (adds +0.0f, exact).
         const int nbatches = (hi - lo + 31) >> 5;
-        uint32_t ord_a = (lo + lane < hi) ? ((uint32_t)rec[begin + lo + lane] & ord_mask) : 0u;
-        uint32_t ord_b = (lo + 32 + lane < hi) ? ((uint32_t)rec[begin + lo + 32 + lane] & ord_mask) : 0u;
-        float4 pr_a = (lo + lane < hi) ? src.param[ord_a] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t zero_row = (uint32_t)cnt->n_cast;
+        const float* lane_tmp = src.tmp + (lane < C ? lane : 0);
+        const bool lane_live = lane < C;
+        uint32_t ord_a = (lo + lane < hi) ? ((uint32_t)rec[begin + lo + lane] & ord_mask) : zero_row;
+        uint32_t ord_b = (lo + 32 + lane < hi) ? ((uint32_t)rec[begin + lo + 32 + lane] & ord_mask) : zero_row;
+        float4 pr_a = (do_tsdf && lo + lane < hi) ? src.param[ord_a] : make_float4(0.f, 0.f, 0.f, 0.f);
         float rv_a[32];
+        if (do_sem) {
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const uint32_t o = __shfl_sync(0xffffffffu, ord_a, u);
-          rv_a[u] = (lo + u < hi && c < C) ? __ldg(src.tmp + (size_t)o * C + c) : 0.0f;
+          for (int u = 0; u < 32; ++u) rv_a[u] = __ldg(lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_a, u) * C);
         }
         for (int bi = 0; bi < nbatches; ++bi) {
           const int base = lo + (bi << 5);
           const int nb = (hi - base) < 32 ? (hi - base) : 32;
           // ---- issue the loads of the following batches
-          const uint32_t ord_c = (base + 64 + lane < hi) ? ((uint32_t)rec[begin + base + 64 + lane] & ord_mask) : 0u;
-          const float4 pr_b = (base + 32 + lane < hi) ? src.param[ord_b] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t ord_c = (base + 64 + lane < hi) ? ((uint32_t)rec[begin + base + 64 + lane] & ord_mask) : zero_row;
+          float4 pr_b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (do_tsdf && base + 32 + lane < hi) pr_b = src.param[ord_b];
           float rv_b[32];
+          if (do_sem) {
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const uint32_t o = __shfl_sync(0xffffffffu, ord_b, u);
-            rv_b[u] = (base + 32 + u < hi && c < C) ? __ldg(src.tmp + (size_t)o * C + c) : 0.0f;
+            for (int u = 0; u < 32; ++u) rv_b[u] = __ldg(lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_b, u) * C);
           }
           // ---- this batch
-          float sdf = 0.0f, uw = 0.0f;
-          if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), center, pr_a.w, sdf, uw);
+          if (do_sem) {
 #pragma unroll
-          for (int u = 0; u < 32; ++u) p[0] += rv_a[u];   // padded tail adds +0.0f (exact)
-          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
-          // ---- rotate
-          pr_a = pr_b;
+            for (int u = 0; u < 32; ++u) p[0] += rv_a[u];
 #pragma unroll
-          for (int u = 0; u < 32; ++u) rv_a[u] = rv_b[u];
+            for (int u = 0; u < 32; ++u) rv_a[u] = rv_b[u];
+          }
+          if (do_tsdf) {
+            float sdf = 0.0f, uw = 0.0f;
+            if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), center, pr_a.w, sdf, uw);
+            tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
+            pr_a = pr_b;
+          }
           ord_b = ord_c;
         }
+        if (!lane_live) p[0] = 0.0f;
       } else {
       for (int base = lo; base < hi; base += 32) {
         const int k = base + lane;
@@ -1123,42 +1114,46 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
         tsdf_batch(cfg.tp, lane, nb, sdf, uw, col, keep_blend, dist, wgt, rgba);
       }
       }
-      // arg-max, first maximum wins (base.cpp:352-367)
-      float best = -3.402823466e38f;
-      int bi = 0x7fffffff;
+      int bi_lab = 0;
+      float best = 0.0f;
+      if (do_sem) {
+        // arg-max, first maximum wins (base.cpp:352-367)
+        best = -3.402823466e38f;
+        int bi = 0x7fffffff;
 #pragma unroll
-      for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C && (p[q] > best || bi == 0x7fffffff)) { best = p[q]; bi = c; } }
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_down_sync(0xffffffffu, best, o);
-        const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-        if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+        for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C && (p[q] > best || bi == 0x7fffffff)) { best = p[q]; bi = c; } }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_down_sync(0xffffffffu, best, o);
+          const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+          if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        bi_lab = __shfl_sync(0xffffffffu, bi, 0);
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) prow[c] = p[q]; }
       }
-      best = __shfl_sync(0xffffffffu, best, 0);
-      bi = __shfl_sync(0xffffffffu, bi, 0);
-#pragma unroll
-      for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) prow[c] = p[q]; }
       if (lane == 0) {
-        s_dist[v] = dist; s_wgt[v] = wgt;
-        s_label[v] = (uint8_t)bi;
-        const uint32_t sc = luts->label_rgba[bi];          // base.cpp:370-380
-        s_srgba[v] = sc;
-        if (cfg.color_mode == 1) rgba = sc;                 // kSemantic (base.cpp:177-180)
-        else if (cfg.color_mode == 2) rgba = rainbow_color_map((double)expf(best));  // base.cpp:181-185
-        s_rgba[v] = rgba;
+        if (do_tsdf) { s_dist[v] = dist; s_wgt[v] = wgt; }
+        if (do_sem) {
+          s_label[v] = (uint8_t)bi_lab;
+          const uint32_t sc = luts->label_rgba[bi_lab];          // base.cpp:370-380
+          s_srgba[v] = sc;
+          if (cfg.color_mode == 1) s_rgba[v] = sc;               // kSemantic (base.cpp:177-180)
+          else if (cfg.color_mode == 2) s_rgba[v] = rainbow_color_map((double)expf(best));  // base.cpp:181-185
+        }
+        if (do_tsdf && cfg.color_mode == 0) s_rgba[v] = rgba;    // kColor: the blended colour is the result
       }
     }
-    // ---- write the tile back (parts of big tiles already wrote their voxels in place)
-    if (!direct) {
-      if (USE_TMA) {
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) { tma_store_1d(chunk, smem, stage_bytes); tma_store_commit_wait(); }
-      } else {
-        __syncthreads();
-        for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
-      }
+    // ---- write the tile back
+    if (USE_TMA) {
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) { tma_store_1d(chunk, smem, stage_bytes); tma_store_commit_wait(); }
+    } else {
+      __syncthreads();
+      for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)chunk)[t] = ((const uint4*)smem)[t];
     }
-    if (tile_debug && tid == 0 && item < tile_cap) { tile_debug[2 * item] = end - begin; tile_debug[2 * item + 1] = clock64() - t_start; }
+    if (tile_debug && tid == 0) { tile_debug[2 * j] = end - begin; tile_debug[2 * j + 1] = clock64() - t_start; }
     // the loop-top barrier orders the store's completion before the next tile's load
   }
 }
