@@ -912,38 +912,6 @@ __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int n
   wgt = wc;
 }
 
-
-// One stage of the merged-path software pipeline (see k_tile_apply): issues the loads of batch k+1 (parameters, 32 row
-// values) and of batch k+2 (record keys) and then runs the recurrences of batch k on registers that were loaded one stage
-// earlier.  Called alternately with (cur, nxt) swapped, so no register is copied while its load is in flight.
-struct PipeCtx {
-  const uint64_t* rec; long long begin; int hi; uint32_t ord_mask, zero_row; const float* lane_tmp; int C;
-  const float4* param; bool do_tsdf, do_sem;
-};
-__device__ __forceinline__ void merged_stage(const PipeCtx& x, const DevCfg& cfg, F3 origin, F3 center, bool keep_blend, int lane, int base,
-                                             uint32_t& ord_next, float4& pr_cur, float4& pr_nxt, float (&rv_cur)[32], float (&rv_nxt)[32],
-                                             float& psum, float& dist, float& wgt, uint32_t& rgba) {
-  const int nb = (x.hi - base) < 32 ? (x.hi - base) : 32;
-  // ---- issue the loads of the following batches
-  const uint32_t ord_new = (base + 64 + lane < x.hi) ? ((uint32_t)x.rec[x.begin + base + 64 + lane] & x.ord_mask) : x.zero_row;
-  if (x.do_tsdf) pr_nxt = (base + 32 + lane < x.hi) ? x.param[ord_next] : make_float4(0.f, 0.f, 0.f, 0.f);
-  if (x.do_sem) {
-#pragma unroll
-    for (int u = 0; u < 32; ++u) rv_nxt[u] = __ldg(x.lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_next, u) * x.C);
-  }
-  // ---- recurrences of this batch
-  if (x.do_sem) {
-#pragma unroll
-    for (int u = 0; u < 32; ++u) psum += rv_cur[u];   // padded rows are the all-zero row: + 0.0f is exact
-  }
-  if (x.do_tsdf) {
-    float sdf = 0.0f, uw = 0.0f;
-    if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_cur.x, pr_cur.y, pr_cur.z), center, pr_cur.w, sdf, uw);
-    tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
-  }
-  ord_next = ord_new;
-}
-
 // One CTA per touched tile, tiles handed out through a device-side queue.  The tile's voxel planes (and, when
 // they fit, its log-probability rows) are staged in shared memory with ONE TMA bulk copy (cooperative copy when
 // USE_TMA == false) that overlaps the record-segment scan.  Each warp then takes voxels from a CTA-local queue;
@@ -1061,23 +1029,43 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
         // 32 (L * freq) row values of the next batch one batch ahead, so that the recurrences below never wait on L2.
         // Padded lanes / rows point at the all-zero row behind the last bundle (adds +0.0f, exact).
         const int nbatches = (hi - lo + 31) >> 5;
+        const uint32_t zero_row = (uint32_t)cnt->n_cast;
+        const float* lane_tmp = src.tmp + (lane < C ? lane : 0);
         const bool lane_live = lane < C;
-        PipeCtx x;
-        x.rec = rec; x.begin = begin; x.hi = hi; x.ord_mask = ord_mask; x.zero_row = (uint32_t)cnt->n_cast;
-        x.lane_tmp = src.tmp + (lane_live ? lane : 0); x.C = C; x.param = src.param; x.do_tsdf = do_tsdf; x.do_sem = do_sem;
-        const uint32_t ord_first = (lo + lane < hi) ? ((uint32_t)rec[begin + lo + lane] & ord_mask) : x.zero_row;
-        uint32_t ord_next = (lo + 32 + lane < hi) ? ((uint32_t)rec[begin + lo + 32 + lane] & ord_mask) : x.zero_row;
-        float4 pr_a = (do_tsdf && lo + lane < hi) ? src.param[ord_first] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pr_b = make_float4(0.f, 0.f, 0.f, 0.f);
-        float rv_a[32], rv_b[32];
+        uint32_t ord_a = (lo + lane < hi) ? ((uint32_t)rec[begin + lo + lane] & ord_mask) : zero_row;
+        uint32_t ord_b = (lo + 32 + lane < hi) ? ((uint32_t)rec[begin + lo + 32 + lane] & ord_mask) : zero_row;
+        float4 pr_a = (do_tsdf && lo + lane < hi) ? src.param[ord_a] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float rv_a[32];
         if (do_sem) {
 #pragma unroll
-          for (int u = 0; u < 32; ++u) rv_a[u] = __ldg(x.lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_first, u) * C);
+          for (int u = 0; u < 32; ++u) rv_a[u] = __ldg(lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_a, u) * C);
         }
-        for (int bi = 0; bi < nbatches; bi += 2) {
-          merged_stage(x, cfg, origin, center, keep_blend, lane, lo + (bi << 5), ord_next, pr_a, pr_b, rv_a, rv_b, p[0], dist, wgt, rgba);
-          if (bi + 1 < nbatches)
-            merged_stage(x, cfg, origin, center, keep_blend, lane, lo + ((bi + 1) << 5), ord_next, pr_b, pr_a, rv_b, rv_a, p[0], dist, wgt, rgba);
+        for (int bi = 0; bi < nbatches; ++bi) {
+          const int base = lo + (bi << 5);
+          const int nb = (hi - base) < 32 ? (hi - base) : 32;
+          // ---- issue the loads of the following batches
+          const uint32_t ord_c = (base + 64 + lane < hi) ? ((uint32_t)rec[begin + base + 64 + lane] & ord_mask) : zero_row;
+          float4 pr_b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (do_tsdf && base + 32 + lane < hi) pr_b = src.param[ord_b];
+          float rv_b[32];
+          if (do_sem) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) rv_b[u] = __ldg(lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_b, u) * C);
+          }
+          // ---- this batch
+          if (do_sem) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) p[0] += rv_a[u];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) rv_a[u] = rv_b[u];
+          }
+          if (do_tsdf) {
+            float sdf = 0.0f, uw = 0.0f;
+            if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), center, pr_a.w, sdf, uw);
+            tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
+            pr_a = pr_b;
+          }
+          ord_b = ord_c;
         }
         if (!lane_live) p[0] = 0.0f;
       } else {
