@@ -69,7 +69,9 @@ struct ksg_integrator {
   uint32_t *iota = nullptr;
 
   // fast
-  int *start_head = nullptr, *start_next = nullptr;
+  int *start_head = nullptr, *start_next = nullptr, *start_min = nullptr, *start_max = nullptr;
+  uint32_t* start_val = nullptr;
+  uint8_t* start_mixed = nullptr;
   uint32_t *start_table = nullptr;
   uint64_t set_offset = 0;  // both ApproxHashSets share reset times, hence one offset (fast.cpp:165-170)
   int64_t reset_counter = 0;
@@ -160,7 +162,7 @@ void free_all(ksg_integrator* h) {
   void* ptrs[] = {h->map.ht_keys, h->map.ht_slot, h->map.new_list, h->map.pool, h->map.slot_key, h->map.touched_stamp,
                   h->map.touched_list, h->d_luts, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color, h->pt_key,
                   h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota, h->start_head,
-                  h->start_next, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
+                  h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.slot_cnt, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.head, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->tile_debug, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
@@ -317,15 +319,20 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   ApplySrc src{};
   if (fast) {
     KSG_CUDA(cudaMemsetAsync(h->start_head, 0xFF, sizeof(int) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->start_min, 0x7F, sizeof(int) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->start_max, 0xFF, sizeof(int) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->start_val, 0xFF, sizeof(uint32_t) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->start_mixed, 0, kSetSize, s));
     KSG_CUDA(cudaMemsetAsync(h->ob.head, 0xFF, sizeof(int) * kSetSize, s));
     KSG_CUDA(cudaMemsetAsync(h->ob.slot_cnt, 0, sizeof(int) * kSetSize, s));
     ++h->n_launches;
     k_classify<true><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, h->set_offset, cap, h->d_cnt, h->pt_pC, h->pt_pG,
                                                     h->pt_label, h->pt_flags, h->pt_color, h->pt_key);
     ++h->n_launches;
-    k_start_push<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next);
+    StartBuf sbuf{h->start_head, h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table};
+    k_start_push<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, sbuf);
     ++h->n_launches;
-    k_start_eval<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next, h->start_table, h->flags8,
+    k_start_eval<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table, h->flags8,
                                                 h->is_last, cap);
     ++h->n_launches;
     k_start_commit<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->is_last, h->start_table);
@@ -669,6 +676,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   long long rec_cap = cfg->max_updates > 0 ? cfg->max_updates : (fast ? std::max<long long>(4ll << 20, 64ll * (long long)N) : (64ll << 20));
   if (fast) {
     KSG_CUDA(dmalloc(&h->start_head, kSetSize)); KSG_CUDA(dmalloc(&h->start_next, N)); KSG_CUDA(dmalloc(&h->start_table, kSetSize));
+    KSG_CUDA(dmalloc(&h->start_min, kSetSize)); KSG_CUDA(dmalloc(&h->start_max, kSetSize)); KSG_CUDA(dmalloc(&h->start_val, kSetSize));
+    KSG_CUDA(dmalloc(&h->start_mixed, kSetSize));
     KSG_CUDA(dmalloc(&h->cast_seq, N));
     KSG_CUDA(dmalloc(&h->ray_label, N)); KSG_CUDA(dmalloc(&h->ray_color, N)); KSG_CUDA(dmalloc(&h->trunc_flag, N));
     KSG_CUDA(dmalloc(&h->H, N)); KSG_CUDA(dmalloc(&h->L, N)); KSG_CUDA(dmalloc(&h->ray_state, N)); KSG_CUDA(dmalloc(&h->ext_off, N * kExtSegs));

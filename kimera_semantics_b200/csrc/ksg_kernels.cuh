@@ -212,15 +212,31 @@ __global__ void k_classify(DevCfg cfg, Xform T, FrameIn in, const Luts* __restri
 // replaceHash on the slot", so a point is skipped iff the previous visitor of its slot (in sequence
 // order; before the first visitor: the persistent table) carried the same value.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_start_push(const Counters* cnt, const uint64_t* __restrict__ key, int* head, int* next) {
+struct StartBuf {
+  int* head;        // 2^20 list heads (only walked for slots that carry more than one value)
+  int* next;        // per sequence position
+  int* smin;        // 2^20: smallest sequence position that visited the slot this frame
+  int* smax;        // 2^20: largest
+  uint32_t* sval;   // 2^20: (value >> 20) of the first visitor
+  uint8_t* mixed;   // 2^20: 1 when visitors with different values share the slot (20-bit aliasing)
+  const uint32_t* table;
+};
+__global__ void k_start_push(const Counters* cnt, const uint64_t* __restrict__ key, StartBuf sb) {
   const int seq = blockIdx.x * blockDim.x + threadIdx.x;
   if (seq >= cnt->n_points) return;
   const uint64_t v = key[seq];
   if (v == ~0ull) return;
-  next[seq] = atomicExch(&head[(uint32_t)v & kSetMask], seq);
+  const uint32_t slot = (uint32_t)v & kSetMask, hi = (uint32_t)(v >> kSetBits);
+  sb.next[seq] = atomicExch(&sb.head[slot], seq);
+  atomicMin(&sb.smin[slot], seq);
+  atomicMax(&sb.smax[slot], seq);
+  const uint32_t old = atomicCAS(&sb.sval[slot], 0xFFFFFFFFu, hi);
+  if (old != 0xFFFFFFFFu && old != hi) sb.mixed[slot] = 1;
 }
-__global__ void k_start_eval(const Counters* cnt, const uint64_t* __restrict__ key, const int* __restrict__ head,
-                             const int* __restrict__ next, const uint32_t* __restrict__ table, uint8_t* __restrict__ cast_flag,
+// The set's state is the value of the last visit, so a point is cast iff the previous visitor of its slot (sequence
+// order; before the first visitor: the persistent table) carried a different value.  When every visitor of the slot
+// carries the same value (the normal case: all points of one start cell) only the first visitor can be cast.
+__global__ void k_start_eval(const Counters* cnt, const uint64_t* __restrict__ key, StartBuf sb, uint8_t* __restrict__ cast_flag,
                              uint8_t* __restrict__ is_last, int capacity) {
   const int seq = blockIdx.x * blockDim.x + threadIdx.x;
   if (seq >= capacity) return;
@@ -229,15 +245,15 @@ __global__ void k_start_eval(const Counters* cnt, const uint64_t* __restrict__ k
     const uint64_t v = key[seq];
     if (v != ~0ull) {
       const uint32_t slot = (uint32_t)v & kSetMask;
-      int best = -1;
-      bool later = false;
-      for (int e = head[slot]; e >= 0; e = next[e]) {
-        if (e < seq && e > best) best = e;
-        if (e > seq) later = true;
+      last = sb.smax[slot] == seq;
+      if (!sb.mixed[slot]) {
+        cast = (sb.smin[slot] == seq) && (sb.table[slot] != (uint32_t)(v >> kSetBits));
+      } else {
+        int best = -1;
+        for (int e = sb.head[slot]; e >= 0; e = sb.next[e]) if (e < seq && e > best) best = e;
+        if (best >= 0) cast = key[best] != v;
+        else cast = sb.table[slot] != (uint32_t)(v >> kSetBits);
       }
-      if (best >= 0) cast = key[best] != v;
-      else cast = table[slot] != (uint32_t)(v >> kSetBits);
-      last = !later;
     }
   }
   cast_flag[seq] = cast;
