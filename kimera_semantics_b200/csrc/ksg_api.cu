@@ -332,8 +332,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     StartBuf sbuf{h->start_head, h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table};
     k_start_push<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, sbuf);
     ++h->n_launches;
-    k_start_eval<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->start_head, h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table, h->flags8,
-                                                h->is_last, cap);
+    k_start_eval<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, sbuf, h->flags8, h->is_last, cap);
     ++h->n_launches;
     k_start_commit<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->pt_key, h->is_last, h->start_table);
     {
