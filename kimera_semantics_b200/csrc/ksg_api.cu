@@ -72,6 +72,7 @@ struct ksg_integrator {
   int *start_head = nullptr, *start_next = nullptr, *start_min = nullptr, *start_max = nullptr;
   uint32_t* start_val = nullptr;
   uint8_t* start_mixed = nullptr;
+  uint8_t *clear_ff = nullptr, *clear_00 = nullptr;
   uint32_t *start_table = nullptr;
   uint64_t set_offset = 0;  // both ApproxHashSets share reset times, hence one offset (fast.cpp:165-170)
   int64_t reset_counter = 0;
@@ -161,10 +162,10 @@ void free_all(ksg_integrator* h) {
   cudaSetDevice(h->device);
   void* ptrs[] = {h->map.ht_keys, h->map.ht_slot, h->map.new_list, h->map.pool, h->map.slot_key, h->map.touched_stamp,
                   h->map.touched_list, h->d_luts, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color, h->pt_key,
-                  h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota, h->start_head,
-                  h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
-                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.slot_cnt, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
-                  h->ob.cand_next, h->ob.head, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
+                  h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota,
+                  h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
+                  h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
+                  h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->tile_debug, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -318,13 +319,9 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   int iterations = 0;
   ApplySrc src{};
   if (fast) {
-    KSG_CUDA(cudaMemsetAsync(h->start_head, 0xFF, sizeof(int) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->clear_ff, 0xFF, (size_t)kSetSize * 16, s));
+    KSG_CUDA(cudaMemsetAsync(h->clear_00, 0x00, (size_t)kSetSize * 5, s));
     KSG_CUDA(cudaMemsetAsync(h->start_min, 0x7F, sizeof(int) * kSetSize, s));
-    KSG_CUDA(cudaMemsetAsync(h->start_max, 0xFF, sizeof(int) * kSetSize, s));
-    KSG_CUDA(cudaMemsetAsync(h->start_val, 0xFF, sizeof(uint32_t) * kSetSize, s));
-    KSG_CUDA(cudaMemsetAsync(h->start_mixed, 0, kSetSize, s));
-    KSG_CUDA(cudaMemsetAsync(h->ob.head, 0xFF, sizeof(int) * kSetSize, s));
-    KSG_CUDA(cudaMemsetAsync(h->ob.slot_cnt, 0, sizeof(int) * kSetSize, s));
     ++h->n_launches;
     k_classify<true><<<grid_for(cap, B), B, 0, s>>>(dc, T, fin, h->d_luts, h->set_offset, cap, h->d_cnt, h->pt_pC, h->pt_pG,
                                                     h->pt_label, h->pt_flags, h->pt_color, h->pt_key);
@@ -434,14 +431,11 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, 0, end_bit, s));
     if (h->profiling) cudaEventRecord(h->ev[4], s);
     ++h->n_launches;
-    k_block_assign<<<grid_for(h->map.new_cap, B), B, 0, s>>>(h->d_cnt, h->map);
-    ++h->n_launches;
     k_block_init<<<h->sm_count * 4, 256, 0, s>>>(dc, h->d_cnt, h->map);
     ++h->n_launches;
     k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
                                                       h->tile_cap);
-    ++h->n_launches;
-    k_tile_queue_reset<<<1, 1, 0, s>>>(h->d_cnt);
+
     if (h->profiling) cudaEventRecord(h->ev[5], s);
     did_apply = true;
     const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem + 1024))));
@@ -674,9 +668,14 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   KSG_CUDA(dmalloc(&h->ray_param, N)); KSG_CUDA(dmalloc(&h->ray_flags, N)); KSG_CUDA(dmalloc(&h->nsteps, N));
   long long rec_cap = cfg->max_updates > 0 ? cfg->max_updates : (fast ? std::max<long long>(4ll << 20, 64ll * (long long)N) : (64ll << 20));
   if (fast) {
-    KSG_CUDA(dmalloc(&h->start_head, kSetSize)); KSG_CUDA(dmalloc(&h->start_next, N)); KSG_CUDA(dmalloc(&h->start_table, kSetSize));
-    KSG_CUDA(dmalloc(&h->start_min, kSetSize)); KSG_CUDA(dmalloc(&h->start_max, kSetSize)); KSG_CUDA(dmalloc(&h->start_val, kSetSize));
-    KSG_CUDA(dmalloc(&h->start_mixed, kSetSize));
+    KSG_CUDA(dmalloc(&h->start_next, N)); KSG_CUDA(dmalloc(&h->start_table, kSetSize));
+    // per-frame cleared arrays live in two contiguous regions: [0xFF: start_head | start_max | start_val | ob.head] and
+    // [0x00: ob.slot_cnt | start_mixed], so that a frame needs three memsets instead of seven
+    KSG_CUDA(cudaMalloc((void**)&h->clear_ff, (size_t)kSetSize * 16));
+    KSG_CUDA(cudaMalloc((void**)&h->clear_00, (size_t)kSetSize * 5));
+    h->start_head = (int*)h->clear_ff; h->start_max = h->start_head + kSetSize; h->start_val = (uint32_t*)(h->start_max + kSetSize);
+    h->start_mixed = h->clear_00 + (size_t)kSetSize * 4;
+    KSG_CUDA(dmalloc(&h->start_min, kSetSize));
     KSG_CUDA(dmalloc(&h->cast_seq, N));
     KSG_CUDA(dmalloc(&h->ray_label, N)); KSG_CUDA(dmalloc(&h->ray_color, N)); KSG_CUDA(dmalloc(&h->trunc_flag, N));
     KSG_CUDA(dmalloc(&h->H, N)); KSG_CUDA(dmalloc(&h->L, N)); KSG_CUDA(dmalloc(&h->ray_state, N)); KSG_CUDA(dmalloc(&h->ext_off, N * kExtSegs));
@@ -687,8 +686,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     if (h->ob.cand_cap >= 0x7FFFFFFFll) { h->ob.cand_cap = 0x7FFFFFFEll; }
     KSG_CUDA(dmalloc(&h->ob.cand_val, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_order, (size_t)h->ob.cand_cap));
     KSG_CUDA(dmalloc(&h->ob.cand_next, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_pos, (size_t)h->ob.cand_cap));
-    KSG_CUDA(dmalloc(&h->ob.slot_cnt, kSetSize)); KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));
-    KSG_CUDA(dmalloc(&h->ob.head, kSetSize)); KSG_CUDA(dmalloc(&h->ob.table, kSetSize));
+    h->ob.slot_cnt = (int*)h->clear_00; KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));
+    h->ob.head = (int*)(h->clear_ff + (size_t)kSetSize * 12); KSG_CUDA(dmalloc(&h->ob.table, kSetSize));
   } else {
     KSG_CUDA(dmalloc(&h->ks_sorted, N)); KSG_CUDA(dmalloc(&h->seq_sorted, N));
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));

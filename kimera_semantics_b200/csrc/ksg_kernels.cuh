@@ -52,6 +52,8 @@ struct Counters {
   int pool_count;    // blocks allocated in the pool (persistent across frames)
   int tile_cursor;   // dynamic tile queue of k_tile_apply
   int n_big_tiles;   // tiles with many records are queued first (front of tile_begin; the others fill it from the back)
+  int n_small_tiles;
+  int pad1;
   // observed-set solver, indexed by (sweep & 3)
   int changed[4];
   int n_truncated[4];
@@ -95,7 +97,7 @@ __device__ __forceinline__ void warp_add(unsigned long long* counter, unsigned l
 // ---------------------------------------------------------------------------------------------
 __global__ void k_frame_reset(Counters* c, int n_points) {
   c->n_points = n_points; c->n_valid = 0; c->n_cast = 0;
-  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0; c->tile_cursor = 0; c->n_big_tiles = 0;
+  c->n_new_blocks = 0; c->n_tiles = 0; c->n_blocks_touched = 0; c->tile_cursor = 0; c->n_big_tiles = 0; c->n_small_tiles = 0;
   for (int i = 0; i < 4; ++i) { c->changed[i] = 0; c->n_truncated[i] = 0; c->sum_updates[i] = 0; }
   c->n_records = 0; c->n_skipped = 0; c->n_cand_ext = 0; c->ray_steps = 0;
 }
@@ -779,13 +781,18 @@ __global__ void k_block_assign(Counters* cnt, MapRef map) {
   map.slot_key[slot] = map.ht_keys[pos];
 }
 // SemanticVoxel / TsdfVoxel default construction (semantic_voxel.h:14-27; TsdfVoxel A.0)
-__global__ void k_block_init(DevCfg cfg, const Counters* cnt, MapRef map) {
+__global__ void k_block_init(DevCfg cfg, Counters* cnt, MapRef map) {
   const int n_new = cnt->n_new_blocks < map.new_cap ? cnt->n_new_blocks : map.new_cap;
   const int per_block = cfg.tiles_per_block;
   for (long long w = blockIdx.x; w < (long long)n_new * per_block; w += gridDim.x) {
     const int i = (int)(w / per_block), tile = (int)(w % per_block);
     const int slot = cnt->pool_count + i;
-    if (slot >= map.max_blocks) continue;
+    if (slot >= map.max_blocks) { if (tile == 0 && threadIdx.x == 0) set_err(cnt, 3); continue; }
+    if (tile == 0 && threadIdx.x == 0) {   // k_block_assign: hash entry -> pool slot
+      const int pos = map.new_list[i];
+      map.ht_slot[pos] = slot;
+      map.slot_key[slot] = map.ht_keys[pos];
+    }
     uint8_t* chunk = map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
     float* dist = (float*)chunk;
     float* wgt = (float*)(chunk + cfg.plane_f32);
@@ -824,7 +831,7 @@ __global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64
   atomicAdd(&cnt->n_tiles, 1);
   if (big) { const int j = atomicAdd(&cnt->n_big_tiles, 1); if (j < tile_cap) tile_begin[j] = i; }
   else {
-    const int j = atomicAdd(&cnt->tile_cursor, 1);   // borrowed as the small-tile counter; reset by k_tile_queue_reset
+    const int j = atomicAdd(&cnt->n_small_tiles, 1);
     if (j < tile_cap) tile_begin[tile_cap - 1 - j] = i;
   }
   if (cnt->n_tiles > tile_cap) set_err(cnt, 4);
@@ -832,7 +839,6 @@ __global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64
   const int old = atomicExch(&map.touched_stamp[pos], stamp);
   if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
 }
-__global__ void k_tile_queue_reset(Counters* cnt) { cnt->tile_cursor = 0; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
