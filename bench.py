@@ -142,6 +142,26 @@ def best_thread_count(workload, frames, cam):
     return best, res
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tile-apply kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/r01/prof_apply_<workload>.raw.csv); None when there is none."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01", f"prof_apply_{workload}.raw.csv")
+    if not os.path.exists(path):
+        return None
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[-1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(vals[i].replace(",", "")) * scale.get(units[i], 1.0)
+        return tot
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -338,7 +358,8 @@ def main():
             "gpu_launches": int(launches),
             "library_calls": int(libcalls),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "kernel": "k_tile_apply", "peak_kind": peak_kind,
+                         "traffic": ncu_traffic(args.workload), "traffic_source": "profiles/r01/prof_apply_%s.raw.csv (ncu --set full, one launch)" % args.workload,
+                         "kernel": "k_tile_apply", "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": apply_ms,
                          "phase_ms_per_frame": {k: prof[k] / max(1, prof["frames"]) for k in Integrator.PHASES}},
             "cpu_baseline": cpu,
