@@ -116,7 +116,8 @@ struct ksg_integrator {
   int exp_slots_cap = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
-  int sweeps_per_sync = 2;
+  int sweeps_per_sync = 1;
+  int first_batch = 4;   // sweeps launched before the first read-back (a 640x480 frame needs 6-8)
   int apply_smem = 0;
   int apply_nch = 1;
   int rows_per_sub = 32;
@@ -352,7 +353,8 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     h->sweep_counter = (h->sweep_counter + 4) & ~3;  // counters of the first sweep (index 1) were zeroed by k_frame_reset
     for (;;) {
       int sweep = 0;
-      for (int rep = 0; rep < h->sweeps_per_sync; ++rep) {
+      const int batch = (iterations == 0) ? h->first_batch : h->sweeps_per_sync;
+      for (int rep = 0; rep < batch; ++rep) {
         sweep = ++h->sweep_counter;
         h->n_launches += 1;
         k_eval<<<h->sm_count * 8, 256, 0, s>>>(dc, h->d_cnt, h->set_offset, h->ob, h->nsteps, h->H, h->L, h->ray_state, h->ext_off,
@@ -728,7 +730,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_ATTR(false, 1); KSG_ATTR(false, 2); KSG_ATTR(false, 4); KSG_ATTR(false, 8);
 #undef KSG_ATTR
   }
-  if (const char* e = std::getenv("KSG_SWEEPS_PER_SYNC")) h->sweeps_per_sync = std::max(1, std::min(3, std::atoi(e)));
+  if (const char* e = std::getenv("KSG_SWEEPS_PER_SYNC")) h->sweeps_per_sync = std::max(1, std::min(8, std::atoi(e)));
+  if (const char* e = std::getenv("KSG_FIRST_BATCH")) h->first_batch = std::max(1, std::min(8, std::atoi(e)));
   KSG_CUDA(cudaDeviceSynchronize());
   {
     int r2 = reset_map(h, h->own_stream);
