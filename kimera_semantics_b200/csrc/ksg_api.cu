@@ -117,7 +117,10 @@ struct ksg_integrator {
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
   int sweeps_per_sync = 1;
-  int first_batch = 4;   // sweeps launched before the first read-back (a 640x480 frame needs 6-8)
+  int first_batch = 4;
+  bool persistent_eval = true;
+  unsigned int* d_gridbar = nullptr;
+  int eval_grid = 0;   // sweeps launched before the first read-back (a 640x480 frame needs 6-8)
   int apply_smem = 0;
   int apply_nch = 1;
   int rows_per_sub = 32;
@@ -167,7 +170,7 @@ void free_all(ksg_integrator* h) {
                   h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
-                  h->tmp, h->b_key, h->b_base, h->tile_debug, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tmp, h->b_key, h->b_base, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -351,6 +354,26 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       h->sweep_counter = 0;
     }
     h->sweep_counter = (h->sweep_counter + 4) & ~3;  // counters of the first sweep (index 1) were zeroed by k_frame_reset
+    if (h->persistent_eval) {
+      // one cooperative launch sweeps to convergence on the device (grid barrier between sweeps)
+      const int first_sweep = h->sweep_counter + 1;
+      int max_sweeps = 4096;
+      KSG_CUDA(cudaMemsetAsync(h->d_gridbar, 0, sizeof(unsigned int), s));
+      ++h->n_launches;
+      void* args[] = {(void*)&dc, (void*)&h->d_cnt, (void*)&h->set_offset, (void*)&h->ob, (void*)&h->nsteps, (void*)&h->H, (void*)&h->L,
+                      (void*)&h->ray_state, (void*)&h->ext_off, (void*)&h->eval_sweep, (void*)&first_sweep, (void*)&max_sweeps, (void*)&h->d_gridbar};
+      KSG_CUDA(cudaLaunchCooperativeKernel((const void*)k_eval_persistent, dim3(h->eval_grid), dim3(256), args, 0, s));
+      int rc = fetch_counters(h, s);
+      if (rc) return rc;
+      const int last = h->h_cnt->last_sweep;
+      iterations = last - first_sweep + 1;
+      h->sweep_counter = last;
+      n_cast = std::max(1, h->h_cnt->n_cast);
+      if (!h->h_cnt->err) {
+        if (h->h_cnt->changed[last & 3]) { h->deferred_status = KSG_ERR_CUDA; return fail(KSG_ERR_CUDA, "observed-set solver did not converge within 4096 sweeps"); }
+        n_records = (long long)h->h_cnt->sum_updates[last & 3];
+      }
+    } else
     for (;;) {
       int sweep = 0;
       const int batch = (iterations == 0) ? h->first_batch : h->sweeps_per_sync;
@@ -729,6 +752,16 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_ATTR(true, 1); KSG_ATTR(true, 2); KSG_ATTR(true, 4); KSG_ATTR(true, 8);
     KSG_ATTR(false, 1); KSG_ATTR(false, 2); KSG_ATTR(false, 4); KSG_ATTR(false, 8);
 #undef KSG_ATTR
+  }
+  if (fast) {
+    KSG_CUDA(dmalloc(&h->d_gridbar, 1));
+    int per_sm = 0;
+    KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_eval_persistent, 256, 0));
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    h->eval_grid = h->sm_count * std::max(1, std::min(per_sm, 4));
+    h->persistent_eval = coop != 0 && per_sm > 0;
+    if (const char* e = std::getenv("KSG_PERSISTENT_EVAL")) h->persistent_eval = h->persistent_eval && std::atoi(e) != 0;
   }
   if (const char* e = std::getenv("KSG_SWEEPS_PER_SYNC")) h->sweeps_per_sync = std::max(1, std::min(8, std::atoi(e)));
   if (const char* e = std::getenv("KSG_FIRST_BATCH")) h->first_batch = std::max(1, std::min(8, std::atoi(e)));

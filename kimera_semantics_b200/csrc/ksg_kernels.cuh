@@ -53,7 +53,7 @@ struct Counters {
   int tile_cursor;   // dynamic tile queue of k_tile_apply
   int n_big_tiles;   // tiles with many records are queued first (front of tile_begin; the others fill it from the back)
   int n_small_tiles;
-  int pad1;
+  int last_sweep;    // persistent solver: id of the converged sweep
   // observed-set solver, indexed by (sweep & 3)
   int changed[4];
   int n_truncated[4];
@@ -378,10 +378,10 @@ __device__ __forceinline__ int latest_performed_before(const ObsBuf& ob, const i
     // overflow list: pushes may run concurrently (k_eval), so links are read through L2 and the walk is bounded
     int guard = total - kBktK + 8;
     for (int e = __ldcg(&ob.head[slot]); e >= 0 && guard-- > 0; e = __ldcg(&ob.cand_next[e])) {
-      const uint64_t eo = ob.cand_order[e];
+      const uint64_t eo = __ldcg(&ob.cand_order[e]);   // other rays' candidates: written during this kernel, bypass L1
       if (eo < my_order && (long long)eo > best) {
         const int er = (int)(eo >> kOrderStepBits), es = (int)(eo & ((1u << kOrderStepBits) - 1));
-        if (es < ((volatile const int*)L)[er]) { best = (long long)eo; best_hi = (int)(ob.cand_val[e] >> kSetBits); }
+        if (es < ((volatile const int*)L)[er]) { best = (long long)eo; best_hi = (int)(__ldcg(&ob.cand_val[e]) >> kSetBits); }
       }
     }
   }
@@ -437,18 +437,19 @@ __global__ void k_ray_setup(DevCfg cfg, Xform T, Counters* cnt, const int* __res
 // [0,16), [16,32), then 32 at a time, aligned with the geometric storage segments.  A ray is evaluated to completion:
 // when it survives everything materialised so far, lane 0 continues the DDA for the next chunk on the spot.
 // A ray is re-evaluated only if a candidate on one of the slots it depends on toggled since its last evaluation.
-__global__ void k_eval(DevCfg cfg, Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
-                       int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, int* __restrict__ eval_sweep, int sweep) {
+__device__ __forceinline__ void eval_sweep_body(const DevCfg& cfg, Counters* cnt, uint64_t obs_offset, const ObsBuf& ob, const int* __restrict__ nsteps,
+                                                int* __restrict__ H, int* L, RayState* __restrict__ state, long long* __restrict__ ext_off,
+                                                int* __restrict__ eval_sweep, int sweep) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int n_cast = cnt->n_cast;
   if (blockIdx.x == 0 && threadIdx.x == 0) { const int nx = (sweep + 1) & 3; cnt->changed[nx] = 0; cnt->sum_updates[nx] = 0; }
   unsigned long long usum = 0;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_cast; r += warps_total) {
-    int h = H[r];
+    int h = __ldcg(&H[r]);
     const int n = nsteps[r];
     const int old = ((volatile int*)L)[r];
-    const int last = eval_sweep[r];
+    const int last = __ldcg(&eval_sweep[r]);
     bool need = last == 0;
     if (!need) {
       const int upto = (old < h - 1) ? old : h - 1;             // steps 0..upto were examined last time
@@ -544,6 +545,41 @@ __global__ void k_eval(DevCfg cfg, Counters* cnt, uint64_t obs_offset, ObsBuf ob
     unsigned long long t = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
     if (t) atomicAdd(&cnt->sum_updates[sweep & 3], t);
+  }
+}
+
+__global__ void k_eval(DevCfg cfg, Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps, int* __restrict__ H,
+                       int* L, RayState* __restrict__ state, long long* __restrict__ ext_off, int* __restrict__ eval_sweep, int sweep) {
+  eval_sweep_body(cfg, cnt, obs_offset, ob, nsteps, H, L, state, ext_off, eval_sweep, sweep);
+}
+
+// Persistent variant (cooperative launch: every CTA is resident): sweeps until no ray changes, with a grid-wide barrier
+// between sweeps, so that the host reads the counters back once per frame.  cnt->last_sweep tells the host which
+// counter slot holds the converged sums.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (((volatile unsigned int*)bar)[0] < target) { __nanosleep(64); }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) k_eval_persistent(DevCfg cfg, Counters* cnt, uint64_t obs_offset, ObsBuf ob, const int* __restrict__ nsteps,
+                                                         int* __restrict__ H, int* L, RayState* __restrict__ state, long long* __restrict__ ext_off,
+                                                         int* __restrict__ eval_sweep, int first_sweep, int max_sweeps, unsigned int* bar) {
+  unsigned int epoch = 0;
+  for (int it = 0; it < max_sweeps; ++it) {
+    const int sweep = first_sweep + it;
+    eval_sweep_body(cfg, cnt, obs_offset, ob, nsteps, H, L, state, ext_off, eval_sweep, sweep);
+    grid_barrier(bar, (++epoch) * gridDim.x);
+    const int changed = ((volatile int*)cnt->changed)[sweep & 3];
+    const int err = ((volatile int*)&cnt->err)[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->last_sweep = sweep;
+    if (!changed || err) break;
+    // every CTA has read `changed` before any CTA of the next sweep's body can zero the slot of sweep + 1 ... which is a
+    // different slot; the slot read here is only re-zeroed three sweeps later, after three more barriers
   }
 }
 
