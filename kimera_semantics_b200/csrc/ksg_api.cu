@@ -760,8 +760,10 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
     h->eval_grid = h->sm_count * std::max(1, std::min(per_sm, 4));
-    h->persistent_eval = coop != 0 && per_sm > 0;
-    if (const char* e = std::getenv("KSG_PERSISTENT_EVAL")) h->persistent_eval = h->persistent_eval && std::atoi(e) != 0;
+    // measured on B200 (profiles/README.md): the persistent solver is ~3 % slower than launch-per-sweep (the sweeps, not the
+    // launches, dominate), so it is opt-in: KSG_PERSISTENT_EVAL=1
+    h->persistent_eval = false;
+    if (const char* e = std::getenv("KSG_PERSISTENT_EVAL")) h->persistent_eval = coop != 0 && per_sm > 0 && std::atoi(e) != 0;
   }
   if (const char* e = std::getenv("KSG_SWEEPS_PER_SYNC")) h->sweeps_per_sync = std::max(1, std::min(8, std::atoi(e)));
   if (const char* e = std::getenv("KSG_FIRST_BATCH")) h->first_batch = std::max(1, std::min(8, std::atoi(e)));
