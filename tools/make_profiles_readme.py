@@ -38,8 +38,9 @@ mutexes, two shared atomic hash sets, thread creation per frame): 128 threads re
 {dm['value']:.1f} frames/s = {dm['mvoxel_updates_per_s']:.0f} Mvoxel-updates/s (e2e {dm['e2e']['value']:.1f}) vs {cm['value']:.2f} frames/s = {cm['mvoxel_updates_per_s']:.0f}
 Mvoxel-updates/s for the CPU port at its best thread count ({cm['cores']}) — `r01/bench_merged2.json`.
 
-2 GPUs (`torchrun --nproc-per-node 2 bench.py --gpus 2`, one stream + map per rank, no data-path collective): 2916 frames/s at
-the time of that run (1458 per GPU, 98 % of the 1-GPU rate measured in the same session).
+Multi-GPU (`torchrun --nproc-per-node N bench.py --gpus N`, one stream + map per rank, no data-path collective, max over ranks):
+N = 2: 2916 frames/s (1458 per GPU); N = 4: 5871 frames/s resident / 5532 end to end (1468 per GPU) — ≈97–98 % of N x the 1-GPU
+rate measured in the same sessions (40 steps each).
 
 ## Where a `fast5` frame goes (CUDA events inside the library, `roofline.phase_ms_per_frame`)
 
