@@ -87,8 +87,13 @@ typedef struct ksg_config {
   int32_t max_points;                  /* largest cloud / frame (pixels) accepted */
   int64_t max_ray_steps;               /* scratch: upper bound on ray-step candidates per frame */
   int64_t max_updates;                 /* scratch: upper bound on voxel updates per frame */
-  int32_t apply_mode;                  /* 0 = TMA-staged tile apply (default), 1 = direct-global apply */
-  int32_t reserved[7];
+  int32_t apply_mode;                  /* 0 = TMA-staged tile apply (default), 1 = cooperative-copy staging */
+  /* spatial hash-block sharding of ONE map over several GPUs: every rank receives every frame and casts every
+   * ray, but applies only the 8^3 tiles it owns (owner = f(block index, tile)); results per voxel are identical to the
+   * unsharded run. shard_count <= 1: off. */
+  int32_t shard_rank;
+  int32_t shard_count;
+  int32_t reserved[5];
 } ksg_config;
 
 /* per-frame counters (the oracle reports the same numbers; SURVEY.md 8d: one voxel update =
@@ -187,6 +192,12 @@ int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int3
 
 /* Remove every block and reset the fast integrator's two approximate sets. */
 int32_t ksg_reset(ksg_integrator* h);
+
+/* Spatial sharding helper (pure function, no device): mask[b*V + lin] = 1 where rank `shard_rank` of `shard_count` owns voxel
+ * `lin` (voxblox linear order) of block b.  The masks of all ranks partition every block; a caller assembles the full map
+ * from the per-rank exports with them. */
+int32_t ksg_owner_mask(int32_t voxels_per_side, int32_t shard_rank, int32_t shard_count, int64_t n,
+                       const int32_t* block_index, uint8_t* mask);
 
 /* Optional per-phase device timing (CUDA events on the launching stream) and kernel-launch counting.
  * Phases: 0 classify+start-set, 1 observed-set fixpoint (fast) / bundling (merged), 2 ray emit,

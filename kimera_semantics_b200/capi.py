@@ -59,7 +59,9 @@ class KsgConfig(C.Structure):
         ("max_ray_steps", C.c_int64),
         ("max_updates", C.c_int64),
         ("apply_mode", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("shard_rank", C.c_int32),
+        ("shard_count", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -131,6 +133,8 @@ def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float
     cfg.max_ray_steps = 0   # 0 = let the library size it from max_points
     cfg.max_updates = 0
     cfg.apply_mode = 0
+    cfg.shard_rank = 0
+    cfg.shard_count = 1
     return cfg
 
 
@@ -196,6 +200,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_get_profile.restype = C.c_int32
     lib.ksg_debug_tile_times.argtypes = [H, C.c_int32, C.c_int64, C.POINTER(C.c_int64)]
     lib.ksg_debug_tile_times.restype = C.c_int64
+    lib.ksg_owner_mask.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, i32p, u8p]
+    lib.ksg_owner_mask.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -206,7 +212,32 @@ def load_library(path: Optional[str] = None):
 KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index",
-               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times"]
+               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask"]
+
+
+def owner_mask(block_index: np.ndarray, vps: int, shard_rank: int, shard_count: int, lib=None) -> np.ndarray:
+    """[nb, vps^3] uint8 mask of the voxels rank `shard_rank` owns (spatial sharding)."""
+    lib = lib or load_library()
+    bi = np.ascontiguousarray(block_index, np.int32)
+    mask = np.zeros((len(bi), vps ** 3), np.uint8)
+    rc = lib.ksg_owner_mask(vps, shard_rank, shard_count, len(bi), _ptr(bi, C.c_int32), _ptr(mask, C.c_uint8))
+    if rc != 0:
+        raise ValueError(f"ksg_owner_mask: {rc}")
+    return mask
+
+
+def merge_shard_exports(exports, vps: int, lib=None) -> Dict[str, np.ndarray]:
+    """Assemble the full map from the per-rank exports of a spatially sharded run (every rank allocates every block)."""
+    G = len(exports)
+    out = {k: v.copy() for k, v in exports[0].items()}
+    for r in range(G):
+        assert np.array_equal(exports[r]["block_index"], exports[0]["block_index"]), "ranks disagree on the block set"
+        m = owner_mask(exports[r]["block_index"], vps, r, G, lib).astype(bool)
+        for k in ("tsdf_distance", "tsdf_weight", "sem_label"):
+            out[k][m] = exports[r][k][m]
+        for k in ("tsdf_rgba", "sem_rgba", "sem_priors"):
+            out[k][m] = exports[r][k][m]
+    return out
 
 
 class KsgError(RuntimeError):

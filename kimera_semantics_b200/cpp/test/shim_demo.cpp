@@ -12,6 +12,7 @@
 #include "kimera_semantics/semantic_tsdf_integrator_factory.h"
 #include "kimera_semantics/semantic_tsdf_integrator_fast.h"
 #include "kimera_semantics/semantic_tsdf_integrator_merged.h"
+#include "kimera_semantics/semantic_tsdf_server.h"
 
 using namespace kimera;
 template <typename T> static T rd(std::ifstream& f) { T v; f.read(reinterpret_cast<char*>(&v), sizeof(T)); return v; }
@@ -32,26 +33,27 @@ int main(int argc, char** argv) {
   for (int i = 0; i < n_dyn; ++i) sc.dynamic_labels_.push_back(rd<uint8_t>(f));
   vxb::TsdfIntegratorBase::Config config;
   config.default_truncation_distance = 4.0f * voxel_size;  // voxblox_ros
-  vxb::Layer<vxb::TsdfVoxel> tsdf_layer(voxel_size, vps);
-  vxb::Layer<SemanticVoxel> semantic_layer(voxel_size, vps);
-  std::unique_ptr<vxb::TsdfIntegratorBase> integrator =
-      SemanticTsdfIntegratorFactory::create(std::string(argv[1]), config, sc, &tsdf_layer, &semantic_layer);
   const bool lazy = argc > 4 && std::strcmp(argv[4], "lazy") == 0;
-  GpuIntegratorCore* core = nullptr;
-  if (auto* p = dynamic_cast<FastSemanticTsdfIntegrator*>(integrator.get())) core = &p->gpu();
-  if (auto* p = dynamic_cast<MergedSemanticTsdfIntegrator*>(integrator.get())) core = &p->gpu();
-  if (lazy) core->setLayerSyncMode(LayerSyncMode::kLazy);
+  SemanticTsdfServer::Params params;
+  params.tsdf_voxel_size = voxel_size;
+  params.tsdf_voxels_per_side = vps;
+  params.method = argv[1];
+  params.layer_sync = lazy ? LayerSyncMode::kLazy : LayerSyncMode::kEager;
+  SemanticTsdfServer server(params, config, sc);   // builds both layers + SemanticTsdfIntegratorFactory::create(method, ...)
+  vxb::Layer<vxb::TsdfVoxel>& tsdf_layer = *server.getTsdfLayerPtr();
+  vxb::Layer<SemanticVoxel>& semantic_layer = *server.getSemanticLayerPtr();
+  GpuIntegratorCore* core = &server.gpu();
   for (int fr = 0; fr < n_frames; ++fr) {
     const int n = rd<int32_t>(f);
     float T[7]; f.read(reinterpret_cast<char*>(T), sizeof(T));
     vxb::Pointcloud pts(n); vxb::Colors cols(n);
     f.read(reinterpret_cast<char*>(pts.data()), sizeof(float) * 3 * n);
     f.read(reinterpret_cast<char*>(cols.data()), 4 * (size_t)n);
-    integrator->integratePointCloud(vxb::Transformation(T[0], T[1], T[2], T[3], vxb::Point(T[4], T[5], T[6])), pts, cols, false);
+    server.processPointCloud(vxb::Transformation(T[0], T[1], T[2], T[3], vxb::Point(T[4], T[5], T[6])), pts, cols, /*stamp=*/0.2 * fr);
     std::printf("frame %d: %d points, %lld voxel updates, %zu blocks in the host layer\n", fr, n, (long long)core->lastVoxelUpdates(),
                 tsdf_layer.getNumberOfAllocatedBlocks());
   }
-  if (lazy) core->syncLayers();
+  if (lazy) server.updateLayers();
   vxb::BlockIndexList blocks;
   tsdf_layer.getAllAllocatedBlocks(&blocks);
   std::sort(blocks.begin(), blocks.end(), [](const vxb::BlockIndex& a, const vxb::BlockIndex& b) {

@@ -78,7 +78,7 @@ struct ksg_integrator {
   int64_t reset_counter = 0;
   int* cast_seq = nullptr;
   float4* ray_param = nullptr;
-  uint8_t *ray_label = nullptr, *ray_flags = nullptr, *trunc_flag = nullptr;
+  uint8_t *ray_label = nullptr, *ray_flags = nullptr;
   uint32_t* ray_color = nullptr;
   int *nsteps = nullptr, *H = nullptr, *L = nullptr;
   RayState* ray_state = nullptr;
@@ -123,7 +123,6 @@ struct ksg_integrator {
   int eval_grid = 0;   // sweeps launched before the first read-back (a 640x480 frame needs 6-8)
   int apply_smem = 0;
   int apply_nch = 1;
-  int rows_per_sub = 32;
   bool use_tma = true;
 
   // profiling
@@ -155,6 +154,8 @@ int validate(const ksg_config* c, std::string& why) {
   if (c->color_mode < 0 || c->color_mode > 2) { why = "Unknown semantic color mode (base.cpp:186-190)"; return KSG_ERR_INVALID_ARGUMENT; }
   if (c->max_points <= 0 || c->max_points > (1 << kRecOrdBits)) { why = "max_points must be in (0, 2^23]"; return KSG_ERR_INVALID_ARGUMENT; }
   if (c->max_blocks <= 0) { why = "max_blocks must be positive"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->shard_count < 0 || (c->shard_count > 1 && (c->shard_rank < 0 || c->shard_rank >= c->shard_count))) {
+    why = "shard_rank must be in [0, shard_count)"; return KSG_ERR_INVALID_ARGUMENT; }
   if (c->max_consecutive_ray_collisions < 0) { why = "max_consecutive_ray_collisions < 0"; return KSG_ERR_INVALID_ARGUMENT; }
   return KSG_OK;
 }
@@ -167,7 +168,7 @@ void free_all(ksg_integrator* h) {
   void* ptrs[] = {h->map.ht_keys, h->map.ht_slot, h->map.new_list, h->map.pool, h->map.slot_key, h->map.touched_stamp,
                   h->map.touched_list, h->d_luts, h->d_cnt, h->pt_pC, h->pt_pG, h->pt_label, h->pt_flags, h->pt_color, h->pt_key,
                   h->flags8, h->is_last, h->pix_list, h->point_of_seq, h->sq_keys, h->sq_keys_out, h->iota,
-                  h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags, h->trunc_flag,
+                  h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
@@ -179,8 +180,6 @@ void free_all(ksg_integrator* h) {
 }
 
 __global__ void k_iota(uint32_t* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
-__global__ void k_fill_u32(uint32_t* p, long long n, uint32_t v) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
-__global__ void k_fill_u64(uint64_t* p, long long n, uint64_t v) { const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // "sorted" integration order (voxblox SortedThreadSafeIndex, A.3): key = squared norm of the point
 __global__ void k_sqnorm(FrameIn in, const Counters* cnt, int capacity, uint32_t* keys) {
@@ -469,7 +468,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     ++h->n_launches;
 #define KSG_LAUNCH_APPLY_(TMA, NCH, MRG)                                                                                 \
     k_tile_apply<TMA, NCH, MRG><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
-                                                                      n_records, h->tile_begin, h->tile_cap, src, h->rows_per_sub, h->tile_debug)
+                                                                      n_records, h->tile_begin, h->tile_cap, src, h->tile_debug)
 #define KSG_LAUNCH_APPLY(TMA, NCH) do { if (fast) { KSG_LAUNCH_APPLY_(TMA, NCH, false); } else { KSG_LAUNCH_APPLY_(TMA, NCH, true); } } while (0)
     if (h->use_tma) {
       switch (h->apply_nch) { case 1: KSG_LAUNCH_APPLY(true, 1); break; case 2: KSG_LAUNCH_APPLY(true, 2); break;
@@ -579,6 +578,8 @@ void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size
   c->max_ray_steps = 0;
   c->max_updates = 0;
   c->apply_mode = 0;
+  c->shard_rank = 0;
+  c->shard_count = 1;
 }
 
 #define KSG_STR_(x) #x
@@ -647,6 +648,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   dc.ln = std::log(1.0f - cfg->semantic_measurement_probability);
   dc.color_mode = cfg->color_mode;
   dc.type = cfg->integrator_type;
+  dc.shard_rank = cfg->shard_rank;
+  dc.shard_count = cfg->shard_count > 1 ? cfg->shard_count : 1;
 
   // ---- look-up tables
   for (int l = 0; l < 256; ++l) {
@@ -702,7 +705,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     h->start_mixed = h->clear_00 + (size_t)kSetSize * 4;
     KSG_CUDA(dmalloc(&h->start_min, kSetSize));
     KSG_CUDA(dmalloc(&h->cast_seq, N));
-    KSG_CUDA(dmalloc(&h->ray_label, N)); KSG_CUDA(dmalloc(&h->ray_color, N)); KSG_CUDA(dmalloc(&h->trunc_flag, N));
+    KSG_CUDA(dmalloc(&h->ray_label, N)); KSG_CUDA(dmalloc(&h->ray_color, N));
     KSG_CUDA(dmalloc(&h->H, N)); KSG_CUDA(dmalloc(&h->L, N)); KSG_CUDA(dmalloc(&h->ray_state, N)); KSG_CUDA(dmalloc(&h->ext_off, N * kExtSegs));
     KSG_CUDA(dmalloc(&h->eval_sweep, N)); KSG_CUDA(dmalloc(&h->ob.slot_stamp, kSetSize));
     long long ext = cfg->max_ray_steps > 0 ? cfg->max_ray_steps : std::max<long long>(16ll << 20, 64ll * (long long)N);
@@ -740,10 +743,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   {
     const int V = dc.tile_voxels;
     const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
-    const bool fast_cfg = cfg->integrator_type == KSG_INTEGRATOR_FAST;
-    h->rows_per_sub = std::max(1, std::min(32, kRowBufFloats / dc.C));
     h->apply_smem = (int)(stage + (size_t)V * 8 + 64);
-    (void)fast_cfg;
     h->apply_nch = dc.C <= 32 ? 1 : (dc.C <= 64 ? 2 : (dc.C <= 128 ? 4 : 8));
     h->use_tma = cfg->apply_mode == 0;
 #define KSG_ATTR(TMA, NCH) \
@@ -1013,6 +1013,27 @@ int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int3
     block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
   }
   return n;
+}
+
+int32_t ksg_owner_mask(int32_t voxels_per_side, int32_t shard_rank, int32_t shard_count, int64_t n, const int32_t* block_index,
+                       uint8_t* mask) {
+  const int vps = voxels_per_side;
+  if (vps <= 0 || (vps & (vps - 1)) || n < 0 || (n > 0 && (!block_index || !mask))) return KSG_ERR_INVALID_ARGUMENT;
+  const int count = shard_count > 1 ? shard_count : 1;
+  if (shard_rank < 0 || shard_rank >= count) return KSG_ERR_INVALID_ARGUMENT;
+  const int T = std::min(vps, kTileSideMax), tps = vps / T;
+  const size_t V = (size_t)vps * vps * vps;
+  for (int64_t b = 0; b < n; ++b) {
+    I3 bi; bi.x = block_index[3 * b]; bi.y = block_index[3 * b + 1]; bi.z = block_index[3 * b + 2];
+    const uint64_t key = pack_key(bi);
+    for (int z = 0; z < vps; ++z)
+      for (int y = 0; y < vps; ++y)
+        for (int x = 0; x < vps; ++x) {
+          const int tile = (x / T) + tps * ((y / T) + tps * (z / T));
+          mask[b * V + (size_t)x + (size_t)vps * ((size_t)y + (size_t)vps * z)] = tile_owner(key, tile, count) == shard_rank ? 1 : 0;
+        }
+  }
+  return KSG_OK;
 }
 
 int32_t ksg_set_profiling(ksg_integrator* h, int32_t enable) {

@@ -271,6 +271,12 @@ __host__ __device__ __forceinline__ uint32_t mix64(uint64_t k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (uint32_t)k;
 }
+// Spatial sharding: every 8^3 tile of the map has exactly one owner among `count` ranks. The owner is a
+// function of the block index and the tile position only, so every rank computes the same partition.
+__host__ __device__ __forceinline__ int tile_owner(uint64_t block_key, int tile, int count) {
+  if (count <= 1) return 0;
+  return (int)(mix64(block_key * 0x9E3779B97F4A7C15ull + (uint64_t)tile + 1ull) % (uint32_t)count);
+}
 // voxblox getBlockIndexFromGlobalVoxelIndex: floor(float(g) * vps_inv) (A.2)
 __host__ __device__ __forceinline__ I3 block_of_voxel(I3 g, float vps_inv) {
   I3 b;

@@ -7,7 +7,7 @@
 //                                         (asynchronous fixpoint over per-slot visit lists)
 //   k_bundle_heads / k_bundle_merge / k_bundle_loglik [K2] merged: bundleRays + integrateVoxel merge loop
 //   k_emit_fast / k_emit_merged     [K4]  ray cast -> update records + block-hash insertion [K5]
-//   k_block_assign / k_block_init   [K5]  pool allocation of new voxel blocks
+//   k_block_init                    [K5]  pool allocation + default construction of new voxel blocks
 //   k_tile_heads / k_tile_apply     [K6]  per-tile ordered TSDF + semantic update, TMA-staged
 //   k_export                        [K8]  tiles -> voxblox block layout
 #pragma once
@@ -32,6 +32,7 @@ struct DevCfg {
   float lm, ln;
   int color_mode;
   int type;
+  int shard_rank, shard_count;   // spatial sharding: this rank applies only the tiles it owns
 };
 
 struct Luts {
@@ -617,7 +618,7 @@ __global__ void k_obs_commit(Counters* cnt, ObsBuf ob, const int* __restrict__ L
 // ---------------------------------------------------------------------------------------------
 struct MapRef {
   uint64_t* ht_keys;
-  int* ht_slot;          // pool slot of the entry, -1 until k_block_assign ran
+  int* ht_slot;          // pool slot of the entry, -1 until k_block_init ran
   uint32_t ht_mask;
   int* new_list;         // hash positions inserted this frame
   int new_cap;
@@ -806,16 +807,6 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
 // ---------------------------------------------------------------------------------------------
 // block pool
 // ---------------------------------------------------------------------------------------------
-__global__ void k_block_assign(Counters* cnt, MapRef map) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_new = cnt->n_new_blocks < map.new_cap ? cnt->n_new_blocks : map.new_cap;
-  if (i >= n_new) return;
-  const int slot = cnt->pool_count + i;
-  const int pos = map.new_list[i];
-  if (slot >= map.max_blocks) { set_err(cnt, 3); return; }
-  map.ht_slot[pos] = slot;
-  map.slot_key[slot] = map.ht_keys[pos];
-}
 // SemanticVoxel / TsdfVoxel default construction (semantic_voxel.h:14-27; TsdfVoxel A.0)
 __global__ void k_block_init(DevCfg cfg, Counters* cnt, MapRef map) {
   const int n_new = cnt->n_new_blocks < map.new_cap ? cnt->n_new_blocks : map.new_cap;
@@ -861,6 +852,12 @@ __global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64
   if (k == ~0ull) return;
   const uint32_t tk = (uint32_t)(k >> 32);
   if (i > 0 && (uint32_t)(rec[i - 1] >> 32) == tk) return;
+  const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
+  {   // updated() bookkeeping is replicated on every shard
+    const int old = atomicExch(&map.touched_stamp[pos], stamp);
+    if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
+  }
+  if (cfg.shard_count > 1 && tile_owner(map.ht_keys[pos], (int)(tk % (uint32_t)cfg.tiles_per_block), cfg.shard_count) != cfg.shard_rank) return;
   // does the tile hold more than kBigTileRecords records? (longest-processing-time-first scheduling)
   const long long probe = i + kBigTileRecords;
   const bool big = probe < n && (uint32_t)(rec[probe] >> 32) == tk;
@@ -871,9 +868,6 @@ __global__ void k_tile_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64
     if (j < tile_cap) tile_begin[tile_cap - 1 - j] = i;
   }
   if (cnt->n_tiles > tile_cap) set_err(cnt, 4);
-  const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
-  const int old = atomicExch(&map.touched_stamp[pos], stamp);
-  if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -912,7 +906,6 @@ struct ApplySrc {
 };
 
 static constexpr int kApplyThreads = 256;
-static constexpr int kRowBufFloats = 1024;   // per-warp row staging buffer (4 KB)
 
 
 // TSDF recurrence of one batch (<= 32 records, lane j holds record j's sdf / weight / colour) in record order (A.6).
@@ -983,7 +976,7 @@ template <bool USE_TMA, int NCH, bool MERGED>
 __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
-                                                               long long tile_cap, ApplySrc src, int rows_per_sub,
+                                                               long long tile_cap, ApplySrc src,
                                                                long long* __restrict__ tile_debug) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int V = cfg.tile_voxels;
@@ -999,7 +992,6 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
   int* s_seg_lo = (int*)aux;                 // [V]
   int* s_seg_hi = s_seg_lo + V;              // [V]
   uint64_t* s_bar = (uint64_t*)(s_seg_hi + V + (V & 1));
-  float* s_rows = (float*)(s_bar + 2) + (size_t)(threadIdx.x >> 5) * kRowBufFloats;   // per-warp staging of L*freq rows (merged)
   __shared__ long long s_begin, s_end;
   __shared__ uint8_t* s_chunk;
   __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor;

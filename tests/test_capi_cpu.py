@@ -111,3 +111,28 @@ def test_null_handles_are_rejected(lib):
 def test_missing_library_is_an_error_not_a_fallback(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         load_library(str(tmp_path / "libksg_missing.so"))
+
+
+def test_owner_masks_partition_every_block(lib):
+    """Spatial sharding: the per-rank ownership masks are disjoint, cover every voxel, are constant per 8^3 tile
+    and depend only on (block index, tile) - every rank computes the same partition without communication."""
+    from kimera_semantics_b200.capi import owner_mask
+    rng = np.random.default_rng(3)
+    bi = rng.integers(-50, 50, size=(40, 3)).astype(np.int32)
+    for vps in (4, 8, 16, 32):
+        for G in (1, 2, 3, 8):
+            masks = [owner_mask(bi, vps, r, G, lib) for r in range(G)]
+            total = np.sum(masks, axis=0)
+            assert (total == 1).all()
+            T = min(vps, 8)
+            m0 = masks[0].reshape(len(bi), vps, vps, vps)      # [b, z, y, x]
+            tiles = m0.reshape(len(bi), vps // T, T, vps // T, T, vps // T, T)
+            assert (tiles.min(axis=(2, 4, 6)) == tiles.max(axis=(2, 4, 6))).all()
+            if G > 1 and vps >= 16:
+                share = np.array([m.mean() for m in masks])
+                assert share.min() > 0.5 / G               # no rank is starved
+    assert lib.ksg_owner_mask(12, 0, 2, 0, None, None) == 1   # vps must be a power of two
+    cfg = default_config()
+    cfg.shard_count, cfg.shard_rank = 2, 2
+    h = C.c_void_p()
+    assert lib.ksg_create(C.byref(cfg), C.byref(h)) == 1 and b"shard_rank" in lib.ksg_last_error(None)

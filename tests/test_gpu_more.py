@@ -146,3 +146,32 @@ def test_config3_1280x720_5cm_c150_one_frame():
             ok, why = stats_equal(sg, so)
             assert ok, why
         assert_parity(compare_maps(gpu.export(), ora.export()))
+
+
+# ---- spatial hash-block sharding of one map: shards run one after the other on ONE device here -------------
+@pytest.mark.parametrize("itype,G", [(KSG_INTEGRATOR_FAST, 2), (KSG_INTEGRATOR_FAST, 3), (KSG_INTEGRATOR_MERGED, 2), (KSG_INTEGRATOR_MERGED, 4)])
+def test_spatially_sharded_map_equals_unsharded(itype, G):
+    """Every shard sees every frame and casts every ray but applies only the tiles it owns; assembling the per-shard exports
+    with the ownership masks must give exactly the single-integrator (= oracle) map."""
+    from kimera_semantics_b200.capi import merge_shard_exports
+    C_, w, h = 21, 320, 240
+    cfg = make_config(itype, 0.05, C_, max_points=w * h, max_updates=8 << 20)
+    ora = OracleIntegrator(cfg)
+    shards = []
+    for r in range(G):
+        c = make_config(itype, 0.05, C_, max_points=w * h, max_updates=8 << 20, shard_rank=r, shard_count=G)
+        shards.append(Integrator(c))
+    for cam, depth, label, T in frames(w, h, C_, 3):
+        so = ora.integrate_depth(T, depth, label, cam.K)
+        tiles = 0
+        for s in shards:
+            st = s.integrate_depth(T, depth, label, cam.K)
+            assert st.voxel_updates == so.voxel_updates and st.blocks_allocated == so.blocks_allocated
+            tiles += st.tiles_touched
+        assert tiles > 0
+    merged = merge_shard_exports([s.export() for s in shards], 16)
+    assert_parity(compare_maps(merged, ora.export()))
+    # each shard really skipped work: its own export differs from the full map somewhere
+    assert any((s.export()["tsdf_weight"] != merged["tsdf_weight"]).any() for s in shards)
+    for s in shards:
+        s.close()

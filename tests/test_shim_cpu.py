@@ -59,3 +59,23 @@ def test_shim_library_has_no_cuda_or_oracle_dependency():
     for name in ("SemanticTsdfIntegratorFactory6create", "FastSemanticTsdfIntegrator19integratePointCloud",
                  "MergedSemanticTsdfIntegrator19integratePointCloud", "SemanticLabel2Color25getSemanticLabelFromColor"):
         assert name in syms, name
+
+
+def test_label_colour_csv_loader_follows_reference_semantics(demo, tmp_path):
+    """SemanticLabel2Color(filename): CSV rows name,red,green,blue,alpha,id (same shape as the reference's
+    kimera_semantics_ros/cfg/*.csv); the header row parses to (0,0,0,0) -> 0 through atoi, later rows overwrite earlier ones,
+    label 0 is forced to white and white to label 0 (color.cpp:42-67); lookup misses fall back to label 0 / colour (0,0,0,0)."""
+    csv = tmp_path / "simulation.csv"
+    csv.write_text("name,red,green,blue,alpha,id\nCube,255,0,127,255,0\nSphere,255,0,0,255,1\nPlane,0,255,0,255,2\nPlane,255,20,127,255,3\n")
+    out = subprocess.run([os.path.join(CPP, "color_csv_test"), str(csv)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "label 0 -> 255 255 255 255"          # forced white (color.cpp:64-65)
+    assert lines[1] == "label 1 -> 255 0 0 255" and lines[2] == "label 2 -> 0 255 0 255" and lines[3] == "label 3 -> 255 20 127 255"
+    assert lines[4] == "label 4 -> 0 0 0 0"                  # unknown label -> HashableColor() (color.cpp:92)
+    assert "color 255 0 127 255 -> 0" in lines and "color 255 0 0 255 -> 1" in lines and "color 255 20 127 255 -> 3" in lines
+    assert "color 255 255 255 255 -> 0" in lines and "color 0 0 0 0 -> 0" in lines and "color 1 2 3 255 -> 0" in lines
+    bad = tmp_path / "bad.csv"
+    bad.write_text("name,red,green\nA,1,2\n")
+    r = subprocess.run([os.path.join(CPP, "color_csv_test"), str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "Row 1 is invalid" in r.stderr      # CHECK_EQ(loop->size(), 6) color.cpp:51
