@@ -186,6 +186,14 @@ int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* b
 int32_t ksg_export_blocks_by_index(ksg_integrator* h, int64_t n, const int32_t* block_index, uint8_t* found,
                                    float* tsdf_distance, float* tsdf_weight, uint8_t* tsdf_rgba,
                                    uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba);
+/* Inverse of ksg_export_blocks_by_index: writes n blocks (same layouts) into the device map, allocating the blocks that do not
+ * exist yet (a NULL array leaves that field untouched / default-constructed for new blocks).  Restores a saved map the way the
+ * reference reloads a TSDF layer (kimera_semantics_ros/src/semantic_simulation_server.cpp:57-88); SURVEY.md 8f NEXT-3.  The
+ * fast integrator's two approximate sets are not part of a map and start empty, exactly as in a freshly constructed reference
+ * integrator. */
+int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_index, const float* tsdf_distance,
+                          const float* tsdf_weight, const uint8_t* tsdf_rgba, const uint8_t* sem_label,
+                          const float* sem_priors, const uint8_t* sem_rgba);
 /* Indices (nb*3 int32, sorted as above) of the blocks updated by the most recent integrate call:
  * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);

@@ -190,6 +190,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_export_blocks.restype = C.c_int32
     lib.ksg_export_blocks_by_index.argtypes = [H, C.c_int64, i32p, u8p, fp, fp, u8p, u8p, fp, u8p]
     lib.ksg_export_blocks_by_index.restype = C.c_int32
+    lib.ksg_import_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
+    lib.ksg_import_blocks.restype = C.c_int32
     lib.ksg_last_updated_blocks.argtypes = [H, C.c_int64, i32p]
     lib.ksg_last_updated_blocks.restype = C.c_int64
     lib.ksg_reset.argtypes = [H]
@@ -211,7 +213,7 @@ def load_library(path: Optional[str] = None):
 
 KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
-               "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index",
+               "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask"]
 
 
@@ -370,6 +372,14 @@ class Integrator:
 
     def export(self) -> Dict[str, np.ndarray]:
         return export_arrays(self.lib, self.handle, "ksg", self.cfg.voxels_per_side, self.cfg.num_labels)
+
+    def import_blocks(self, exp: Dict[str, np.ndarray]):
+        """Write an export (dict as returned by export()) into this integrator's map."""
+        a = {k: np.ascontiguousarray(v) for k, v in exp.items()}
+        self._check(self.lib.ksg_import_blocks(self.handle, len(a["block_index"]), _ptr(a["block_index"].astype(np.int32), C.c_int32),
+                                               _ptr(a["tsdf_distance"], C.c_float), _ptr(a["tsdf_weight"], C.c_float),
+                                               _ptr(a["tsdf_rgba"], C.c_uint8), _ptr(a["sem_label"], C.c_uint8),
+                                               _ptr(a["sem_priors"], C.c_float), _ptr(a["sem_rgba"], C.c_uint8)), "ksg_import_blocks")
 
     def last_updated_blocks(self) -> np.ndarray:
         n = int(self.lib.ksg_last_updated_blocks(self.handle, 0, None))

@@ -995,6 +995,91 @@ int32_t ksg_export_blocks_by_index(ksg_integrator* h, int64_t n, const int32_t* 
   return KSG_OK;
 }
 
+int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_index, const float* tsdf_distance, const float* tsdf_weight,
+                          const uint8_t* tsdf_rgba, const uint8_t* sem_label, const float* sem_priors, const uint8_t* sem_rgba) {
+  if (!h || n < 0 || (n > 0 && !block_index)) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
+  if (n == 0) return KSG_OK;
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  const DevCfg& dc = h->dc;
+  // host mirror of the block hash: look up / insert exactly as the device does (linear probing from mix64(key))
+  std::vector<uint64_t> keys((size_t)h->ht_cap);
+  std::vector<int> slot_of((size_t)h->ht_cap);
+  KSG_CUDA(cudaMemcpy(keys.data(), h->map.ht_keys, sizeof(uint64_t) * h->ht_cap, cudaMemcpyDeviceToHost));
+  KSG_CUDA(cudaMemcpy(slot_of.data(), h->map.ht_slot, sizeof(int) * h->ht_cap, cudaMemcpyDeviceToHost));
+  std::vector<int> slots((size_t)n);
+  std::vector<uint8_t> fresh((size_t)n, 0);
+  std::vector<uint64_t> new_keys;
+  int64_t nb = h->num_blocks;
+  for (int64_t i = 0; i < n; ++i) {
+    I3 b; b.x = block_index[3 * i]; b.y = block_index[3 * i + 1]; b.z = block_index[3 * i + 2];
+    if (!key_in_range(b)) return fail(KSG_ERR_INDEX_RANGE, err_text(5));
+    const uint64_t key = pack_key(b);
+    uint32_t pos = mix64(key) & h->map.ht_mask;
+    for (uint32_t probe = 0;; ++probe) {
+      if (probe > h->map.ht_mask) return fail(KSG_ERR_POOL_FULL, err_text(3));
+      if (keys[pos] == key) { slots[i] = slot_of[pos]; break; }
+      if (keys[pos] == kEmptyKey) {
+        if (nb >= h->map.max_blocks) return fail(KSG_ERR_POOL_FULL, err_text(3));
+        keys[pos] = key; slot_of[pos] = (int)nb; slots[i] = (int)nb; fresh[i] = 1; new_keys.push_back(key); ++nb;
+        break;
+      }
+      pos = (pos + 1) & h->map.ht_mask;
+    }
+  }
+  if (!new_keys.empty()) {
+    KSG_CUDA(cudaMemcpy(h->map.ht_keys, keys.data(), sizeof(uint64_t) * h->ht_cap, cudaMemcpyHostToDevice));
+    KSG_CUDA(cudaMemcpy(h->map.ht_slot, slot_of.data(), sizeof(int) * h->ht_cap, cudaMemcpyHostToDevice));
+    KSG_CUDA(cudaMemcpy(h->map.slot_key + h->num_blocks, new_keys.data(), sizeof(uint64_t) * new_keys.size(), cudaMemcpyHostToDevice));
+    const int pc = (int)nb;
+    KSG_CUDA(cudaMemcpy(&h->d_cnt->pool_count, &pc, sizeof(int), cudaMemcpyHostToDevice));
+    h->num_blocks = nb;
+  }
+  const size_t VB = (size_t)dc.vps * dc.vps * dc.vps;
+  const size_t per_block = VB * (4 + 4 + 4 + 1 + 4 + 4 * (size_t)dc.C) + 64;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)((256ull << 20) / per_block)));
+  if (h->exp_slots_cap < batch) {
+    if (h->d_exp_slots) cudaFree(h->d_exp_slots);
+    h->d_exp_slots = nullptr;
+    KSG_CUDA(dmalloc(&h->d_exp_slots, (size_t)batch));
+    h->exp_slots_cap = (int)batch;
+  }
+  const size_t need = (size_t)batch * per_block + (size_t)batch;
+  if (h->d_exp_bytes < need) {
+    if (h->d_exp) cudaFree(h->d_exp);
+    h->d_exp = nullptr;
+    KSG_CUDA(cudaMalloc((void**)&h->d_exp, need));
+    h->d_exp_bytes = need;
+  }
+  for (int64_t b0 = 0; b0 < n; b0 += batch) {
+    const int64_t cnt = std::min(batch, n - b0);
+    KSG_CUDA(cudaMemcpy(h->d_exp_slots, slots.data() + b0, sizeof(int) * cnt, cudaMemcpyHostToDevice));
+    uint8_t* p = h->d_exp;
+    float* i_dist = (float*)p; p += cnt * VB * 4;
+    float* i_wgt = (float*)p; p += cnt * VB * 4;
+    uint32_t* i_rgba = (uint32_t*)p; p += cnt * VB * 4;
+    uint32_t* i_srgba = (uint32_t*)p; p += cnt * VB * 4;
+    float* i_prior = (float*)p; p += cnt * VB * 4 * dc.C;
+    uint8_t* i_label = p; p += cnt * VB;
+    uint8_t* d_fresh = p;
+    if (tsdf_distance) KSG_CUDA(cudaMemcpy(i_dist, tsdf_distance + b0 * VB, cnt * VB * 4, cudaMemcpyHostToDevice));
+    if (tsdf_weight) KSG_CUDA(cudaMemcpy(i_wgt, tsdf_weight + b0 * VB, cnt * VB * 4, cudaMemcpyHostToDevice));
+    if (tsdf_rgba) KSG_CUDA(cudaMemcpy(i_rgba, tsdf_rgba + b0 * VB * 4, cnt * VB * 4, cudaMemcpyHostToDevice));
+    if (sem_rgba) KSG_CUDA(cudaMemcpy(i_srgba, sem_rgba + b0 * VB * 4, cnt * VB * 4, cudaMemcpyHostToDevice));
+    if (sem_label) KSG_CUDA(cudaMemcpy(i_label, sem_label + b0 * VB, cnt * VB, cudaMemcpyHostToDevice));
+    if (sem_priors) KSG_CUDA(cudaMemcpy(i_prior, sem_priors + b0 * VB * dc.C, cnt * VB * 4 * dc.C, cudaMemcpyHostToDevice));
+    KSG_CUDA(cudaMemcpy(d_fresh, fresh.data() + b0, cnt, cudaMemcpyHostToDevice));
+    k_import<<<h->sm_count * 4, 256, 0, h->own_stream>>>(dc, h->map, h->d_exp_slots, d_fresh, (int)cnt, tsdf_distance ? i_dist : nullptr,
+                                                         tsdf_weight ? i_wgt : nullptr, tsdf_rgba ? i_rgba : nullptr,
+                                                         sem_label ? i_label : nullptr, sem_priors ? i_prior : nullptr,
+                                                         sem_rgba ? i_srgba : nullptr);
+    KSG_CUDA(cudaStreamSynchronize(h->own_stream));
+  }
+  return KSG_OK;
+}
+
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index) {
   if (!h) return 0;
   const int64_t n = h->last_blocks_touched;

@@ -1209,6 +1209,43 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
 }
 
 // ---------------------------------------------------------------------------------------------
+// import: voxblox block layout -> tiles (inverse of k_export); `fresh[bi]` = 1: default-construct the block first
+// ---------------------------------------------------------------------------------------------
+__global__ void k_import(DevCfg cfg, MapRef map, const int* __restrict__ slots, const uint8_t* __restrict__ fresh, int nb,
+                         const float* __restrict__ i_dist, const float* __restrict__ i_wgt, const uint32_t* __restrict__ i_rgba,
+                         const uint8_t* __restrict__ i_label, const float* __restrict__ i_prior, const uint32_t* __restrict__ i_srgba) {
+  const int per_block = cfg.tiles_per_block;
+  const int V = cfg.tile_voxels;
+  const size_t VB = (size_t)cfg.vps * cfg.vps * cfg.vps;
+  for (long long w = blockIdx.x; w < (long long)nb * per_block; w += gridDim.x) {
+    const int bi = (int)(w / per_block), tile = (int)(w % per_block);
+    uint8_t* chunk = map.pool + (uint64_t)slots[bi] * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
+    float* dist = (float*)chunk;
+    float* wgt = (float*)(chunk + cfg.plane_f32);
+    uint32_t* rgba = (uint32_t*)(chunk + 2 * cfg.plane_f32);
+    uint32_t* srgba = (uint32_t*)(chunk + 3 * cfg.plane_f32);
+    uint8_t* label = chunk + 4 * cfg.plane_f32;
+    float* prior = (float*)(chunk + cfg.head_bytes);
+    const int tps = cfg.tiles_per_side, ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+    const int tx = tile % tps, ty = (tile / tps) % tps, tz = tile / (tps * tps);
+    const bool fr = fresh[bi] != 0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const int lx = tx * cfg.tile_side + (v & tm), ly = ty * cfg.tile_side + ((v >> ts) & tm), lz = tz * cfg.tile_side + (v >> (2 * ts));
+      const size_t lin = (size_t)bi * VB + (size_t)lx + (size_t)cfg.vps * ((size_t)ly + (size_t)cfg.vps * lz);
+      if (i_dist) dist[v] = i_dist[lin]; else if (fr) dist[v] = 0.0f;
+      if (i_wgt) wgt[v] = i_wgt[lin]; else if (fr) wgt[v] = 0.0f;
+      if (i_rgba) rgba[v] = i_rgba[lin]; else if (fr) rgba[v] = 0u;
+      if (i_srgba) srgba[v] = i_srgba[lin]; else if (fr) srgba[v] = 0xFF7F7F7Fu;
+      if (i_label) label[v] = i_label[lin]; else if (fr) label[v] = 0;
+      for (int c = 0; c < cfg.C; ++c) {
+        if (i_prior) prior[(size_t)v * cfg.C + c] = i_prior[lin * cfg.C + c];
+        else if (fr) prior[(size_t)v * cfg.C + c] = (float)-0.60205999132;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // export: tiles -> voxblox block layout (linear index x + vps*(y + vps*z))
 // ---------------------------------------------------------------------------------------------
 __global__ void k_export(DevCfg cfg, MapRef map, const int* __restrict__ slots, int nb, float* __restrict__ o_dist,

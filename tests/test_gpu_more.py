@@ -175,3 +175,39 @@ def test_spatially_sharded_map_equals_unsharded(itype, G):
     assert any((s.export()["tsdf_weight"] != merged["tsdf_weight"]).any() for s in shards)
     for s in shards:
         s.close()
+
+
+def test_import_blocks_restores_a_map_and_integration_continues_identically():
+    """ksg_import_blocks (SURVEY.md 8f NEXT-3): export -> import into a fresh integrator -> identical export; for `merged` (no
+    cross-frame state besides the map) integrating further frames into the restored map equals the uninterrupted run."""
+    C_, w, h = 21, 320, 240
+    cfg = make_config(KSG_INTEGRATOR_MERGED, 0.05, C_, max_points=w * h, max_updates=8 << 20)
+    a, ora = Integrator(cfg), OracleIntegrator(cfg)
+    fr = list(frames(w, h, C_, 4))
+    for cam, depth, label, T in fr[:2]:
+        a.integrate_depth(T, depth, label, cam.K)
+        ora.integrate_depth(T, depth, label, cam.K)
+    snap = a.export()
+    b = Integrator(cfg)
+    b.import_blocks(snap)
+    assert b.num_blocks() == a.num_blocks()
+    rep = compare_maps(b.export(), snap)
+    assert rep["same_blocks"] == 1 and rep["tsdf_distance_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0 and rep["label_mismatch"] == 0
+    for cam, depth, label, T in fr[2:]:
+        sb, so = b.integrate_depth(T, depth, label, cam.K), ora.integrate_depth(T, depth, label, cam.K)
+        ok, why = stats_equal(sb, so)
+        assert ok, why
+    assert_parity(compare_maps(b.export(), ora.export()))
+    # partial import: only distances of two blocks, everything else untouched
+    two = {k: v[:2].copy() for k, v in snap.items()}
+    two["tsdf_distance"][:] = 0.125
+    c = Integrator(make_config(KSG_INTEGRATOR_FAST, 0.05, C_, max_points=w * h))
+    c.import_blocks(snap)
+    c._check(c.lib.ksg_import_blocks(c.handle, 2, two["block_index"].ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_int32)),
+                                     two["tsdf_distance"].ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_float)),
+                                     None, None, None, None, None), "partial import")
+    e = c.export()
+    idx = [int(np.where((e["block_index"] == two["block_index"][i]).all(axis=1))[0][0]) for i in range(2)]
+    assert (e["tsdf_distance"][idx] == 0.125).all()
+    mask = np.ones(len(e["block_index"]), bool); mask[idx] = False
+    assert np.array_equal(e["tsdf_distance"][mask], snap["tsdf_distance"][mask]) and np.array_equal(e["tsdf_weight"], snap["tsdf_weight"])
