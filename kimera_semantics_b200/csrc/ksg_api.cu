@@ -424,9 +424,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
                                           &h->d_cnt->n_cast, 2 * cap, s));
     }
     ++h->n_launches;
-    k_bundle_merge<<<grid_for(cap, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, h->seq_sorted, cap,
-                                                      h->pt_pC, h->pt_label, h->hist, h->ray_param, h->ray_flags, h->b_key,
-                                                      h->nsteps, h->b_base, h->rec_cap);
+    k_bundle_merge<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, h->seq_sorted, cap, h->pt_pC,
+                                                   h->pt_label, h->hist, h->ray_param, h->ray_flags, h->b_key, h->nsteps);
+    ++h->n_launches;
+    k_bundle_alloc<<<grid_for(cap, 256), 256, 0, s>>>(h->d_cnt, h->nsteps, h->b_base, h->rec_cap);
     int rc = fetch_counters(h, s);
     if (rc) return rc;
     if (h->profiling) cudaEventRecord(h->ev[2], s);

@@ -704,46 +704,76 @@ __global__ void k_bundle_heads(const uint64_t* __restrict__ ks, const uint32_t* 
   bstart[f] = i;
 }
 
+// One warp per bundle (grid-stride).  The points of a bundle are gathered 32 at a time (lane = point); the weighted-mean
+// recurrence of merged.cpp:271-275 runs over them in sequence order (uniform across lanes, operands by shuffle) because it
+// is order dependent in floating point; the label histogram (merged.cpp:277-279) has lanes = classes.
 __global__ void k_bundle_merge(DevCfg cfg, Xform T, Counters* cnt, const int* __restrict__ bundle_f, const int* __restrict__ bstart,
                                const uint64_t* __restrict__ ks, const uint32_t* __restrict__ seq_sorted, int capacity,
                                const float4* __restrict__ pt_pC, const uint8_t* __restrict__ pt_label, float* __restrict__ hist,
                                float4* __restrict__ b_param, uint8_t* __restrict__ b_flags, uint64_t* __restrict__ b_key,
-                               int* __restrict__ b_nsteps, long long* __restrict__ b_base, long long rec_cap) {
+                               int* __restrict__ b_nsteps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_bundles = cnt->n_cast;
+  const int C = cfg.C;
+  unsigned long long steps = 0;
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_bundles; b += warps_total) {
+    const int f = bundle_f[b];
+    const int i0 = bstart[f];
+    const uint64_t key = ks[i0];
+    const bool clearing = (key >> 63) != 0;
+    float hcount[8];   // classes lane, lane+32, ... (C <= 256)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) hcount[q] = 0.0f;
+    F3 mp = f3(0.0f, 0.0f, 0.0f);
+    float mw = 0.0f;
+    bool done = false;
+    for (int base = i0; !done; base += 32) {
+      const int idx = base + lane;
+      const bool in = idx < capacity && ks[idx] == key;
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      const int nb = (m == 0xffffffffu) ? 32 : (__ffs(~m) - 1);   // the bundle's points are contiguous in the sorted array
+      if (nb < 32) done = true;
+      float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int lab = 0;
+      if (lane < nb) { const uint32_t seq = seq_sorted[idx]; pc = pt_pC[seq]; lab = pt_label[seq]; }
+      for (int jj = 0; jj < nb; ++jj) {
+        const float pw = __shfl_sync(0xffffffffu, pc.w, jj);
+        if (pw < kEps) continue;                                   // merged.cpp:268-270
+        const float px = __shfl_sync(0xffffffffu, pc.x, jj), py = __shfl_sync(0xffffffffu, pc.y, jj), pz = __shfl_sync(0xffffffffu, pc.z, jj);
+        const int l = __shfl_sync(0xffffffffu, lab, jj);
+        const float tot = mw + pw;
+        mp = f3((mp.x * mw + px * pw) / tot, (mp.y * mw + py * pw) / tot, (mp.z * mw + pz * pw) / tot);
+        mw += pw;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (q * 32 + lane == l) hcount[q] += 1.0f;
+        if (clearing) { done = true; break; }                      // only take first point when clearing (merged.cpp:282-284)
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const int c = q * 32 + lane; if (c < C) hist[(size_t)b * C + c] = hcount[q]; }
+    if (lane == 0) {
+      const F3 pG = xform_apply(T, mp);
+      b_param[b] = make_float4(pG.x, pG.y, pG.z, mw);
+      b_flags[b] = clearing ? 2 : 0;
+      b_key[b] = key & ~(1ull << 63);
+      Dda d;
+      raycaster_init(d, f3(T.tx, T.ty, T.tz), pG, clearing, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc, true);
+      int n = d.length_in_steps + 1;
+      if (!d.in_range) { set_err(cnt, 5); n = 0; }
+      b_nsteps[b] = n;
+      steps += (unsigned long long)n;
+    }
+  }
+  warp_add(&cnt->ray_steps, steps);
+}
+
+// record ranges of the bundles: one warp-aggregated bump allocation per 32 bundles
+__global__ void k_bundle_alloc(Counters* cnt, int* __restrict__ b_nsteps, long long* __restrict__ b_base, long long rec_cap) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = b < cnt->n_cast;
-  int n = 0;
-  if (live) {
-  const int f = bundle_f[b];
-  const int i0 = bstart[f];
-  const uint64_t key = ks[i0];
-  const bool clearing = (key >> 63) != 0;
-  float* h = hist + (size_t)b * cfg.C;
-  for (int c = 0; c < cfg.C; ++c) h[c] = 0.0f;
-  F3 mp = f3(0.0f, 0.0f, 0.0f);
-  float mw = 0.0f;
-  for (int i = i0; i < capacity && ks[i] == key; ++i) {   // merged.cpp:263-285
-    const uint32_t seq = seq_sorted[i];
-    const float4 pc = pt_pC[seq];
-    const float pw = pc.w;
-    if (pw < kEps) continue;
-    const float tot = mw + pw;
-    mp = f3((mp.x * mw + pc.x * pw) / tot, (mp.y * mw + pc.y * pw) / tot, (mp.z * mw + pc.z * pw) / tot);
-    mw += pw;
-    h[pt_label[seq]] += 1.0f;
-    if (clearing) break;
-  }
-  const F3 pG = xform_apply(T, mp);
-  b_param[b] = make_float4(pG.x, pG.y, pG.z, mw);
-  b_flags[b] = clearing ? 2 : 0;
-  b_key[b] = key & ~(1ull << 63);
-  Dda d;
-  raycaster_init(d, f3(T.tx, T.ty, T.tz), pG, clearing, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc, true);
-  n = d.length_in_steps + 1;
-  if (!d.in_range) { set_err(cnt, 5); n = 0; }
-  b_nsteps[b] = n;
-  }
-  const long long base = (long long)warp_alloc(&cnt->n_records, (unsigned long long)n);   // every lane arrives here
-  warp_add(&cnt->ray_steps, (unsigned long long)n);
+  const int n = live ? b_nsteps[b] : 0;
+  const long long base = (long long)warp_alloc(&cnt->n_records, (unsigned long long)n);
   if (live) {
     if (base + n > rec_cap) { set_err(cnt, 4); b_nsteps[b] = 0; }
     b_base[b] = base;
