@@ -5,7 +5,7 @@
 //   k_start_push/eval/commit        [K3]  exact emulation of fast's start_voxel_approx_set_
 //   k_ray_setup / k_eval / k_obs_commit              [K4] exact emulation of voxel_observed_approx_set_
 //                                         (asynchronous fixpoint over per-slot visit lists)
-//   k_bundle_heads / k_bundle_merge / k_bundle_loglik [K2] merged: bundleRays + integrateVoxel merge loop
+//   k_bundle_heads / k_bundle_merge / k_bundle_alloc / k_bundle_loglik [K2] merged: bundleRays + integrateVoxel merge loop
 //   k_emit_fast / k_emit_merged     [K4]  ray cast -> update records + block-hash insertion [K5]
 //   k_block_init                    [K5]  pool allocation + default construction of new voxel blocks
 //   k_tile_heads / k_tile_apply     [K6]  per-tile ordered TSDF + semantic update, TMA-staged
