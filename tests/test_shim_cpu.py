@@ -79,3 +79,10 @@ def test_label_colour_csv_loader_follows_reference_semantics(demo, tmp_path):
     bad.write_text("name,red,green\nA,1,2\n")
     r = subprocess.run([os.path.join(CPP, "color_csv_test"), str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and "Row 1 is invalid" in r.stderr      # CHECK_EQ(loop->size(), 6) color.cpp:51
+
+
+def test_reference_call_patterns_compile_and_run_against_the_shim(demo):
+    """cpp/test/api_compat_test.cpp: inheritance, enum values, Layer/Block accessors, factory overload signatures, default
+    Config values - the call sites of the reference compile unchanged."""
+    out = subprocess.run([os.path.join(CPP, "api_compat_test")], capture_output=True, text=True)
+    assert out.returncode == 0 and "api compat ok" in out.stdout, out.stdout + out.stderr
