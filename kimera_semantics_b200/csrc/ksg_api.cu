@@ -641,7 +641,9 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   dc.start_inv = cfg->start_voxel_subsampling_factor * dc.vsi;  // fast.cpp:89
   dc.carving = cfg->voxel_carving_enabled;
   dc.const_weight = cfg->use_const_weight;
-  dc.allow_clear = cfg->allow_clear;
+  // voxblox TsdfIntegratorBase ctor: clearing rays have no use without carving, so allow_clear is forced off there
+  // (explicit freespace clouds still clear, isPointValid tests allow_clear || freespace_points)
+  dc.allow_clear = (cfg->allow_clear && cfg->voxel_carving_enabled) ? 1 : 0;
   dc.maxc = cfg->max_consecutive_ray_collisions;
   dc.anti_grazing = cfg->enable_anti_grazing;
   // setSemanticProbabilities (base.cpp:93-128): std::log on float, on the host (same libm as the reference)

@@ -339,6 +339,9 @@ struct Integrator {
     voxel_size_inv = (float)(1.0 / voxel_size);
     block_size = voxel_size * vps;
     vps_inv = (float)(1.0f / (float)vps);
+    // voxblox TsdfIntegratorBase ctor: allow_clear is switched off when carving is disabled (found by running the
+    // reference's own sources against the stand-in voxblox, oracle/ref_hybrid.cpp)
+    if (cfg.allow_clear && !cfg.voxel_carving_enabled) cfg.allow_clear = 0;
     setSemanticProbabilities();
   }
 

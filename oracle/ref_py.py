@@ -1,0 +1,87 @@
+"""ctypes binding of oracle/_ref/libks_ref_hybrid.so: the reference's own kimera_semantics sources compiled against
+the stand-in dependency headers of oracle/ref_stubs/ (see oracle/ref_hybrid.cpp).  TEST INFRASTRUCTURE ONLY: it pins the
+oracle; nothing in the product, smoke() or bench.py loads it.
+
+The library is built by `make -C oracle ref` where /root/reference exists and travels to the GPU box as a prebuilt file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from kimera_semantics_b200.capi import KsgConfig, export_arrays, _ptr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libks_ref_hybrid.so")
+_LIB: Optional[C.CDLL] = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def load() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        lib = C.CDLL(LIB_PATH)
+        H = C.c_void_p
+        fp, u8p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+        lib.kref_num_labels.restype = C.c_int
+        lib.kref_create.argtypes = [C.POINTER(KsgConfig)]
+        lib.kref_create.restype = H
+        lib.kref_destroy.argtypes = [H]
+        lib.kref_integrate_points.argtypes = [H, fp, fp, u8p, C.c_int64, C.c_int]
+        lib.kref_integrate_points.restype = C.c_int
+        lib.kref_num_blocks.argtypes = [H]
+        lib.kref_num_blocks.restype = C.c_int64
+        lib.kref_num_semantic_blocks.argtypes = [H]
+        lib.kref_num_semantic_blocks.restype = C.c_int64
+        lib.kref_export_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
+        lib.kref_export_blocks.restype = C.c_int
+        _LIB = lib
+    return _LIB
+
+
+class RefHybridIntegrator:
+    """kimera::FastSemanticTsdfIntegrator / MergedSemanticTsdfIntegrator (the reference's classes) behind the export
+    layout of the oracle.  num_labels is the reference's compile-time 21 (common.h:27)."""
+
+    def __init__(self, cfg: KsgConfig):
+        self.lib = load()
+        self.cfg = cfg
+        self.handle = self.lib.kref_create(C.byref(cfg))
+        if not self.handle:
+            raise ValueError(f"kref_create rejected the config (num_labels must be {self.lib.kref_num_labels()})")
+
+    def close(self):
+        if self.handle:
+            self.lib.kref_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def integrate_points(self, T_G_C, xyz, rgba=None, freespace: bool = False) -> None:
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        assert rgba.shape == (xyz.shape[0], 4)
+        rc = self.lib.kref_integrate_points(self.handle, _ptr(T, C.c_float), _ptr(xyz, C.c_float), _ptr(rgba, C.c_uint8),
+                                            xyz.shape[0], int(freespace))
+        if rc != 0:
+            raise ValueError(f"kref_integrate_points: {rc}")
+
+    def num_blocks(self) -> int:
+        return int(self.lib.kref_num_blocks(self.handle))
+
+    def num_semantic_blocks(self) -> int:
+        return int(self.lib.kref_num_semantic_blocks(self.handle))
+
+    def export(self) -> Dict[str, np.ndarray]:
+        return export_arrays(self.lib, self.handle, "kref", self.cfg.voxels_per_side, self.cfg.num_labels)
