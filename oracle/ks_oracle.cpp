@@ -5,15 +5,21 @@
 // path (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs) and is
 // never linked, imported or executed by the product path in kimera_semantics_b200/.
 //
-// PARITY STATUS: "parity unpinned".  The reference ships no tests, golden vectors or fixtures for
-// this path and it cannot be compiled here (needs catkin, voxblox, minkindr,
-// Eigen, glog — all absent; voxblox is un-vendored and un-pinned in
-// install/kimera_semantics_https.rosinstall:34-36).  The in-tree half (kimera_semantics/src/*.cpp)
-// is followed line by line; the voxblox half is restated from the published upstream
-// ethz-asl/voxblox sources (voxblox/integrator/{tsdf_integrator,integrator_utils}.{h,cc},
-// voxblox/utils/approx_hash_array.h, voxblox/core/{common,block_hash,color}.h) as summarised in
-// SURVEY.md Appendix A.  The oracle is pinned by this repo's own known-answer tests
-// (tests/test_oracle_kat.py) and golden fixtures (tests/golden/), not by the reference.
+// PARITY STATUS: pinned for the in-tree half, "parity unpinned" for the voxblox half.
+//   * In-tree half (kimera_semantics/src/*.cpp, followed line by line here): pinned against the reference's OWN
+//     translation units.  `make -C oracle ref` compiles semantic_tsdf_integrator_{fast,merged}.cpp,
+//     semantic_integrator_base.cpp, color.cpp and csv_iterator.cpp where they lie under /root/reference against
+//     stand-in dependency headers (oracle/ref_stubs/) into oracle/_ref/libks_ref_hybrid.so;
+//     tests/test_oracle_vs_ref_hybrid.py requires this oracle to equal that library bit for bit on 29 seeded
+//     sequences (every Config / SemanticConfig switch of the path), and the digests are committed as
+//     tests/golden/ref_hybrid_golden.json for boxes without /root/reference.
+//   * voxblox half (RayCaster, updateTsdfVoxel, ApproxHashSet, ThreadSafeIndex, bundleRays, Layer/Block, hashes,
+//     minkindr transform): the reference ships no tests, golden vectors or fixtures, cannot be
+//     built as it stands (catkin, voxblox, minkindr, Eigen, glog absent) and does not vendor or pin voxblox
+//     (install/kimera_semantics_https.rosinstall:34-36).  It is restated from the published upstream ethz-asl/voxblox
+//     sources as summarised in SURVEY.md Appendix A -- twice, independently (here and in oracle/ref_stubs/voxblox), plus
+//     a third time in numpy for the control flow (tests/test_oracle_crosscheck.py) -- and pinned only by this repo's
+//     own known-answer tests (tests/test_oracle_kat.py).  Agreement of restatements is not agreement with voxblox.
 //
 // Build: parity build `-O2 -ffp-contract=off` (no FMA contraction, so every float expression
 // rounds exactly as written); timing build `-O3 -march=native -ffp-contract=off`.
