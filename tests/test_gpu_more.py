@@ -211,3 +211,22 @@ def test_import_blocks_restores_a_map_and_integration_continues_identically():
     assert (e["tsdf_distance"][idx] == 0.125).all()
     mask = np.ones(len(e["block_index"]), bool); mask[idx] = False
     assert np.array_equal(e["tsdf_distance"][mask], snap["tsdf_distance"][mask]) and np.array_equal(e["tsdf_weight"], snap["tsdf_weight"])
+
+
+@pytest.mark.gpu
+def test_fast_sets_full_reset_after_10000_frames():
+    """ApproxHashSet::resetApproxSet (A.4): the per-frame offset reaches full_reset_threshold = 10 000, both tables are
+    wiped and the offset restarts.  10 012 tiny clouds through the C-ABI vs the oracle (the same sequence is checked against
+    the reference's own sources in tests/test_oracle_vs_ref_hybrid.py)."""
+    from test_oracle_vs_ref_hybrid import tiny_frames
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.10, 21, max_points=64, max_blocks=512)
+    gpu, ora = Integrator(cfg), OracleIntegrator(cfg)
+    worst = None
+    for i, (T, xyz, lab) in enumerate(tiny_frames(10012)):
+        sg = gpu.integrate_points(T, xyz, labels=lab)
+        so = ora.integrate_points(T, xyz, labels=lab)
+        if worst is None and (sg.voxel_updates, sg.rays_cast) != (so.voxel_updates, so.rays_cast):
+            worst = (i, sg.as_dict(), so.as_dict())
+    assert worst is None, f"first frame whose counters differ: {worst}"
+    assert_parity(compare_maps(gpu.export(), ora.export()))
+    gpu.close()

@@ -96,3 +96,33 @@ def test_canonical_bundle_order_keeps_the_order_insensitive_part_of_the_referenc
         for k in ("block_index", "observed_mask", "touched_mask", "observed_voxels", "touched_voxels"):
             assert got[k] == want[k], (name, k)
         assert abs(got["weight_sum"] - want["weight_sum"]) <= 1e-5 * want["weight_sum"]
+
+
+def tiny_frames(n_frames, points_per_frame=24, seed=5):
+    """Many tiny clouds: drives the ApproxHashSet offset through its full-reset threshold (A.4: 10 000 resets)."""
+    from kimera_semantics_b200 import synth
+    rng = np.random.default_rng(seed)
+    cam = synth.make_camera(64, 48)
+    for f in range(n_frames):
+        T = synth.pose(f % 300)
+        xyz = np.stack([rng.uniform(-0.4, 0.4, points_per_frame), rng.uniform(-0.3, 0.3, points_per_frame),
+                        rng.uniform(0.8, 1.6, points_per_frame)], axis=1).astype(np.float32)
+        lab = rng.integers(0, 20, points_per_frame).astype(np.uint8)
+        yield T, xyz, lab
+
+
+@needs_ref
+def test_full_reset_of_the_approximate_sets_after_10000_frames_matches_the_reference():
+    """fast.cpp:165-170 + ApproxHashSet::resetApproxSet: offset++ per frame, table wiped when it reaches 10 000."""
+    from kimera_semantics_b200.capi import KSG_INTEGRATOR_FAST
+    from parity_utils import make_config
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.10, 21, max_points=64)
+    pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(256)], np.uint8)
+    ref, ora = ref_py.RefHybridIntegrator(cfg), OracleIntegrator(cfg)
+    ora.set_color_to_label(*mrg.color_table(cfg))
+    for T, xyz, lab in tiny_frames(10012):
+        rgba = np.ascontiguousarray(pal[lab])
+        ref.integrate_points(T, xyz, rgba=rgba)
+        ora.integrate_points(T, xyz, rgba=rgba)
+    rep = compare_maps(ref.export(), ora.export())
+    assert rep["same_blocks"] == 1.0 and not {k: v for k, v in rep.items() if k.endswith("mismatch") and v}, rep
