@@ -13,8 +13,9 @@ region; for `value` they are already resident in HBM).  One JSON line is printed
   e2e       the same through the host-buffer C-ABI call (ksg_integrate_depth): pinned staging + H2D copy of
             depth+label and the D2H read of the frame counters inside the timed region
   roofline  tile-apply kernel: algorithmic bytes (updates * (34 + 8C) + pixels * 5) / its device time
-  cpu_baseline  the CPU oracle (port of the reference integrator) timed on this box's host cores
-  --impl reference   times that CPU path alone (all host threads) and prints the same line shape
+  cpu_baseline  the reference's CPU path timed on this box's host cores: the faster of (a) the oracle port and (b) the reference's
+            own integrator sources built against stand-in dependency headers (oracle/_ref), each at its best thread count
+  --impl reference   times that CPU path alone and prints the same line shape
 
 Multi-GPU (torchrun, one rank per GPU): the path shards by sequence - every rank integrates its own camera
 stream into its own map (independent robots / sequences), no data-path collective; "scaling": "weak".
@@ -110,36 +111,88 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-def cpu_baseline(workload, frames, cam, threads, budget_s=20.0, max_frames=40):
-    """CPU oracle (timing build) on a bounded sample of the same frames. Timed span = integratePointCloud body."""
-    from oracle.oracle_py import OracleIntegrator
+CPU_ARMS = {
+    "port": "oracle port of the reference integrator (oracle/ks_oracle.cpp, timing build -O3 -march=x86-64-v3)",
+    "reference": "the reference's own integrator sources (semantic_tsdf_integrator_{fast,merged}.cpp, semantic_integrator_base.cpp, "
+                 "color.cpp) compiled -O3 -march=x86-64-v3 against stand-in Eigen/glog/voxblox headers (oracle/_ref, see oracle/ref_hybrid.cpp)",
+}
+
+
+def cpu_arms(workload):
+    """Which CPU implementations can be timed on this box: the port always, the reference-source build when its prebuilt
+    library travelled with the snapshot and the workload has the reference's compile-time 21 labels (common.h:27)."""
+    arms = ["port"]
+    try:
+        from oracle import ref_py
+        if ref_py.available(fast_build=True) and WORKLOADS[workload][4] == ref_py.load(fast_build=True).kref_num_labels():
+            arms.append("reference")
+    except Exception:
+        pass
+    return arms
+
+
+class _ReferenceSourceArm:
+    """Feeds depth+label frames to the reference boundary integratePointCloud(T_G_C, points_C, colors): back-projection and the
+    label -> colour encoding happen outside the timed span, exactly as the ROS front end does them before the call."""
+
+    def __init__(self, cfg, cam):
+        from oracle.ref_py import RefHybridIntegrator
+        self.integ = RefHybridIntegrator(cfg, fast_build=True)
+        self.cam = cam
+        self.pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(256)], np.uint8)
+
+    def integrate_depth(self, T, depth, label, K):
+        xyz, pix = synth.backproject(depth, self.cam)
+        self.integ.integrate_points(T, xyz, rgba=np.ascontiguousarray(self.pal[label.reshape(-1)[pix]]))
+        return None
+
+    def last_integrate_seconds(self):
+        return self.integ.last_integrate_seconds()
+
+    def close(self):
+        self.integ.close()
+
+
+def make_cpu_integrator(arm, workload, cam, threads):
     cfg = make_cfg(workload, threads=threads)
-    ora = OracleIntegrator(cfg, canonical_merged=True, fast_build=True)
+    if arm == "reference":
+        return _ReferenceSourceArm(cfg, cam)
+    from oracle.oracle_py import OracleIntegrator
+    return OracleIntegrator(cfg, canonical_merged=True, fast_build=True)
+
+
+def cpu_baseline(workload, frames, cam, threads, budget_s=20.0, max_frames=40, arm="port", updates_per_frame=None):
+    """One CPU arm on a bounded sample of the same frames. Timed span = integratePointCloud body."""
+    integ = make_cpu_integrator(arm, workload, cam, threads)
     t_total, updates, n = 0.0, 0, 0
     t0 = time.time()
     for depth, label, T in frames[:max_frames]:
-        st = ora.integrate_depth(T, depth, label, cam.K)
-        t_total += ora.last_integrate_seconds()
-        updates += st.voxel_updates
+        st = integ.integrate_depth(T, depth, label, cam.K)
+        t_total += integ.last_integrate_seconds()
+        if st is not None:
+            updates += st.voxel_updates
+        elif updates_per_frame is not None:   # the reference's code does not count; the port's count of the same frame applies
+            updates += updates_per_frame[n]
         n += 1
         if time.time() - t0 > budget_s:
             break
-    ora.close()
+    integ.close()
     return {"frames": n, "seconds": t_total, "fps": n / t_total if t_total > 0 else 0.0,
             "mupdates_per_s": updates / t_total / 1e6 if t_total > 0 else 0.0}
 
 
-def best_thread_count(workload, frames, cam):
+def best_cpu_arm(workload, frames, cam):
     """The reference spawns config.integrator_threads threads per frame (default hardware_concurrency) that contend on 4096
-    striped mutexes and two atomic hash sets; on many-core hosts that is slower than a few threads. Calibrate on 3 frames."""
+    striped mutexes and two atomic hash sets; on many-core hosts that is slower than a few threads.  Calibrate every available
+    arm on a few frames at several thread counts and keep the fastest (arm, threads) pair - the most favourable CPU number."""
     cores = os.cpu_count() or 1
     cands = sorted({1, 4, 16, cores} & set(range(1, cores + 1)) | {1})
     res = {}
-    for t in cands:
-        r = cpu_baseline(workload, frames, cam, t, budget_s=6.0, max_frames=4)
-        res[t] = r["fps"]
+    for arm in cpu_arms(workload):
+        for t in cands:
+            res[(arm, t)] = cpu_baseline(workload, frames, cam, t, budget_s=5.0, max_frames=4, arm=arm)["fps"]
     best = max(res, key=res.get)
-    return best, res
+    return best[0], best[1], {f"{a}@{t}": v for (a, t), v in res.items()}
 
 
 def ncu_traffic(workload):
@@ -173,7 +226,8 @@ def peaks():
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) with all host threads."""
+    """--impl reference: the reference's CPU implementation of the path - the faster of the oracle port and the reference-source
+    build (oracle/_ref), at the thread count that is fastest on this host."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -181,16 +235,18 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n = args.warmup + args.steps
     cam, frames = gen_frames(args.workload, n)
-    from oracle.oracle_py import OracleIntegrator
-    threads, calib = best_thread_count(args.workload, frames[args.warmup:], cam)
-    cfg = make_cfg(args.workload, threads=threads)
-    ora = OracleIntegrator(cfg, canonical_merged=True, fast_build=True)
+    arm, threads, calib = best_cpu_arm(args.workload, frames[args.warmup:], cam)
+    integ = make_cpu_integrator(arm, args.workload, cam, threads)
+    counter = make_cpu_integrator("port", args.workload, cam, 1) if arm != "port" else None   # untimed: counts voxel updates
     t_total, updates = 0.0, 0
     for i, (depth, label, T) in enumerate(frames):
-        st = ora.integrate_depth(T, depth, label, cam.K)
+        st = integ.integrate_depth(T, depth, label, cam.K)
+        if counter is not None:
+            st = counter.integrate_depth(T, depth, label, cam.K)
         if i >= args.warmup:
-            t_total += ora.last_integrate_seconds()
+            t_total += integ.last_integrate_seconds()
             updates += st.voxel_updates
+    integ.close()
     fps = args.steps / t_total
     line = {
         "impl": "reference", "metric": "depth_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
@@ -200,10 +256,10 @@ def run_reference(args):
         "config": {"workload": f"{w}x{h} depth+label stream, {vs * 100:.0f} cm voxels, {C} classes, "
                                f"{'fast' if itype == KSG_INTEGRATOR_FAST else 'merged'} integrator (BASELINE.json configs)",
                    "name": args.workload},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "host_cores": cores,
-                         "thread_calibration_fps": {str(k): v for k, v in calib.items()},
-                         "sample": f"{args.steps} frames after {args.warmup} warm-up, oracle timing build (-O3 -march=x86-64-v3), "
-                                   f"integrator_threads={threads} (fastest of the calibrated counts; the host has {cores} cores)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": arm, "host_cores": cores,
+                         "implementation": CPU_ARMS[arm], "calibration_fps": calib,
+                         "sample": f"{args.steps} frames after {args.warmup} warm-up; fastest (implementation, integrator_threads) pair of the "
+                                   f"calibration = {arm} with {threads} threads (the host has {cores} cores)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -360,13 +416,15 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            threads, calib = best_thread_count(args.workload, frames[args.warmup:], cam)
-            c_all = cpu_baseline(args.workload, frames[args.warmup:], cam, threads)
-            cpu = {"value": c_all["fps"], "unit": "frames/s", "cores": threads, "kind": "port", "host_cores": cores,
-                   "sample": f"{c_all['frames']} frames of the same stream (from the first timed frame, empty map), oracle timing build "
-                             f"(-O3 -march=x86-64-v3), integrator_threads={threads} = fastest of the calibrated counts",
-                   "thread_calibration_fps": {str(k): v for k, v in calib.items()},
-                   "mvoxel_updates_per_s": c_all["mupdates_per_s"]}
+            arm, threads, calib = best_cpu_arm(args.workload, frames[args.warmup:], cam)
+            c_all = cpu_baseline(args.workload, frames[args.warmup:], cam, threads, arm=arm)
+            cpu = {"value": c_all["fps"], "unit": "frames/s", "cores": threads, "kind": arm, "host_cores": cores,
+                   "implementation": CPU_ARMS[arm],
+                   "sample": f"{c_all['frames']} frames of the same stream (from the first timed frame, empty map); fastest (implementation, "
+                             f"integrator_threads) pair of the calibration = {arm} with {threads} threads",
+                   "calibration_fps": calib}
+            if arm == "port":
+                cpu["mvoxel_updates_per_s"] = c_all["mupdates_per_s"]
         line = {
             "metric": "depth_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if spatial else "weak",

@@ -14,6 +14,7 @@
 //
 // This file is the only code of ours in the library: a C wrapper with the kso_* export layout so that
 // tests/parity_utils.compare_maps can diff reference-hybrid vs oracle maps directly.
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -33,6 +34,7 @@ struct Hybrid {
   std::unique_ptr<voxblox::Layer<voxblox::TsdfVoxel>> tsdf;
   std::unique_ptr<voxblox::Layer<kimera::SemanticVoxel>> sem;
   std::unique_ptr<voxblox::TsdfIntegratorBase> integrator;
+  double last_integrate_seconds = 0.0;
 };
 
 std::vector<voxblox::BlockIndex> sortedBlocks(const Hybrid& h) {
@@ -122,9 +124,15 @@ int kref_integrate_points(void* hh, const float* T, const float* xyz, const uint
     points[i] = voxblox::Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     colors[i] = voxblox::Color(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], rgba[4 * i + 3]);
   }
+  const auto t0 = std::chrono::steady_clock::now();
   h->integrator->integratePointCloud(T_G_C, points, colors, freespace != 0);
+  h->last_integrate_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return 0;
 }
+
+// Wall time of the last integratePointCloud call alone (the span of the reference's "integrate/fast" +
+// "inserting_missed_blocks" / "semantic_tsdf/integrate" timers).
+double kref_last_integrate_seconds(void* hh) { return ((Hybrid*)hh)->last_integrate_seconds; }
 
 int64_t kref_num_blocks(void* hh) { return (int64_t)((Hybrid*)hh)->tsdf->getNumberOfAllocatedBlocks(); }
 int64_t kref_num_semantic_blocks(void* hh) { return (int64_t)((Hybrid*)hh)->sem->getNumberOfAllocatedBlocks(); }

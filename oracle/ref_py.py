@@ -16,17 +16,18 @@ from kimera_semantics_b200.capi import KsgConfig, export_arrays, _ptr
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libks_ref_hybrid.so")
-_LIB: Optional[C.CDLL] = None
+FAST_LIB_PATH = os.path.join(_HERE, "_ref", "libks_ref_hybrid_fast.so")   # -O3 timing build, same results
+_LIBS: Dict[str, C.CDLL] = {}
 
 
-def available() -> bool:
-    return os.path.exists(LIB_PATH)
+def available(fast_build: bool = False) -> bool:
+    return os.path.exists(FAST_LIB_PATH if fast_build else LIB_PATH)
 
 
-def load() -> C.CDLL:
-    global _LIB
-    if _LIB is None:
-        lib = C.CDLL(LIB_PATH)
+def load(fast_build: bool = False) -> C.CDLL:
+    path = FAST_LIB_PATH if fast_build else LIB_PATH
+    if path not in _LIBS:
+        lib = C.CDLL(path)
         H = C.c_void_p
         fp, u8p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
         lib.kref_num_labels.restype = C.c_int
@@ -41,16 +42,18 @@ def load() -> C.CDLL:
         lib.kref_num_semantic_blocks.restype = C.c_int64
         lib.kref_export_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
         lib.kref_export_blocks.restype = C.c_int
-        _LIB = lib
-    return _LIB
+        lib.kref_last_integrate_seconds.argtypes = [H]
+        lib.kref_last_integrate_seconds.restype = C.c_double
+        _LIBS[path] = lib
+    return _LIBS[path]
 
 
 class RefHybridIntegrator:
     """kimera::FastSemanticTsdfIntegrator / MergedSemanticTsdfIntegrator (the reference's classes) behind the export
     layout of the oracle.  num_labels is the reference's compile-time 21 (common.h:27)."""
 
-    def __init__(self, cfg: KsgConfig):
-        self.lib = load()
+    def __init__(self, cfg: KsgConfig, fast_build: bool = False):
+        self.lib = load(fast_build)
         self.cfg = cfg
         self.handle = self.lib.kref_create(C.byref(cfg))
         if not self.handle:
@@ -76,6 +79,9 @@ class RefHybridIntegrator:
                                             xyz.shape[0], int(freespace))
         if rc != 0:
             raise ValueError(f"kref_integrate_points: {rc}")
+
+    def last_integrate_seconds(self) -> float:
+        return float(self.lib.kref_last_integrate_seconds(self.handle))
 
     def num_blocks(self) -> int:
         return int(self.lib.kref_num_blocks(self.handle))

@@ -105,4 +105,21 @@ def test_reference_impl_line_shape():
     import json
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0   # 5 labels: only the port can run it
+
+
+def test_reference_impl_times_the_reference_sources_when_built():
+    """At the reference's 21 labels both CPU arms are calibrated and the faster (arm, threads) pair is the reported one."""
+    from oracle import ref_py
+    if not ref_py.available(fast_build=True):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "fast5", "--steps", "3",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cal = line["cpu_baseline"]["calibration_fps"]
+    assert any(k.startswith("reference@") for k in cal) and any(k.startswith("port@") for k in cal)
+    best = max(cal, key=cal.get)
+    assert best == f'{line["cpu_baseline"]["kind"]}@{line["cpu_baseline"]["cores"]}'
+    assert line["value"] > 0 and line["mvoxel_updates_per_s"] > 0
