@@ -47,10 +47,20 @@ def read_shim_output(path, vps, C):
     return out
 
 
-@pytest.mark.parametrize("method,mode", [("fast", "eager"), ("merged", "eager"), ("fast", "lazy")])
-def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mode):
+REF_FACTORY_DEMO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "shim_demo_ref_factory")
+
+
+@pytest.mark.parametrize("method,mode,factory", [("fast", "eager", "shim"), ("merged", "eager", "shim"), ("fast", "lazy", "shim"),
+                                                 ("fast", "eager", "reference"), ("merged", "eager", "reference")])
+def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mode, factory):
     """SemanticTsdfIntegratorFactory::create(method, ...) + integratePointCloud(T_G_C, points_C, colors) through the C++ shim
-    fill the host Layer<TsdfVoxel> / Layer<SemanticVoxel> exactly as the oracle's layers."""
+    fill the host Layer<TsdfVoxel> / Layer<SemanticVoxel> exactly as the oracle's layers.
+    factory="reference": the same driver linked with the reference's OWN semantic_tsdf_integrator_factory.cpp (compiled
+    unmodified against the shim headers, `make -C oracle ref`), i.e. the reference's creation code constructs our classes."""
+    if factory == "reference":
+        if not os.path.exists(REF_FACTORY_DEMO):
+            pytest.skip("oracle/_ref/shim_demo_ref_factory not built (needs /root/reference)")
+        demo = REF_FACTORY_DEMO
     C, w, h, vs = 21, 320, 240, 0.10
     itype = KSG_INTEGRATOR_FAST if method == "fast" else KSG_INTEGRATOR_MERGED
     cfg = make_config(itype, vs, C, max_points=w * h)

@@ -86,3 +86,23 @@ def test_reference_call_patterns_compile_and_run_against_the_shim(demo):
     Config values - the call sites of the reference compile unchanged."""
     out = subprocess.run([os.path.join(CPP, "api_compat_test")], capture_output=True, text=True)
     assert out.returncode == 0 and "api compat ok" in out.stdout, out.stdout + out.stderr
+
+
+REF_FACTORY_DEMO = os.path.join(ROOT, "oracle", "_ref", "shim_demo_ref_factory")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference sources (build container only)")
+def test_reference_factory_source_compiles_and_links_against_the_shim(demo, tmp_path):
+    """SURVEY.md 8b "Creation": the reference's own semantic_tsdf_integrator_factory.cpp builds unmodified against the shim's
+    headers (constructor signatures, enum, type-name table, make_unique) and links in front of the shim library."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(REF_FACTORY_DEMO)
+    syms = subprocess.run(["nm", "-C", "--defined-only", REF_FACTORY_DEMO], capture_output=True, text=True).stdout
+    assert "T kimera::SemanticTsdfIntegratorFactory::create(" in syms      # the reference's definition is the one in the binary
+    fr = tmp_path / "f.bin"
+    write_frames(fr, [], 0.1, 16, [(255, 255, 255, 255)], [])
+    r = subprocess.run([REF_FACTORY_DEMO, "bogus", str(fr), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode != 0 and "semantic_tsdf_integrator_factory.cpp:61] Unknown TSDF integrator type: bogus" in r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([REF_FACTORY_DEMO, "merged", str(fr), str(tmp_path / "o.bin")], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr       # the reference's factory reached OUR constructor
