@@ -50,7 +50,9 @@ CASES = {
     "fast_unknown_colors": (FAST, 128, 96, 0.10, 2, {}, {"unknown_colors": True}),
     "fast_clear_sets_every_2nd_frame": (FAST, 128, 96, 0.10, 4, {"clear_checks_every_n_frames": 2}, {}),
     "fast_min_range_gate": (FAST, 128, 96, 0.10, 2, {"min_ray_length_m": 2.0}, {}),
+    "fast_fullsize_640x480_5cm_4f": (FAST, 640, 480, 0.05, 4, {}, {}),             # BASELINE.json configs[1] geometry
     "merged_default_2f": (MERGED, 160, 120, 0.10, 2, {}, {}),
+    "merged_fullsize_640x480_5cm_1f": (MERGED, 640, 480, 0.05, 1, {}, {}),
     "merged_5cm": (MERGED, 128, 96, 0.05, 2, {}, {}),
     "merged_antigrazing": (MERGED, 128, 96, 0.10, 2, {"enable_anti_grazing": 1}, {}),
     "merged_clearing_rays": (MERGED, 128, 96, 0.10, 2, {"max_ray_length_m": 2.5}, {}),
