@@ -894,6 +894,20 @@ void kso_blend(const uint8_t* c1, float w1, const uint8_t* c2, float w2, uint8_t
 }
 void kso_rainbow(double h, uint8_t* out) { const Color c = rainbowColorMap(h); out[0] = c.r; out[1] = c.g; out[2] = c.b; out[3] = c.a; }
 
+// libstdc++ probe for tests/test_unordered_map_order.py: insert n distinct voxel keys (int64 xyz triples, first-insertion order)
+// into the map type merged.cpp:110-113 uses and report (a) the iteration order as indices into the input and (b) the bucket count
+// after every insertion.  This is what `merged` in faithful mode iterates (merged.cpp:210-231).
+int64_t kso_unordered_map_order(const int64_t* keys, int64_t n, int64_t* order_out, int64_t* bucket_count_after_insert) {
+  std::unordered_map<GIdx, size_t, LongIndexHash> m;
+  for (int64_t i = 0; i < n; ++i) {
+    m.emplace(GIdx{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]}, (size_t)i);
+    if (bucket_count_after_insert) bucket_count_after_insert[i] = (int64_t)m.bucket_count();
+  }
+  int64_t k = 0;
+  for (const auto& kv : m) order_out[k++] = (int64_t)kv.second;
+  return k;
+}
+
 // debug hooks used by tests/ to validate the parallel observed-set solver against the sequential sets
 void kso_trace_fast(void* hh, int enable) { ((Integrator*)hh)->trace_fast = enable != 0; }
 int64_t kso_get_fast_trace(void* hh, int64_t capacity, int64_t* point_idx, int64_t* updates) {

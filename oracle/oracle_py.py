@@ -69,6 +69,8 @@ def load(fast_build: bool = False) -> C.CDLL:
     lib.kso_approx_set_script.argtypes = [C.POINTER(C.c_uint64), C.c_int, u8p]
     lib.kso_blend.argtypes = [u8p, C.c_float, u8p, C.c_float, u8p]
     lib.kso_rainbow.argtypes = [C.c_double, u8p]
+    lib.kso_unordered_map_order.argtypes = [i64p, C.c_int64, i64p, i64p]
+    lib.kso_unordered_map_order.restype = C.c_int64
     _LIBS[name] = lib
     return lib
 
