@@ -44,6 +44,8 @@ enum { KSG_INTEGRATOR_MERGED = 0, KSG_INTEGRATOR_FAST = 1 };
 enum { KSG_COLOR_MODE_COLOR = 0, KSG_COLOR_MODE_SEMANTIC = 1, KSG_COLOR_MODE_SEMANTIC_PROBABILITY = 2 };
 /* integration order: voxblox ThreadSafeIndexFactory ("mixed" | "sorted"), fast.cpp:172-174 */
 enum { KSG_ORDER_MIXED = 0, KSG_ORDER_SORTED = 1 };
+/* ksg_config.merged_bundle_order */
+enum { KSG_BUNDLE_ORDER_CANONICAL = 0, KSG_BUNDLE_ORDER_LIBSTDCXX = 1 };
 
 /*
  * One POD that carries vxb::TsdfIntegratorBase::Config (voxblox tsdf_integrator.h, defaults in
@@ -93,7 +95,13 @@ typedef struct ksg_config {
    * unsharded run. shard_count <= 1: off. */
   int32_t shard_rank;
   int32_t shard_count;
-  int32_t reserved[5];
+  /* merged only: the order in which the bundles of a frame are applied (per-voxel results depend on it, updateTsdfVoxel clamps
+   * after averaging).  KSG_BUNDLE_ORDER_CANONICAL (0, default): first-insertion order of bundleRays.
+   * KSG_BUNDLE_ORDER_LIBSTDCXX (1): the iteration order of the std::unordered_map<LongIndex, ..., LongIndexHash> the reference
+   * fills in bundleRays and walks in integrateVoxels (merged.cpp:110-124, 210-231) - i.e. the reference's result with
+   * integrator_threads = 1 on a platform whose libstdc++ has this library's rehash policy. */
+  int32_t merged_bundle_order;
+  int32_t reserved[4];
 } ksg_config;
 
 /* per-frame counters (the oracle reports the same numbers; SURVEY.md 8d: one voxel update =
@@ -206,6 +214,11 @@ int32_t ksg_reset(ksg_integrator* h);
  * from the per-rank exports with them. */
 int32_t ksg_owner_mask(int32_t voxels_per_side, int32_t shard_rank, int32_t shard_count, int64_t n,
                        const int32_t* block_index, uint8_t* mask);
+
+/* Host-only helper behind KSG_BUNDLE_ORDER_LIBSTDCXX (no device needed): bucket_count() of a std::unordered_map after each of
+ * n successive insertions of distinct keys into an empty map, probed from the C++ runtime this library is linked with.
+ * Writes n values; returns n, or -1 for bad arguments. */
+int64_t ksg_unordered_map_schedule(int64_t n, int64_t* bucket_count_after_insert);
 
 /* Optional per-phase device timing (CUDA events on the launching stream) and kernel-launch counting.
  * Phases: 0 classify+start-set, 1 observed-set fixpoint (fast) / bundling (merged), 2 ray emit,

@@ -19,6 +19,8 @@ KSG_COLOR_MODE_SEMANTIC = 1
 KSG_COLOR_MODE_SEMANTIC_PROBABILITY = 2
 KSG_ORDER_MIXED = 0
 KSG_ORDER_SORTED = 1
+KSG_BUNDLE_ORDER_CANONICAL = 0
+KSG_BUNDLE_ORDER_LIBSTDCXX = 1
 
 KSG_STATUS = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "POOL_FULL", 4: "SCRATCH_FULL", 5: "INDEX_RANGE",
               6: "NO_DEVICE"}
@@ -61,7 +63,8 @@ class KsgConfig(C.Structure):
         ("apply_mode", C.c_int32),
         ("shard_rank", C.c_int32),
         ("shard_count", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("merged_bundle_order", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -135,6 +138,7 @@ def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float
     cfg.apply_mode = 0
     cfg.shard_rank = 0
     cfg.shard_count = 1
+    cfg.merged_bundle_order = KSG_BUNDLE_ORDER_CANONICAL
     return cfg
 
 
@@ -204,6 +208,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_debug_tile_times.restype = C.c_int64
     lib.ksg_owner_mask.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, i32p, u8p]
     lib.ksg_owner_mask.restype = C.c_int32
+    lib.ksg_unordered_map_schedule.argtypes = [C.c_int64, C.POINTER(C.c_int64)]
+    lib.ksg_unordered_map_schedule.restype = C.c_int64
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -214,7 +220,17 @@ def load_library(path: Optional[str] = None):
 KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_error", "ksg_integrate_points",
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
-               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask"]
+               "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
+               "ksg_unordered_map_schedule"]
+
+
+def unordered_map_schedule(n: int, lib=None) -> np.ndarray:
+    """bucket_count() of the platform's std::unordered_map after each of n insertions (host only; KSG_BUNDLE_ORDER_LIBSTDCXX)."""
+    lib = lib or load_library()
+    out = np.zeros(n, np.int64)
+    if lib.ksg_unordered_map_schedule(n, _ptr(out, C.c_int64)) != n:
+        raise KsgError("ksg_unordered_map_schedule failed")
+    return out
 
 
 def owner_mask(block_index: np.ndarray, vps: int, shard_rank: int, shard_count: int, lib=None) -> np.ndarray:

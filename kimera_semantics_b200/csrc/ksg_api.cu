@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/ksg.h"
@@ -94,6 +96,11 @@ struct ksg_integrator {
   float *hist = nullptr, *tmp = nullptr;
   uint64_t* b_key = nullptr;
   long long* b_base = nullptr;
+  // merged, KSG_BUNDLE_ORDER_LIBSTDCXX
+  std::vector<std::pair<int, uint32_t>> bord_phases;   // (first insertion index, bucket count) of every rehash phase
+  uint32_t* bord_hash = nullptr;
+  int *bord_ord_a = nullptr, *bord_ord_b = nullptr, *bord_vals = nullptr, *bord_first = nullptr, *bundle_f2 = nullptr;
+  uint64_t *bord_keys_a = nullptr, *bord_keys_b = nullptr;
 
   // records
   uint64_t *rec_a = nullptr, *rec_b = nullptr;
@@ -157,6 +164,8 @@ int validate(const ksg_config* c, std::string& why) {
   if (c->shard_count < 0 || (c->shard_count > 1 && (c->shard_rank < 0 || c->shard_rank >= c->shard_count))) {
     why = "shard_rank must be in [0, shard_count)"; return KSG_ERR_INVALID_ARGUMENT; }
   if (c->max_consecutive_ray_collisions < 0) { why = "max_consecutive_ray_collisions < 0"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->merged_bundle_order != KSG_BUNDLE_ORDER_CANONICAL && c->merged_bundle_order != KSG_BUNDLE_ORDER_LIBSTDCXX) {
+    why = "unknown merged_bundle_order"; return KSG_ERR_INVALID_ARGUMENT; }
   return KSG_OK;
 }
 
@@ -171,7 +180,8 @@ void free_all(ksg_integrator* h) {
                   h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
-                  h->tmp, h->b_key, h->b_base, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_ord_a, h->bord_ord_b, h->bord_vals, h->bord_first, h->bundle_f2,
+                  h->bord_keys_a, h->bord_keys_b, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -243,6 +253,34 @@ const char* err_text(int e) {
     case 5: return "voxel or block index outside the supported range";
     default: return "device-side error";
   }
+}
+
+// KSG_BUNDLE_ORDER_LIBSTDCXX: iteration order of one of the reference's two bundle maps (see the kernels' comment).  `off`/`n`:
+// the map's bundles in canonical order inside bundle_f; writes the re-ordered heads to bundle_f2 at the same offset.
+int bundle_order_segment(ksg_integrator* h, cudaStream_t s, int off, int n) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  const uint32_t* hash = h->bord_hash + off;
+  int *cur = h->bord_ord_a, *nxt = h->bord_ord_b;
+  int n_old = 0;
+  for (size_t p = 0; p < h->bord_phases.size() && n_old < n; ++p) {
+    const uint32_t n_buckets = h->bord_phases[p].second;
+    const int end = p + 1 < h->bord_phases.size() ? h->bord_phases[p + 1].first : 0x7fffffff;
+    const int m = std::min(end, n);
+    KSG_CUDA(cudaMemsetAsync(h->bord_first, 0x7F, sizeof(int) * (size_t)n_buckets, s));
+    h->n_launches += 2;
+    k_bord_first<<<grid_for(m, 256), 256, 0, s>>>(hash, cur, n_old, m, n_buckets, h->bord_first);
+    k_bord_keys<<<grid_for(m, 256), 256, 0, s>>>(hash, cur, n_old, m, n_buckets, h->bord_first, h->bord_keys_a, h->bord_vals);
+    int end_bit = 33;   // key = first << 32 | arrival, both < m
+    while (end_bit < 64 && (1ull << (end_bit - 32)) < (unsigned long long)m) ++end_bit;
+    size_t tb = h->cub_temp_bytes;
+    ++h->n_libcalls;
+    KSG_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->cub_temp, tb, h->bord_keys_a, h->bord_keys_b, h->bord_vals, nxt, m, 0, end_bit, s));
+    std::swap(cur, nxt);
+    n_old = m;
+  }
+  ++h->n_launches;
+  k_bord_scatter<<<grid_for(n, 256), 256, 0, s>>>(h->bundle_f + off, cur, n, h->bundle_f2 + off);
+  return KSG_OK;
 }
 
 int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaStream_t s, ksg_frame_stats* stats) {
@@ -423,8 +461,22 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       KSG_CUDA(cub::DeviceSelect::Flagged(h->cub_temp, tb, cub::CountingInputIterator<int>(0), h->flags8, h->bundle_f,
                                           &h->d_cnt->n_cast, 2 * cap, s));
     }
+    const int* bundle_heads = h->bundle_f;   // canonical: first-insertion order
+    if (h->cfg.merged_bundle_order == KSG_BUNDLE_ORDER_LIBSTDCXX) {
+      ++h->n_launches;
+      k_bord_hash<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, cap, h->bord_hash);
+      int rc0 = fetch_counters(h, s);
+      if (rc0) return rc0;
+      const int nb_all = h->h_cnt->n_cast, nb_vox = h->h_cnt->n_nonclear;
+      if (nb_all > 0) {
+        if (nb_vox < 0 || nb_vox > nb_all) return fail(KSG_ERR_CUDA, "internal: bundle map split out of range");
+        if (nb_vox > 0 && (rc0 = bundle_order_segment(h, s, 0, nb_vox))) return rc0;                 // voxel_map  (merged.cpp:126-134)
+        if (nb_all > nb_vox && (rc0 = bundle_order_segment(h, s, nb_vox, nb_all - nb_vox))) return rc0;   // clear_map (merged.cpp:138-145)
+        bundle_heads = h->bundle_f2;
+      }
+    }
     ++h->n_launches;
-    k_bundle_merge<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, h->seq_sorted, cap, h->pt_pC,
+    k_bundle_merge<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, bundle_heads, h->bstart, h->ks_sorted, h->seq_sorted, cap, h->pt_pC,
                                                    h->pt_label, h->hist, h->ray_param, h->ray_flags, h->b_key, h->nsteps);
     ++h->n_launches;
     k_bundle_alloc<<<grid_for(cap, 256), 256, 0, s>>>(h->d_cnt, h->nsteps, h->b_base, h->rec_cap);
@@ -581,6 +633,7 @@ void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size
   c->apply_mode = 0;
   c->shard_rank = 0;
   c->shard_count = 1;
+  c->merged_bundle_order = KSG_BUNDLE_ORDER_CANONICAL;
 }
 
 #define KSG_STR_(x) #x
@@ -724,6 +777,19 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
     KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
+    if (cfg->merged_bundle_order == KSG_BUNDLE_ORDER_LIBSTDCXX) {
+      // rehash schedule of the platform's libstdc++ (depends on the size only): probe a real container once
+      std::unordered_map<uint64_t, char> probe;
+      size_t last = 0;
+      for (size_t i = 0; i < N; ++i) {
+        probe.emplace((uint64_t)i, 0);
+        if (probe.bucket_count() != last) { last = probe.bucket_count(); h->bord_phases.push_back(std::make_pair((int)i, (uint32_t)last)); }
+      }
+      if (last >= 0x7fffffffull) return fail(KSG_ERR_INVALID_ARGUMENT, "max_points too large for merged_bundle_order");
+      KSG_CUDA(dmalloc(&h->bord_hash, N)); KSG_CUDA(dmalloc(&h->bord_ord_a, N)); KSG_CUDA(dmalloc(&h->bord_ord_b, N));
+      KSG_CUDA(dmalloc(&h->bord_vals, N)); KSG_CUDA(dmalloc(&h->bundle_f2, N)); KSG_CUDA(dmalloc(&h->bord_first, last));
+      KSG_CUDA(dmalloc(&h->bord_keys_a, N)); KSG_CUDA(dmalloc(&h->bord_keys_b, N));
+    }
   }
   h->rec_cap = rec_cap;
   KSG_CUDA(dmalloc(&h->rec_a, (size_t)rec_cap)); KSG_CUDA(dmalloc(&h->rec_b, (size_t)rec_cap));
@@ -736,6 +802,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     cub::DeviceRadixSort::SortKeys(nullptr, t, h->rec_a, h->rec_b, rec_cap, 0, 64); need = std::max(need, t);
     cub::DeviceRadixSort::SortPairs(nullptr, t, h->pt_key, h->pt_key, h->iota, h->iota, (int)N, 0, 64); need = std::max(need, t);
     cub::DeviceRadixSort::SortPairs(nullptr, t, h->iota, h->iota, h->iota, h->iota, (int)N, 0, 32); need = std::max(need, t);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, t, h->pt_key, h->pt_key, (int*)h->iota, (int*)h->iota, (int)N, 0, 64); need = std::max(need, t);
     cub::DeviceSelect::Flagged(nullptr, t, cub::CountingInputIterator<int>(0), h->flags8, h->pix_list, (int*)nullptr, (int)(2 * N));
     need = std::max(need, t);
     h->cub_temp_bytes = need + 256;
@@ -1099,6 +1166,16 @@ int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int3
   for (int64_t i = 0; i < n; ++i) {
     const I3 b = unpack_key(keys[i]);
     block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
+  }
+  return n;
+}
+
+int64_t ksg_unordered_map_schedule(int64_t n, int64_t* bucket_count_after_insert) {
+  if (n < 0 || (n > 0 && !bucket_count_after_insert)) return -1;
+  std::unordered_map<uint64_t, char> probe;
+  for (int64_t i = 0; i < n; ++i) {
+    probe.emplace((uint64_t)i, 0);
+    bucket_count_after_insert[i] = (int64_t)probe.bucket_count();
   }
   return n;
 }

@@ -63,6 +63,8 @@ struct Counters {
   unsigned long long n_skipped;   // merged anti-grazing: ray steps that emit no update
   unsigned long long n_cand_ext;
   unsigned long long ray_steps;
+  int n_nonclear;    // merged, KSG_BUNDLE_ORDER_LIBSTDCXX: bundles of the non-clearing map (they precede the clearing ones)
+  int pad0;
 };
 
 static constexpr int kH0 = 16;           // ray steps materialised before the first observed-set sweep
@@ -832,6 +834,49 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
     }
     records[base + s] = (htpos >= 0) ? make_record(cfg, htpos, g, (uint32_t)b) : ~0ull;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merged, KSG_BUNDLE_ORDER_LIBSTDCXX: bundle order = iteration order of the reference's std::unordered_map (merged.cpp:210-231)
+// ---------------------------------------------------------------------------------------------
+// libstdc++ keeps one singly linked node list; inserting into an empty bucket puts the node at the list FRONT, into a non-empty
+// bucket at the front of that bucket's run, and a rehash re-inserts all nodes in list order by the same two rules.  Hence every
+// phase (rehash + the insertions up to the next rehash) is one sort of the nodes by
+//     (arrival of the FIRST node of the node's bucket, descending ; own arrival, descending)
+// with arrival = position in the old list for rehashed nodes, then insertion time.  Prototype + proof against the real container:
+// tools/libstdcxx_order.py, tests/test_unordered_map_order.py.  The host drives one (k_bord_first, k_bord_keys, radix sort) round per phase.
+__global__ void k_bord_hash(Counters* cnt, const int* __restrict__ bundle_f, const int* __restrict__ bstart,
+                            const uint64_t* __restrict__ ks, int capacity, uint32_t* __restrict__ hash) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = cnt->n_cast;
+  if (b >= nb) return;
+  const int f = bundle_f[b];
+  hash[b] = index_hash(unpack_key(ks[bstart[f]]));              // LongIndexHash of the bundle's voxel (A.2); bit 63 = clearing flag
+  const bool clr = f >= capacity;
+  if (clr && (b == 0 || bundle_f[b - 1] < capacity)) cnt->n_nonclear = b;   // bundle_f is ascending: non-clearing heads first
+  if (!clr && b == nb - 1) cnt->n_nonclear = nb;
+}
+
+__global__ void k_bord_first(const uint32_t* __restrict__ hash, const int* __restrict__ ord_cur, int n_old, int m, uint32_t n_buckets,
+                             int* __restrict__ first) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int node = t < n_old ? ord_cur[t] : t;                  // the list holds nodes 0..n_old-1; nodes n_old..m-1 arrive in order
+  atomicMin(&first[hash[node] % n_buckets], t);
+}
+
+__global__ void k_bord_keys(const uint32_t* __restrict__ hash, const int* __restrict__ ord_cur, int n_old, int m, uint32_t n_buckets,
+                            const int* __restrict__ first, uint64_t* __restrict__ keys, int* __restrict__ vals) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int node = t < n_old ? ord_cur[t] : t;
+  keys[t] = ((uint64_t)(uint32_t)first[hash[node] % n_buckets] << 32) | (uint32_t)t;
+  vals[t] = node;
+}
+
+__global__ void k_bord_scatter(const int* __restrict__ bundle_f, const int* __restrict__ order, int n, int* __restrict__ bundle_f_out) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos < n) bundle_f_out[pos] = bundle_f[order[pos]];
 }
 
 // ---------------------------------------------------------------------------------------------

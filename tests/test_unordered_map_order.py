@@ -65,3 +65,12 @@ def test_rehash_schedule_depends_only_on_the_size():
     _, a = probe(distinct_keys(rng, 3000, 100))
     _, b = probe(distinct_keys(rng, 3000, 12))
     assert np.array_equal(a, b)
+
+
+def test_product_library_probes_the_same_rehash_schedule_as_the_reference_container():
+    """KSG_BUNDLE_ORDER_LIBSTDCXX sizes its phases from ksg_unordered_map_schedule (host only, callable without a GPU)."""
+    from kimera_semantics_b200 import capi
+    rng = np.random.default_rng(2)
+    _, bc = probe(distinct_keys(rng, 20000, 60))
+    assert np.array_equal(capi.unordered_map_schedule(20000), bc)
+    assert capi.unordered_map_schedule(0).shape == (0,)
