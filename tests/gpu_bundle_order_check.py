@@ -1,7 +1,7 @@
 """Helper run in its OWN process by tests/test_gpu_bundle_order.py: `merged` with ksg_config.merged_bundle_order =
 KSG_BUNDLE_ORDER_LIBSTDCXX through the C-ABI, compared field by field with the digests produced by the reference's own sources
 (tests/golden/ref_hybrid_golden.json).  Prints one JSON object {case: {field: equal?}}.  A separate process keeps a CUDA fault in
-this not-yet-GPU-validated mode from poisoning the context of the rest of the GPU suite."""
+this young mode from poisoning the context of the rest of the GPU suite."""
 import importlib.util
 import json
 import os
