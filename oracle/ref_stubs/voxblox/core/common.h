@@ -54,9 +54,22 @@ constexpr FloatingPoint kCoordinateEpsilon = 1e-6;
 // minkindr QuatTransformationTemplate<float>, reduced to what the integrators call (A.8).
 class Transformation {
  public:
+  // getRotation().toImplementation() is Eigen::Quaternionf in minkindr; callers read w() x() y() z().
+  struct QuaternionImplementation {
+    float qw, qx, qy, qz;
+    float w() const { return qw; }
+    float x() const { return qx; }
+    float y() const { return qy; }
+    float z() const { return qz; }
+  };
+  struct Rotation {
+    QuaternionImplementation q;
+    const QuaternionImplementation& toImplementation() const { return q; }
+  };
   Transformation() : w_(1.0f), v_(0.0f, 0.0f, 0.0f), t_(0.0f, 0.0f, 0.0f) {}
   Transformation(float qw, float qx, float qy, float qz, const Point& t) : w_(qw), v_(qx, qy, qz), t_(t) {}
   const Point& getPosition() const { return t_; }
+  Rotation getRotation() const { return Rotation{QuaternionImplementation{w_, v_[0], v_[1], v_[2]}}; }
   Point operator*(const Point& p) const {
     // Eigen's quaternion * vector: uv = 2 * (q.vec x p);  p + w * uv + q.vec x uv;  then + t.
     Point uv = cross(v_, p);

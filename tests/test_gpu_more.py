@@ -84,6 +84,38 @@ def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mod
     assert_parity(compare_maps(got, ora.export()))
 
 
+BINDING_CHECK = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "gpu_binding_check")
+
+
+@pytest.mark.xfail(strict=False, reason="INTEGRATION.md section B binding: built and link-checked against the reference's real headers on the CPU, "
+                                        "first GPU run pending (written after the round-1 GPU budget was spent)")
+@pytest.mark.parametrize("method", ["fast", "merged"])
+def test_integration_md_binding_against_reference_headers_matches_oracle(tmp_path, method):
+    """integration/kimera_semantics/semantic_tsdf_integrator_gpu.h (what a kimera_semantics maintainer adds) compiled against the
+    reference's REAL SemanticIntegratorBase / SemanticLabel2Color / SemanticVoxel and driven like the shim demo: both host layers
+    must equal the oracle's (merged in the reference's bundle order, which the binding selects)."""
+    if not os.path.exists(BINDING_CHECK):
+        pytest.skip("oracle/_ref/gpu_binding_check not built (needs /root/reference)")
+    C, w, h, vs = 21, 320, 240, 0.10
+    itype = KSG_INTEGRATOR_FAST if method == "fast" else KSG_INTEGRATOR_MERGED
+    cfg = make_config(itype, vs, C, max_points=w * h)
+    pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(C)], np.uint8)
+    ora = OracleIntegrator(cfg, canonical_merged=False)
+    ora.set_color_to_label(pal[:, :3], np.arange(C, dtype=np.uint8))
+    fr = []
+    for cam, depth, label, T in frames(w, h, C, 2):
+        xyz, pix = synth.backproject(depth, cam)
+        rgba = pal[label.reshape(-1)[pix]].copy()
+        rgba[::53] = (9, 8, 7, 255)
+        fr.append((T, xyz, rgba))
+        ora.integrate_points(T, xyz, rgba=rgba)
+    fpath, opath = tmp_path / "frames.bin", tmp_path / "out.bin"
+    write_frames(fpath, fr, vs, 16, pal, [C - 1])
+    r = subprocess.run([BINDING_CHECK, method, str(fpath), str(opath)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout
+    assert_parity(compare_maps(read_shim_output(opath, 16, C), ora.export()))
+
+
 # ---- BASELINE.json full-size configurations -------------------------------------------------------------------------
 def test_fullsize_config1_fast_640x480_5cm_c21_ten_frames():
     cfg = make_config(KSG_INTEGRATOR_FAST, 0.05, 21)

@@ -106,3 +106,21 @@ def test_reference_factory_source_compiles_and_links_against_the_shim(demo, tmp_
     if not torch.cuda.is_available():
         r = subprocess.run([REF_FACTORY_DEMO, "merged", str(fr), str(tmp_path / "o.bin")], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr       # the reference's factory reached OUR constructor
+
+
+BINDING_CHECK = os.path.join(ROOT, "oracle", "_ref", "gpu_binding_check")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference sources (build container only)")
+def test_integration_md_binding_builds_against_the_reference_headers(demo, tmp_path):
+    """INTEGRATION.md section B is real code: integration/kimera_semantics/semantic_tsdf_integrator_gpu.h compiles against the
+    reference's own semantic_integrator_base.h / color.h / semantic_voxel.h, links with libksg.so, and reaches ksg_create."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(BINDING_CHECK)
+    out = subprocess.run(["ldd", BINDING_CHECK], capture_output=True, text=True).stdout
+    assert "libksg.so" in out and "ks_oracle" not in out and "ks_ref_hybrid" not in out
+    fr = tmp_path / "f.bin"
+    write_frames(fr, [], 0.1, 16, [(255, 255, 255, 255)], [])
+    if not torch.cuda.is_available():
+        r = subprocess.run([BINDING_CHECK, "fast", str(fr), str(tmp_path / "o.bin")], capture_output=True, text=True)
+        assert r.returncode != 0 and "semantic_tsdf_integrator_gpu.h" in r.stderr and "no CPU fallback" in r.stderr
