@@ -126,3 +126,24 @@ def test_full_reset_of_the_approximate_sets_after_10000_frames_matches_the_refer
         ora.integrate_points(T, xyz, rgba=rgba)
     rep = compare_maps(ref.export(), ora.export())
     assert rep["same_blocks"] == 1.0 and not {k: v for k, v in rep.items() if k.endswith("mismatch") and v}, rep
+
+
+@needs_ref
+def test_the_reference_itself_is_not_reproducible_with_several_threads():
+    """Why parity is defined at integrator_threads = 1: the reference's own code (default: hardware_concurrency threads) races on
+    the two approximate sets (`fast`) and on the per-voxel update order (both integrators), so its result changes from run to run.
+    Reported here for the record; the assertion only requires that 8 threads do NOT reproduce the 1-thread map."""
+    name = "fast_fullsize_640x480_5cm_4f"
+
+    def run(threads):
+        def make(cfg):
+            cfg.integrator_threads = threads
+            return ref_py.RefHybridIntegrator(cfg)
+        return mrg.run_case(name, make)
+    one = run(1)
+    assert mrg.digest(one) == GOLDEN[name]
+    rep = compare_maps(run(8), one)
+    observed = float((one["tsdf_weight"] > 0).sum())
+    print(f"reference sources, 8 threads vs 1 thread ({name}): labels differ on {rep.get('label_mismatch', -1):.0f} of {observed:.0f} observed "
+          f"voxels, distance bits on {rep.get('tsdf_distance_bit_mismatch', -1):.0f}, log-probability bits on {rep.get('sem_priors_bit_mismatch', -1):.0f}")
+    assert rep["same_blocks"] != 1.0 or rep["sem_priors_bit_mismatch"] + rep["tsdf_weight_bit_mismatch"] > 0
