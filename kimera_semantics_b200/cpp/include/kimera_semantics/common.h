@@ -1,6 +1,7 @@
 // Mirror of kimera_semantics/include/kimera_semantics/common.h (reference common.h:17-38).
 #pragma once
 #include <array>
+#include <cmath>
 #include <memory>
 #include "voxblox/core/common.h"
 namespace kimera {
@@ -24,6 +25,16 @@ struct SemanticProbabilities {
   const SemanticProbability& operator[](size_t i) const { return v[i]; }
   size_t size() const { return kTotalNumberOfLabels; }
   SemanticProbability* data() { return v.data(); }
+  const SemanticProbability* data() const { return v.data(); }
+  void setConstant(SemanticProbability c) { v.fill(c); }
+  bool hasNaN() const { for (size_t i = 0; i < kTotalNumberOfLabels; ++i) if (v[i] != v[i]) return true; return false; }
+  // Eigen norm()/normalize(): L2 norm (left-to-right accumulation here), division by it when it is positive
+  SemanticProbability norm() const {
+    SemanticProbability s = v[0] * v[0];
+    for (size_t i = 1; i < kTotalNumberOfLabels; ++i) s += v[i] * v[i];
+    return std::sqrt(s);
+  }
+  void normalize() { const SemanticProbability n = norm(); if (n > 0.0f) for (size_t i = 0; i < kTotalNumberOfLabels; ++i) v[i] /= n; }
   // Eigen maxCoeff(&index): first maximum wins
   SemanticProbability maxCoeff(SemanticLabel* index) const {
     size_t best = 0;

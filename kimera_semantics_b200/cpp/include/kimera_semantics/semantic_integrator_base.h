@@ -23,7 +23,14 @@ class SemanticIntegratorBase {
   virtual ~SemanticIntegratorBase() = default;
 
   SemanticProbability computeMeasurementProbability(vxb::FloatingPoint ray_distance) { (void)ray_distance; return 1.0; }  // base.cpp:131-134
-  // THREAD SAFE helpers that do not touch the map (base.cpp:352-380)
+  // THREAD SAFE helpers that do not touch the map (base.cpp:283-380).  They are the reference's public per-vector utilities; the
+  // integrators here never call them (the per-voxel update runs in the CUDA tile kernel) - they exist for callers that post-process
+  // a voxel's probabilities on the host.
+  // *prior += semantic_log_likelihood_ * measurement_frequencies   (base.cpp:283-314; columns accumulated in ascending order)
+  void updateSemanticVoxelProbabilities(const SemanticProbabilities& measurement_frequencies,
+                                        SemanticProbabilities* semantic_prior_probability) const;
+  // L2-normalises the vector (sic, base.cpp:317-350); aborts like the reference when (*p)[0] >= 0
+  void normalizeProbabilities(SemanticProbabilities* unnormalized_probs) const;
   void calculateMaximumLikelihoodLabel(const SemanticProbabilities& semantic_posterior, SemanticLabel* semantic_label) const;
   void updateSemanticVoxelColor(const SemanticLabel& semantic_label, HashableColor* semantic_voxel_color) const;
 

@@ -87,6 +87,30 @@ void SemanticIntegratorBase::setSemanticProbabilities() {
       semantic_log_likelihood_(i, j) = (i == j) ? log_match_probability_ : log_non_match_probability_;
   for (size_t i = 0; i < kTotalNumberOfLabels; ++i) semantic_log_likelihood_(i, kUnknownSemanticLabelId) = 0.0f;  // base.cpp:127
 }
+void SemanticIntegratorBase::updateSemanticVoxelProbabilities(const SemanticProbabilities& measurement_frequencies,
+                                                              SemanticProbabilities* semantic_prior_probability) const {
+  KSG_CHECK(semantic_prior_probability != nullptr);
+  // dense product as in base.cpp:306-307, accumulated column by column (j ascending) before it is added to the prior
+  SemanticProbabilities product;
+  for (size_t i = 0; i < kTotalNumberOfLabels; ++i) product[i] = semantic_log_likelihood_(i, 0) * measurement_frequencies[0];
+  for (size_t j = 1; j < kTotalNumberOfLabels; ++j)
+    for (size_t i = 0; i < kTotalNumberOfLabels; ++i) product[i] += semantic_log_likelihood_(i, j) * measurement_frequencies[j];
+  for (size_t i = 0; i < kTotalNumberOfLabels; ++i) (*semantic_prior_probability)[i] += product[i];
+}
+void SemanticIntegratorBase::normalizeProbabilities(SemanticProbabilities* unnormalized_probs) const {
+  KSG_CHECK(unnormalized_probs != nullptr);
+  KSG_CHECK((*unnormalized_probs)[0] < 0.0) << "Are you sure you are usinglog odds?";   // base.cpp:322-323 (text as upstream)
+  const SemanticProbability normalization_factor = unnormalized_probs->norm();
+  KSG_CHECK(normalization_factor >= 0.0);
+  if (normalization_factor != 0.0) {
+    unnormalized_probs->normalize();
+  } else {
+    // base.cpp:335-341: std::log(1 / kTotalNumberOfLabels) with INTEGER division, i.e. log(0) = -inf; unreachable after the
+    // CHECK_LT above (a vector whose first entry is negative has a positive norm), kept for fidelity
+    unnormalized_probs->setConstant(std::log(static_cast<SemanticProbability>(1 / kTotalNumberOfLabels)));
+  }
+  KSG_CHECK(std::abs(unnormalized_probs->norm() - 1.0f) <= vxb::kFloatEpsilon);           // the reference's kDebug CHECK_NEAR
+}
 void SemanticIntegratorBase::calculateMaximumLikelihoodLabel(const SemanticProbabilities& semantic_posterior,
                                                              SemanticLabel* semantic_label) const {
   KSG_CHECK(semantic_label != nullptr);

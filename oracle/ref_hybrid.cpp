@@ -34,6 +34,7 @@ struct Hybrid {
   std::unique_ptr<voxblox::Layer<voxblox::TsdfVoxel>> tsdf;
   std::unique_ptr<voxblox::Layer<kimera::SemanticVoxel>> sem;
   std::unique_ptr<voxblox::TsdfIntegratorBase> integrator;
+  kimera::SemanticIntegratorBase* semantic_base = nullptr;   // the same object seen through its second base class
   double last_integrate_seconds = 0.0;
 };
 
@@ -104,10 +105,15 @@ void* kref_create(const ksg_config* c) {
   for (int l = 0; l < 256; ++l)
     if (c->dynamic_label[l]) sc.dynamic_labels_.push_back((kimera::SemanticLabel)l);
 
-  if (c->integrator_type == KSG_INTEGRATOR_FAST)
-    h->integrator.reset(new kimera::FastSemanticTsdfIntegrator(tc, sc, h->tsdf.get(), h->sem.get()));
-  else
-    h->integrator.reset(new kimera::MergedSemanticTsdfIntegrator(tc, sc, h->tsdf.get(), h->sem.get()));
+  if (c->integrator_type == KSG_INTEGRATOR_FAST) {
+    auto* p = new kimera::FastSemanticTsdfIntegrator(tc, sc, h->tsdf.get(), h->sem.get());
+    h->integrator.reset(p);
+    h->semantic_base = p;
+  } else {
+    auto* p = new kimera::MergedSemanticTsdfIntegrator(tc, sc, h->tsdf.get(), h->sem.get());
+    h->integrator.reset(p);
+    h->semantic_base = p;
+  }
   return h.release();
 }
 
@@ -133,6 +139,33 @@ int kref_integrate_points(void* hh, const float* T, const float* xyz, const uint
 // Wall time of the last integratePointCloud call alone (the span of the reference's "integrate/fast" +
 // "inserting_missed_blocks" / "semantic_tsdf/integrate" timers).
 double kref_last_integrate_seconds(void* hh) { return ((Hybrid*)hh)->last_integrate_seconds; }
+
+// The reference's public per-vector helpers (base.cpp:283-314, 317-350, 370-380), for checking the shim's copies of them.
+void kref_update_probabilities(void* hh, const float* frequencies, float* prior_inout) {
+  kimera::SemanticProbabilities f, p;
+  for (size_t i = 0; i < kimera::kTotalNumberOfLabels; ++i) { f[i] = frequencies[i]; p[i] = prior_inout[i]; }
+  ((Hybrid*)hh)->semantic_base->updateSemanticVoxelProbabilities(f, &p);
+  for (size_t i = 0; i < kimera::kTotalNumberOfLabels; ++i) prior_inout[i] = p[i];
+}
+void kref_normalize_probabilities(void* hh, float* probs_inout) {   // aborts (CHECK) exactly where the reference does
+  kimera::SemanticProbabilities p;
+  for (size_t i = 0; i < kimera::kTotalNumberOfLabels; ++i) p[i] = probs_inout[i];
+  ((Hybrid*)hh)->semantic_base->normalizeProbabilities(&p);
+  for (size_t i = 0; i < kimera::kTotalNumberOfLabels; ++i) probs_inout[i] = p[i];
+}
+void kref_label_color(void* hh, int label, uint8_t* rgba) {
+  kimera::HashableColor c;
+  ((Hybrid*)hh)->semantic_base->updateSemanticVoxelColor((kimera::SemanticLabel)label, &c);
+  rgba[0] = c.r; rgba[1] = c.g; rgba[2] = c.b; rgba[3] = c.a;
+}
+void kref_log_likelihood(void* hh, float* matrix_row_major, float* log_match, float* log_non_match) {
+  const kimera::SemanticIntegratorBase* b = ((Hybrid*)hh)->semantic_base;
+  const size_t C = kimera::kTotalNumberOfLabels;
+  for (size_t i = 0; i < C; ++i)
+    for (size_t j = 0; j < C; ++j) matrix_row_major[i * C + j] = b->semantic_log_likelihood_(i, j);
+  *log_match = b->log_match_probability_;
+  *log_non_match = b->log_non_match_probability_;
+}
 
 int64_t kref_num_blocks(void* hh) { return (int64_t)((Hybrid*)hh)->tsdf->getNumberOfAllocatedBlocks(); }
 int64_t kref_num_semantic_blocks(void* hh) { return (int64_t)((Hybrid*)hh)->sem->getNumberOfAllocatedBlocks(); }

@@ -42,6 +42,10 @@ def load(fast_build: bool = False) -> C.CDLL:
         lib.kref_num_semantic_blocks.restype = C.c_int64
         lib.kref_export_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
         lib.kref_export_blocks.restype = C.c_int
+        lib.kref_update_probabilities.argtypes = [H, fp, fp]
+        lib.kref_normalize_probabilities.argtypes = [H, fp]
+        lib.kref_label_color.argtypes = [H, C.c_int, u8p]
+        lib.kref_log_likelihood.argtypes = [H, fp, fp, fp]
         lib.kref_last_integrate_seconds.argtypes = [H]
         lib.kref_last_integrate_seconds.restype = C.c_double
         _LIBS[path] = lib
@@ -79,6 +83,30 @@ class RefHybridIntegrator:
                                             xyz.shape[0], int(freespace))
         if rc != 0:
             raise ValueError(f"kref_integrate_points: {rc}")
+
+    # the reference's public per-vector helpers (SemanticIntegratorBase), on plain arrays
+    def update_probabilities(self, frequencies, prior) -> np.ndarray:
+        f = np.ascontiguousarray(frequencies, np.float32)
+        p = np.array(prior, np.float32, copy=True)
+        self.lib.kref_update_probabilities(self.handle, _ptr(f, C.c_float), _ptr(p, C.c_float))
+        return p
+
+    def normalize_probabilities(self, probs) -> np.ndarray:
+        p = np.array(probs, np.float32, copy=True)
+        self.lib.kref_normalize_probabilities(self.handle, _ptr(p, C.c_float))
+        return p
+
+    def label_color(self, label: int) -> np.ndarray:
+        out = np.zeros(4, np.uint8)
+        self.lib.kref_label_color(self.handle, int(label), _ptr(out, C.c_uint8))
+        return out
+
+    def log_likelihood(self):
+        n = self.lib.kref_num_labels()
+        m = np.zeros((n, n), np.float32)
+        a, b = C.c_float(), C.c_float()
+        self.lib.kref_log_likelihood(self.handle, _ptr(m, C.c_float), C.byref(a), C.byref(b))
+        return m, a.value, b.value
 
     def last_integrate_seconds(self) -> float:
         return float(self.lib.kref_last_integrate_seconds(self.handle))

@@ -124,3 +124,49 @@ def test_integration_md_binding_builds_against_the_reference_headers(demo, tmp_p
     if not torch.cuda.is_available():
         r = subprocess.run([BINDING_CHECK, "fast", str(fr), str(tmp_path / "o.bin")], capture_output=True, text=True)
         assert r.returncode != 0 and "semantic_tsdf_integrator_gpu.h" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_host_helpers_of_the_shim_equal_the_reference_implementations(demo, tmp_path):
+    """SURVEY.md 8b "public surface": setSemanticProbabilities (the log-likelihood matrix), updateSemanticVoxelProbabilities,
+    calculateMaximumLikelihoodLabel, updateSemanticVoxelColor, normalizeProbabilities of the shim's SemanticIntegratorBase against
+    the reference's own compiled code (oracle/_ref) on random vectors: bit-exact, except normalizeProbabilities whose L2 norm Eigen
+    may accumulate in another order (1e-6 relative)."""
+    import numpy as np
+    from oracle import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref not built")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(ROOT, "tests", "golden", "make_ref_golden.py"))
+    mrg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mrg)
+    cfg = mrg.case_config("fast_p08")                      # p = 0.8
+    ref = ref_py.RefHybridIntegrator(cfg)
+    C, n = 21, 200
+    rng = np.random.default_rng(7)
+    priors = (-rng.uniform(0.1, 40.0, (n, C))).astype(np.float32)
+    freqs = rng.integers(0, 6, (n, C)).astype(np.float32)
+    freqs[::5] = np.eye(C, dtype=np.float32)[rng.integers(0, C, len(freqs[::5]))]      # one-hot rows, as `fast` produces them
+    pal = [tuple(int(cfg.label_color[l][k]) for k in range(4)) for l in range(C)]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(np.int32(n).tobytes() + np.int32(C).tobytes())
+        for l, c in enumerate(pal):
+            f.write(bytes([c[0], c[1], c[2], c[3], l]))
+        f.write(np.float32(cfg.semantic_measurement_probability).tobytes())
+        for k in range(n):
+            f.write(priors[k].tobytes() + freqs[k].tobytes())
+    r = subprocess.run([os.path.join(CPP, "base_helpers_test"), str(fin), str(fout)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(fout, "rb").read()
+    lm, ln = np.frombuffer(raw, "<f4", 2, 0)
+    L = np.frombuffer(raw, "<f4", C * C, 8).reshape(C, C)
+    Lr, lmr, lnr = ref.log_likelihood()
+    assert np.array_equal(L, Lr) and lm == np.float32(lmr) and ln == np.float32(lnr)
+    rec = np.dtype([("upd", "<f4", C), ("label", "u1"), ("rgba", "u1", 4), ("norm", "<f4", C)])
+    got = np.frombuffer(raw, rec, n, 8 + 4 * C * C)
+    for k in range(n):
+        upd = ref.update_probabilities(freqs[k], priors[k])
+        assert np.array_equal(got["upd"][k], upd), k
+        assert got["label"][k] == int(np.argmax(upd))                                   # first maximum
+        assert np.array_equal(got["rgba"][k], ref.label_color(int(got["label"][k])))
+        np.testing.assert_allclose(got["norm"][k], ref.normalize_probabilities(upd), rtol=1e-6)
