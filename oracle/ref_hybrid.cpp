@@ -14,6 +14,8 @@
 //
 // This file is the only code of ours in the library: a C wrapper with the kso_* export layout so that
 // tests/parity_utils.compare_maps can diff reference-hybrid vs oracle maps directly.
+#include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -165,6 +167,29 @@ void kref_log_likelihood(void* hh, float* matrix_row_major, float* log_match, fl
     for (size_t j = 0; j < C; ++j) matrix_row_major[i * C + j] = b->semantic_log_likelihood_(i, j);
   *log_match = b->log_match_probability_;
   *log_non_match = b->log_non_match_probability_;
+}
+
+// SemanticLabel2Color's two tables for a CSV file, parsed by the reference's own reader (color.cpp:42-67, csv_iterator.cpp), in the
+// text format of the shim's `color_csv_test <file> --dump`.  Returns the number of characters written (or needed).
+int64_t kref_csv_dump(const char* path, char* out, int64_t capacity) {
+  const kimera::SemanticLabel2Color lut{std::string(path)};
+  std::string text;
+  char row[64];
+  for (int l = 0; l < 256; ++l) {
+    const auto it = lut.semantic_label_to_color_map_.find((kimera::SemanticLabel)l);
+    if (it == lut.semantic_label_to_color_map_.end()) continue;
+    std::snprintf(row, sizeof(row), "L %d %d %d %d %d\n", l, it->second.r, it->second.g, it->second.b, it->second.a);
+    text += row;
+  }
+  std::vector<std::array<int, 5>> rows;
+  for (const auto& kv : lut.color_to_semantic_label_) rows.push_back({{kv.first.r, kv.first.g, kv.first.b, kv.first.a, kv.second}});
+  std::sort(rows.begin(), rows.end());
+  for (const auto& r : rows) {
+    std::snprintf(row, sizeof(row), "C %d %d %d %d %d\n", r[0], r[1], r[2], r[3], r[4]);
+    text += row;
+  }
+  if ((int64_t)text.size() <= capacity && out) std::memcpy(out, text.data(), text.size());
+  return (int64_t)text.size();
 }
 
 int64_t kref_num_blocks(void* hh) { return (int64_t)((Hybrid*)hh)->tsdf->getNumberOfAllocatedBlocks(); }

@@ -46,10 +46,21 @@ def load(fast_build: bool = False) -> C.CDLL:
         lib.kref_normalize_probabilities.argtypes = [H, fp]
         lib.kref_label_color.argtypes = [H, C.c_int, u8p]
         lib.kref_log_likelihood.argtypes = [H, fp, fp, fp]
+        lib.kref_csv_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+        lib.kref_csv_dump.restype = C.c_int64
         lib.kref_last_integrate_seconds.argtypes = [H]
         lib.kref_last_integrate_seconds.restype = C.c_double
         _LIBS[path] = lib
     return _LIBS[path]
+
+
+def csv_dump(path: str) -> str:
+    """Both SemanticLabel2Color tables of a CSV file as parsed by the reference's own reader."""
+    lib = load()
+    n = lib.kref_csv_dump(path.encode(), None, 0)
+    buf = C.create_string_buffer(int(n))
+    lib.kref_csv_dump(path.encode(), buf, n)
+    return buf.raw.decode()
 
 
 class RefHybridIntegrator:

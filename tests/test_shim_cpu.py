@@ -2,6 +2,7 @@
 error convention (abort with a message) and never integrates on the CPU."""
 import os
 import subprocess
+import sys
 
 import pytest
 import torch
@@ -170,3 +171,30 @@ def test_host_helpers_of_the_shim_equal_the_reference_implementations(demo, tmp_
         assert got["label"][k] == int(np.argmax(upd))                                   # first maximum
         assert np.array_equal(got["rgba"][k], ref.label_color(int(got["label"][k])))
         np.testing.assert_allclose(got["norm"][k], ref.normalize_probabilities(upd), rtol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/kimera_semantics_ros/cfg"), reason="needs the reference's CSV fixtures (build container only)")
+def test_label_csv_files_of_the_reference_parse_identically(demo):
+    """The only data fixtures the reference ships are its label tables (kimera_semantics_ros/cfg/*.csv): the shim's
+    SemanticLabel2Color must build the same two tables from them as the reference's own reader (header row, duplicate colours,
+    label 0 -> white override and all)."""
+    from oracle import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref not built")
+    cfg_dir = "/root/reference/kimera_semantics_ros/cfg"
+    files = [f for f in sorted(os.listdir(cfg_dir)) if f.endswith("_mapping.csv") or f == "simulation.csv"]
+    assert len(files) >= 4
+    parsed = 0
+    for name in files:
+        path = os.path.join(cfg_dir, name)
+        got = subprocess.run([os.path.join(CPP, "color_csv_test"), path, "--dump"], capture_output=True, text=True)
+        # the reference aborts (CHECK_EQ(loop->size(), 6), color.cpp:51) on a malformed file, so it runs in its own process
+        want = subprocess.run([sys.executable, "-c", "import sys; from oracle import ref_py; sys.stdout.write(ref_py.csv_dump(sys.argv[1]))", path],
+                              capture_output=True, text=True, cwd=ROOT)
+        assert (got.returncode == 0) == (want.returncode == 0), (name, got.stderr, want.stderr)
+        if want.returncode == 0:
+            assert got.stdout == want.stdout, name
+            parsed += 1
+        else:   # one of the shipped files (mask_rcnn_mapping.csv) has two-column rows: both readers refuse it the same way
+            assert "Row 2 is invalid" in got.stderr and "Row 2 is invalid" in want.stderr, name
+    assert parsed >= 4
