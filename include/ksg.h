@@ -160,7 +160,12 @@ int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T_G_C_host, 
 /* Depth + label frame entry (SURVEY.md 8f NEXT-1): fuses PointCloudFromDepth::convert<float>
  * (kimera_semantics_ros/include/kimera_semantics_ros/depth_map_to_pointcloud.h:222-266; x=(u-cx)*d*(1/fx),
  * y=(v-cy)*d*(1/fy), z=d, non-finite depth -> dropped point as voxblox_ros convertPointcloud does)
- * with integratePointCloud.  depth: h*w float32 metres, label: h*w uint8, K = fx fy cx cy. */
+ * with integratePointCloud.  depth: h*w float32 metres, label: h*w uint8, K = fx fy cx cy.
+ * Precision note: the reference derives constant_x = float(1.0 / fx) from the DOUBLE fx of sensor_msgs/CameraInfo and
+ * center_x = float(cx) (depth_map_to_pointcloud.h:222-230); here fx, fy arrive as float, so the two agree bit for bit when the
+ * intrinsics are exactly representable in float (true for the usual integral or half-integral values); otherwise 1/fx can be
+ * one float ulp apart.  Callers that need the last bit with such intrinsics should pre-build the cloud and use
+ * ksg_integrate_points. */
 int32_t ksg_integrate_depth(ksg_integrator* h, const float* T_G_C, const float* depth,
                             const uint8_t* label, int32_t width, int32_t height, const float* K,
                             ksg_frame_stats* stats);
