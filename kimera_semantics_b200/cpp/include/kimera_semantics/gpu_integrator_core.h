@@ -24,6 +24,9 @@ class GpuIntegratorCore {
   void setLayerSyncMode(LayerSyncMode m) { sync_mode_ = m; }
   void syncLayers();           // copy every device block into the host layers
   void syncUpdatedBlocks();    // copy the blocks of the last integrate call
+  // The other direction: replace the device map by the contents of the host layers (ksg_reset + ksg_import_blocks), e.g. after
+  // map_io::loadLayers.  The fast integrator's two approximate sets start empty, as in a freshly constructed reference integrator.
+  void uploadLayers();
   int64_t lastVoxelUpdates() const { return last_voxel_updates_; }
   ksg_integrator* handle() { return handle_; }
 

@@ -5,6 +5,7 @@
 #pragma once
 #include <memory>
 #include <string>
+#include "kimera_semantics/map_io.h"
 #include "kimera_semantics/semantic_tsdf_integrator_factory.h"
 #include "kimera_semantics/semantic_tsdf_integrator_fast.h"
 #include "kimera_semantics/semantic_tsdf_integrator_merged.h"
@@ -53,6 +54,20 @@ class SemanticTsdfServer {
   }
   // bring the host layers up to date (needed before meshing / saving when layer_sync == kLazy)
   void updateLayers() { gpu().syncLayers(); }
+
+  // Checkpoint / resume (the reference saves its TSDF layer with TsdfServer::saveMap, kimera_semantics_rosbag.cpp:150; here both
+  // layers go into one file, see map_io.h).  saveMap brings the host layers up to date first; loadMap replaces the host layers
+  // AND the device map by the file's contents, after which integration continues as if it had never stopped (the fast
+  // integrator's per-scan approximate sets restart empty, exactly as after constructing a new reference integrator).
+  bool saveMap(const std::string& path) {
+    updateLayers();
+    return map_io::saveLayers(path, *tsdf_layer_, *semantic_layer_);
+  }
+  bool loadMap(const std::string& path) {
+    if (!map_io::loadLayers(path, tsdf_layer_.get(), semantic_layer_.get())) return false;
+    gpu().uploadLayers();
+    return true;
+  }
 
   vxb::Layer<vxb::TsdfVoxel>* getTsdfLayerPtr() { return tsdf_layer_.get(); }
   vxb::Layer<SemanticVoxel>* getSemanticLayerPtr() { return semantic_layer_.get(); }

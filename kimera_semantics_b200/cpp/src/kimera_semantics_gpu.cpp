@@ -241,6 +241,38 @@ void GpuIntegratorCore::syncUpdatedBlocks() {
   if (n) ksg_last_updated_blocks(handle_, n, idx.data());
   copyBlocks(idx);
 }
+void GpuIntegratorCore::uploadLayers() {
+  vxb::BlockIndexList blocks;
+  tsdf_layer_->getAllAllocatedBlocks(&blocks);
+  KSG_CHECK(ksg_reset(handle_) == KSG_OK) << "ksg_reset failed: " << ksg_last_error(handle_);
+  const size_t nb = blocks.size();
+  if (nb == 0) return;
+  const size_t vps = tsdf_layer_->voxels_per_side(), V = vps * vps * vps, C = kTotalNumberOfLabels;
+  std::vector<int32_t> idx(nb * 3);
+  std::vector<float> dist(nb * V), wgt(nb * V), priors(nb * V * C);
+  std::vector<uint8_t> rgba(nb * V * 4), srgba(nb * V * 4), label(nb * V);
+  for (size_t b = 0; b < nb; ++b) {
+    const vxb::BlockIndex& bi = blocks[b];
+    idx[3 * b] = bi.x(); idx[3 * b + 1] = bi.y(); idx[3 * b + 2] = bi.z();
+    vxb::Block<vxb::TsdfVoxel>::Ptr tb = tsdf_layer_->getBlockPtrByIndex(bi);
+    vxb::Block<SemanticVoxel>::Ptr sb = semantic_layer_->allocateBlockPtrByIndex(bi);   // a TSDF-only block gets default semantics
+    for (size_t v = 0; v < V; ++v) {
+      const vxb::TsdfVoxel& tv = tb->getVoxelByLinearIndex(v);
+      const SemanticVoxel& sv = sb->getVoxelByLinearIndex(v);
+      dist[b * V + v] = tv.distance;
+      wgt[b * V + v] = tv.weight;
+      uint8_t* c = &rgba[(b * V + v) * 4];
+      c[0] = tv.color.r; c[1] = tv.color.g; c[2] = tv.color.b; c[3] = tv.color.a;
+      label[b * V + v] = sv.semantic_label;
+      std::memcpy(&priors[(b * V + v) * C], sv.semantic_priors.data(), C * sizeof(float));
+      uint8_t* s = &srgba[(b * V + v) * 4];
+      s[0] = sv.color.r; s[1] = sv.color.g; s[2] = sv.color.b; s[3] = sv.color.a;
+    }
+  }
+  const int rc = ksg_import_blocks(handle_, (int64_t)nb, idx.data(), dist.data(), wgt.data(), rgba.data(), label.data(), priors.data(),
+                                   srgba.data());
+  KSG_CHECK(rc == KSG_OK) << "ksg_import_blocks failed: " << ksg_last_error(handle_);
+}
 void GpuIntegratorCore::syncLayers() {
   const int64_t n = ksg_num_blocks(handle_);
   std::vector<int32_t> idx((size_t)n * 3);

@@ -1,12 +1,14 @@
 // Drives the drop-in C++ API exactly the way SemanticTsdfServer does (kimera_semantics_ros/src/semantic_tsdf_server.cpp:58-79):
 // build both layers, SemanticTsdfIntegratorFactory::create(method, ...), then integratePointCloud per frame.
-//   shim_demo <fast|merged|bogus> <frames.bin> <out.bin> [lazy]
+//   shim_demo <fast|merged|bogus> <frames.bin> <out.bin> [lazy] [--load ckpt] [--save ckpt] [--skip N]
+//     --load: SemanticTsdfServer::loadMap before the first frame; --save: saveMap after the last; --skip: ignore the first N frames
 // frames.bin : int32 n_frames, float voxel_size, int32 vps, int32 n_palette, palette n*(r,g,b,a,id), int32 n_dynamic, ids...,
 //              then per frame: int32 n, float T[7], float xyz[3n], uint8 rgba[4n]
 // out.bin    : int32 n_blocks, then per block (sorted z,y,x): int32 idx[3], per voxel: float d, float w, u8 rgba[4], u8 label,
 //              float priors[C], u8 sem_rgba[4]
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include "kimera_semantics/semantic_tsdf_integrator_factory.h"
@@ -33,7 +35,15 @@ int main(int argc, char** argv) {
   for (int i = 0; i < n_dyn; ++i) sc.dynamic_labels_.push_back(rd<uint8_t>(f));
   vxb::TsdfIntegratorBase::Config config;
   config.default_truncation_distance = 4.0f * voxel_size;  // voxblox_ros
-  const bool lazy = argc > 4 && std::strcmp(argv[4], "lazy") == 0;
+  bool lazy = false;
+  const char *load_path = nullptr, *save_path = nullptr;
+  int skip = 0;
+  for (int a = 4; a < argc; ++a) {
+    if (std::strcmp(argv[a], "lazy") == 0) lazy = true;
+    else if (std::strcmp(argv[a], "--load") == 0 && a + 1 < argc) load_path = argv[++a];
+    else if (std::strcmp(argv[a], "--save") == 0 && a + 1 < argc) save_path = argv[++a];
+    else if (std::strcmp(argv[a], "--skip") == 0 && a + 1 < argc) skip = std::atoi(argv[++a]);
+  }
   SemanticTsdfServer::Params params;
   params.tsdf_voxel_size = voxel_size;
   params.tsdf_voxels_per_side = vps;
@@ -43,17 +53,20 @@ int main(int argc, char** argv) {
   vxb::Layer<vxb::TsdfVoxel>& tsdf_layer = *server.getTsdfLayerPtr();
   vxb::Layer<SemanticVoxel>& semantic_layer = *server.getSemanticLayerPtr();
   GpuIntegratorCore* core = &server.gpu();
+  if (load_path) KSG_CHECK(server.loadMap(load_path)) << "cannot load " << load_path;
   for (int fr = 0; fr < n_frames; ++fr) {
     const int n = rd<int32_t>(f);
     float T[7]; f.read(reinterpret_cast<char*>(T), sizeof(T));
     vxb::Pointcloud pts(n); vxb::Colors cols(n);
     f.read(reinterpret_cast<char*>(pts.data()), sizeof(float) * 3 * n);
     f.read(reinterpret_cast<char*>(cols.data()), 4 * (size_t)n);
+    if (fr < skip) continue;
     server.processPointCloud(vxb::Transformation(T[0], T[1], T[2], T[3], vxb::Point(T[4], T[5], T[6])), pts, cols, /*stamp=*/0.2 * fr);
     std::printf("frame %d: %d points, %lld voxel updates, %zu blocks in the host layer\n", fr, n, (long long)core->lastVoxelUpdates(),
                 tsdf_layer.getNumberOfAllocatedBlocks());
   }
   if (lazy) server.updateLayers();
+  if (save_path) KSG_CHECK(server.saveMap(save_path)) << "cannot save " << save_path;
   vxb::BlockIndexList blocks;
   tsdf_layer.getAllAllocatedBlocks(&blocks);
   std::sort(blocks.begin(), blocks.end(), [](const vxb::BlockIndex& a, const vxb::BlockIndex& b) {

@@ -84,6 +84,32 @@ def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mod
     assert_parity(compare_maps(got, ora.export()))
 
 
+@pytest.mark.xfail(strict=False, reason="SemanticTsdfServer::saveMap / loadMap: host file round trip tested on the CPU, device upload goes through the "
+                                        "GPU-tested ksg_import_blocks, but this end-to-end path has not run on a B200 yet (written after the GPU budget was spent)")
+def test_checkpoint_and_resume_through_the_shim_continues_bit_exactly(demo, tmp_path):
+    """merged has no cross-frame integrator state, so integrate(0..1) -> saveMap | new process: loadMap -> integrate(2..3) must
+    equal integrate(0..3) in every voxel of both host layers."""
+    C, w, h, vs = 21, 160, 120, 0.10
+    cfg = make_config(KSG_INTEGRATOR_MERGED, vs, C, max_points=w * h)
+    pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(C)], np.uint8)
+    fr = []
+    for cam, depth, label, T in frames(w, h, C, 4):
+        xyz, pix = synth.backproject(depth, cam)
+        fr.append((T, xyz, pal[label.reshape(-1)[pix]].copy()))
+    fpath, ckpt = tmp_path / "frames.bin", tmp_path / "map.ksgm"
+    write_frames(fpath, fr, vs, 16, pal, [C - 1])
+    write_frames(tmp_path / "first.bin", fr[:2], vs, 16, pal, [C - 1])
+    env = dict(os.environ, KSG_MAX_POINTS=str(w * h), KSG_MAX_UPDATES=str(8 << 20))
+    runs = {"all": [demo, "merged", str(fpath), str(tmp_path / "all.bin")],
+            "first": [demo, "merged", str(tmp_path / "first.bin"), str(tmp_path / "first_out.bin"), "--save", str(ckpt)],
+            "resumed": [demo, "merged", str(fpath), str(tmp_path / "resumed.bin"), "--load", str(ckpt), "--skip", "2"]}
+    for name in ("all", "first", "resumed"):
+        r = subprocess.run(runs[name], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, (name, r.stderr + r.stdout)
+    assert open(tmp_path / "resumed.bin", "rb").read() == open(tmp_path / "all.bin", "rb").read()
+    assert open(tmp_path / "first_out.bin", "rb").read() != open(tmp_path / "all.bin", "rb").read()
+
+
 BINDING_CHECK = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "gpu_binding_check")
 
 

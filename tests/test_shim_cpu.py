@@ -198,3 +198,12 @@ def test_label_csv_files_of_the_reference_parse_identically(demo):
         else:   # one of the shipped files (mask_rcnn_mapping.csv) has two-column rows: both readers refuse it the same way
             assert "Row 2 is invalid" in got.stderr and "Row 2 is invalid" in want.stderr, name
     assert parsed >= 4
+
+
+def test_map_checkpoint_file_round_trip_on_the_host(demo, tmp_path):
+    """map_io.h (SURVEY.md 8f NEXT-3 / checkpoint-resume): both layers -> one file -> fresh layers, every voxel bit-equal; foreign,
+    mismatching and truncated files are refused."""
+    r = subprocess.run([os.path.join(CPP, "map_io_test"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and "map io ok" in r.stdout, r.stderr
+    raw = open(tmp_path / "map.ksgm", "rb").read()
+    assert raw[:4] == b"KSGM" and len(raw) == 28 + 4 * (12 + 16 ** 3 * (4 + 4 + 4 + 1 + 4 * 21 + 4))
