@@ -21,11 +21,14 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <unistd.h>
 
 #include "kimera_semantics/semantic_tsdf_integrator_fast.h"
 #include "kimera_semantics/semantic_tsdf_integrator_merged.h"
+
+#include "kimera_semantics_ros/ros_params.h"
 
 #include "../include/ksg.h"
 
@@ -190,6 +193,33 @@ int64_t kref_csv_dump(const char* path, char* out, int64_t capacity) {
   }
   if ((int64_t)text.size() <= capacity && out) std::memcpy(out, text.data(), text.size());
   return (int64_t)text.size();
+}
+
+// The reference's own parameter reading (kimera_semantics_ros/src/ros_params.cpp:20-77) on a "key: value" text, one pair per line.
+// Writes "method=<m>\ncsv=<path>\nprobability=<%.9g>\ncolor_mode=<int>\ndynamic=<a,b,...>\n"; aborts where the reference aborts.
+int64_t kref_ros_params(const char* text, char* out, int64_t capacity) {
+  ros::NodeHandle nh;
+  std::stringstream ss{std::string(text)};
+  std::string line;
+  while (std::getline(ss, line)) {
+    const size_t colon = line.find(':');
+    if (colon == std::string::npos) continue;
+    auto trim = [](std::string s) {
+      const size_t b = s.find_first_not_of(" \t"), e = s.find_last_not_of(" \t");
+      return b == std::string::npos ? std::string() : s.substr(b, e - b + 1);
+    };
+    nh.values[trim(line.substr(0, colon))] = trim(line.substr(colon + 1));
+  }
+  const std::string method = kimera::getSemanticTsdfIntegratorTypeFromRosParam(nh);
+  const std::string csv = kimera::getSemanticLabelToColorCsvFilepathFromRosParam(nh);
+  const kimera::SemanticIntegratorBase::SemanticConfig sc = kimera::getSemanticTsdfIntegratorConfigFromRosParam(nh);
+  char num[64];
+  std::snprintf(num, sizeof(num), "%.9g", (double)sc.semantic_measurement_probability_);
+  std::string r = "method=" + method + "\ncsv=" + csv + "\nprobability=" + num + "\ncolor_mode=" + std::to_string((int)sc.color_mode) + "\ndynamic=";
+  for (size_t i = 0; i < sc.dynamic_labels_.size(); ++i) r += (i ? "," : "") + std::to_string((int)sc.dynamic_labels_[i]);
+  r += "\nlabels=" + std::to_string(sc.semantic_label_to_color_->semantic_label_to_color_map_.size()) + "\n";
+  if ((int64_t)r.size() <= capacity && out) std::memcpy(out, r.data(), r.size());
+  return (int64_t)r.size();
 }
 
 int64_t kref_num_blocks(void* hh) { return (int64_t)((Hybrid*)hh)->tsdf->getNumberOfAllocatedBlocks(); }

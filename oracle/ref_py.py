@@ -63,6 +63,17 @@ def csv_dump(path: str) -> str:
     return buf.raw.decode()
 
 
+def ros_params(text: str) -> str:
+    """The reference's ros_params.cpp (method / csv path / SemanticConfig) evaluated on "key: value" lines; aborts where it aborts."""
+    lib = load()
+    lib.kref_ros_params.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    lib.kref_ros_params.restype = C.c_int64
+    n = lib.kref_ros_params(text.encode(), None, 0)
+    buf = C.create_string_buffer(int(n))
+    lib.kref_ros_params(text.encode(), buf, n)
+    return buf.raw.decode()
+
+
 class RefHybridIntegrator:
     """kimera::FastSemanticTsdfIntegrator / MergedSemanticTsdfIntegrator (the reference's classes) behind the export
     layout of the oracle.  num_labels is the reference's compile-time 21 (common.h:27)."""

@@ -207,3 +207,61 @@ def test_map_checkpoint_file_round_trip_on_the_host(demo, tmp_path):
     assert r.returncode == 0 and "map io ok" in r.stdout, r.stderr
     raw = open(tmp_path / "map.ksgm", "rb").read()
     assert raw[:4] == b"KSGM" and len(raw) == 28 + 4 * (12 + 16 ** 3 * (4 + 4 + 4 + 1 + 4 * 21 + 4))
+
+
+LAUNCH_PARAMS = """# kimera_semantics_ros/launch/kimera_semantics.launch:98-122 as key: value lines
+tsdf_voxel_size: 0.05
+tsdf_voxels_per_side: 32
+max_ray_length_m: 5
+min_time_between_msgs_sec: 0.2
+voxel_carving_enabled: true
+use_const_weight: false
+method: fast
+semantic_color_mode: semantic
+semantic_measurement_probability: 0.8
+dynamic_semantic_labels: [20]
+semantic_label_2_color_csv_filepath: {csv}
+"""
+
+
+def _write_small_csv(path):
+    path.write_text("name,red,green,blue,alpha,id\nfloor,10,20,30,255,1\nwall,40,50,60,255,2\n")
+
+
+def test_params_reader_applies_the_launch_file_values(demo, tmp_path):
+    csv = tmp_path / "labels.csv"
+    _write_small_csv(csv)
+    pf = tmp_path / "params.txt"
+    pf.write_text(LAUNCH_PARAMS.format(csv=csv))
+    out = subprocess.run([os.path.join(CPP, "params_test"), str(pf)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "method=fast" in out.stdout and "probability=0.800000012" in out.stdout and "color_mode=1" in out.stdout and "dynamic=20\n" in out.stdout
+    assert "voxel_size=0.0500000007 vps=32 trunc=0.200000003 max_ray=5 carving=1 const_weight=0 throttle=0.2 order=mixed" in out.stdout
+
+
+@pytest.mark.parametrize("text,fatal", [
+    ("method: merged\nsemantic_color_mode: semantic_probability\nsemantic_measurement_probability: 0.75\ndynamic_semantic_labels: [20, 3, 7]\n", None),
+    ("dynamic_semantic_labels: []\n", None),                                  # every default: fast, colour mode "color", p = 0.9
+    ("semantic_color_mode: rainbow\ndynamic_semantic_labels: [1]\n", "Unknown semantic color mode: rainbow"),
+    ("method: fast\n", "dynamic_semantic_labels"),                            # CHECK(getParam("dynamic_semantic_labels")) ros_params.cpp:69
+])
+def test_params_reader_equals_the_reference_ros_params(demo, tmp_path, text, fatal):
+    """kimera_semantics/params.h against the reference's own kimera_semantics_ros/src/ros_params.cpp (compiled against a stand-in
+    ros::NodeHandle into oracle/_ref): same values, same defaults, same fatal errors."""
+    from oracle import ref_py
+    if not ref_py.available():
+        pytest.skip("oracle/_ref not built")
+    csv = tmp_path / "labels.csv"
+    _write_small_csv(csv)
+    text = text + f"semantic_label_2_color_csv_filepath: {csv}\n"
+    pf = tmp_path / "params.txt"
+    pf.write_text(text)
+    got = subprocess.run([os.path.join(CPP, "params_test"), str(pf)], capture_output=True, text=True)
+    want = subprocess.run([sys.executable, "-c", "import sys; from oracle import ref_py; sys.stdout.write(ref_py.ros_params(open(sys.argv[1]).read()))",
+                           str(pf)], capture_output=True, text=True, cwd=ROOT)
+    if fatal:
+        assert got.returncode != 0 and want.returncode != 0
+        assert fatal in got.stderr and fatal in want.stderr
+    else:
+        assert got.returncode == 0 and want.returncode == 0, (got.stderr, want.stderr)
+        assert got.stdout.startswith(want.stdout) and want.stdout.count("\n") == 6
