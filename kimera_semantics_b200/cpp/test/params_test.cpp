@@ -1,5 +1,5 @@
 // Prints what the shim's ROS-free parameter reading (kimera_semantics/params.h) makes of a "key: value" file, in the format of the
-// reference-side probe (oracle/ref_hybrid.cpp kref_ros_params), followed by the voxblox-side values.   params_test <file>
+// reference-side probe used by tests/test_shim_cpu.py, followed by the voxblox-side values.   params_test <file>
 #include <cstdio>
 #include "kimera_semantics/params.h"
 using namespace kimera;
