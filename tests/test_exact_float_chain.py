@@ -58,3 +58,13 @@ def test_block_size_does_not_matter_and_long_run_of_one_term():
     for block in (1, 7, 32, 1024):
         assert bits(xc.scan_sum(F(-0.60205999132), terms, block=block)) == bits(want)
     assert float(want) < -1.0e5
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_two_level_chunked_version_is_exact_and_rarely_falls_back(seed):
+    rng = np.random.default_rng(50 + seed)
+    terms = realistic_terms(rng, 92000)                 # one frame of the hottest `merged2` voxel
+    for s0 in (F(-0.60205999132), F(-2.5e5)):           # first frame / steady state
+        got, fallbacks = xc.chunked_sum(s0, terms, chunk=1024)
+        assert bits(got) == bits(xc.sequential(s0, terms))
+        assert fallbacks <= 20                          # of 90 chunks: only the ones in which |s| doubles

@@ -102,3 +102,42 @@ def scan_sum(s0, terms, block=32):
         s = F(s + chunk[leave])                 # the crossing step itself: one ordinary addition on the coarser grid
         i += leave + 1
     return s
+
+
+def chunk_table(terms, grid_exp):
+    """Composite two-entry function of a whole chunk on one grid (what one warp produces for its share of a long chain)."""
+    acc = None
+    for a in terms:
+        t = record_table(F(a), grid_exp)
+        acc = t if acc is None else compose(acc, t)
+    return acc
+
+
+def chunked_sum(s0, terms, chunk=1024):
+    """Two-level version for chains that are split over many warps (the hot voxels): pass A is embarrassingly parallel over chunks,
+    pass B is a short sequential walk over one table per chunk.
+      A: every chunk guesses the binade it will start in from a float64 prefix sum of the raw terms (cheap, order-insensitive)
+         and folds its records into ONE two-entry table on that grid;
+      B: with the exact running value, a chunk's table is applied if the guess was right and the chunk stays inside the binade
+         (the overwhelmingly common case: same-sign terms cross a binade only ~once per doubling of |s|); otherwise that one
+         chunk is re-evaluated exactly with scan_sum()."""
+    s = F(s0)
+    terms = np.asarray(terms, dtype=np.float32)
+    n = len(terms)
+    starts = list(range(0, n, chunk))
+    approx = float(s) + np.concatenate([[0.0], np.cumsum(terms.astype(np.float64))])
+    guesses, tables = [], []
+    for c0 in starts:                                                     # pass A (parallel on the device)
+        g = _decompose(F(approx[c0]))[1] if approx[c0] != 0 else -149
+        guesses.append(g)
+        tables.append(chunk_table(terms[c0:c0 + chunk], g))
+    fallbacks = 0
+    for k, c0 in enumerate(starts):                                       # pass B
+        m, e = _decompose(s)
+        inc, _ = tables[k][m & 1]
+        if m >= 0x800000 and e == guesses[k] and m + inc < (1 << 24):
+            s = F(-np.ldexp(float(m + inc), e))
+        else:
+            s = scan_sum(s, terms[c0:c0 + chunk])
+            fallbacks += 1
+    return s, fallbacks
