@@ -32,4 +32,14 @@ class SemanticLabel2Color {
   ColorToSemanticLabelMap color_to_semantic_label_;
   SemanticLabelToColorMap semantic_label_to_color_map_;
 };
+
+// color.h:58-82 of the reference: a colour for every label 0..254, random except the eight fixed simulation colours.
+inline SemanticLabelToColorMap getRandomSemanticLabelToColorMap() {
+  SemanticLabelToColorMap table;
+  for (int label = 0; label < 255; ++label) table[static_cast<SemanticLabel>(label)] = HashableColor(vxb::randomColor());
+  const vxb::Color fixed[8] = {vxb::Color::Gray(),  vxb::Color::Green(), vxb::Color::Blue(),   vxb::Color::Purple(),
+                               vxb::Color::Pink(),  vxb::Color::Teal(),  vxb::Color::Orange(), vxb::Color::Yellow()};
+  for (int label = 0; label < 8; ++label) table.at(static_cast<SemanticLabel>(label)) = HashableColor(fixed[label]);
+  return table;
+}
 }  // namespace kimera

@@ -88,6 +88,7 @@ struct Color {
   static const Color Pink() { return Color(255, 0, 127); }
 };
 typedef AlignedVector<Color> Colors;
+inline Color randomColor() { return Color(std::rand() % 256, std::rand() % 256, std::rand() % 256); }   // voxblox/core/color.h
 
 // AnyIndexHash / LongIndexHash (A.2)
 struct AnyIndexHash {

@@ -80,6 +80,10 @@ int main() {
   const vxb::Transformation T(1.0f, 0.0f, 0.0f, 0.0f, vxb::Point(1.0f, 2.0f, 3.0f));
   const vxb::Point q = T * vxb::Point(0.5f, 0.25f, -4.0f);
   if (q.x() != 1.5f || q.y() != 2.25f || q.z() != -1.0f || T.getPosition().z() != 3.0f) return 8;
+  // color.h:58-82: label -> colour table of the simulation (fixed colours for labels 0..7, random for the rest)
+  const SemanticLabelToColorMap random_table = getRandomSemanticLabelToColorMap();
+  if (random_table.size() != 255u || !(random_table.at(0) == HashableColor(vxb::Color::Gray())) ||
+      !(random_table.at(3) == HashableColor(vxb::Color::Purple())) || !(random_table.at(7) == HashableColor(vxb::Color::Yellow()))) return 9;
   std::printf("api compat ok\n");
   return 0;
 }
