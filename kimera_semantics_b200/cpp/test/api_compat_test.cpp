@@ -2,9 +2,13 @@
 // (SURVEY.md 7.3 item 7): SemanticTsdfServer's constructor sequence (kimera_semantics_ros/src/semantic_tsdf_server.cpp:58-79),
 // the Layer/Block accessors used by kimera_semantics/src/simulation/semantic_simulation_world.cpp:62-73,99-109, SemanticConfig
 // fields (ros_params.cpp:38-77) and the enum/string factory overloads (semantic_simulation_server.cpp:19-24).
-// No integrator is constructed when no CUDA device is present (the program is then a pure API / layout check).
+// No integrator is constructed (the program is a pure API / layout check).  It uses ONLY the reference's API, and the same file is
+// also compiled and run against the reference's real headers (test_shim_cpu.py::test_api_compat_source_also_builds_against_the_
+// reference_headers): what compiles and passes there must compile and pass here.
 #include <cstdio>
+#include <fstream>
 #include <type_traits>
+#include <unistd.h>
 #include "kimera_semantics/semantic_tsdf_integrator_factory.h"
 #include "kimera_semantics/semantic_tsdf_integrator_fast.h"
 #include "kimera_semantics/semantic_tsdf_integrator_merged.h"
@@ -32,9 +36,17 @@ int main() {
   SemanticIntegratorBase::SemanticConfig semantic_config;
   semantic_config.semantic_measurement_probability_ = 0.8f;
   semantic_config.color_mode = ColorMode::kSemantic;
-  SemanticLabelToColorMap pal;
-  pal[1] = HashableColor(vxb::Color::Green());
-  semantic_config.semantic_label_to_color_ = std::make_shared<SemanticLabel2Color>(pal);
+  char csv_path[] = "/tmp/api_compat_labels_XXXXXX";
+  const int fd = mkstemp(csv_path);
+  if (fd < 0) return 10;
+  close(fd);
+  {
+    std::ofstream csv(csv_path);
+    csv << "name,red,green,blue,alpha,id\ngrass,0,255,0,255,1\n";
+  }
+  semantic_config.semantic_label_to_color_ = std::make_shared<SemanticLabel2Color>(std::string(csv_path));   // color.cpp:42-67
+  unlink(csv_path);
+  if (semantic_config.semantic_label_to_color_->getSemanticLabelFromColor(HashableColor(0, 255, 0, 255)) != 1u) return 11;
   semantic_config.dynamic_labels_.push_back(20u);
 
   vxb::TsdfIntegratorBase::Config config;   // voxblox defaults (A.6)

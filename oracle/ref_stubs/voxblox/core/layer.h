@@ -54,6 +54,7 @@ class Layer {
     for (const auto& kv : block_map_) blocks->emplace_back(kv.first);
   }
   size_t getNumberOfAllocatedBlocks() const { return block_map_.size(); }
+  BlockIndex computeBlockIndexFromCoordinates(const Point& coords) const { return getGridIndexFromPoint<BlockIndex>(coords, block_size_inv_); }
   const BlockType& getBlockByIndex(const BlockIndex& index) const { return *block_map_.at(index); }
 
   FloatingPoint voxel_size() const { return voxel_size_; }

@@ -265,3 +265,14 @@ def test_params_reader_equals_the_reference_ros_params(demo, tmp_path, text, fat
     else:
         assert got.returncode == 0 and want.returncode == 0, (got.stderr, want.stderr)
         assert got.stdout.startswith(want.stdout) and want.stdout.count("\n") == 6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference sources (build container only)")
+def test_api_compat_source_also_builds_against_the_reference_headers(demo):
+    """cpp/test/api_compat_test.cpp uses only the reference's API; `make -C oracle ref` compiles the SAME file against the
+    reference's real headers and sources (oracle/_ref/api_compat_ref).  Both binaries must pass: the client code the shim accepts
+    is valid reference client code, and vice versa."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+    for exe in (os.path.join(CPP, "api_compat_test"), os.path.join(ROOT, "oracle", "_ref", "api_compat_ref")):
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and "api compat ok" in out.stdout, (exe, out.stdout, out.stderr)
