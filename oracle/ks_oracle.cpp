@@ -10,7 +10,7 @@
 //     translation units.  `make -C oracle ref` compiles semantic_tsdf_integrator_{fast,merged}.cpp,
 //     semantic_integrator_base.cpp, color.cpp and csv_iterator.cpp where they lie under /root/reference against
 //     stand-in dependency headers (oracle/ref_stubs/) into oracle/_ref/libks_ref_hybrid.so;
-//     tests/test_oracle_vs_ref_hybrid.py requires this oracle to equal that library bit for bit on 31 seeded
+//     tests/test_oracle_vs_ref_hybrid.py requires this oracle to equal that library bit for bit on 32 seeded
 //     sequences (every Config / SemanticConfig switch of the path), and the digests are committed as
 //     tests/golden/ref_hybrid_golden.json for boxes without /root/reference.
 //   * voxblox half (RayCaster, updateTsdfVoxel, ApproxHashSet, ThreadSafeIndex, bundleRays, Layer/Block, hashes,

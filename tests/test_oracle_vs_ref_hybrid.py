@@ -3,7 +3,7 @@
 oracle/_ref/libks_ref_hybrid.so is built from the reference's kimera_semantics translation units (fast / merged integrators,
 semantic_integrator_base, color, csv_iterator), compiled where they lie against stand-in Eigen / glog / voxblox headers
 (oracle/ref_stubs; voxblox is un-vendored and none of the three is in the image).  tests/golden/ref_hybrid_golden.json holds
-digests of its output for 31 seeded sequences covering every Config / SemanticConfig switch on the path.
+digests of its output for 32 seeded sequences covering every Config / SemanticConfig switch on the path.
 
   * test_oracle_matches_reference_golden     runs everywhere (GPU box included): oracle output == committed digests, bit for bit
     (`merged` in the oracle's faithful mode, which iterates bundles in libstdc++'s unordered_map order like merged.cpp:210-231);
