@@ -51,7 +51,7 @@ CASES = {
     "fast_clear_sets_every_2nd_frame": (FAST, 128, 96, 0.10, 4, {"clear_checks_every_n_frames": 2}, {}),
     "fast_min_range_gate": (FAST, 128, 96, 0.10, 2, {"min_ray_length_m": 2.0}, {}),
     # kimera_semantics_ros/launch/kimera_semantics.launch:98-122: 5 cm, 32 voxels per side, p = 0.8, semantic colours, fast
-    "fast_launch_file_config": (FAST, 320, 240, 0.05, 3, {"voxels_per_side": 32, "semantic_measurement_probability": 0.8}, {}),
+    "fast_launch_file_config": (FAST, 320, 240, 0.05, 3, {"voxels_per_side": 32, "semantic_measurement_probability": 0.8, "max_blocks": 1024}, {}),
     "fast_fullsize_640x480_5cm_4f": (FAST, 640, 480, 0.05, 4, {}, {}),             # BASELINE.json configs[1] geometry
     "merged_default_2f": (MERGED, 160, 120, 0.10, 2, {}, {}),
     "merged_fullsize_640x480_5cm_1f": (MERGED, 640, 480, 0.05, 1, {}, {}),
