@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.gpu
 def test_merged_in_libstdcxx_bundle_order_equals_the_reference_sources_bit_for_bit():
-    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_bundle_order_check.py")], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_bundle_order_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("REPORT ")][-1]
     report = json.loads(line[len("REPORT "):])

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.gpu
 @pytest.mark.xfail(strict=False, reason="random corner-case configurations not yet run on a B200 (written after the round-1 GPU budget was spent)")
 def test_random_cases_cuda_path_equals_oracle_bit_for_bit():
-    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_fuzz_check.py"), "0", "24"], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_fuzz_check.py"), "0", "24"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("REPORT ")][-1]
     report = json.loads(line[len("REPORT "):])
