@@ -162,16 +162,23 @@ int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T_G_C_host, 
  * y=(v-cy)*d*(1/fy), z=d, non-finite depth -> dropped point as voxblox_ros convertPointcloud does)
  * with integratePointCloud.  depth: h*w float32 metres, label: h*w uint8, K = fx fy cx cy.
  * Precision note: the reference derives constant_x = float(1.0 / fx) from the DOUBLE fx of sensor_msgs/CameraInfo and
- * center_x = float(cx) (depth_map_to_pointcloud.h:222-230); here fx, fy arrive as float, so the two agree bit for bit when the
- * intrinsics are exactly representable in float (true for the usual integral or half-integral values); otherwise 1/fx can be
- * one float ulp apart.  Callers that need the last bit with such intrinsics should pre-build the cloud and use
- * ksg_integrate_points. */
+ * center_x = float(cx) (depth_map_to_pointcloud.h:222-230).  The *_k64 variants below take the intrinsics as double and
+ * reproduce that exactly; the float-K entries are the same call with K widened, i.e. bit-identical to the reference when the
+ * intrinsics are representable in float (integral / half-integral values) and up to one float ulp off in 1/fx otherwise
+ * (e.g. fx = 415.69219381653056 of a 60-degree, 480-line simulator camera). */
 int32_t ksg_integrate_depth(ksg_integrator* h, const float* T_G_C, const float* depth,
                             const uint8_t* label, int32_t width, int32_t height, const float* K,
                             ksg_frame_stats* stats);
 int32_t ksg_integrate_depth_device(ksg_integrator* h, const float* T_G_C_host, const float* d_depth,
                                    const uint8_t* d_label, int32_t width, int32_t height,
                                    const float* K_host, void* cuda_stream, ksg_frame_stats* stats);
+/* The same two calls with double intrinsics (K = fx fy cx cy as float64, the type of sensor_msgs/CameraInfo::K). */
+int32_t ksg_integrate_depth_k64(ksg_integrator* h, const float* T_G_C, const float* depth,
+                                const uint8_t* label, int32_t width, int32_t height, const double* K,
+                                ksg_frame_stats* stats);
+int32_t ksg_integrate_depth_device_k64(ksg_integrator* h, const float* T_G_C_host, const float* d_depth,
+                                       const uint8_t* d_label, int32_t width, int32_t height,
+                                       const double* K_host, void* cuda_stream, ksg_frame_stats* stats);
 
 /* Colour -> label table: SemanticLabel2Color::getSemanticLabelFromColor (color.cpp:69-82). n entries
  * of (r,g,b) -> label (alpha is forced to 255 by the callers fast.cpp:157, merged.cpp:87). A colour

@@ -208,6 +208,11 @@ def load_library(path: Optional[str] = None):
     lib.ksg_debug_tile_times.restype = C.c_int64
     lib.ksg_owner_mask.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, i32p, u8p]
     lib.ksg_owner_mask.restype = C.c_int32
+    dp = C.POINTER(C.c_double)
+    lib.ksg_integrate_depth_k64.argtypes = [H, fp, fp, u8p, C.c_int32, C.c_int32, dp, sp]
+    lib.ksg_integrate_depth_k64.restype = C.c_int32
+    lib.ksg_integrate_depth_device_k64.argtypes = [H, fp, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, dp, C.c_void_p, sp]
+    lib.ksg_integrate_depth_device_k64.restype = C.c_int32
     lib.ksg_unordered_map_schedule.argtypes = [C.c_int64, C.POINTER(C.c_int64)]
     lib.ksg_unordered_map_schedule.restype = C.c_int64
     lib.ksg_build_info.argtypes = []
@@ -221,7 +226,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
-               "ksg_unordered_map_schedule"]
+               "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64"]
 
 
 def unordered_map_schedule(n: int, lib=None) -> np.ndarray:
@@ -338,6 +343,18 @@ class Integrator:
         h, w = depth.shape
         self._check(self.lib.ksg_integrate_depth(self.handle, _ptr(T, C.c_float), _ptr(depth, C.c_float), _ptr(label, C.c_uint8),
                                                  w, h, _ptr(K, C.c_float), C.byref(st)), "ksg_integrate_depth")
+        return st
+
+    def integrate_depth_k64(self, T_G_C, depth, label, K64) -> KsgFrameStats:
+        """Depth entry with float64 intrinsics (fx fy cx cy), as sensor_msgs/CameraInfo holds them."""
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        label = np.ascontiguousarray(label, np.uint8)
+        K = np.ascontiguousarray(K64, np.float64)
+        st = KsgFrameStats()
+        h, w = depth.shape
+        self._check(self.lib.ksg_integrate_depth_k64(self.handle, _ptr(T, C.c_float), _ptr(depth, C.c_float), _ptr(label, C.c_uint8),
+                                                     w, h, _ptr(K, C.c_double), C.byref(st)), "ksg_integrate_depth_k64")
         return st
 
     def integrate_depth_device(self, T_G_C, d_depth_ptr: int, d_label_ptr: int, width: int, height: int, K,

@@ -233,7 +233,7 @@ struct InputDesc {
   const float* d_depth = nullptr;
   const uint8_t* d_label_img = nullptr;
   int width = 0, height = 0;
-  float K[4] = {0, 0, 0, 0};
+  double K[4] = {0, 0, 0, 0};   // fx fy cx cy as the reference holds them (sensor_msgs/CameraInfo: float64)
   int64_t n = 0;  // points (points entry) or pixels (depth entry)
   int freespace = 0;
 };
@@ -316,10 +316,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   fin.depth = in.d_depth; fin.label_img = in.d_label_img; fin.pix_list = h->pix_list;
   fin.point_of_seq = nullptr;
   fin.width = in.width;
-  fin.cx = in.K[2]; fin.cy = in.K[3];
+  fin.cx = (float)in.K[2]; fin.cy = (float)in.K[3];   // depth_map_to_pointcloud.h:222-223 float center = model_.cx()
   if (in.d_depth) {  // depth_map_to_pointcloud.h:228-230: float constant = unit_scaling / f  (double division)
-    fin.constant_x = (float)(1.0 / (double)in.K[0]);
-    fin.constant_y = (float)(1.0 / (double)in.K[1]);
+    fin.constant_x = (float)(1.0 / in.K[0]);
+    fin.constant_y = (float)(1.0 / in.K[1]);
   }
   fin.freespace = in.freespace;
 
@@ -875,12 +875,18 @@ int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T, const flo
   return integrate(h, in, T, stream ? (cudaStream_t)stream : h->own_stream, stats);
 }
 
-int32_t ksg_integrate_depth_device(ksg_integrator* h, const float* T, const float* d_depth, const uint8_t* d_label, int32_t width,
-                                   int32_t height, const float* K, void* stream, ksg_frame_stats* stats) {
+int32_t ksg_integrate_depth_device_k64(ksg_integrator* h, const float* T, const float* d_depth, const uint8_t* d_label, int32_t width,
+                                       int32_t height, const double* K, void* stream, ksg_frame_stats* stats) {
   if (!h || !T || !K || width <= 0 || height <= 0 || !d_depth || !d_label) return KSG_ERR_INVALID_ARGUMENT;
   InputDesc in; in.d_depth = d_depth; in.d_label_img = d_label; in.width = width; in.height = height;
   in.n = (int64_t)width * height; std::memcpy(in.K, K, sizeof(in.K));
   return integrate(h, in, T, stream ? (cudaStream_t)stream : h->own_stream, stats);
+}
+int32_t ksg_integrate_depth_device(ksg_integrator* h, const float* T, const float* d_depth, const uint8_t* d_label, int32_t width,
+                                   int32_t height, const float* K, void* stream, ksg_frame_stats* stats) {
+  if (!K) return KSG_ERR_INVALID_ARGUMENT;
+  const double K64[4] = {K[0], K[1], K[2], K[3]};   // exact widening: same results as before for float intrinsics
+  return ksg_integrate_depth_device_k64(h, T, d_depth, d_label, width, height, K64, stream, stats);
 }
 
 int32_t ksg_integrate_points(ksg_integrator* h, const float* T, const float* xyz, const uint8_t* rgba, const uint8_t* labels,
@@ -905,8 +911,8 @@ int32_t ksg_integrate_points(ksg_integrator* h, const float* T, const float* xyz
   return integrate(h, in, T, h->own_stream, stats ? stats : &local);
 }
 
-int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* depth, const uint8_t* label, int32_t width,
-                            int32_t height, const float* K, ksg_frame_stats* stats) {
+int32_t ksg_integrate_depth_k64(ksg_integrator* h, const float* T, const float* depth, const uint8_t* label, int32_t width,
+                                int32_t height, const double* K, ksg_frame_stats* stats) {
   if (!h || !T || !K || width <= 0 || height <= 0 || !depth || !label) return KSG_ERR_INVALID_ARGUMENT;
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   KSG_CUDA(cudaSetDevice(h->device));
@@ -927,6 +933,12 @@ int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* dept
   in.n = (int64_t)P; std::memcpy(in.K, K, sizeof(in.K));
   ksg_frame_stats local;
   return integrate(h, in, T, h->own_stream, stats ? stats : &local);
+}
+int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* depth, const uint8_t* label, int32_t width,
+                            int32_t height, const float* K, ksg_frame_stats* stats) {
+  if (!K) return KSG_ERR_INVALID_ARGUMENT;
+  const double K64[4] = {K[0], K[1], K[2], K[3]};
+  return ksg_integrate_depth_k64(h, T, depth, label, width, height, K64, stats);
 }
 
 int32_t ksg_sync(ksg_integrator* h) {

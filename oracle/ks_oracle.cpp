@@ -744,11 +744,11 @@ int kso_integrate_points(void* hh, const float* T_G_C, const float* xyz, const u
 
 // depth_map_to_pointcloud.h:222-266 (convert<float>) followed by voxblox_ros convertPointcloud's
 // finite-point filter, then integratePointCloud.
-int64_t kso_backproject(const float* depth, int width, int height, const float* K, float* xyz_out, int32_t* pix_out) {
-  const float center_x = K[2], center_y = K[3];
+int64_t kso_backproject_k64(const float* depth, int width, int height, const double* K, float* xyz_out, int32_t* pix_out) {
+  const float center_x = (float)K[2], center_y = (float)K[3];   // float center_x = model_.cx() (double)
   const double unit_scaling = 1.0;  // DepthTraits<float>::toMeters(1)
-  const float constant_x = (float)(unit_scaling / (double)K[0]);
-  const float constant_y = (float)(unit_scaling / (double)K[1]);
+  const float constant_x = (float)(unit_scaling / K[0]);        // float constant_x = unit_scaling / model_.fx() (double)
+  const float constant_y = (float)(unit_scaling / K[1]);
   int64_t n = 0;
   for (int v = 0; v < height; ++v)
     for (int u = 0; u < width; ++u) {
@@ -762,16 +762,25 @@ int64_t kso_backproject(const float* depth, int width, int height, const float* 
     }
   return n;
 }
+int64_t kso_backproject(const float* depth, int width, int height, const float* K, float* xyz_out, int32_t* pix_out) {
+  const double K64[4] = {K[0], K[1], K[2], K[3]};
+  return kso_backproject_k64(depth, width, height, K64, xyz_out, pix_out);
+}
 
-int kso_integrate_depth(void* hh, const float* T_G_C, const float* depth, const uint8_t* label, int width,
-                        int height, const float* K, ksg_frame_stats* stats) {
+int kso_integrate_depth_k64(void* hh, const float* T_G_C, const float* depth, const uint8_t* label, int width,
+                            int height, const double* K, ksg_frame_stats* stats) {
   const size_t P = (size_t)width * height;
   std::vector<float> xyz(3 * P);
   std::vector<int32_t> pix(P);
-  const int64_t n = kso_backproject(depth, width, height, K, xyz.data(), pix.data());
+  const int64_t n = kso_backproject_k64(depth, width, height, K, xyz.data(), pix.data());
   std::vector<uint8_t> labels((size_t)n);
   for (int64_t i = 0; i < n; ++i) labels[i] = label[pix[i]];
   return kso_integrate_points(hh, T_G_C, xyz.data(), nullptr, labels.data(), n, 0, stats);
+}
+int kso_integrate_depth(void* hh, const float* T_G_C, const float* depth, const uint8_t* label, int width,
+                        int height, const float* K, ksg_frame_stats* stats) {
+  const double K64[4] = {K[0], K[1], K[2], K[3]};
+  return kso_integrate_depth_k64(hh, T_G_C, depth, label, width, height, K64, stats);
 }
 
 int64_t kso_num_blocks(void* hh) { return (int64_t)((Integrator*)hh)->layer.size(); }

@@ -44,6 +44,10 @@ def load(fast_build: bool = False) -> C.CDLL:
     lib.kso_integrate_points.restype = C.c_int
     lib.kso_integrate_depth.argtypes = [H, fp, fp, u8p, C.c_int, C.c_int, fp, sp]
     lib.kso_integrate_depth.restype = C.c_int
+    lib.kso_integrate_depth_k64.argtypes = [H, fp, fp, u8p, C.c_int, C.c_int, C.POINTER(C.c_double), sp]
+    lib.kso_integrate_depth_k64.restype = C.c_int
+    lib.kso_backproject_k64.argtypes = [fp, C.c_int, C.c_int, C.POINTER(C.c_double), fp, i32p]
+    lib.kso_backproject_k64.restype = C.c_int64
     lib.kso_backproject.argtypes = [fp, C.c_int, C.c_int, fp, fp, i32p]
     lib.kso_backproject.restype = C.c_int64
     lib.kso_num_blocks.argtypes = [H]
@@ -124,6 +128,19 @@ class OracleIntegrator:
                                           _ptr(K, C.c_float), C.byref(st))
         if rc != 0:
             raise ValueError(f"kso_integrate_depth: {rc}")
+        return st
+
+    def integrate_depth_k64(self, T_G_C, depth, label, K64) -> KsgFrameStats:
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        label = np.ascontiguousarray(label, np.uint8)
+        K = np.ascontiguousarray(K64, np.float64)
+        st = KsgFrameStats()
+        h, w = depth.shape
+        rc = self.lib.kso_integrate_depth_k64(self.handle, _ptr(T, C.c_float), _ptr(depth, C.c_float), _ptr(label, C.c_uint8), w, h,
+                                              _ptr(K, C.c_double), C.byref(st))
+        if rc != 0:
+            raise ValueError(f"kso_integrate_depth_k64: {rc}")
         return st
 
     def last_integrate_seconds(self) -> float:

@@ -303,3 +303,19 @@ def test_fast_sets_full_reset_after_10000_frames():
     assert worst is None, f"first frame whose counters differ: {worst}"
     assert_parity(compare_maps(gpu.export(), ora.export()))
     gpu.close()
+
+
+@pytest.mark.xfail(strict=False, reason="ksg_integrate_depth_k64 (float64 intrinsics): host-side widening only, the float-K entries are unchanged; "
+                                        "first GPU run pending (written after the round-1 GPU budget was spent)")
+def test_depth_entry_with_float64_intrinsics_matches_oracle():
+    """fx = 415.69219381653056 (60 degree FOV, 480 lines) is not representable in float; the k64 entry must reproduce the reference's
+    float(1.0 / fx_double) exactly (depth_map_to_pointcloud.h:228-230)."""
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.10, 21, max_points=320 * 240)
+    gpu, ora = Integrator(cfg), OracleIntegrator(cfg)
+    for cam, depth, label, T in frames(320, 240, 21, 2):
+        K64 = np.array([415.69219381653056 / 2, 415.69219381653056 / 2 * 1.0001, 159.5 + 0.123456789, 119.5], np.float64)
+        sg, so = gpu.integrate_depth_k64(T, depth, label, K64), ora.integrate_depth_k64(T, depth, label, K64)
+        ok, why = stats_equal(sg, so)
+        assert ok, why
+    assert_parity(compare_maps(gpu.export(), ora.export()))
+    gpu.close()
