@@ -21,6 +21,12 @@ class GpuIntegratorCore {
 
   void integrate(const vxb::Transformation& T_G_C, const vxb::Pointcloud& points_C, const vxb::Color* colors,
                  const SemanticLabel* labels, bool freespace_points);
+  // Depth + label frame entry (SURVEY.md 8f NEXT-1): the back-projection of PointCloudFromDepth::convert<float>
+  // (kimera_semantics_ros/include/kimera_semantics_ros/depth_map_to_pointcloud.h:222-266) fused into the device path, so the caller
+  // skips the point-cloud round trip.  depth: height*width float32 metres (non-finite = invalid), label: height*width uint8,
+  // K = fx fy cx cy as the doubles of sensor_msgs/CameraInfo.
+  void integrateDepth(const vxb::Transformation& T_G_C, const float* depth, const SemanticLabel* label, int width, int height,
+                      const double K[4]);
   void setLayerSyncMode(LayerSyncMode m) { sync_mode_ = m; }
   void syncLayers();           // copy every device block into the host layers
   void syncUpdatedBlocks();    // copy the blocks of the last integrate call

@@ -46,6 +46,17 @@ class SemanticTsdfServer {
     return true;
   }
 
+  // The same for a depth + label frame (what kimera_semantics_rosbag.cpp:112-134 turns into a coloured cloud first): the
+  // back-projection runs on the device.  K = fx fy cx cy of the camera info message.
+  bool processDepthFrame(const vxb::Transformation& T_G_C, const float* depth, const SemanticLabel* label, int width, int height,
+                         const double K[4], double stamp_sec) {
+    if (have_last_ && stamp_sec - last_stamp_sec_ < params_.min_time_between_msgs_sec) return false;
+    last_stamp_sec_ = stamp_sec;
+    have_last_ = true;
+    gpu().integrateDepth(T_G_C, depth, label, width, height, K);
+    return true;
+  }
+
   GpuIntegratorCore& gpu() {
     if (auto* f = dynamic_cast<FastSemanticTsdfIntegrator*>(tsdf_integrator_.get())) return f->gpu();
     auto* m = dynamic_cast<MergedSemanticTsdfIntegrator*>(tsdf_integrator_.get());

@@ -202,6 +202,19 @@ void GpuIntegratorCore::integrate(const vxb::Transformation& T_G_C, const vxb::P
   if (sync_mode_ == LayerSyncMode::kEager) syncUpdatedBlocks();
 }
 
+void GpuIntegratorCore::integrateDepth(const vxb::Transformation& T_G_C, const float* depth, const SemanticLabel* label, int width,
+                                       int height, const double K[4]) {
+  KSG_CHECK(depth != nullptr && label != nullptr && width > 0 && height > 0);
+  const vxb::FloatingPoint* q = T_G_C.getRotationWxyz();
+  const vxb::Point& t = T_G_C.getPosition();
+  const float T[7] = {q[0], q[1], q[2], q[3], t.x(), t.y(), t.z()};
+  ksg_frame_stats st;
+  const int rc = ksg_integrate_depth_k64(handle_, T, depth, label, width, height, K, &st);
+  KSG_CHECK(rc == KSG_OK) << "ksg_integrate_depth_k64 failed (" << rc << "): " << ksg_last_error(handle_);
+  last_voxel_updates_ = st.voxel_updates;
+  if (sync_mode_ == LayerSyncMode::kEager) syncUpdatedBlocks();
+}
+
 void GpuIntegratorCore::copyBlocks(const std::vector<int32_t>& idx) {
   const size_t nb = idx.size() / 3;
   if (nb == 0) return;

@@ -2,6 +2,8 @@
 // build both layers, SemanticTsdfIntegratorFactory::create(method, ...), then integratePointCloud per frame.
 //   shim_demo <fast|merged|bogus> <frames.bin> <out.bin> [lazy] [--load ckpt] [--save ckpt] [--skip N]
 //     --load: SemanticTsdfServer::loadMap before the first frame; --save: saveMap after the last; --skip: ignore the first N frames
+//     --depth file: instead of the clouds of frames.bin (whose frame count must then be 0) feed depth + label frames:
+//              int32 n, int32 width, int32 height, double K[4], then per frame float T[7], float depth[w*h], uint8 label[w*h]
 // frames.bin : int32 n_frames, float voxel_size, int32 vps, int32 n_palette, palette n*(r,g,b,a,id), int32 n_dynamic, ids...,
 //              then per frame: int32 n, float T[7], float xyz[3n], uint8 rgba[4n]
 // out.bin    : int32 n_blocks, then per block (sorted z,y,x): int32 idx[3], per voxel: float d, float w, u8 rgba[4], u8 label,
@@ -11,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <vector>
 #include "kimera_semantics/semantic_tsdf_integrator_factory.h"
 #include "kimera_semantics/semantic_tsdf_integrator_fast.h"
 #include "kimera_semantics/semantic_tsdf_integrator_merged.h"
@@ -36,13 +39,14 @@ int main(int argc, char** argv) {
   vxb::TsdfIntegratorBase::Config config;
   config.default_truncation_distance = 4.0f * voxel_size;  // voxblox_ros
   bool lazy = false;
-  const char *load_path = nullptr, *save_path = nullptr;
+  const char *load_path = nullptr, *save_path = nullptr, *depth_path = nullptr;
   int skip = 0;
   for (int a = 4; a < argc; ++a) {
     if (std::strcmp(argv[a], "lazy") == 0) lazy = true;
     else if (std::strcmp(argv[a], "--load") == 0 && a + 1 < argc) load_path = argv[++a];
     else if (std::strcmp(argv[a], "--save") == 0 && a + 1 < argc) save_path = argv[++a];
     else if (std::strcmp(argv[a], "--skip") == 0 && a + 1 < argc) skip = std::atoi(argv[++a]);
+    else if (std::strcmp(argv[a], "--depth") == 0 && a + 1 < argc) depth_path = argv[++a];
   }
   SemanticTsdfServer::Params params;
   params.tsdf_voxel_size = voxel_size;
@@ -64,6 +68,24 @@ int main(int argc, char** argv) {
     server.processPointCloud(vxb::Transformation(T[0], T[1], T[2], T[3], vxb::Point(T[4], T[5], T[6])), pts, cols, /*stamp=*/0.2 * fr);
     std::printf("frame %d: %d points, %lld voxel updates, %zu blocks in the host layer\n", fr, n, (long long)core->lastVoxelUpdates(),
                 tsdf_layer.getNumberOfAllocatedBlocks());
+  }
+  if (depth_path) {
+    std::ifstream df(depth_path, std::ios::binary);
+    KSG_CHECK(df.good()) << "cannot open " << depth_path;
+    const int n = rd<int32_t>(df), w = rd<int32_t>(df), h = rd<int32_t>(df);
+    double K[4];
+    df.read(reinterpret_cast<char*>(K), sizeof(K));
+    std::vector<float> depth((size_t)w * h);
+    std::vector<uint8_t> label((size_t)w * h);
+    for (int fr = 0; fr < n; ++fr) {
+      float T[7];
+      df.read(reinterpret_cast<char*>(T), sizeof(T));
+      df.read(reinterpret_cast<char*>(depth.data()), 4 * depth.size());
+      df.read(reinterpret_cast<char*>(label.data()), label.size());
+      server.processDepthFrame(vxb::Transformation(T[0], T[1], T[2], T[3], vxb::Point(T[4], T[5], T[6])), depth.data(), label.data(), w, h, K,
+                               /*stamp=*/0.2 * fr);
+      std::printf("depth frame %d: %lld voxel updates\n", fr, (long long)core->lastVoxelUpdates());
+    }
   }
   if (lazy) server.updateLayers();
   if (save_path) KSG_CHECK(server.saveMap(save_path)) << "cannot save " << save_path;

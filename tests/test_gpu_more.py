@@ -319,3 +319,26 @@ def test_depth_entry_with_float64_intrinsics_matches_oracle():
         assert ok, why
     assert_parity(compare_maps(gpu.export(), ora.export()))
     gpu.close()
+
+
+@pytest.mark.xfail(strict=False, reason="SemanticTsdfServer::processDepthFrame (shim-level depth entry): first GPU run pending "
+                                        "(written after the round-1 GPU budget was spent)")
+def test_shim_depth_frame_entry_matches_oracle(demo, tmp_path):
+    C, w, h, vs = 21, 320, 240, 0.10
+    cfg = make_config(KSG_INTEGRATOR_FAST, vs, C, max_points=w * h)
+    pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(C)], np.uint8)
+    ora = OracleIntegrator(cfg)
+    K64 = np.array([207.84609690826528, 207.9, 159.5, 119.5], np.float64)
+    dpath = tmp_path / "depth.bin"
+    with open(dpath, "wb") as f:
+        fr = list(frames(w, h, C, 2))
+        f.write(np.int32(len(fr)).tobytes() + np.int32(w).tobytes() + np.int32(h).tobytes() + K64.tobytes())
+        for cam, depth, label, T in fr:
+            f.write(np.ascontiguousarray(T, np.float32).tobytes() + np.ascontiguousarray(depth, np.float32).tobytes() + np.ascontiguousarray(label, np.uint8).tobytes())
+            ora.integrate_depth_k64(T, depth, label, K64)
+    fpath, opath = tmp_path / "frames.bin", tmp_path / "out.bin"
+    write_frames(fpath, [], vs, 16, pal, [C - 1])
+    env = dict(os.environ, KSG_MAX_POINTS=str(w * h))
+    r = subprocess.run([demo, "fast", str(fpath), str(opath), "--depth", str(dpath)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert_parity(compare_maps(read_shim_output(opath, 16, C), ora.export()))
