@@ -245,6 +245,12 @@ int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms /* KSG_NUM_PHASES */
  * number of tiles of the last frame and copies 2 int64 per tile when records_and_cycles has room. */
 int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity, int64_t* records_and_cycles);
 
+/* Debug aid for the next optimisation (not on the integration path): evaluates  s <- fl(s + terms[k]), k = 0..n-1  (s0 < 0, terms <= 0,
+ * float32, round to nearest even) with ONE warp as an exact associative scan (lanes = records, csrc/ksg_chain.cuh) and returns the
+ * final s, which must equal the sequential loop bit for bit.  This is the per-voxel, per-class log-probability recurrence of the
+ * `merged` integrator (base.cpp:306-307).  Host buffers. */
+int32_t ksg_debug_chain_sum(const float* terms, int64_t n, float s0, float* result);
+
 /* Build information: "sm_100a" etc. */
 const char* ksg_build_info(void);
 

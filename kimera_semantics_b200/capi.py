@@ -213,6 +213,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_integrate_depth_k64.restype = C.c_int32
     lib.ksg_integrate_depth_device_k64.argtypes = [H, fp, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, dp, C.c_void_p, sp]
     lib.ksg_integrate_depth_device_k64.restype = C.c_int32
+    lib.ksg_debug_chain_sum.argtypes = [fp, C.c_int64, C.c_float, fp]
+    lib.ksg_debug_chain_sum.restype = C.c_int32
     lib.ksg_unordered_map_schedule.argtypes = [C.c_int64, C.POINTER(C.c_int64)]
     lib.ksg_unordered_map_schedule.restype = C.c_int64
     lib.ksg_build_info.argtypes = []
@@ -226,7 +228,19 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_integrate_points_device", "ksg_integrate_depth", "ksg_integrate_depth_device",
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
-               "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64"]
+               "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
+               "ksg_debug_chain_sum"]
+
+
+def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
+    """One warp's exact scan of the float32 chain s <- fl(s + terms[k]) (ksg_debug_chain_sum); needs a device."""
+    lib = lib or load_library()
+    t = np.ascontiguousarray(terms, np.float32)
+    out = np.zeros(1, np.float32)
+    rc = lib.ksg_debug_chain_sum(_ptr(t, C.c_float), len(t), C.c_float(float(s0)), _ptr(out, C.c_float))
+    if rc != 0:
+        raise KsgError(f"ksg_debug_chain_sum failed: {KSG_STATUS.get(rc, rc)}")
+    return out[0]
 
 
 def unordered_map_schedule(n: int, lib=None) -> np.ndarray:

@@ -15,6 +15,7 @@
 
 #include "../../include/ksg.h"
 #include "ksg_kernels.cuh"
+#include "ksg_chain.cuh"
 
 using namespace ksg;
 
@@ -1229,6 +1230,30 @@ int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms, int64_t* frames, in
   if (kernel_launches) *kernel_launches = h->n_launches;
   if (library_calls) *library_calls = h->n_libcalls;
   return KSG_OK;
+}
+
+namespace {
+__global__ void k_chain_debug(const float* __restrict__ terms, long long n, float s0, float* __restrict__ out) {
+  const float s = chain_sum_warp(s0, terms, n);
+  if ((threadIdx.x & 31) == 0) *out = s;
+}
+}  // namespace
+
+int32_t ksg_debug_chain_sum(const float* terms, int64_t n, float s0, float* result) {
+  if (n < 0 || (n > 0 && !terms) || !result || !(s0 < 0.0f)) return KSG_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return KSG_ERR_NO_DEVICE; }
+  float *d_terms = nullptr, *d_out = nullptr;
+  int32_t rc = KSG_ERR_CUDA;
+  if (cudaMalloc((void**)&d_terms, sizeof(float) * (size_t)std::max<int64_t>(n, 1)) == cudaSuccess &&
+      cudaMalloc((void**)&d_out, sizeof(float)) == cudaSuccess &&
+      (n == 0 || cudaMemcpy(d_terms, terms, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice) == cudaSuccess)) {
+    k_chain_debug<<<1, 32>>>(d_terms, (long long)n, s0, d_out);
+    if (cudaMemcpy(result, d_out, sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess) rc = KSG_OK;
+  }
+  if (d_terms) cudaFree(d_terms);
+  if (d_out) cudaFree(d_out);
+  return rc;
 }
 
 int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity, int64_t* records_and_cycles) {

@@ -131,4 +131,45 @@ __host__ __device__ inline float chain_sum_reference(float s, const float* terms
   return s;
 }
 
+#if defined(__CUDACC__)
+// One warp evaluates one chain with lanes = records: the device form of chain_sum_reference (width 32).  Every lane ends with the
+// same running value.  Not used by the tile kernel yet; exercised through ksg_debug_chain_sum.
+__device__ __forceinline__ float chain_sum_warp(float s, const float* __restrict__ terms, long long n) {
+  const int lane = threadIdx.x & 31;
+  long long i = 0;
+  while (i < n) {
+    uint32_t m;
+    int g;
+    chain_decompose(s, m, g);
+    if (m < 0x800000u) { s = s + terms[i]; ++i; continue; }               // uniform: every lane holds the same s
+    const long long rest = n - i;
+    const int cnt = rest < 32 ? (int)rest : 32;
+    ChainTable t;
+    if (lane < cnt) t = chain_record_table(terms[i + lane], g);
+    else { t.inc[0] = t.inc[1] = 0u; t.par = 2u; }                         // identity
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {                              // inclusive scan: earlier records compose first
+      ChainTable o;
+      o.inc[0] = __shfl_up_sync(0xffffffffu, t.inc[0], off);
+      o.inc[1] = __shfl_up_sync(0xffffffffu, t.inc[1], off);
+      o.par = __shfl_up_sync(0xffffffffu, t.par, off);
+      if (lane >= off) t = chain_compose(o, t);
+    }
+    const uint32_t mine = (m & 1u) ? t.inc[1] : t.inc[0];
+    const unsigned leaves = __ballot_sync(0xffffffffu, lane < cnt && m + mine >= (1u << 24));
+    if (!leaves) {
+      s = chain_make_negative(m + __shfl_sync(0xffffffffu, mine, cnt - 1), g);
+      i += cnt;
+    } else {
+      const int leave = __ffs(leaves) - 1;
+      const uint32_t before = __shfl_sync(0xffffffffu, mine, leave > 0 ? leave - 1 : 0);
+      if (leave > 0) s = chain_make_negative(m + before, g);
+      s = s + terms[i + leave];                                            // the crossing record: one ordinary addition
+      i += leave + 1;
+    }
+  }
+  return s;
+}
+#endif
+
 }  // namespace ksg
