@@ -147,3 +147,13 @@ def test_the_reference_itself_is_not_reproducible_with_several_threads():
     print(f"reference sources, 8 threads vs 1 thread ({name}): labels differ on {rep.get('label_mismatch', -1):.0f} of {observed:.0f} observed "
           f"voxels, distance bits on {rep.get('tsdf_distance_bit_mismatch', -1):.0f}, log-probability bits on {rep.get('sem_priors_bit_mismatch', -1):.0f}")
     assert rep["same_blocks"] != 1.0 or rep["sem_priors_bit_mismatch"] + rep["tsdf_weight_bit_mismatch"] > 0
+
+
+@pytest.mark.skipif(not ref_py.available(fast_build=True), reason="oracle/_ref timing build not present")
+@pytest.mark.parametrize("name", ["fast_default_3f", "merged_default_2f", "merged_clearing_antigrazing", "fast_color_mode_probability"])
+def test_timing_build_of_the_reference_sources_gives_the_same_maps(name):
+    """bench.py times the -O3 -march=x86-64-v3 build of the reference sources; it must compute exactly what the -O2 parity build does
+    (no contraction, no reassociation: vectorisation alone does not change a float result)."""
+    with quiet_stderr():
+        fast = mrg.run_case(name, lambda cfg: ref_py.RefHybridIntegrator(cfg, fast_build=True))
+    assert mrg.digest(fast) == GOLDEN[name]
