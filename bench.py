@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--workload", default="fast5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hot-voxels", action="store_true", help="merged workloads: ksg_config.hot_voxel_mode = 1 (parallel pre-pass for hot voxels)")
     ap.add_argument("--merged-bundle-order", default="canonical", choices=["canonical", "libstdcxx"],
                     help="merged workloads: bundle order (ksg_config.merged_bundle_order); libstdcxx = the reference's unordered_map order")
     ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial"],
@@ -316,6 +317,7 @@ def main():
     total_in = sum(t.numel() * t.element_size() for t in d_depth + d_label)
     cfg = make_cfg(args.workload, device=local_rank)
     cfg.merged_bundle_order = 1 if args.merged_bundle_order == "libstdcxx" else 0
+    cfg.hot_voxel_mode = 1 if args.hot_voxels else 0
     if spatial:
         cfg.shard_rank, cfg.shard_count = rank, world
     integ = Integrator(cfg)
@@ -438,7 +440,7 @@ def main():
             "mvoxel_updates_per_s": mups,
             "config": {"workload": f"{w}x{h} depth+label stream, {vs * 100:.0f} cm voxels, {C} classes, "
                                    f"{'fast' if itype == KSG_INTEGRATOR_FAST else 'merged'} integrator (BASELINE.json configs)",
-                       "name": args.workload, "voxels_per_side": 16, "frames_distinct": n, "merged_bundle_order": args.merged_bundle_order,
+                       "name": args.workload, "voxels_per_side": 16, "frames_distinct": n, "merged_bundle_order": args.merged_bundle_order, "hot_voxel_mode": int(args.hot_voxels),
                        "l2_policy": f"every step reads a different frame ({total_in / 1e6:.0f} MB of inputs cycled, larger than the 126 MB L2 "
                                     "when steps >= 90) and a different part of the map; no explicit flush",
                        "parallelism": ("one map spatially sharded by tile owner over the GPUs; frames broadcast from rank 0 with NCCL" if spatial

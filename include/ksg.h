@@ -101,7 +101,12 @@ typedef struct ksg_config {
    * fills in bundleRays and walks in integrateVoxels (merged.cpp:110-124, 210-231) - i.e. the reference's result with
    * integrator_threads = 1 on a platform whose libstdc++ has this library's rehash policy. */
   int32_t merged_bundle_order;
-  int32_t reserved[4];
+  /* merged only, C <= 32, apply_mode 0.  1 = the semantic log-probability rows of the few voxels that receive thousands of updates in
+   * one frame (the voxels next to the camera) are computed by a parallel pre-pass (an exact scan of the float addition chain,
+   * csrc/ksg_hot.cuh) instead of one warp's sequential loop; results are bit-identical.  0 (default) = off.  Experimental: written
+   * at the end of round 1, not yet measured. */
+  int32_t hot_voxel_mode;
+  int32_t reserved[3];
 } ksg_config;
 
 /* per-frame counters (the oracle reports the same numbers; SURVEY.md 8d: one voxel update =
@@ -116,7 +121,9 @@ typedef struct ksg_frame_stats {
   int64_t blocks_touched;     /* blocks that received >= 1 update this frame */
   int64_t tiles_touched;      /* 8^3 tiles staged by the apply kernel */
   int64_t fixpoint_iterations;/* fast: iterations of the observed-set solver */
-  int64_t reserved[7];
+  int64_t hot_voxels;         /* merged, hot_voxel_mode = 1: voxels whose semantic row was finished by the pre-pass this frame */
+  int64_t hot_fallback_chunks;/* ... and how many of their 1024-record chunks had to be re-evaluated sequentially (cumulative) */
+  int64_t reserved[5];
 } ksg_frame_stats;
 
 typedef struct ksg_integrator ksg_integrator; /* opaque */

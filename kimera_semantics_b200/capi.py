@@ -64,7 +64,8 @@ class KsgConfig(C.Structure):
         ("shard_rank", C.c_int32),
         ("shard_count", C.c_int32),
         ("merged_bundle_order", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("hot_voxel_mode", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -80,7 +81,9 @@ class KsgFrameStats(C.Structure):
         ("blocks_touched", C.c_int64),
         ("tiles_touched", C.c_int64),
         ("fixpoint_iterations", C.c_int64),
-        ("reserved", C.c_int64 * 7),
+        ("hot_voxels", C.c_int64),
+        ("hot_fallback_chunks", C.c_int64),
+        ("reserved", C.c_int64 * 5),
     ]
 
     def as_dict(self) -> Dict[str, int]:
@@ -139,6 +142,7 @@ def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float
     cfg.shard_rank = 0
     cfg.shard_count = 1
     cfg.merged_bundle_order = KSG_BUNDLE_ORDER_CANONICAL
+    cfg.hot_voxel_mode = 0
     return cfg
 
 

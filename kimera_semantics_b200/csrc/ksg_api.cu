@@ -16,6 +16,7 @@
 #include "../../include/ksg.h"
 #include "ksg_kernels.cuh"
 #include "ksg_chain.cuh"
+#include "ksg_hot.cuh"
 
 using namespace ksg;
 
@@ -103,6 +104,18 @@ struct ksg_integrator {
   int *bord_ord_a = nullptr, *bord_ord_b = nullptr, *bord_vals = nullptr, *bord_first = nullptr, *bundle_f2 = nullptr;
   uint64_t *bord_keys_a = nullptr, *bord_keys_b = nullptr;
 
+  // merged, hot_voxel_mode = 1 (ksg_hot.cuh)
+  bool hot_enabled = false;
+  HotSeg* d_hot_segs = nullptr;
+  HotSeg* h_hot_segs = nullptr;      // pinned
+  int *d_hot_counts = nullptr;       // [0] segments found, [1] chunks that fell back to the plain loop (accumulated)
+  int *d_hot_chunk_seg = nullptr, *h_hot_chunk_seg = nullptr, *d_hot_guess = nullptr;
+  double* d_hot_sums = nullptr;
+  ChainTable* d_hot_tables = nullptr;
+  float* d_hot_prior = nullptr;
+  long long hot_chunk_cap = 0;
+  int64_t hot_segments_total = 0, hot_chunks_total = 0;
+
   // records
   uint64_t *rec_a = nullptr, *rec_b = nullptr;
   long long rec_cap = 0;
@@ -167,6 +180,7 @@ int validate(const ksg_config* c, std::string& why) {
   if (c->max_consecutive_ray_collisions < 0) { why = "max_consecutive_ray_collisions < 0"; return KSG_ERR_INVALID_ARGUMENT; }
   if (c->merged_bundle_order != KSG_BUNDLE_ORDER_CANONICAL && c->merged_bundle_order != KSG_BUNDLE_ORDER_LIBSTDCXX) {
     why = "unknown merged_bundle_order"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->hot_voxel_mode != 0 && c->hot_voxel_mode != 1) { why = "unknown hot_voxel_mode"; return KSG_ERR_INVALID_ARGUMENT; }
   return KSG_OK;
 }
 
@@ -182,10 +196,13 @@ void free_all(ksg_integrator* h) {
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_ord_a, h->bord_ord_b, h->bord_vals, h->bord_first, h->bundle_f2,
-                  h->bord_keys_a, h->bord_keys_b, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->bord_keys_a, h->bord_keys_b, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
+                  h->d_hot_tables, h->d_hot_prior, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_hot_segs) cudaFreeHost(h->h_hot_segs);
+  if (h->h_hot_chunk_seg) cudaFreeHost(h->h_hot_chunk_seg);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
@@ -254,6 +271,51 @@ const char* err_text(int e) {
     case 5: return "voxel or block index outside the supported range";
     default: return "device-side error";
   }
+}
+
+// hot_voxel_mode = 1: finish the log-probability rows of the frame's hot voxels ahead of the tile kernel (ksg_hot.cuh).
+// Returns the number of hot segments (0: nothing to do) through *n_hot.
+int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, long long n_records, int* n_hot) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  const DevCfg& dc = h->dc;
+  *n_hot = 0;
+  KSG_CUDA(cudaMemsetAsync(h->d_hot_counts, 0, sizeof(int), s));
+  ++h->n_launches;
+  k_hot_find<<<grid_for(n_records, 256), 256, 0, s>>>(dc, h->map, h->rec_b, n_records, h->d_hot_segs, h->d_hot_counts);
+  int found = 0;
+  KSG_CUDA(cudaMemcpyAsync(&found, h->d_hot_counts, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaStreamSynchronize(s));
+  const int n = std::min(found, kHotMaxSegs);
+  if (n <= 0) return KSG_OK;
+  KSG_CUDA(cudaMemcpyAsync(h->h_hot_segs, h->d_hot_segs, sizeof(HotSeg) * (size_t)n, cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaStreamSynchronize(s));
+  std::sort(h->h_hot_segs, h->h_hot_segs + n, [](const HotSeg& a, const HotSeg& b) { return a.begin < b.begin; });
+  long long chunks = 0;
+  int kept = 0;
+  for (int i = 0; i < n; ++i) {                       // segments that do not fit the chunk scratch stay on the ordinary path
+    HotSeg& g = h->h_hot_segs[i];
+    if (chunks + g.n_chunks > h->hot_chunk_cap) break;
+    g.first_chunk = (int)chunks;
+    for (int k = 0; k < g.n_chunks; ++k) h->h_hot_chunk_seg[chunks + k] = i;
+    chunks += g.n_chunks;
+    ++kept;
+  }
+  if (kept == 0) return KSG_OK;
+  KSG_CUDA(cudaMemcpyAsync(h->d_hot_segs, h->h_hot_segs, sizeof(HotSeg) * (size_t)kept, cudaMemcpyHostToDevice, s));
+  KSG_CUDA(cudaMemcpyAsync(h->d_hot_chunk_seg, h->h_hot_chunk_seg, sizeof(int) * (size_t)chunks, cudaMemcpyHostToDevice, s));
+  const int nch = (int)chunks;
+  h->n_launches += 4;
+  k_hot_chunk_sums<<<grid_for((long long)nch * 32, 128), 128, 0, s>>>(dc.C, h->d_hot_segs, h->d_hot_chunk_seg, nch, h->rec_b, h->tmp, h->d_hot_sums);
+  k_hot_guess<<<grid_for((long long)kept * 32, 128), 128, 0, s>>>(dc.C, h->d_hot_segs, kept, h->map.pool, h->d_hot_sums, h->d_hot_guess);
+  k_hot_chunk_tables<<<nch, 128, sizeof(float) * (size_t)dc.C * kHotColStride, s>>>(dc.C, h->d_hot_segs, h->d_hot_chunk_seg, h->rec_b, h->tmp,
+                                                                                  h->d_hot_guess, h->d_hot_tables);
+  k_hot_apply<<<grid_for((long long)kept * 32, 128), 128, 0, s>>>(dc.C, h->d_hot_segs, kept, h->map.pool, h->rec_b, h->tmp, h->d_hot_guess,
+                                                                  h->d_hot_tables, h->d_hot_prior, h->d_hot_counts + 1);
+  KSG_CUDA(cudaGetLastError());
+  h->hot_segments_total += kept;
+  h->hot_chunks_total += chunks;
+  *n_hot = kept;
+  return KSG_OK;
 }
 
 // KSG_BUNDLE_ORDER_LIBSTDCXX: iteration order of one of the reference's two bundle maps (see the kernels' comment).  `off`/`n`:
@@ -359,6 +421,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
 
   long long n_records = 0;
   int iterations = 0;
+  int64_t last_hot_voxels = 0;
   ApplySrc src{};
   if (fast) {
     KSG_CUDA(cudaMemsetAsync(h->clear_ff, 0xFF, (size_t)kSetSize * 16, s));
@@ -519,7 +582,18 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_smem + 1024))));
     const int grid = h->sm_count * ctas_per_sm;
     const int apply_threads = fast ? 512 : 256;  // fast: few records per voxel, latency bound -> more warps per tile
+    int n_hot = 0;
+    if (h->hot_enabled) {
+      const int rch = hot_voxel_prepass(h, s, n_records, &n_hot);
+      if (rch) return rch;
+      src.hot_segs = h->d_hot_segs; src.hot_prior = h->d_hot_prior; src.n_hot = n_hot; src.hot_thresh = kHotThresh;
+      last_hot_voxels = n_hot;
+    }
     ++h->n_launches;
+    if (n_hot > 0) {   // merged, C <= 32, TMA staging (checked when hot_enabled was set)
+      k_tile_apply<true, 1, true, true><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, n_records,
+                                                                                  h->tile_begin, h->tile_cap, src, h->tile_debug);
+    } else
 #define KSG_LAUNCH_APPLY_(TMA, NCH, MRG)                                                                                 \
     k_tile_apply<TMA, NCH, MRG><<<grid, apply_threads, h->apply_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, \
                                                                       n_records, h->tile_begin, h->tile_cap, src, h->tile_debug)
@@ -561,6 +635,12 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     stats->blocks_touched = h->h_cnt->n_blocks_touched;
     stats->tiles_touched = h->h_cnt->n_tiles;
     stats->fixpoint_iterations = iterations;
+    stats->hot_voxels = last_hot_voxels;
+    if (h->hot_enabled && last_hot_voxels > 0) {
+      int fb = 0;
+      if (cudaMemcpyAsync(&fb, h->d_hot_counts + 1, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess)
+        stats->hot_fallback_chunks = fb;
+    }
   }
   if (dev_err) {
     h->deferred_status = dev_err;  // the map may be inconsistent from here on
@@ -635,6 +715,7 @@ void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size
   c->shard_rank = 0;
   c->shard_count = 1;
   c->merged_bundle_order = KSG_BUNDLE_ORDER_CANONICAL;
+  c->hot_voxel_mode = 0;
 }
 
 #define KSG_STR_(x) #x
@@ -778,6 +859,18 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
     KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
+    if (cfg->hot_voxel_mode == 1 && dc.C <= 32 && cfg->apply_mode == 0) {
+      h->hot_enabled = true;
+      h->hot_chunk_cap = rec_cap / kHotChunk + kHotMaxSegs;
+      KSG_CUDA(dmalloc(&h->d_hot_segs, kHotMaxSegs)); KSG_CUDA(dmalloc(&h->d_hot_counts, 2));
+      KSG_CUDA(cudaMemset(h->d_hot_counts, 0, 2 * sizeof(int)));
+      KSG_CUDA(cudaMallocHost((void**)&h->h_hot_segs, sizeof(HotSeg) * kHotMaxSegs));
+      KSG_CUDA(cudaMallocHost((void**)&h->h_hot_chunk_seg, sizeof(int) * (size_t)h->hot_chunk_cap));
+      KSG_CUDA(dmalloc(&h->d_hot_chunk_seg, (size_t)h->hot_chunk_cap)); KSG_CUDA(dmalloc(&h->d_hot_guess, (size_t)h->hot_chunk_cap * 32));
+      KSG_CUDA(dmalloc(&h->d_hot_sums, (size_t)h->hot_chunk_cap * 32)); KSG_CUDA(dmalloc(&h->d_hot_tables, (size_t)h->hot_chunk_cap * 32));
+      KSG_CUDA(dmalloc(&h->d_hot_prior, (size_t)kHotMaxSegs * 32));
+      KSG_CUDA(cudaFuncSetAttribute(k_hot_chunk_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 32 * kHotColStride)));
+    }
     if (cfg->merged_bundle_order == KSG_BUNDLE_ORDER_LIBSTDCXX) {
       // rehash schedule of the platform's libstdc++ (depends on the size only): probe a real container once
       std::unordered_map<uint64_t, char> probe;
@@ -820,6 +913,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
 #define KSG_ATTR(TMA, NCH) \
     KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<TMA, NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem)); \
     KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<TMA, NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem))
+    KSG_CUDA(cudaFuncSetAttribute(k_tile_apply<true, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_smem));
     KSG_ATTR(true, 1); KSG_ATTR(true, 2); KSG_ATTR(true, 4); KSG_ATTR(true, 8);
     KSG_ATTR(false, 1); KSG_ATTR(false, 2); KSG_ATTR(false, 4); KSG_ATTR(false, 8);
 #undef KSG_ATTR

@@ -973,11 +973,24 @@ __device__ __forceinline__ void tma_store_commit_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// A "hot" voxel of a merged frame (ksg_hot.cuh): a run of >= kHotThresh records whose log-probability row was finished by the
+// pre-pass, so that the tile kernel's semantic warp can skip the run.
+struct HotSeg {
+  long long begin, end;   // record range in the sorted array
+  long long prior_off;    // byte offset of the voxel's log-probability row in the tile pool
+  int first_chunk, n_chunks;
+};
+
 struct ApplySrc {
   const float4* param;   // per order id: (point_G xyz, weight)
   const uint8_t* label;  // fast: measured label (one-hot frequencies, fast.cpp:132-135); NULL for merged
   const uint32_t* color; // fast: point colour; NULL -> (0,0,0,0) (merged.cpp:70 unfilled hash_colors)
   const float* tmp;      // merged: C floats per bundle = L * freq; NULL for fast
+  // HOTSEM instantiation only: segments sorted by begin, and their finished rows (32 floats per segment)
+  const HotSeg* hot_segs;
+  const float* hot_prior;
+  int n_hot;
+  int hot_thresh;
 };
 
 static constexpr int kApplyThreads = 256;
@@ -1047,7 +1060,7 @@ __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int n
 //   * lanes = classes : semantic log-probability rows, prior[c] += (L * freq)[c]  (base.cpp:283-314)
 // followed by the arg-max label (base.cpp:352-367) and the colour hand-off (base.cpp:370-191).  The tile is
 // written back once with a TMA bulk store.  NCH = ceil(C / 32) register chunks per lane.
-template <bool USE_TMA, int NCH, bool MERGED>
+template <bool USE_TMA, int NCH, bool MERGED, bool HOTSEM = false>
 __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Counters* cnt, MapRef map,
                                                                const Luts* __restrict__ luts, const uint64_t* __restrict__ rec,
                                                                long long n_rec, const long long* __restrict__ tile_begin,
@@ -1149,7 +1162,20 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
 #pragma unroll
       for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
 
-      if (MERGED && NCH == 1) {
+      bool hot_done = false;
+      if (HOTSEM && MERGED && NCH == 1 && split && role == 1 && (hi - lo) >= src.hot_thresh) {
+        // the pre-pass may have finished this voxel's log-probability row: look the run up by its first record
+        const long long first = begin + lo;
+        int a = 0, b = src.n_hot;
+        while (a < b) { const int mid = (a + b) >> 1; if (src.hot_segs[mid].begin < first) a = mid + 1; else b = mid; }
+        if (a < src.n_hot && src.hot_segs[a].begin == first && src.hot_segs[a].end == begin + hi) {
+          p[0] = (lane < C) ? src.hot_prior[(size_t)a * 32 + lane] : 0.0f;
+          hot_done = true;
+        }
+      }
+      if (hot_done) {
+        // nothing to accumulate
+      } else if (MERGED && NCH == 1) {
         // software pipeline over batches of 32 records: record keys are fetched two batches ahead, the parameters and the
         // 32 (L * freq) row values of the next batch one batch ahead, so that the recurrences below never wait on L2.
         // Padded lanes / rows point at the all-zero row behind the last bundle (adds +0.0f, exact).
