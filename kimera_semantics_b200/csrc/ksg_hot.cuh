@@ -153,7 +153,15 @@ __global__ void k_hot_apply(int C, const HotSeg* __restrict__ segs, int n_segs, 
     } else {                                                                // wrong guess, binade crossing, or p >= 0: plain loop
       const long long b = h.begin + (long long)k * kHotChunk;
       const long long e = (b + kHotChunk < h.end) ? b + kHotChunk : h.end;
-      for (long long i = b; i < e; ++i) p += __ldg(tmp + (size_t)((uint32_t)rec[i] & ord_mask) * C + lane);
+      long long i = b;
+      for (; i + 8 <= e; i += 8) {                                         // loads run ahead, the additions stay in record order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(tmp + (size_t)((uint32_t)rec[i + u] & ord_mask) * C + lane);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p += v[u];
+      }
+      for (; i < e; ++i) p += __ldg(tmp + (size_t)((uint32_t)rec[i] & ord_mask) * C + lane);
       ++fallbacks;
     }
   }

@@ -78,3 +78,74 @@ def test_host_device_primitives_of_the_future_kernel_are_exact():
     subprocess.check_call(["make", "-C", csrc, "-s", "test/chain_host_test"])
     out = subprocess.run([os.path.join(csrc, "test", "chain_host_test")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "chain ok" in out.stdout, out.stdout[-2000:]
+
+
+def test_index_level_model_of_the_hot_voxel_prepass():
+    """Line-by-line Python model of csrc/ksg_hot.cuh (chunking with a ragged last chunk, float64 binade guesses, lane-wise folding of
+    32-record sub-chunks in the skewed shared-memory layout, warp scan, table application with the plain-loop fallback) on a
+    synthetic hot voxel: the finished row must equal the sequential sums for every class."""
+    C, CH, STRIDE = 21, 1024, 1024 + 32 + 1
+    rng = np.random.default_rng(9)
+    n_bundles, n_rec = 12000, 4096 + 3 * 1024 + 517                     # ragged tail
+    counts = rng.integers(0, 3, (n_bundles, C)).astype(np.float32)
+    L = np.full((C, C), LN, np.float32); np.fill_diagonal(L, LM); L[:, 0] = 0.0
+    tmp = np.zeros((n_bundles, C), np.float32)
+    for j in range(C):                                                  # j ascending, one multiply and one add per term
+        tmp = (tmp + (L[:, j][None, :] * counts[:, j][:, None]).astype(np.float32)).astype(np.float32)
+    orders = np.sort(rng.choice(n_bundles, n_rec, replace=False))       # the voxel's records, in bundle order
+    n_chunks = (n_rec + CH - 1) // CH
+    for regime, prior0 in (("first frames", (-rng.uniform(0.6, 3.0e3, C)).astype(np.float32)),
+                           ("steady state", (-rng.uniform(2.0e6, 4.0e6, C)).astype(np.float32))):
+        fallbacks = _run_hot_model(C, CH, STRIDE, tmp, orders, prior0, n_chunks)
+        if regime == "steady state":
+            assert fallbacks <= C                   # a class crosses a binade at most once in these 8 chunks
+
+
+def _run_hot_model(C, CH, STRIDE, tmp, orders, prior0, n_chunks):
+    # k_hot_chunk_sums + k_hot_guess
+    sums = np.zeros((n_chunks, C))
+    for w in range(n_chunks):
+        sums[w] = tmp[orders[w * CH:(w + 1) * CH]].astype(np.float64).sum(axis=0)
+    guess = np.zeros((n_chunks, C), np.int64)
+    for c in range(C):
+        run = float(prior0[c])
+        for w in range(n_chunks):
+            guess[w, c] = xc._decompose(F(run))[1]
+            run += sums[w, c]
+    # k_hot_chunk_tables
+    tables = {}
+    for w in range(n_chunks):
+        rows = orders[w * CH:(w + 1) * CH]
+        s_cols = np.zeros(C * STRIDE, np.float32)
+        for r in range(CH):
+            v = tmp[rows[r]] if r < len(rows) else np.zeros(C, np.float32)
+            for lane in range(C):
+                s_cols[lane * STRIDE + r + (r >> 5)] = v[lane]
+        for c in range(C):
+            lane_tables = []
+            for lane in range(32):
+                col = c * STRIDE + lane * 33
+                t = xc.record_table(s_cols[col], int(guess[w, c]))
+                for k in range(1, 32):
+                    t = xc.compose(t, xc.record_table(s_cols[col + k], int(guess[w, c])))
+                lane_tables.append(t)
+            off = 1
+            while off < 32:                                             # Hillis-Steele inclusive scan
+                lane_tables = [xc.compose(lane_tables[l - off], lane_tables[l]) if l >= off else lane_tables[l] for l in range(32)]
+                off <<= 1
+            tables[(w, c)] = lane_tables[31]
+    # k_hot_apply
+    fallbacks = 0
+    for c in range(C):
+        p = prior0[c]
+        for w in range(n_chunks):
+            m, g = xc._decompose(p)
+            inc = tables[(w, c)][m & 1][0]
+            if p < 0 and m >= 0x800000 and g == guess[w, c] and m + inc < (1 << 24):
+                p = F(-np.ldexp(float(m + inc), g))
+            else:
+                for o in orders[w * CH:(w + 1) * CH]:
+                    p = F(p + tmp[o, c])
+                fallbacks += 1
+        assert bits(p) == bits(xc.sequential(prior0[c], tmp[orders, c])), c
+    return fallbacks
