@@ -82,6 +82,7 @@ def test_default_config_matches_python_mirror(lib):
     (lambda c: setattr(c, "color_mode", 3), "color mode"),
     (lambda c: setattr(c, "max_points", 0), "max_points"),
     (lambda c: setattr(c, "merged_bundle_order", 2), "merged_bundle_order"),
+    (lambda c: setattr(c, "hot_voxel_mode", 5), "hot_voxel_mode"),
 ])
 def test_create_rejects_invalid_configs_before_touching_the_device(lib, mutate, msg):
     cfg = default_config()
