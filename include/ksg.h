@@ -103,8 +103,10 @@ typedef struct ksg_config {
   int32_t merged_bundle_order;
   /* merged only, C <= 32, apply_mode 0.  1 = the semantic log-probability rows of the few voxels that receive thousands of updates in
    * one frame (the voxels next to the camera) are computed by a parallel pre-pass (an exact scan of the float addition chain,
-   * csrc/ksg_hot.cuh) instead of one warp's sequential loop; results are bit-identical.  0 (default) = off.  Experimental: written
-   * at the end of round 1, not yet measured. */
+   * csrc/ksg_hot.cuh) instead of one warp's sequential loop; results are bit-identical.  2 = additionally, a hot voxel that sits at
+   * (distance, weight) = (+truncation, max_weight) is CHECKED in parallel to be left untouched by every record of the frame, and
+   * its sequential TSDF recurrence is then skipped.  0 (default) = off.  Experimental: written at the end of round 1, not yet
+   * measured. */
   int32_t hot_voxel_mode;
   int32_t reserved[3];
 } ksg_config;

@@ -113,6 +113,7 @@ struct ksg_integrator {
   double* d_hot_sums = nullptr;
   ChainTable* d_hot_tables = nullptr;
   float* d_hot_prior = nullptr;
+  int* d_hot_same = nullptr;          // hot_voxel_mode 2
   long long hot_chunk_cap = 0;
   int64_t hot_segments_total = 0, hot_chunks_total = 0;
 
@@ -180,7 +181,7 @@ int validate(const ksg_config* c, std::string& why) {
   if (c->max_consecutive_ray_collisions < 0) { why = "max_consecutive_ray_collisions < 0"; return KSG_ERR_INVALID_ARGUMENT; }
   if (c->merged_bundle_order != KSG_BUNDLE_ORDER_CANONICAL && c->merged_bundle_order != KSG_BUNDLE_ORDER_LIBSTDCXX) {
     why = "unknown merged_bundle_order"; return KSG_ERR_INVALID_ARGUMENT; }
-  if (c->hot_voxel_mode != 0 && c->hot_voxel_mode != 1) { why = "unknown hot_voxel_mode"; return KSG_ERR_INVALID_ARGUMENT; }
+  if (c->hot_voxel_mode < 0 || c->hot_voxel_mode > 2) { why = "unknown hot_voxel_mode"; return KSG_ERR_INVALID_ARGUMENT; }
   return KSG_OK;
 }
 
@@ -197,7 +198,7 @@ void free_all(ksg_integrator* h) {
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_ord_a, h->bord_ord_b, h->bord_vals, h->bord_first, h->bundle_f2,
                   h->bord_keys_a, h->bord_keys_b, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
-                  h->d_hot_tables, h->d_hot_prior, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -275,7 +276,7 @@ const char* err_text(int e) {
 
 // hot_voxel_mode = 1: finish the log-probability rows of the frame's hot voxels ahead of the tile kernel (ksg_hot.cuh).
 // Returns the number of hot segments (0: nothing to do) through *n_hot.
-int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, long long n_records, int* n_hot) {
+int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, const Xform& T, const float4* bundle_param, long long n_records, int* n_hot) {
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   const DevCfg& dc = h->dc;
   *n_hot = 0;
@@ -311,6 +312,11 @@ int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, long long n_records, in
                                                                                   h->d_hot_guess, h->d_hot_tables);
   k_hot_apply<<<grid_for((long long)kept * 32, 128), 128, 0, s>>>(dc.C, h->d_hot_segs, kept, h->map.pool, h->rec_b, h->tmp, h->d_hot_guess,
                                                                   h->d_hot_tables, h->d_hot_prior, h->d_hot_counts + 1);
+  if (h->cfg.hot_voxel_mode == 2) {
+    KSG_CUDA(cudaMemsetAsync(h->d_hot_same, 0x01, sizeof(int) * (size_t)kept, s));   // 0x01010101: non-zero = "same" until refuted
+    ++h->n_launches;
+    k_hot_tsdf_same<<<nch, 128, 0, s>>>(dc, T, h->d_hot_segs, h->d_hot_chunk_seg, h->map.pool, h->rec_b, bundle_param, h->d_hot_same);
+  }
   KSG_CUDA(cudaGetLastError());
   h->hot_segments_total += kept;
   h->hot_chunks_total += chunks;
@@ -584,9 +590,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     const int apply_threads = fast ? 512 : 256;  // fast: few records per voxel, latency bound -> more warps per tile
     int n_hot = 0;
     if (h->hot_enabled) {
-      const int rch = hot_voxel_prepass(h, s, n_records, &n_hot);
+      const int rch = hot_voxel_prepass(h, s, T, src.param, n_records, &n_hot);
       if (rch) return rch;
       src.hot_segs = h->d_hot_segs; src.hot_prior = h->d_hot_prior; src.n_hot = n_hot; src.hot_thresh = kHotThresh;
+      src.hot_tsdf_same = (h->cfg.hot_voxel_mode == 2) ? h->d_hot_same : nullptr;
       last_hot_voxels = n_hot;
     }
     ++h->n_launches;
@@ -859,7 +866,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
     KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
-    if (cfg->hot_voxel_mode == 1 && dc.C <= 32 && cfg->apply_mode == 0) {
+    if (cfg->hot_voxel_mode >= 1 && dc.C <= 32 && cfg->apply_mode == 0) {
       h->hot_enabled = true;
       h->hot_chunk_cap = rec_cap / kHotChunk + kHotMaxSegs;
       KSG_CUDA(dmalloc(&h->d_hot_segs, kHotMaxSegs)); KSG_CUDA(dmalloc(&h->d_hot_counts, 2));
@@ -868,7 +875,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       KSG_CUDA(cudaMallocHost((void**)&h->h_hot_chunk_seg, sizeof(int) * (size_t)h->hot_chunk_cap));
       KSG_CUDA(dmalloc(&h->d_hot_chunk_seg, (size_t)h->hot_chunk_cap)); KSG_CUDA(dmalloc(&h->d_hot_guess, (size_t)h->hot_chunk_cap * 32));
       KSG_CUDA(dmalloc(&h->d_hot_sums, (size_t)h->hot_chunk_cap * 32)); KSG_CUDA(dmalloc(&h->d_hot_tables, (size_t)h->hot_chunk_cap * 32));
-      KSG_CUDA(dmalloc(&h->d_hot_prior, (size_t)kHotMaxSegs * 32));
+      KSG_CUDA(dmalloc(&h->d_hot_prior, (size_t)kHotMaxSegs * 32)); KSG_CUDA(dmalloc(&h->d_hot_same, (size_t)kHotMaxSegs));
       KSG_CUDA(cudaFuncSetAttribute(k_hot_chunk_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * 32 * kHotColStride)));
     }
     if (cfg->merged_bundle_order == KSG_BUNDLE_ORDER_LIBSTDCXX) {

@@ -49,8 +49,54 @@ __global__ void k_hot_find(DevCfg cfg, MapRef map, const uint64_t* __restrict__ 
   HotSeg h;
   h.begin = i; h.end = lo;
   h.prior_off = (long long)((uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride + cfg.head_bytes + (uint64_t)v * cfg.C * 4u);
+  h.tile_off = (long long)((uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride);
   h.first_chunk = 0; h.n_chunks = (int)((lo - i + kHotChunk - 1) / kHotChunk);
+  h.vox = v;
+  {   // global voxel index of (block, tile, voxel) and its centre, as k_tile_apply derives them
+    const I3 bi = unpack_key(map.ht_keys[pos]);
+    const int tps = cfg.tiles_per_side, ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+    const int tx = tile % tps, ty = (tile / tps) % tps, tz = tile / (tps * tps);
+    I3 g;
+    g.x = bi.x * cfg.vps + tx * cfg.tile_side + (v & tm);
+    g.y = bi.y * cfg.vps + ty * cfg.tile_side + ((v >> ts) & tm);
+    g.z = bi.z * cfg.vps + tz * cfg.tile_side + (v >> (2 * ts));
+    const F3 c = voxel_center(g, cfg.voxel_size);
+    h.cx = c.x; h.cy = c.y; h.cz = c.z;
+  }
   segs[s] = h;
+}
+
+// hot_voxel_mode 2.  A hot voxel in free space sits at (distance, weight) = (+truncation, max_weight), and every record of the frame
+// leaves it there: min(max_weight, max_weight + uw) = max_weight for uw >= 0, and the clamped running mean stays at +truncation.
+// This kernel CHECKS that, record by record and in parallel (the recurrence is not evaluated, only its fixed point is verified):
+// same[seg] stays 1 iff the state is the saturated one and no record moves the distance, the weight or (kColor mode) the colour.
+// One CTA per chunk; same[] must be preset to 1.
+__global__ void __launch_bounds__(128) k_hot_tsdf_same(DevCfg cfg, Xform T, const HotSeg* __restrict__ segs, const int* __restrict__ chunk_seg,
+                                                       const uint8_t* __restrict__ pool, const uint64_t* __restrict__ rec,
+                                                       const float4* __restrict__ param, int* __restrict__ same) {
+  const int w = blockIdx.x, seg = chunk_seg[w];
+  const HotSeg h = segs[seg];
+  const float dist0 = ((const float*)(pool + h.tile_off))[h.vox];
+  const float wgt0 = ((const float*)(pool + h.tile_off + cfg.plane_f32))[h.vox];
+  if (!(dist0 == cfg.tp.trunc && wgt0 == cfg.tp.max_weight)) { if (threadIdx.x == 0) same[seg] = 0; return; }
+  const long long b = h.begin + (long long)(w - h.first_chunk) * kHotChunk;
+  const long long e = (b + kHotChunk < h.end) ? b + kHotChunk : h.end;
+  const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
+  const F3 origin = f3(T.tx, T.ty, T.tz), center = f3(h.cx, h.cy, h.cz);
+  const bool keep_blend = cfg.color_mode == 0;
+  bool ok = true;
+  for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+    const float4 pr = param[(uint32_t)rec[i] & ord_mask];
+    float sdf, uw;
+    tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), center, pr.w, sdf, uw);
+    if (!(uw >= 0.0f)) { ok = false; break; }                              // weight could drop below the cap (or NaN)
+    const float nw = wgt0 + uw;
+    const float nd = (sdf * uw + dist0 * wgt0) / nw;
+    const float dn = (nd > 0.0f) ? fminf(cfg.tp.trunc, nd) : fmaxf(-cfg.tp.trunc, nd);
+    if (__float_as_uint(dn) != __float_as_uint(dist0)) { ok = false; break; }
+    if (keep_blend && fabsf(sdf) < cfg.tp.trunc) { ok = false; break; }    // the record would blend the colour
+  }
+  if (!ok) same[seg] = 0;
 }
 
 // One warp per chunk, lanes = classes: float64 column sums of the chunk's (L * freq) rows.

@@ -978,7 +978,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 struct HotSeg {
   long long begin, end;   // record range in the sorted array
   long long prior_off;    // byte offset of the voxel's log-probability row in the tile pool
+  long long tile_off;     // byte offset of the voxel's tile chunk (distance plane first, then weight, ...)
   int first_chunk, n_chunks;
+  int vox;                // voxel index inside the tile
+  float cx, cy, cz;       // voxel centre (A.2 getCenterPointFromGridIndex)
 };
 
 struct ApplySrc {
@@ -989,6 +992,7 @@ struct ApplySrc {
   // HOTSEM instantiation only: segments sorted by begin, and their finished rows (32 floats per segment)
   const HotSeg* hot_segs;
   const float* hot_prior;
+  const int* hot_tsdf_same;   // hot_voxel_mode 2: 1 = the frame provably leaves the voxel's (distance, weight, colour) untouched
   int n_hot;
   int hot_thresh;
 };
@@ -1163,14 +1167,18 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply(DevCfg cfg, Xform T, Coun
       for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
 
       bool hot_done = false;
-      if (HOTSEM && MERGED && NCH == 1 && split && role == 1 && (hi - lo) >= src.hot_thresh) {
-        // the pre-pass may have finished this voxel's log-probability row: look the run up by its first record
+      if (HOTSEM && MERGED && NCH == 1 && split && (hi - lo) >= src.hot_thresh) {
+        // the pre-pass may have dealt with this voxel: look the run up by its first record
         const long long first = begin + lo;
         int a = 0, b = src.n_hot;
         while (a < b) { const int mid = (a + b) >> 1; if (src.hot_segs[mid].begin < first) a = mid + 1; else b = mid; }
         if (a < src.n_hot && src.hot_segs[a].begin == first && src.hot_segs[a].end == begin + hi) {
-          p[0] = (lane < C) ? src.hot_prior[(size_t)a * 32 + lane] : 0.0f;
-          hot_done = true;
+          if (role == 1) {                       // semantic role: the finished log-probability row
+            p[0] = (lane < C) ? src.hot_prior[(size_t)a * 32 + lane] : 0.0f;
+            hot_done = true;
+          } else if (src.hot_tsdf_same != nullptr && src.hot_tsdf_same[a] != 0) {
+            hot_done = true;                     // TSDF role: every record was checked to leave the saturated state as it is
+          }
         }
       }
       if (hot_done) {

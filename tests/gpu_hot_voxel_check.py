@@ -17,11 +17,11 @@ def main(make_integrator=None):
     if make_integrator is None:
         make_integrator = capi.Integrator
     report = {}
-    for order in (0, 1):
+    for order, mode in ((0, 1), (1, 1), (0, 2), (1, 2)):
         cfg = make_config(capi.KSG_INTEGRATOR_MERGED, 0.02, 21, max_points=320 * 240, max_updates=48 << 20, max_blocks=4096)
         cfg.merged_bundle_order = order
         ora = OracleIntegrator(cfg, canonical_merged=(order == 0))
-        cfg.hot_voxel_mode = 1
+        cfg.hot_voxel_mode = mode
         gpu = make_integrator(cfg)
         hot, fallback, stats_ok = 0, 0, True
         for cam, depth, label, T in frames(320, 240, 21, 3):
@@ -33,7 +33,7 @@ def main(make_integrator=None):
         rep = compare_maps(gpu.export(), ora.export())
         entry = {k: v for k, v in rep.items() if k.endswith("mismatch") or k == "same_blocks"}
         entry.update(stats_ok=bool(stats_ok), hot_voxels=hot, hot_fallback_chunks=fallback)
-        report["libstdcxx" if order else "canonical"] = entry
+        report[("libstdcxx" if order else "canonical") + f"/mode{mode}"] = entry
         gpu.close()
     print("REPORT " + json.dumps(report), flush=True)
     return report
