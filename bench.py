@@ -273,7 +273,8 @@ def main():
     ap.add_argument("--workload", default="fast5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hot-voxels", action="store_true", help="merged workloads: ksg_config.hot_voxel_mode = 1 (parallel pre-pass for hot voxels)")
+    ap.add_argument("--hot-voxels", type=int, default=0, choices=[0, 1, 2],
+                    help="merged workloads: ksg_config.hot_voxel_mode (1 = parallel pre-pass for the semantic rows of hot voxels, 2 = + TSDF fixed-point check)")
     ap.add_argument("--merged-bundle-order", default="canonical", choices=["canonical", "libstdcxx"],
                     help="merged workloads: bundle order (ksg_config.merged_bundle_order); libstdcxx = the reference's unordered_map order")
     ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial"],
@@ -317,7 +318,7 @@ def main():
     total_in = sum(t.numel() * t.element_size() for t in d_depth + d_label)
     cfg = make_cfg(args.workload, device=local_rank)
     cfg.merged_bundle_order = 1 if args.merged_bundle_order == "libstdcxx" else 0
-    cfg.hot_voxel_mode = 1 if args.hot_voxels else 0
+    cfg.hot_voxel_mode = int(args.hot_voxels)
     if spatial:
         cfg.shard_rank, cfg.shard_count = rank, world
     integ = Integrator(cfg)

@@ -71,7 +71,7 @@ class FakeEvent:
         return max(1e-3, (other.t - self.t) * 1e3)
 
 
-@pytest.mark.parametrize("workload,extra", [("fast10", []), ("merged5", ["--merged-bundle-order", "libstdcxx", "--hot-voxels"])])
+@pytest.mark.parametrize("workload,extra", [("fast10", []), ("merged5", ["--merged-bundle-order", "libstdcxx", "--hot-voxels", "2"])])
 def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extra):
     if workload == "merged5":
         monkeypatch.setitem(bench.WORKLOADS, "merged5", (capi.KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 21, 16 << 20, 8192))   # small frames
@@ -100,5 +100,5 @@ def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extr
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"]) and line["roofline"]["bound"] == "hbm"
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"]) and line["cpu_baseline"]["value"] > 0
     assert line["config"]["merged_bundle_order"] == ("libstdcxx" if extra else "canonical")
-    assert line["config"]["hot_voxel_mode"] == (1 if extra else 0)
+    assert line["config"]["hot_voxel_mode"] == (2 if extra else 0)
     assert line["gpu_launches"] > 0

@@ -12,9 +12,11 @@ for order in canonical libstdcxx; do
       > gpurun_out/bench_${wl}_${order}.json 2> gpurun_out/bench_${wl}_${order}.err
   done
 done
-for wl in merged5 merged2; do
-  timeout 300 python bench.py --workload $wl --steps 40 --warmup 5 --no-cpu-baseline --hot-voxels \
-    > gpurun_out/bench_${wl}_hot.json 2> gpurun_out/bench_${wl}_hot.err
+for mode in 1 2; do
+  for wl in merged5 merged2; do
+    timeout 300 python bench.py --workload $wl --steps 40 --warmup 5 --no-cpu-baseline --hot-voxels $mode \
+      > gpurun_out/bench_${wl}_hot${mode}.json 2> gpurun_out/bench_${wl}_hot${mode}.err
+  done
 done
 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_fast5.json 2> gpurun_out/bench_fast5.err
 tail -5 gpurun_out/gpu_suite_rxX.log
