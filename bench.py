@@ -158,7 +158,7 @@ def make_cpu_integrator(arm, workload, cam, threads):
     if arm == "reference":
         return _ReferenceSourceArm(cfg, cam)
     from oracle.oracle_py import OracleIntegrator
-    return OracleIntegrator(cfg, canonical_merged=True, fast_build=True)
+    return OracleIntegrator(cfg, fast_build=True)   # merged: bundle order of cfg (default = the reference's unordered_map walk)
 
 
 def cpu_baseline(workload, frames, cam, threads, budget_s=20.0, max_frames=40, arm="port", updates_per_frame=None):

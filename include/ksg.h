@@ -96,8 +96,8 @@ typedef struct ksg_config {
   int32_t shard_rank;
   int32_t shard_count;
   /* merged only: the order in which the bundles of a frame are applied (per-voxel results depend on it, updateTsdfVoxel clamps
-   * after averaging).  KSG_BUNDLE_ORDER_CANONICAL (0, default): first-insertion order of bundleRays.
-   * KSG_BUNDLE_ORDER_LIBSTDCXX (1): the iteration order of the std::unordered_map<LongIndex, ..., LongIndexHash> the reference
+   * after averaging).  KSG_BUNDLE_ORDER_CANONICAL (0): first-insertion order of bundleRays.
+   * KSG_BUNDLE_ORDER_LIBSTDCXX (1, default since round 2): the iteration order of the std::unordered_map<LongIndex, ..., LongIndexHash> the reference
    * fills in bundleRays and walks in integrateVoxels (merged.cpp:110-124, 210-231) - i.e. the reference's result with
    * integrator_threads = 1 on a platform whose libstdc++ has this library's rehash policy. */
   int32_t merged_bundle_order;

@@ -141,7 +141,7 @@ def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float
     cfg.apply_mode = 0
     cfg.shard_rank = 0
     cfg.shard_count = 1
-    cfg.merged_bundle_order = KSG_BUNDLE_ORDER_CANONICAL
+    cfg.merged_bundle_order = KSG_BUNDLE_ORDER_LIBSTDCXX   # the reference's order (merged.cpp:210-231)
     cfg.hot_voxel_mode = 0
     return cfg
 

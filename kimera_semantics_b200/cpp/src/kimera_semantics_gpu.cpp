@@ -172,7 +172,8 @@ GpuIntegratorCore::GpuIntegratorCore(int integrator_type, const vxb::TsdfIntegra
   if (const char* e = std::getenv("KSG_MAX_BLOCKS")) c.max_blocks = std::atoi(e);
   if (const char* e = std::getenv("KSG_MAX_UPDATES")) c.max_updates = std::atoll(e);
   if (const char* e = std::getenv("KSG_DEVICE")) c.device = std::atoi(e);
-  // merged only: 1 = apply bundles in the reference's std::unordered_map iteration order (ksg.h KSG_BUNDLE_ORDER_LIBSTDCXX)
+  // merged only: the default (ksg_default_config) is the reference's std::unordered_map iteration order (ksg.h KSG_BUNDLE_ORDER_LIBSTDCXX = 1);
+  // KSG_MERGED_BUNDLE_ORDER=0 selects first-insertion order
   if (const char* e = std::getenv("KSG_MERGED_BUNDLE_ORDER")) c.merged_bundle_order = std::atoi(e);
   const int rc = ksg_create(&c, &handle_);
   KSG_CHECK(rc == KSG_OK) << "ksg_create failed (" << rc << "): " << ksg_last_error(nullptr);

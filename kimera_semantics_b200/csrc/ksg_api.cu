@@ -17,6 +17,7 @@
 #include "ksg_kernels.cuh"
 #include "ksg_chain.cuh"
 #include "ksg_hot.cuh"
+#include "ksg_bundle_order.cuh"
 
 using namespace ksg;
 
@@ -101,8 +102,9 @@ struct ksg_integrator {
   // merged, KSG_BUNDLE_ORDER_LIBSTDCXX
   std::vector<std::pair<int, uint32_t>> bord_phases;   // (first insertion index, bucket count) of every rehash phase
   uint32_t* bord_hash = nullptr;
-  int *bord_ord_a = nullptr, *bord_ord_b = nullptr, *bord_vals = nullptr, *bord_first = nullptr, *bundle_f2 = nullptr;
-  uint64_t *bord_keys_a = nullptr, *bord_keys_b = nullptr;
+  int* bundle_f2 = nullptr;
+  int* bord_scratch = nullptr;       // one allocation behind every array of BordBuf
+  BordBuf bord{};
 
   // merged, hot_voxel_mode = 1 (ksg_hot.cuh)
   bool hot_enabled = false;
@@ -196,8 +198,7 @@ void free_all(ksg_integrator* h) {
                   h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
-                  h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_ord_a, h->bord_ord_b, h->bord_vals, h->bord_first, h->bundle_f2,
-                  h->bord_keys_a, h->bord_keys_b, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
+                  h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -321,34 +322,6 @@ int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, const Xform& T, const f
   h->hot_segments_total += kept;
   h->hot_chunks_total += chunks;
   *n_hot = kept;
-  return KSG_OK;
-}
-
-// KSG_BUNDLE_ORDER_LIBSTDCXX: iteration order of one of the reference's two bundle maps (see the kernels' comment).  `off`/`n`:
-// the map's bundles in canonical order inside bundle_f; writes the re-ordered heads to bundle_f2 at the same offset.
-int bundle_order_segment(ksg_integrator* h, cudaStream_t s, int off, int n) {
-  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
-  const uint32_t* hash = h->bord_hash + off;
-  int *cur = h->bord_ord_a, *nxt = h->bord_ord_b;
-  int n_old = 0;
-  for (size_t p = 0; p < h->bord_phases.size() && n_old < n; ++p) {
-    const uint32_t n_buckets = h->bord_phases[p].second;
-    const int end = p + 1 < h->bord_phases.size() ? h->bord_phases[p + 1].first : 0x7fffffff;
-    const int m = std::min(end, n);
-    KSG_CUDA(cudaMemsetAsync(h->bord_first, 0x7F, sizeof(int) * (size_t)n_buckets, s));
-    h->n_launches += 2;
-    k_bord_first<<<grid_for(m, 256), 256, 0, s>>>(hash, cur, n_old, m, n_buckets, h->bord_first);
-    k_bord_keys<<<grid_for(m, 256), 256, 0, s>>>(hash, cur, n_old, m, n_buckets, h->bord_first, h->bord_keys_a, h->bord_vals);
-    int end_bit = 33;   // key = first << 32 | arrival, both < m
-    while (end_bit < 64 && (1ull << (end_bit - 32)) < (unsigned long long)m) ++end_bit;
-    size_t tb = h->cub_temp_bytes;
-    ++h->n_libcalls;
-    KSG_CUDA(cub::DeviceRadixSort::SortPairsDescending(h->cub_temp, tb, h->bord_keys_a, h->bord_keys_b, h->bord_vals, nxt, m, 0, end_bit, s));
-    std::swap(cur, nxt);
-    n_old = m;
-  }
-  ++h->n_launches;
-  k_bord_scatter<<<grid_for(n, 256), 256, 0, s>>>(h->bundle_f + off, cur, n, h->bundle_f2 + off);
   return KSG_OK;
 }
 
@@ -533,17 +506,11 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     }
     const int* bundle_heads = h->bundle_f;   // canonical: first-insertion order
     if (h->cfg.merged_bundle_order == KSG_BUNDLE_ORDER_LIBSTDCXX) {
-      ++h->n_launches;
+      h->n_launches += 2;
       k_bord_hash<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, h->bundle_f, h->bstart, h->ks_sorted, cap, h->bord_hash);
-      int rc0 = fetch_counters(h, s);
-      if (rc0) return rc0;
-      const int nb_all = h->h_cnt->n_cast, nb_vox = h->h_cnt->n_nonclear;
-      if (nb_all > 0) {
-        if (nb_vox < 0 || nb_vox > nb_all) return fail(KSG_ERR_CUDA, "internal: bundle map split out of range");
-        if (nb_vox > 0 && (rc0 = bundle_order_segment(h, s, 0, nb_vox))) return rc0;                 // voxel_map  (merged.cpp:126-134)
-        if (nb_all > nb_vox && (rc0 = bundle_order_segment(h, s, nb_vox, nb_all - nb_vox))) return rc0;   // clear_map (merged.cpp:138-145)
-        bundle_heads = h->bundle_f2;
-      }
+      // every rehash phase of both maps (voxel_map merged.cpp:126-134, clear_map :138-145) in one launch: one cluster per map
+      k_bundle_order<<<2 * kBordCluster, kBordThreads, 0, s>>>(h->d_cnt, h->bord, h->bundle_f, h->bundle_f2);
+      bundle_heads = h->bundle_f2;
     }
     ++h->n_launches;
     k_bundle_merge<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, bundle_heads, h->bstart, h->ks_sorted, h->seq_sorted, cap, h->pt_pC,
@@ -721,7 +688,7 @@ void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size
   c->apply_mode = 0;
   c->shard_rank = 0;
   c->shard_count = 1;
-  c->merged_bundle_order = KSG_BUNDLE_ORDER_CANONICAL;
+  c->merged_bundle_order = KSG_BUNDLE_ORDER_LIBSTDCXX;   // the reference's unordered_map iteration order (merged.cpp:210-231)
   c->hot_voxel_mode = 0;
 }
 
@@ -887,9 +854,23 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
         if (probe.bucket_count() != last) { last = probe.bucket_count(); h->bord_phases.push_back(std::make_pair((int)i, (uint32_t)last)); }
       }
       if (last >= 0x7fffffffull) return fail(KSG_ERR_INVALID_ARGUMENT, "max_points too large for merged_bundle_order");
-      KSG_CUDA(dmalloc(&h->bord_hash, N)); KSG_CUDA(dmalloc(&h->bord_ord_a, N)); KSG_CUDA(dmalloc(&h->bord_ord_b, N));
-      KSG_CUDA(dmalloc(&h->bord_vals, N)); KSG_CUDA(dmalloc(&h->bundle_f2, N)); KSG_CUDA(dmalloc(&h->bord_first, last));
-      KSG_CUDA(dmalloc(&h->bord_keys_a, N)); KSG_CUDA(dmalloc(&h->bord_keys_b, N));
+      KSG_CUDA(dmalloc(&h->bord_hash, N)); KSG_CUDA(dmalloc(&h->bundle_f2, N));
+      {   // scratch of k_bundle_order: [ord_a | ord_b | next | size_at | rank : N each][first | head : 2 * last each][cta_tot][phase tables]
+        const size_t np = h->bord_phases.size();
+        const size_t ints = 5 * N + 4 * last + 2 * kBordCluster + 2 * np + 64;
+        KSG_CUDA(dmalloc(&h->bord_scratch, ints));
+        int* p = h->bord_scratch;
+        BordBuf& bb = h->bord;
+        bb.hash = h->bord_hash;
+        bb.ord_a = p; p += N; bb.ord_b = p; p += N; bb.next = p; p += N; bb.size_at = p; p += N; bb.rank = p; p += N;
+        bb.first = p; p += 2 * last; bb.head = p; p += 2 * last; bb.cta_tot = p; p += 2 * kBordCluster;
+        bb.bucket_cap = (uint32_t)last;
+        bb.n_phases = (int)np;
+        std::vector<int> ps(np); std::vector<uint32_t> pb(np);
+        for (size_t i = 0; i < np; ++i) { ps[i] = h->bord_phases[i].first; pb[i] = h->bord_phases[i].second; }
+        KSG_CUDA(cudaMemcpy(p, ps.data(), sizeof(int) * np, cudaMemcpyHostToDevice)); bb.phase_start = p; p += np;
+        KSG_CUDA(cudaMemcpy(p, pb.data(), sizeof(uint32_t) * np, cudaMemcpyHostToDevice)); bb.phase_buckets = (const uint32_t*)p;
+      }
     }
   }
   h->rec_cap = rec_cap;
@@ -903,7 +884,6 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     cub::DeviceRadixSort::SortKeys(nullptr, t, h->rec_a, h->rec_b, rec_cap, 0, 64); need = std::max(need, t);
     cub::DeviceRadixSort::SortPairs(nullptr, t, h->pt_key, h->pt_key, h->iota, h->iota, (int)N, 0, 64); need = std::max(need, t);
     cub::DeviceRadixSort::SortPairs(nullptr, t, h->iota, h->iota, h->iota, h->iota, (int)N, 0, 32); need = std::max(need, t);
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, t, h->pt_key, h->pt_key, (int*)h->iota, (int*)h->iota, (int)N, 0, 64); need = std::max(need, t);
     cub::DeviceSelect::Flagged(nullptr, t, cub::CountingInputIterator<int>(0), h->flags8, h->pix_list, (int*)nullptr, (int)(2 * N));
     need = std::max(need, t);
     h->cub_temp_bytes = need + 256;

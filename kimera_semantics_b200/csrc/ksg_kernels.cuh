@@ -844,7 +844,7 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
 // phase (rehash + the insertions up to the next rehash) is one sort of the nodes by
 //     (arrival of the FIRST node of the node's bucket, descending ; own arrival, descending)
 // with arrival = position in the old list for rehashed nodes, then insertion time.  Prototype + proof against the real container:
-// tools/libstdcxx_order.py, tests/test_unordered_map_order.py.  The host drives one (k_bord_first, k_bord_keys, radix sort) round per phase.
+// tools/libstdcxx_order.py, tests/test_unordered_map_order.py.  All phases run in one launch: k_bundle_order (ksg_bundle_order.cuh).
 __global__ void k_bord_hash(Counters* cnt, const int* __restrict__ bundle_f, const int* __restrict__ bstart,
                             const uint64_t* __restrict__ ks, int capacity, uint32_t* __restrict__ hash) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -855,28 +855,6 @@ __global__ void k_bord_hash(Counters* cnt, const int* __restrict__ bundle_f, con
   const bool clr = f >= capacity;
   if (clr && (b == 0 || bundle_f[b - 1] < capacity)) cnt->n_nonclear = b;   // bundle_f is ascending: non-clearing heads first
   if (!clr && b == nb - 1) cnt->n_nonclear = nb;
-}
-
-__global__ void k_bord_first(const uint32_t* __restrict__ hash, const int* __restrict__ ord_cur, int n_old, int m, uint32_t n_buckets,
-                             int* __restrict__ first) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m) return;
-  const int node = t < n_old ? ord_cur[t] : t;                  // the list holds nodes 0..n_old-1; nodes n_old..m-1 arrive in order
-  atomicMin(&first[hash[node] % n_buckets], t);
-}
-
-__global__ void k_bord_keys(const uint32_t* __restrict__ hash, const int* __restrict__ ord_cur, int n_old, int m, uint32_t n_buckets,
-                            const int* __restrict__ first, uint64_t* __restrict__ keys, int* __restrict__ vals) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= m) return;
-  const int node = t < n_old ? ord_cur[t] : t;
-  keys[t] = ((uint64_t)(uint32_t)first[hash[node] % n_buckets] << 32) | (uint32_t)t;
-  vals[t] = node;
-}
-
-__global__ void k_bord_scatter(const int* __restrict__ bundle_f, const int* __restrict__ order, int n, int* __restrict__ bundle_f_out) {
-  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos < n) bundle_f_out[pos] = bundle_f[order[pos]];
 }
 
 // ---------------------------------------------------------------------------------------------

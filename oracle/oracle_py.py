@@ -82,7 +82,10 @@ def load(fast_build: bool = False) -> C.CDLL:
 class OracleIntegrator:
     """CPU oracle with the same call surface as kimera_semantics_b200.Integrator."""
 
-    def __init__(self, cfg: KsgConfig, canonical_merged: bool = True, fast_build: bool = False):
+    def __init__(self, cfg: KsgConfig, canonical_merged=None, fast_build: bool = False):
+        """canonical_merged: None = follow cfg.merged_bundle_order (0 = first-insertion order, 1 = the reference's unordered_map order)."""
+        if canonical_merged is None:
+            canonical_merged = int(cfg.merged_bundle_order) == 0
         self.lib = load(fast_build)
         self.cfg = cfg
         self.handle = self.lib.kso_create(C.byref(cfg), int(canonical_merged))

@@ -20,9 +20,14 @@ CASES = {
     # name: (integrator, width, height, voxel, classes, frames, extra config)
     "fast_160x120_10cm_c5": (KSG_INTEGRATOR_FAST, 160, 120, 0.10, 5, 3, {}),
     "fast_320x240_5cm_c21": (KSG_INTEGRATOR_FAST, 320, 240, 0.05, 21, 3, {}),
-    "merged_160x120_10cm_c5": (KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 5, 2, {}),
-    "merged_160x120_5cm_c21": (KSG_INTEGRATOR_MERGED, 160, 120, 0.05, 21, 2, {}),
-    "merged_antigrazing_160x120_10cm_c5": (KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 5, 2, {"enable_anti_grazing": 1}),
+    # first-insertion ("canonical") bundle order, opt-in since round 2
+    "merged_160x120_10cm_c5": (KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 5, 2, {"merged_bundle_order": 0}),
+    "merged_160x120_5cm_c21": (KSG_INTEGRATOR_MERGED, 160, 120, 0.05, 21, 2, {"merged_bundle_order": 0}),
+    "merged_antigrazing_160x120_10cm_c5": (KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 5, 2, {"enable_anti_grazing": 1, "merged_bundle_order": 0}),
+    # default = the reference's std::unordered_map bundle order (merged.cpp:210-231)
+    "merged_reforder_160x120_10cm_c5": (KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 5, 2, {}),
+    "merged_reforder_160x120_5cm_c21": (KSG_INTEGRATOR_MERGED, 160, 120, 0.05, 21, 2, {}),
+    "merged_reforder_antigrazing_160x120_10cm_c5": (KSG_INTEGRATOR_MERGED, 160, 120, 0.10, 5, 2, {"enable_anti_grazing": 1}),
 }
 KEYS = ("block_index", "tsdf_distance", "tsdf_weight", "tsdf_rgba", "sem_label", "sem_priors", "sem_rgba")
 

@@ -7,8 +7,8 @@ after small seeded sequences pushed through the reference boundary integratePoin
 
 They travel to the GPU box (where neither /root/reference nor, necessarily, the hybrid library exists) and anchor
   * the oracle            (tests/test_oracle_vs_ref_hybrid.py, CPU)  - every digest, bit for bit;
-  * the CUDA path          (tests/test_gpu_ref_golden.py, GPU)        - `fast`: every digest, bit for bit; `merged`: the
-    order-insensitive ones (the product uses the canonical bundle order, the reference libstdc++'s hash-map order).
+  * the CUDA path          (tests/test_gpu_ref_golden.py, GPU)        - `fast` and `merged`: every digest, bit for bit (the product's
+    default bundle order for `merged` is the reference's libstdc++ hash-map order).
 
 Regenerate (only in a container that has /root/reference):   make -C oracle ref && python tests/golden/make_ref_golden.py
 """
@@ -55,6 +55,8 @@ CASES = {
     "fast_fullsize_640x480_5cm_4f": (FAST, 640, 480, 0.05, 4, {}, {}),             # BASELINE.json configs[1] geometry
     "merged_default_2f": (MERGED, 160, 120, 0.10, 2, {}, {}),
     "merged_fullsize_640x480_5cm_1f": (MERGED, 640, 480, 0.05, 1, {}, {}),
+    # BASELINE.json configs[2] at full size: 640x480, 2 cm, `merged` (31 M voxel updates in the frame)
+    "merged_fullsize_640x480_2cm_1f": (MERGED, 640, 480, 0.02, 1, {"max_updates": 80 << 20, "max_blocks": 32768}, {}),
     "merged_5cm": (MERGED, 128, 96, 0.05, 2, {}, {}),
     "merged_antigrazing": (MERGED, 128, 96, 0.10, 2, {"enable_anti_grazing": 1}, {}),
     "merged_clearing_rays": (MERGED, 128, 96, 0.10, 2, {"max_ray_length_m": 2.5}, {}),
@@ -70,7 +72,7 @@ KEYS = ("block_index", "tsdf_distance", "tsdf_weight", "tsdf_rgba", "sem_label",
 
 def case_config(name):
     itype, w, h, vs, nf, kw, sc = CASES[name]
-    return make_config(itype, vs, C21, max_points=w * h, max_updates=8 << 20, **kw)
+    return make_config(itype, vs, C21, max_points=w * h, **{"max_updates": 8 << 20, **kw})
 
 
 def case_frames(name, cfg):
