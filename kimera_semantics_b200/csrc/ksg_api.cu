@@ -18,6 +18,7 @@
 #include "ksg_chain.cuh"
 #include "ksg_hot.cuh"
 #include "ksg_bundle_order.cuh"
+#include "ksg_fast.cuh"
 
 using namespace ksg;
 
@@ -139,6 +140,21 @@ struct ksg_integrator {
   int* d_exp_slots = nullptr;
   int exp_slots_cap = 0;
 
+  // fast, round-2 frame driver (ksg_fast.cuh): no host read-back inside the frame
+  bool fast_v2 = false;
+  FastCounters* d_fc = nullptr;
+  FastCounters* h_fc = nullptr;      // pinned
+  int *blk_cnt = nullptr, *blk_off = nullptr, *warp_cnt = nullptr, *warp_off = nullptr, *seq_of_i = nullptr;
+  uint32_t* keys32 = nullptr;
+  int *tile_cnt = nullptr, *tile_slot = nullptr;
+  TileDesc* tile_list = nullptr;
+  int solve_grid = 0, apply_fast_smem = 0;
+  double clock_khz = 1965000.0;
+  cudaEvent_t ev_frame = nullptr;    // recorded behind the frame's counter copy
+  bool frame_pending = false;
+  int pending_iterations = 0;
+  long long pending_records = -1;    // legacy paths know the record count on the host; -1: read it from the counters
+
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
   int sweeps_per_sync = 1;
   int first_batch = 4;
@@ -199,9 +215,12 @@ void free_all(ksg_integrator* h) {
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
-                  h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
+                  h->tile_cnt, h->tile_slot, h->tile_list, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->h_fc) cudaFreeHost(h->h_fc);
+  if (h->ev_frame) cudaEventDestroy(h->ev_frame);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_hot_segs) cudaFreeHost(h->h_hot_segs);
   if (h->h_hot_chunk_seg) cudaFreeHost(h->h_hot_chunk_seg);
@@ -235,6 +254,10 @@ int reset_map(ksg_integrator* h, cudaStream_t s) {
   if (h->start_table) KSG_CUDA(cudaMemsetAsync(h->start_table, 0xFF, sizeof(uint32_t) * kSetSize, s));
   if (h->ob.table) KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
   if (h->ob.slot_stamp) KSG_CUDA(cudaMemsetAsync(h->ob.slot_stamp, 0, sizeof(int) * kSetSize, s));
+  if (h->d_fc) KSG_CUDA(cudaMemsetAsync(h->d_fc, 0, sizeof(FastCounters), s));
+  if (h->tile_cnt) KSG_CUDA(cudaMemsetAsync(h->tile_cnt, 0, sizeof(int) * (size_t)h->ht_cap * h->dc.tiles_per_block, s));
+  h->frame_pending = false;
+  std::memset(h->h_cnt, 0, sizeof(Counters));
   h->sweep_counter = 0;
   h->set_offset = 0;
   h->reset_counter = 0;
@@ -268,6 +291,7 @@ int fetch_counters(ksg_integrator* h, cudaStream_t s) {
 const char* err_text(int e) {
   switch (e) {
     case 1: return "invalid argument: a semantic label >= num_labels (CHECK_LT fast.cpp:134 / merged.cpp:278)";
+    case 2: return "observed-set solver did not converge within its sweep budget";
     case 3: return "block pool / hash table full: raise ksg_config.max_blocks";
     case 4: return "per-frame scratch full: raise ksg_config.max_ray_steps / max_updates";
     case 5: return "voxel or block index outside the supported range";
@@ -325,10 +349,154 @@ int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, const Xform& T, const f
   return KSG_OK;
 }
 
+
+// Completes the frame that was enqueued last (fast, round-2 driver): waits for its counter copy, mirrors the counters on the host
+// and reports a device-side error.  No-op when nothing is pending.
+int finish_frame(ksg_integrator* h, ksg_frame_stats* stats) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (h->frame_pending) {
+    KSG_CUDA(cudaEventSynchronize(h->ev_frame));
+    h->frame_pending = false;
+    h->num_blocks = h->h_cnt->pool_count;
+    h->last_blocks_touched = h->h_cnt->n_blocks_touched;
+    if (h->profiling) {
+      // events: 0 frame start, 1 before k_fast_solve, 2 after it, 3 after the tile kernel; the solve kernel's own phases come from
+      // the clock64 marks block 0 left in FastCounters::timeline
+      float a = 0, b = 0, c = 0, tot = 0;
+      cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+      cudaEventElapsedTime(&c, h->ev[2], h->ev[3]); cudaEventElapsedTime(&tot, h->ev[0], h->ev[3]);
+      const long long* tl = h->h_fc->timeline;
+      const int sweeps_end = (int)tl[kTimelineSlots - 1];
+      const int tb = kTimelineSlots - 12;
+      const double span = (double)(tl[tb + 4] - tl[0]);
+      if (span > 0 && sweeps_end >= 3 && sweeps_end < tb) {
+        const double k = (double)b / span;
+        h->phase_ms[0] += a + k * (double)(tl[2] - tl[0]);                 // count + classify + start set + compaction + ray set-up
+        h->phase_ms[1] += k * (double)(tl[tb] - tl[2]);                    // observed-set sweeps
+        h->phase_ms[2] += k * (double)(tl[tb + 1] - tl[tb]);               // table commit + ray emit
+        h->phase_ms[3] += k * (double)(tl[tb + 4] - tl[tb + 1]);           // records -> tile segments (count, allocate + new blocks, scatter)
+      } else { h->phase_ms[0] += a; h->phase_ms[1] += b; }
+      h->phase_ms[5] += c;
+      h->phase_ms[6] += tot;
+      h->prof_frames += 1;
+    }
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->points_in = h->h_cnt->n_points;
+    stats->points_valid = h->h_cnt->n_valid;
+    stats->rays_cast = h->h_cnt->n_cast;
+    stats->ray_steps = (int64_t)h->h_cnt->ray_steps;
+    stats->voxel_updates = (int64_t)h->h_cnt->n_records - (int64_t)h->h_cnt->n_skipped;
+    stats->blocks_allocated = h->num_blocks;
+    stats->blocks_touched = h->h_cnt->n_blocks_touched;
+    stats->tiles_touched = h->h_cnt->n_tiles;
+    stats->fixpoint_iterations = h->h_fc ? h->h_fc->sweeps_last : 0;
+  }
+  const int dev_err = h->h_cnt->err;
+  if (dev_err) {
+    h->deferred_status = dev_err;  // the map may be inconsistent from here on
+    return fail(dev_err, err_text(dev_err));
+  }
+  return KSG_OK;
+}
+
+// `fast`, round-2 frame driver: five launches, no host read-back inside the frame (ksg_fast.cuh).
+int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin, const Xform& T, int cap, cudaStream_t s,
+                      ksg_frame_stats* stats) {
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  const bool sorted = h->cfg.integration_order_mode == KSG_ORDER_SORTED;
+  // ApproxHashSet resets (fast.cpp:165-170, A.4)
+  if ((++h->reset_counter) >= h->cfg.clear_checks_every_n_frames) {
+    h->reset_counter = 0;
+    if (++h->set_offset >= 10000) {
+      h->set_offset = 0;
+      KSG_CUDA(cudaMemsetAsync(h->start_table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+      KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
+    }
+  }
+  FastFrame f{};
+  f.cfg = h->dc; f.T = T; f.in = fin; f.in.pix_list = nullptr; f.in.point_of_seq = nullptr;
+  f.luts = h->d_luts; f.cnt = h->d_cnt; f.fc = h->d_fc; f.map = h->map; f.ob = h->ob;
+  f.sb = StartBuf{h->start_head, h->start_next, h->start_min, h->start_max, h->start_val, h->start_mixed, h->start_table};
+  f.set_offset = h->set_offset;
+  f.capacity = cap;
+  f.n_count_blocks = (cap + kCountBlock - 1) / kCountBlock;
+  f.vec_ok = in.d_depth ? (((uintptr_t)in.d_depth % 16 == 0 && (uintptr_t)in.d_label_img % 4 == 0) ? 1 : 0) : 0;
+  f.frame_stamp = h->frame_stamp;
+  f.profile = h->profiling ? 1 : 0;
+  f.seq_of_i = sorted ? h->seq_of_i : nullptr;
+  f.block_cnt = h->blk_cnt; f.block_off = h->blk_off; f.warp_cnt = h->warp_cnt; f.warp_off = h->warp_off;
+  f.pt_pG = h->pt_pG; f.pt_label = h->pt_label; f.pt_flags = h->pt_flags; f.pt_color = h->pt_color; f.pt_key = h->pt_key;
+  f.cast_flag = h->flags8;
+  f.cast_seq = h->cast_seq; f.ray_param = h->ray_param; f.ray_label = h->ray_label; f.ray_flags = h->ray_flags; f.ray_color = h->ray_color;
+  f.nsteps = h->nsteps; f.H = h->H; f.L = h->L; f.ray_state = h->ray_state; f.ext_off = h->ext_off; f.eval_sweep = h->eval_sweep;
+  f.rec = h->rec_a; f.rec_cap = h->rec_cap; f.keys = h->keys32;
+  f.tile_cnt = h->tile_cnt; f.tile_slot = h->tile_slot; f.tile_list = h->tile_list; f.tile_cap = h->tile_cap;
+
+  if (h->profiling) cudaEventRecord(h->ev[0], s);
+  KSG_CUDA(cudaMemsetAsync(h->clear_ff, 0xFF, (size_t)kSetSize * 16, s));
+  KSG_CUDA(cudaMemsetAsync(h->clear_00, 0x00, (size_t)kSetSize * 5, s));
+  KSG_CUDA(cudaMemsetAsync(h->start_min, 0x7F, sizeof(int) * kSetSize, s));
+  const int B = 256;
+  ++h->n_launches;
+  if (in.d_depth) k_fast_count<<<f.n_count_blocks, 256, 0, s>>>(f);
+  else k_fast_reset<<<1, 1, 0, s>>>(f);
+  if (sorted) {   // voxblox SortedThreadSafeIndex (A.3): stable order by squared norm
+    h->n_launches += 3;
+    if (in.d_depth) k_fast_sqnorm<<<f.n_count_blocks, 256, 0, s>>>(f, h->sq_keys);
+    else k_fast_sqnorm_points<<<grid_for(cap, B), B, 0, s>>>(f, h->sq_keys);
+    k_fast_pad_keys<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, cap, h->sq_keys);
+    size_t tb = h->cub_temp_bytes;
+    ++h->n_libcalls;
+    KSG_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_temp, tb, h->sq_keys, h->sq_keys_out, h->iota, (uint32_t*)h->point_of_seq, cap, 0, 32, s));
+    k_fast_invert_perm<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, (const uint32_t*)h->point_of_seq, h->seq_of_i);
+  }
+  ++h->n_launches;
+  if (in.d_depth) k_fast_classify<true><<<f.n_count_blocks, 256, 0, s>>>(f);
+  else k_fast_classify<false><<<grid_for(cap, B), B, 0, s>>>(f);
+  const int n_eval_blocks = (cap + kEvalBlock - 1) / kEvalBlock;
+  ++h->n_launches;
+  k_fast_start_eval<<<n_eval_blocks, kEvalBlock, 0, s>>>(f, n_eval_blocks);
+  if (h->profiling) cudaEventRecord(h->ev[1], s);
+  {
+    int max_sweeps = 4096;   // theory: <= rays + 1 sweeps, practice 6-8; the kernel flags an error rather than spin for ever
+    void* args[] = {(void*)&f, (void*)&max_sweeps};
+    ++h->n_launches;
+    KSG_CUDA(cudaLaunchCooperativeKernel((const void*)k_fast_solve, dim3(h->solve_grid), dim3(kSolveThreads), args, 0, s));
+  }
+  if (h->profiling) cudaEventRecord(h->ev[2], s);
+  {
+    ApplySrc src{};
+    src.param = h->ray_param; src.label = h->ray_label; src.color = h->ray_color; src.tmp = nullptr;
+    const int ctas_per_sm = std::max(1, std::min(8, (int)(220 * 1024 / std::max(1, h->apply_fast_smem + 1024))));
+    const int grid = h->sm_count * ctas_per_sm;
+    ++h->n_launches;
+#define KSG_LAUNCH_FAST(TMA, NCH) k_tile_apply_fast<TMA, NCH><<<grid, 512, h->apply_fast_smem, s>>>(f, src)
+    if (h->use_tma) {
+      switch (h->apply_nch) { case 1: KSG_LAUNCH_FAST(true, 1); break; case 2: KSG_LAUNCH_FAST(true, 2); break;
+                              case 4: KSG_LAUNCH_FAST(true, 4); break; default: KSG_LAUNCH_FAST(true, 8); break; }
+    } else {
+      switch (h->apply_nch) { case 1: KSG_LAUNCH_FAST(false, 1); break; case 2: KSG_LAUNCH_FAST(false, 2); break;
+                              case 4: KSG_LAUNCH_FAST(false, 4); break; default: KSG_LAUNCH_FAST(false, 8); break; }
+    }
+#undef KSG_LAUNCH_FAST
+  }
+  if (h->profiling) cudaEventRecord(h->ev[3], s);
+  KSG_CUDA(cudaGetLastError());
+  KSG_CUDA(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaMemcpyAsync(h->h_fc, h->d_fc, sizeof(FastCounters), cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaEventRecord(h->ev_frame, s));
+  h->frame_pending = true;
+  if (stats || h->profiling) return finish_frame(h, stats);
+  return KSG_OK;
+}
+
 int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaStream_t s, ksg_frame_stats* stats) {
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
   if (in.n > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");
+  if (in.n == 0 && h->frame_pending) { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
   KSG_CUDA(cudaSetDevice(h->device));
   const DevCfg& dc = h->dc;
   const bool fast = h->cfg.integrator_type == KSG_INTEGRATOR_FAST;
@@ -364,6 +532,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     fin.constant_y = (float)(1.0 / in.K[1]);
   }
   fin.freespace = in.freespace;
+  if (fast && h->fast_v2) return integrate_fast_v2(h, in, fin, T, cap, s, stats);
 
   if (h->profiling) cudaEventRecord(h->ev[0], s);
   ++h->n_launches;
@@ -790,6 +959,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   KSG_CUDA(dmalloc(&h->d_cnt, 1));
   KSG_CUDA(cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)));
   std::memset(h->h_cnt, 0, sizeof(Counters));
+  KSG_CUDA(cudaEventCreateWithFlags(&h->ev_frame, cudaEventDisableTiming));
 
   // ---- frame scratch
   const size_t N = (size_t)cfg->max_points;
@@ -906,6 +1076,40 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
 #undef KSG_ATTR
   }
   if (fast) {
+    // round-2 frame driver (ksg_fast.cuh)
+    h->fast_v2 = true;
+    if (const char* e = std::getenv("KSG_FAST_LEGACY")) h->fast_v2 = std::atoi(e) == 0;
+    KSG_CUDA(dmalloc(&h->d_fc, 1));
+    KSG_CUDA(cudaMemset(h->d_fc, 0, sizeof(FastCounters)));
+    KSG_CUDA(cudaMallocHost((void**)&h->h_fc, sizeof(FastCounters)));
+    std::memset(h->h_fc, 0, sizeof(FastCounters));
+    KSG_CUDA(dmalloc(&h->blk_cnt, N / kCountBlock + 2)); KSG_CUDA(dmalloc(&h->blk_off, N / kCountBlock + 2));
+    KSG_CUDA(dmalloc(&h->warp_cnt, N / 32 + 64)); KSG_CUDA(dmalloc(&h->warp_off, N / 32 + 64));
+    if (cfg->integration_order_mode == KSG_ORDER_SORTED) KSG_CUDA(dmalloc(&h->seq_of_i, N));
+    KSG_CUDA(dmalloc(&h->keys32, (size_t)rec_cap));
+    const size_t n_tk = (size_t)h->ht_cap * dc.tiles_per_block;
+    KSG_CUDA(dmalloc(&h->tile_cnt, n_tk)); KSG_CUDA(dmalloc(&h->tile_slot, n_tk));
+    KSG_CUDA(cudaMemset(h->tile_cnt, 0, sizeof(int) * n_tk));
+    KSG_CUDA(dmalloc(&h->tile_list, (size_t)h->tile_cap));
+    {
+      int per_sm = 0;
+      KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_solve, kSolveThreads, 0));
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+      if (!coop || per_sm <= 0) h->fast_v2 = false;
+      h->solve_grid = h->sm_count * std::max(1, per_sm);
+      if (const char* e = std::getenv("KSG_SOLVE_CTAS_PER_SM")) h->solve_grid = h->sm_count * std::max(1, std::min(per_sm, std::atoi(e)));
+      int khz = 0;
+      if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device) == cudaSuccess && khz > 0) h->clock_khz = khz;
+    }
+    {
+      const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
+      h->apply_fast_smem = (int)(stage + (size_t)dc.tile_voxels * 10 + 16 + sizeof(uint32_t) * kFastKeyCap + 64);
+#define KSG_ATTRF(TMA, NCH) KSG_CUDA(cudaFuncSetAttribute(k_tile_apply_fast<TMA, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_fast_smem))
+      KSG_ATTRF(true, 1); KSG_ATTRF(true, 2); KSG_ATTRF(true, 4); KSG_ATTRF(true, 8);
+      KSG_ATTRF(false, 1); KSG_ATTRF(false, 2); KSG_ATTRF(false, 4); KSG_ATTRF(false, 8);
+#undef KSG_ATTRF
+    }
     KSG_CUDA(dmalloc(&h->d_gridbar, 1));
     int per_sm = 0;
     KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_eval_persistent, 256, 0));
@@ -1028,11 +1232,16 @@ int32_t ksg_sync(ksg_integrator* h) {
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   KSG_CUDA(cudaSetDevice(h->device));
   KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
   if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
   return KSG_OK;
 }
 
-int64_t ksg_num_blocks(ksg_integrator* h) { return h ? h->num_blocks : 0; }
+int64_t ksg_num_blocks(ksg_integrator* h) {
+  if (!h) return 0;
+  if (h->frame_pending) { cudaSetDevice(h->device); finish_frame(h, nullptr); }
+  return h->num_blocks;
+}
 
 static bool key_less_zyx(uint64_t a, uint64_t b) { return a < b; }  // packed as z:y:x, biased -> numeric order = (z, y, x)
 
@@ -1089,6 +1298,7 @@ int32_t ksg_export_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* b
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   KSG_CUDA(cudaSetDevice(h->device));
   KSG_CUDA(cudaDeviceSynchronize());
+  finish_frame(h, nullptr);
   const int64_t nb = h->num_blocks;
   if (nb > capacity_blocks) return fail(KSG_ERR_INVALID_ARGUMENT, "export capacity too small");
   if (nb == 0) return KSG_OK;
@@ -1113,6 +1323,7 @@ int32_t ksg_export_blocks_by_index(ksg_integrator* h, int64_t n, const int32_t* 
   if (n == 0) return KSG_OK;
   KSG_CUDA(cudaSetDevice(h->device));
   KSG_CUDA(cudaDeviceSynchronize());
+  finish_frame(h, nullptr);
   // host copy of the hash table: look the keys up exactly as the device does
   std::vector<uint64_t> keys((size_t)h->ht_cap);
   std::vector<int> slot_of((size_t)h->ht_cap);
@@ -1167,6 +1378,7 @@ int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_ind
   if (n == 0) return KSG_OK;
   KSG_CUDA(cudaSetDevice(h->device));
   KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
   const DevCfg& dc = h->dc;
   // host mirror of the block hash: look up / insert exactly as the device does (linear probing from mix64(key))
   std::vector<uint64_t> keys((size_t)h->ht_cap);
@@ -1246,9 +1458,10 @@ int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_ind
 
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index) {
   if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->frame_pending) finish_frame(h, nullptr);
   const int64_t n = h->last_blocks_touched;
   if (!block_index || capacity_blocks < n || n == 0) return n;
-  cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   std::vector<int> pos((size_t)n);
   if (cudaMemcpy(pos.data(), h->map.touched_list, sizeof(int) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
@@ -1355,6 +1568,7 @@ int32_t ksg_reset(ksg_integrator* h) {
   if (!h) return KSG_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  h->frame_pending = false;
   return reset_map(h, h->own_stream);
 }
 

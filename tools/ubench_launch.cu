@@ -43,6 +43,7 @@ __global__ void k_set_counter(int* counter, int v, cudaGraphConditionalHandle h)
 static float elapsed(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
   cudaStream_t s;
   CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   cudaEvent_t e0, e1;
