@@ -254,6 +254,13 @@ int32_t ksg_get_profile(ksg_integrator* h, double* phase_ms /* KSG_NUM_PHASES */
  * number of tiles of the last frame and copies 2 int64 per tile when records_and_cycles has room. */
 int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity, int64_t* records_and_cycles);
 
+/* Debug aid (fast integrator, profiling enabled): SM-clock stamps that block 0 of the frame's persistent solve kernel took at its phase
+ * boundaries during the LAST frame: out[0] kernel start, out[1] rays compacted, out[2] rays set up, out[3 .. 2+sweeps] end of each
+ * observed-set sweep, out[52] sweeps done, out[53] table commit + ray emit done, out[54] records counted per tile, out[55] tile
+ * segments allocated + new blocks constructed, out[56] records scattered (kernel end); *sweeps = sweeps of that frame, *clock_khz = SM
+ * clock the stamps count in.  Returns the number of slots written (64) or 0. */
+int64_t ksg_debug_fast_timeline(ksg_integrator* h, int64_t* out64, int64_t* sweeps, double* clock_khz);
+
 /* Debug aid for the next optimisation (not on the integration path): evaluates  s <- fl(s + terms[k]), k = 0..n-1  (s0 < 0, terms <= 0,
  * float32, round to nearest even) with ONE warp as an exact associative scan (lanes = records, csrc/ksg_chain.cuh) and returns the
  * final s, which must equal the sequential loop bit for bit.  This is the per-voxel, per-class log-probability recurrence of the

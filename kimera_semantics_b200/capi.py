@@ -221,6 +221,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_debug_chain_sum.restype = C.c_int32
     lib.ksg_unordered_map_schedule.argtypes = [C.c_int64, C.POINTER(C.c_int64)]
     lib.ksg_unordered_map_schedule.restype = C.c_int64
+    lib.ksg_debug_fast_timeline.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    lib.ksg_debug_fast_timeline.restype = C.c_int64
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -233,7 +235,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
-               "ksg_debug_chain_sum"]
+               "ksg_debug_chain_sum", "ksg_debug_fast_timeline"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -411,6 +413,21 @@ class Integrator:
         out["kernel_launches"] = int(launches.value)
         out["library_calls"] = int(libcalls.value)
         return out
+
+    def fast_timeline(self) -> Dict[str, object]:
+        """Phase boundaries of the last frame's persistent solve kernel in microseconds from its start (fast integrator, profiling on)."""
+        out = (C.c_int64 * 64)()
+        sweeps, khz = C.c_int64(), C.c_double()
+        n = int(self.lib.ksg_debug_fast_timeline(self.handle, out, C.byref(sweeps), C.byref(khz)))
+        if n == 0:
+            return {}
+        t = [int(v) for v in out]
+        us = lambda a, b: (t[b] - t[a]) / (khz.value / 1e3)
+        ns = int(sweeps.value)
+        return {"sweeps": ns, "compact_us": us(0, 1), "ray_setup_us": us(1, 2),
+                "sweep_us": [us(2 + i, 3 + i) for i in range(max(0, min(ns, 48)))],
+                "commit_emit_us": us(52, 53), "tile_count_us": us(53, 54), "tile_alloc_block_init_us": us(54, 55), "scatter_us": us(55, 56),
+                "solve_kernel_us": us(0, 56)}
 
     def sync(self):
         self._check(self.lib.ksg_sync(self.handle), "ksg_sync")

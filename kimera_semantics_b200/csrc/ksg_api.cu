@@ -19,6 +19,8 @@
 #include "ksg_hot.cuh"
 #include "ksg_bundle_order.cuh"
 #include "ksg_fast.cuh"
+#include "ksg_fast3.cuh"
+#include "ksg_voxel.cuh"
 
 using namespace ksg;
 
@@ -149,11 +151,36 @@ struct ksg_integrator {
   int *tile_cnt = nullptr, *tile_slot = nullptr;
   TileDesc* tile_list = nullptr;
   int solve_grid = 0, apply_fast_smem = 0;
+  int solver = 3;                    // 3: rank-group solver (ksg_fast3.cuh), 2: first persistent formulation (k_fast_solve)
+  Cand* cand16 = nullptr;
+  OvfEnt* ovf = nullptr;
+  RayRec* rayrec = nullptr;
+  int ovf_cap = 0;
   double clock_khz = 1965000.0;
-  cudaEvent_t ev_frame = nullptr;    // recorded behind the frame's counter copy
-  bool frame_pending = false;
+  // frames whose counters have not been read back yet (at most two: the counter copies land in two pinned slots)
+  Counters* h_cnt_base = nullptr;    // [2] pinned; h_cnt points at the slot read last
+  FastCounters* h_fc_base = nullptr; // [2] pinned
+  cudaEvent_t ev_frame_s[2] = {nullptr, nullptr};   // recorded behind the frame's counter copy
+  int pend[2] = {0, 0};
+  int n_pend = 0, next_slot = 0;
+  // pipelined host-buffer entry (ksg_integrate_depth_async): the H2D copy of frame t+1 overlaps the kernels of frame t
+  cudaStream_t copy_stream = nullptr;
+  uint8_t* d_in2[2] = {nullptr, nullptr};
+  uint8_t* h_stage2[2] = {nullptr, nullptr};
+  size_t in2_bytes[2] = {0, 0};
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  bool in2_used[2] = {false, false};
+  int in_slot = 0;
+  ksg_frame_stats stash[4];
+  int n_stash = 0;
   int pending_iterations = 0;
   long long pending_records = -1;    // legacy paths know the record count on the host; -1: read it from the counters
+
+  // merged, round-2 per-voxel apply (ksg_voxel.cuh)
+  bool voxel_apply = false;
+  VoxelQueues vq{};
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
   int sweeps_per_sync = 1;
@@ -216,11 +243,21 @@ void free_all(ksg_integrator* h) {
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
-                  h->tile_cnt, h->tile_slot, h->tile_list, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (h->h_cnt) cudaFreeHost(h->h_cnt);
-  if (h->h_fc) cudaFreeHost(h->h_fc);
-  if (h->ev_frame) cudaEventDestroy(h->ev_frame);
+  if (h->h_cnt_base) cudaFreeHost(h->h_cnt_base);
+  if (h->h_fc_base) cudaFreeHost(h->h_fc_base);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_frame_s[i]) cudaEventDestroy(h->ev_frame_s[i]);
+    if (h->ev_copy[i]) cudaEventDestroy(h->ev_copy[i]);
+    if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+    if (h->d_in2[i]) cudaFree(h->d_in2[i]);
+    if (h->h_stage2[i]) cudaFreeHost(h->h_stage2[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_hot_segs) cudaFreeHost(h->h_hot_segs);
   if (h->h_hot_chunk_seg) cudaFreeHost(h->h_hot_chunk_seg);
@@ -256,8 +293,8 @@ int reset_map(ksg_integrator* h, cudaStream_t s) {
   if (h->ob.slot_stamp) KSG_CUDA(cudaMemsetAsync(h->ob.slot_stamp, 0, sizeof(int) * kSetSize, s));
   if (h->d_fc) KSG_CUDA(cudaMemsetAsync(h->d_fc, 0, sizeof(FastCounters), s));
   if (h->tile_cnt) KSG_CUDA(cudaMemsetAsync(h->tile_cnt, 0, sizeof(int) * (size_t)h->ht_cap * h->dc.tiles_per_block, s));
-  h->frame_pending = false;
-  std::memset(h->h_cnt, 0, sizeof(Counters));
+  h->n_pend = 0; h->n_stash = 0;
+  std::memset(h->h_cnt_base, 0, 2 * sizeof(Counters));
   h->sweep_counter = 0;
   h->set_offset = 0;
   h->reset_counter = 0;
@@ -350,54 +387,67 @@ int hot_voxel_prepass(ksg_integrator* h, cudaStream_t s, const Xform& T, const f
 }
 
 
-// Completes the frame that was enqueued last (fast, round-2 driver): waits for its counter copy, mirrors the counters on the host
-// and reports a device-side error.  No-op when nothing is pending.
-int finish_frame(ksg_integrator* h, ksg_frame_stats* stats) {
+void fill_stats(ksg_integrator* h, ksg_frame_stats* stats) {
+  std::memset(stats, 0, sizeof(*stats));
+  stats->points_in = h->h_cnt->n_points;
+  stats->points_valid = h->h_cnt->n_valid;
+  stats->rays_cast = h->h_cnt->n_cast;
+  stats->ray_steps = (int64_t)h->h_cnt->ray_steps;
+  stats->voxel_updates = (int64_t)h->h_cnt->n_records - (int64_t)h->h_cnt->n_skipped;
+  stats->blocks_allocated = h->num_blocks;
+  stats->blocks_touched = h->h_cnt->n_blocks_touched;
+  stats->tiles_touched = h->h_cnt->n_tiles;
+  stats->fixpoint_iterations = h->h_fc ? h->h_fc->sweeps_last : 0;
+}
+
+// Completes the OLDEST frame whose counters are still in flight (fast, round-2 driver): waits for its counter copy, mirrors the
+// counters on the host and reports a device-side error.
+int finish_oldest(ksg_integrator* h, ksg_frame_stats* stats) {
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
-  if (h->frame_pending) {
-    KSG_CUDA(cudaEventSynchronize(h->ev_frame));
-    h->frame_pending = false;
-    h->num_blocks = h->h_cnt->pool_count;
-    h->last_blocks_touched = h->h_cnt->n_blocks_touched;
-    if (h->profiling) {
-      // events: 0 frame start, 1 before k_fast_solve, 2 after it, 3 after the tile kernel; the solve kernel's own phases come from
-      // the clock64 marks block 0 left in FastCounters::timeline
-      float a = 0, b = 0, c = 0, tot = 0;
-      cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
-      cudaEventElapsedTime(&c, h->ev[2], h->ev[3]); cudaEventElapsedTime(&tot, h->ev[0], h->ev[3]);
-      const long long* tl = h->h_fc->timeline;
-      const int sweeps_end = (int)tl[kTimelineSlots - 1];
-      const int tb = kTimelineSlots - 12;
-      const double span = (double)(tl[tb + 4] - tl[0]);
-      if (span > 0 && sweeps_end >= 3 && sweeps_end < tb) {
-        const double k = (double)b / span;
-        h->phase_ms[0] += a + k * (double)(tl[2] - tl[0]);                 // count + classify + start set + compaction + ray set-up
-        h->phase_ms[1] += k * (double)(tl[tb] - tl[2]);                    // observed-set sweeps
-        h->phase_ms[2] += k * (double)(tl[tb + 1] - tl[tb]);               // table commit + ray emit
-        h->phase_ms[3] += k * (double)(tl[tb + 4] - tl[tb + 1]);           // records -> tile segments (count, allocate + new blocks, scatter)
-      } else { h->phase_ms[0] += a; h->phase_ms[1] += b; }
-      h->phase_ms[5] += c;
-      h->phase_ms[6] += tot;
-      h->prof_frames += 1;
-    }
+  if (h->n_pend <= 0) return KSG_OK;
+  const int slot = h->pend[0];
+  h->pend[0] = h->pend[1];
+  --h->n_pend;
+  KSG_CUDA(cudaEventSynchronize(h->ev_frame_s[slot]));
+  h->h_cnt = h->h_cnt_base + slot;
+  if (h->h_fc_base) h->h_fc = h->h_fc_base + slot;
+  h->num_blocks = h->h_cnt->pool_count;
+  h->last_blocks_touched = h->h_cnt->n_blocks_touched;
+  if (h->profiling && h->h_fc) {
+    // events: 0 frame start, 1 before the solve kernel, 2 after it, 3 after the tile kernel; the solve kernel's own phases come from
+    // the clock64 marks block 0 left in FastCounters::timeline
+    float a = 0, b = 0, c = 0, tot = 0;
+    cudaEventElapsedTime(&a, h->ev[0], h->ev[1]); cudaEventElapsedTime(&b, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&c, h->ev[2], h->ev[3]); cudaEventElapsedTime(&tot, h->ev[0], h->ev[3]);
+    const long long* tl = h->h_fc->timeline;
+    const int sweeps_end = (int)tl[kTimelineSlots - 1];
+    const int tb = kTimelineSlots - 12;
+    const double span = (double)(tl[tb + 4] - tl[0]);
+    if (span > 0 && sweeps_end >= 3 && sweeps_end <= tb) {
+      const double k = (double)b / span;
+      h->phase_ms[0] += a + k * (double)(tl[2] - tl[0]);                 // count + classify + start set + compaction + ray set-up
+      h->phase_ms[1] += k * (double)(tl[tb] - tl[2]);                    // observed-set sweeps
+      h->phase_ms[2] += k * (double)(tl[tb + 1] - tl[tb]);               // table commit + ray emit / block allocation
+      h->phase_ms[3] += k * (double)(tl[tb + 4] - tl[tb + 1]);           // records -> tile segments (count, allocate + new blocks, scatter)
+    } else { h->phase_ms[0] += a; h->phase_ms[1] += b; }
+    h->phase_ms[5] += c;
+    h->phase_ms[6] += tot;
+    h->prof_frames += 1;
   }
-  if (stats) {
-    std::memset(stats, 0, sizeof(*stats));
-    stats->points_in = h->h_cnt->n_points;
-    stats->points_valid = h->h_cnt->n_valid;
-    stats->rays_cast = h->h_cnt->n_cast;
-    stats->ray_steps = (int64_t)h->h_cnt->ray_steps;
-    stats->voxel_updates = (int64_t)h->h_cnt->n_records - (int64_t)h->h_cnt->n_skipped;
-    stats->blocks_allocated = h->num_blocks;
-    stats->blocks_touched = h->h_cnt->n_blocks_touched;
-    stats->tiles_touched = h->h_cnt->n_tiles;
-    stats->fixpoint_iterations = h->h_fc ? h->h_fc->sweeps_last : 0;
-  }
+  if (stats) fill_stats(h, stats);
   const int dev_err = h->h_cnt->err;
   if (dev_err) {
     h->deferred_status = dev_err;  // the map may be inconsistent from here on
     return fail(dev_err, err_text(dev_err));
   }
+  return KSG_OK;
+}
+// Completes every outstanding frame; `stats` receives the newest frame's counters.
+int finish_frame(ksg_integrator* h, ksg_frame_stats* stats) {
+  while (h->n_pend > 1) { const int rc = finish_oldest(h, nullptr); if (rc) return rc; }
+  if (h->n_pend == 1) return finish_oldest(h, stats);
+  if (stats) fill_stats(h, stats);
+  if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
   return KSG_OK;
 }
 
@@ -433,6 +483,9 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   f.nsteps = h->nsteps; f.H = h->H; f.L = h->L; f.ray_state = h->ray_state; f.ext_off = h->ext_off; f.eval_sweep = h->eval_sweep;
   f.rec = h->rec_a; f.rec_cap = h->rec_cap; f.keys = h->keys32;
   f.tile_cnt = h->tile_cnt; f.tile_slot = h->tile_slot; f.tile_list = h->tile_list; f.tile_cap = h->tile_cap;
+  f.o3.cand = h->cand16; f.o3.ext_base = h->ob.ext_base; f.o3.cand_cap = h->ob.cand_cap; f.o3.slot_cnt = h->ob.slot_cnt; f.o3.bkt = h->ob.bkt;
+  f.o3.head = h->ob.head; f.o3.ovf = h->ovf; f.o3.ovf_cap = h->ovf_cap; f.o3.stamp = (uint32_t*)h->ob.slot_stamp; f.o3.table = h->ob.table;
+  f.rayrec = h->rayrec;
 
   if (h->profiling) cudaEventRecord(h->ev[0], s);
   KSG_CUDA(cudaMemsetAsync(h->clear_ff, 0xFF, (size_t)kSetSize * 16, s));
@@ -463,7 +516,8 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
     int max_sweeps = 4096;   // theory: <= rays + 1 sweeps, practice 6-8; the kernel flags an error rather than spin for ever
     void* args[] = {(void*)&f, (void*)&max_sweeps};
     ++h->n_launches;
-    KSG_CUDA(cudaLaunchCooperativeKernel((const void*)k_fast_solve, dim3(h->solve_grid), dim3(kSolveThreads), args, 0, s));
+    KSG_CUDA(cudaLaunchCooperativeKernel(h->solver == 3 ? (const void*)k_fast_solve3 : (const void*)k_fast_solve, dim3(h->solve_grid),
+                                         dim3(kSolveThreads), args, 0, s));
   }
   if (h->profiling) cudaEventRecord(h->ev[2], s);
   {
@@ -484,10 +538,18 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   }
   if (h->profiling) cudaEventRecord(h->ev[3], s);
   KSG_CUDA(cudaGetLastError());
-  KSG_CUDA(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-  KSG_CUDA(cudaMemcpyAsync(h->h_fc, h->d_fc, sizeof(FastCounters), cudaMemcpyDeviceToHost, s));
-  KSG_CUDA(cudaEventRecord(h->ev_frame, s));
-  h->frame_pending = true;
+  if (h->n_pend == 2) {   // both counter slots in flight: complete the older frame first (its statistics stay retrievable)
+    ksg_frame_stats old_stats;
+    const int rco = finish_oldest(h, &old_stats);
+    if (h->n_stash < 4) h->stash[h->n_stash++] = old_stats;
+    if (rco) return rco;
+  }
+  const int slot = h->next_slot;
+  KSG_CUDA(cudaMemcpyAsync(h->h_cnt_base + slot, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaMemcpyAsync(h->h_fc_base + slot, h->d_fc, sizeof(FastCounters), cudaMemcpyDeviceToHost, s));
+  KSG_CUDA(cudaEventRecord(h->ev_frame_s[slot], s));
+  h->pend[h->n_pend++] = slot;
+  h->next_slot ^= 1;
   if (stats || h->profiling) return finish_frame(h, stats);
   return KSG_OK;
 }
@@ -496,7 +558,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
   if (in.n > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");
-  if (in.n == 0 && h->frame_pending) { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  if (in.n == 0 && h->n_pend > 0) { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
   KSG_CUDA(cudaSetDevice(h->device));
   const DevCfg& dc = h->dc;
   const bool fast = h->cfg.integrator_type == KSG_INTEGRATOR_FAST;
@@ -715,6 +777,26 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     if (h->profiling) cudaEventRecord(h->ev[4], s);
     ++h->n_launches;
     k_block_init<<<h->sm_count * 4, 256, 0, s>>>(dc, h->d_cnt, h->map);
+    if (h->voxel_apply && !fast) {
+      // per-voxel update (ksg_voxel.cuh): segment heads -> two queues; the long and the short kernel run concurrently
+      KSG_CUDA(cudaMemsetAsync(h->vq.counters, 0, sizeof(int) * 8, s));
+      ++h->n_launches;
+      k_voxel_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->vq);
+      if (h->profiling) cudaEventRecord(h->ev[5], s);
+      did_apply = true;
+      KSG_CUDA(cudaEventRecord(h->ev_fork, s));
+      KSG_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+      h->n_launches += 2;
+#define KSG_LAUNCH_VOXEL(NCH)                                                                                                             \
+      do {                                                                                                                                \
+        k_voxel_apply_long<NCH><<<h->sm_count, 256, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);          \
+        k_voxel_apply_short<NCH><<<h->sm_count * 6, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);                 \
+      } while (0)
+      switch (h->apply_nch) { case 1: KSG_LAUNCH_VOXEL(1); break; case 2: KSG_LAUNCH_VOXEL(2); break; case 4: KSG_LAUNCH_VOXEL(4); break; default: KSG_LAUNCH_VOXEL(8); break; }
+#undef KSG_LAUNCH_VOXEL
+      KSG_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+      KSG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+    } else {
     ++h->n_launches;
     k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
                                                       h->tile_cap);
@@ -750,6 +832,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     }
 #undef KSG_LAUNCH_APPLY_
 #undef KSG_LAUNCH_APPLY
+    }
   }
   if (h->profiling) { if (!did_apply) { cudaEventRecord(h->ev[4], s); cudaEventRecord(h->ev[5], s); } cudaEventRecord(h->ev[6], s); }
   ++h->n_launches;
@@ -957,9 +1040,15 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   KSG_CUDA(dmalloc(&h->map.slot_key, (size_t)cfg->max_blocks));
   KSG_CUDA(cudaMalloc((void**)&h->map.pool, (size_t)dc.block_stride * (size_t)cfg->max_blocks));
   KSG_CUDA(dmalloc(&h->d_cnt, 1));
-  KSG_CUDA(cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)));
-  std::memset(h->h_cnt, 0, sizeof(Counters));
-  KSG_CUDA(cudaEventCreateWithFlags(&h->ev_frame, cudaEventDisableTiming));
+  KSG_CUDA(cudaMallocHost((void**)&h->h_cnt_base, 2 * sizeof(Counters)));
+  std::memset(h->h_cnt_base, 0, 2 * sizeof(Counters));
+  h->h_cnt = h->h_cnt_base;
+  for (int i = 0; i < 2; ++i) {
+    KSG_CUDA(cudaEventCreateWithFlags(&h->ev_frame_s[i], cudaEventDisableTiming));
+    KSG_CUDA(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+    KSG_CUDA(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+  }
+  KSG_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 
   // ---- frame scratch
   const size_t N = (size_t)cfg->max_points;
@@ -994,8 +1083,20 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     h->ob.ext_base = (long long)N * kH0;
     h->ob.cand_cap = h->ob.ext_base + ext;
     if (h->ob.cand_cap >= 0x7FFFFFFFll) { h->ob.cand_cap = 0x7FFFFFFEll; }
-    KSG_CUDA(dmalloc(&h->ob.cand_val, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_order, (size_t)h->ob.cand_cap));
-    KSG_CUDA(dmalloc(&h->ob.cand_next, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_pos, (size_t)h->ob.cand_cap));
+    {
+      bool legacy = false;
+      if (const char* e = std::getenv("KSG_FAST_LEGACY")) legacy = std::atoi(e) != 0;
+      if (const char* e = std::getenv("KSG_SOLVER")) h->solver = (std::atoi(e) == 2) ? 2 : 3;
+      if (legacy || h->solver == 2) {
+        KSG_CUDA(dmalloc(&h->ob.cand_val, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_order, (size_t)h->ob.cand_cap));
+        KSG_CUDA(dmalloc(&h->ob.cand_next, (size_t)h->ob.cand_cap)); KSG_CUDA(dmalloc(&h->ob.cand_pos, (size_t)h->ob.cand_cap));
+      } else {
+        KSG_CUDA(cudaMalloc((void**)&h->cand16, sizeof(Cand) * (size_t)h->ob.cand_cap));
+        h->ovf_cap = (int)std::min<long long>(std::max<long long>(1ll << 20, 4ll * (long long)N), 1ll << 28);
+        KSG_CUDA(cudaMalloc((void**)&h->ovf, sizeof(OvfEnt) * (size_t)h->ovf_cap));
+        KSG_CUDA(cudaMalloc((void**)&h->rayrec, sizeof(RayRec) * N));
+      }
+    }
     h->ob.slot_cnt = (int*)h->clear_00; KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));
     h->ob.head = (int*)(h->clear_ff + (size_t)kSetSize * 12); KSG_CUDA(dmalloc(&h->ob.table, kSetSize));
   } else {
@@ -1003,6 +1104,18 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
     KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
+    // per-voxel apply kernels (default); the tile kernel stays for hot_voxel_mode > 0, apply_mode 1 and KSG_MERGED_TILE_APPLY=1
+    h->voxel_apply = cfg->hot_voxel_mode == 0 && cfg->apply_mode == 0;
+    if (const char* e = std::getenv("KSG_MERGED_TILE_APPLY")) if (std::atoi(e) != 0) h->voxel_apply = false;
+    if (h->voxel_apply) {
+      h->vq.long_cap = 4 * (rec_cap / kLongLen) + 64;
+      h->vq.short_cap = rec_cap;
+      KSG_CUDA(dmalloc(&h->vq.long_items, (size_t)h->vq.long_cap));
+      KSG_CUDA(dmalloc(&h->vq.counters, 8));
+      KSG_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      KSG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
     if (cfg->hot_voxel_mode >= 1 && dc.C <= 32 && cfg->apply_mode == 0) {
       h->hot_enabled = true;
       h->hot_chunk_cap = rec_cap / kHotChunk + kHotMaxSegs;
@@ -1045,6 +1158,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
   }
   h->rec_cap = rec_cap;
   KSG_CUDA(dmalloc(&h->rec_a, (size_t)rec_cap)); KSG_CUDA(dmalloc(&h->rec_b, (size_t)rec_cap));
+  h->vq.short_items = (unsigned long long*)h->rec_a;   // the unsorted record buffer is free once the sort has run
   h->tile_cap = (long long)std::min<unsigned long long>((unsigned long long)cfg->max_blocks * dc.tiles_per_block, (unsigned long long)rec_cap);
   KSG_CUDA(dmalloc(&h->tile_begin, (size_t)h->tile_cap));
 
@@ -1081,8 +1195,9 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     if (const char* e = std::getenv("KSG_FAST_LEGACY")) h->fast_v2 = std::atoi(e) == 0;
     KSG_CUDA(dmalloc(&h->d_fc, 1));
     KSG_CUDA(cudaMemset(h->d_fc, 0, sizeof(FastCounters)));
-    KSG_CUDA(cudaMallocHost((void**)&h->h_fc, sizeof(FastCounters)));
-    std::memset(h->h_fc, 0, sizeof(FastCounters));
+    KSG_CUDA(cudaMallocHost((void**)&h->h_fc_base, 2 * sizeof(FastCounters)));
+    std::memset(h->h_fc_base, 0, 2 * sizeof(FastCounters));
+    h->h_fc = h->h_fc_base;
     KSG_CUDA(dmalloc(&h->blk_cnt, N / kCountBlock + 2)); KSG_CUDA(dmalloc(&h->blk_off, N / kCountBlock + 2));
     KSG_CUDA(dmalloc(&h->warp_cnt, N / 32 + 64)); KSG_CUDA(dmalloc(&h->warp_off, N / 32 + 64));
     if (cfg->integration_order_mode == KSG_ORDER_SORTED) KSG_CUDA(dmalloc(&h->seq_of_i, N));
@@ -1094,6 +1209,9 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     {
       int per_sm = 0;
       KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_solve, kSolveThreads, 0));
+      int per_sm3 = 0;
+      KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_fast_solve3, kSolveThreads, 0));
+      if (h->solver == 3) per_sm = per_sm3;
       int coop = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
       if (!coop || per_sm <= 0) h->fast_v2 = false;
@@ -1239,7 +1357,7 @@ int32_t ksg_sync(ksg_integrator* h) {
 
 int64_t ksg_num_blocks(ksg_integrator* h) {
   if (!h) return 0;
-  if (h->frame_pending) { cudaSetDevice(h->device); finish_frame(h, nullptr); }
+  if (h->n_pend > 0) { cudaSetDevice(h->device); finish_frame(h, nullptr); }
   return h->num_blocks;
 }
 
@@ -1459,7 +1577,7 @@ int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_ind
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  if (h->frame_pending) finish_frame(h, nullptr);
+  if (h->n_pend > 0) finish_frame(h, nullptr);
   const int64_t n = h->last_blocks_touched;
   if (!block_index || capacity_blocks < n || n == 0) return n;
   cudaDeviceSynchronize();
@@ -1564,11 +1682,21 @@ int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity
   return n;
 }
 
+int64_t ksg_debug_fast_timeline(ksg_integrator* h, int64_t* out64, int64_t* sweeps, double* clock_khz) {
+  if (!h || !out64 || !h->h_fc) return 0;
+  cudaSetDevice(h->device);
+  if (h->n_pend > 0) finish_frame(h, nullptr);
+  for (int i = 0; i < kTimelineSlots; ++i) out64[i] = (int64_t)h->h_fc->timeline[i];
+  if (sweeps) *sweeps = h->h_fc->sweeps_last;
+  if (clock_khz) *clock_khz = h->clock_khz;
+  return kTimelineSlots;
+}
+
 int32_t ksg_reset(ksg_integrator* h) {
   if (!h) return KSG_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  h->frame_pending = false;
+  h->n_pend = 0;
   return reset_map(h, h->own_stream);
 }
 

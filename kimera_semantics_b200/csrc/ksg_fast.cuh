@@ -25,7 +25,7 @@ namespace ksg {
 
 static constexpr int kCountBlock = 1024;      // pixels per block of k_fast_count / k_fast_classify (256 threads x 4)
 static constexpr int kEvalBlock = 512;        // sequence positions per block of k_fast_start_eval
-static constexpr int kSolveThreads = 256;
+static constexpr int kSolveThreads = 1024;     // one CTA per SM: a grid barrier is 148 arrivals
 static constexpr int kFastKeyCap = 4096;      // update records of one tile sorted in shared memory (more: sorted in place in global memory)
 static constexpr int kTimelineSlots = 64;
 
@@ -38,10 +38,29 @@ struct FastCounters {      // device-resident state of the frame driver (persist
   int n_tile_list;
   int pool_base;                             // pool_count before this frame's new blocks
   unsigned long long rec_cursor;             // allocation cursor of the per-tile key segments
+  int ovf_count;                             // overflow pool cursor (solver 3)
+  int pad0;
   long long timeline[kTimelineSlots];        // clock64 of block 0 at the phase boundaries of k_fast_solve (profiling)
 };
 
 struct TileDesc { uint32_t tk; int n; long long off; };
+
+// observed-set solver, third formulation (ksg_fast3.cuh)
+static constexpr int kGroup0 = 512;           // first rank group; the following groups are 4x larger each
+struct Cand;
+struct OvfEnt;
+struct RayRec;
+struct Obs3 {
+  Cand* cand;              // one 16-byte record per materialised ray step
+  long long ext_base, cand_cap;
+  int* slot_cnt;           // [2^20] performed-ever candidates of the slot this frame (cleared per frame)
+  uint64_t* bkt;           // [2^20][kBktK] entries [performed:1][order:39][value >> 20 : 13]
+  int* head;               // [2^20] overflow list head (cleared to -1 per frame)
+  OvfEnt* ovf;             // overflow pool (slots with more than kBktK performed-ever candidates)
+  int ovf_cap;
+  uint32_t* stamp;         // [2^20] (sweep << 8) | toggles of the slot in that sweep
+  uint32_t* table;         // persistent compact table: value >> 20
+};
 
 // everything the fast frame kernels need (passed by value)
 struct FastFrame {
@@ -74,6 +93,9 @@ struct FastFrame {
   int* tile_cnt;             // [hash capacity * tiles_per_block] records of the tile this frame (returns to 0 by itself)
   int* tile_slot;            // ... index of the tile in tile_list
   TileDesc* tile_list; long long tile_cap;
+  // solver 3
+  Obs3 o3;
+  RayRec* rayrec;
 };
 
 __device__ __forceinline__ int inv_mixed_index(int i, int n) {   // inverse of mixed_index (voxblox MixedThreadSafeIndex, A.3)
@@ -386,7 +408,8 @@ __device__ __forceinline__ void fast_obs_commit(const FastFrame& f, int n_cast) 
   const ObsBuf& ob = f.ob;
   const int groups_total = (gridDim.x * blockDim.x) / G;
   const int gl = threadIdx.x % G;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) / G; r < n_cast; r += groups_total) {
+  const int gt = ((((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31));   // CTA-balanced, see k_fast_solve
+  for (int r = gt / G; r < n_cast; r += groups_total) {
     const int U = f.L[r];
     for (int s = gl; s < U; s += G) {
       const uint64_t v = __ldcg(&ob.cand_val[cand_index(ob, f.ext_off, r, s)]);
@@ -416,8 +439,9 @@ __device__ __forceinline__ void fast_emit(const FastFrame& f, int n_cast) {
   const DevCfg& cfg = f.cfg;
   const int threads_total = gridDim.x * blockDim.x;
   const int rounds = (n_cast + threads_total - 1) / threads_total;
+  const int gt = ((((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31));   // CTA-balanced, see k_fast_solve
   for (int it = 0; it < rounds; ++it) {                     // every lane takes part in the warp-aggregated allocation
-    const int r = it * threads_total + blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = it * threads_total + gt;
     const int U = (r < n_cast) ? __ldcg(&f.L[r]) : 0;
     const long long base = (long long)warp_alloc(&f.cnt->n_records, (unsigned long long)(U > 0 ? U : 0));
     if (U <= 0) continue;
@@ -468,12 +492,14 @@ __device__ __forceinline__ void fast_block_init(const FastFrame& f, int n_new, i
   }
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_fast_solve(FastFrame f, int max_sweeps) {
+__global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve(FastFrame f, int max_sweeps) {
   unsigned int epoch = 0;
   unsigned int* bar = &f.fc->gridbar;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int gthreads = gridDim.x * blockDim.x;
+  // thread id for the item loops: consecutive 32-item chunks go to DIFFERENT CTAs (warp w of CTA b takes chunk w * gridDim.x + b),
+  // so that a phase with fewer items than threads still uses every SM
   const int lane = threadIdx.x & 31;
+  const int gtid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | lane;
+  const int gthreads = gridDim.x * blockDim.x;
   Counters* cnt = f.cnt;
   const int n_points = cnt->n_points;
   const int n_cast = cnt->n_cast;

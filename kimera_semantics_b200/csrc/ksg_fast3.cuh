@@ -1,0 +1,429 @@
+// ksg_fast3.cuh — observed-set solver, third formulation (round 2), used by k_fast_solve3.
+//
+// What the first measurements of the persistent kernel showed (profiles/r02/bench_fast5_v2.json: sweeps of 90 / 81 / 54 / 20 us):
+//   * sweep 1 starts from "nothing but the guaranteed first steps is performed", so nearly every ray runs its full length
+//     (~1.9 M candidate steps materialised for ~57 K final updates), and sweep 2 takes almost all of it back;
+//   * every ray that toggles a slot re-evaluates itself in the next sweep (it sees its own stamp);
+//   * per candidate the solver chased four arrays (value, order, position, link).
+// Changes, none of which alters the fixpoint (the dependency is triangular in rank order, the fixpoint unique):
+//   1. RANK GROUPS.  A ray depends only on rays of lower rank, so once ranks [0, n) have converged they are FINAL whatever the
+//      higher ranks do.  Rays are solved in groups of growing size (512, then x4); a group iterates to convergence against the
+//      finished lower groups.  With the `mixed` order the low ranks are a uniform sub-sample of the image, so a new group already
+//      sees most of the free space carved: its first evaluation is close to the answer, finished groups are never polled again.
+//   2. one 16-byte record per candidate {packed voxel index, bucket position, sweep of the owner's last toggle} and one per ray
+//      {materialised steps, updates, length, last evaluation}: one load each; the set value (hash + offset) is recomputed from the
+//      voxel index; flipping a candidate's "performed" bit is a plain store (the owner knows the whole entry).
+//   3. the per-slot stamp is (sweep << 8 | toggles in that sweep): a ray is NOT dirty when the only toggle of the slot in its last
+//      sweep was its own.
+//   4. no record buffer: after convergence the performed candidates are walked twice, fully parallel (8 lanes per ray):
+//      pass 1 commits the persistent table, allocates blocks and counts records per tile; pass 2 writes the (voxel, rank) keys
+//      straight into the tile's segment.  The voxel index kept per candidate replaces the second ray walk.
+#pragma once
+#include "ksg_fast.cuh"
+
+namespace ksg {
+
+struct __align__(16) Cand { uint64_t vkey; int pos; int tog; };      // pos: >= 0 bucket entry, -2 not inserted, <= -3 overflow entry -3-pos
+struct __align__(16) OvfEnt { uint64_t order_perf; uint32_t hi; int next; };
+struct __align__(16) RayRec { int H, L, nsteps, eval_sweep; };
+
+__device__ __forceinline__ Cand ld_cand(const Cand* p) {
+  const int4 v = __ldcg((const int4*)p);
+  Cand c; c.vkey = ((uint64_t)(uint32_t)v.y << 32) | (uint32_t)v.x; c.pos = v.z; c.tog = v.w;
+  return c;
+}
+__device__ __forceinline__ void st_cand(Cand* p, uint64_t vkey, int pos, int tog) {
+  __stcg((int4*)p, make_int4((int)(uint32_t)vkey, (int)(uint32_t)(vkey >> 32), pos, tog));
+}
+__device__ __forceinline__ void st_cand_state(Cand* p, int pos, int tog) { __stcg((int2*)p + 1, make_int2(pos, tog)); }
+__device__ __forceinline__ uint64_t cand_value(uint64_t vkey, uint64_t offset) { return (uint64_t)index_hash(unpack_key(vkey)) + offset; }
+__device__ __forceinline__ uint64_t make_entry(bool on, uint64_t order, uint64_t v) { return (on ? kEntPerf : 0ull) | (order << 13) | (v >> kSetBits); }
+__device__ __forceinline__ long long cand_index3(const Obs3& o, const long long* ext_off, int r, int s) {
+  if (s < kH0) return (long long)r * kH0 + s;
+  const int k = 31 - __clz(s >> 4);
+  return o.ext_base + __ldcg(&ext_off[(size_t)r * kExtSegs + k]) + (s - (kH0 << k));
+}
+
+__device__ __forceinline__ void stamp_toggle(uint32_t* stamp, uint32_t slot, int sweep) {
+  uint32_t cur = __ldcg(&stamp[slot]);
+  for (;;) {
+    const uint32_t nw = ((int)(cur >> 8) < sweep) ? (((uint32_t)sweep << 8) | 1u) : (((cur & 255u) < 255u) ? cur + 1u : cur);
+    if (nw == cur) break;
+    const uint32_t old = atomicCAS(&stamp[slot], cur, nw);
+    if (old == cur) break;
+    cur = old;
+  }
+}
+
+// first time a candidate turns performed: it enters the slot's bucket (or the overflow pool); returns its position code
+__device__ __forceinline__ int cand_insert3(const FastFrame& f, uint32_t slot, uint64_t entry) {
+  const Obs3& o = f.o3;
+  const int idx = atomicAdd(&o.slot_cnt[slot], 1);
+  if (idx < kBktK) { const int pos = (int)slot * kBktK + idx; __stcg(&o.bkt[pos], entry); return pos; }
+  const int id = atomicAdd(&f.fc->ovf_count, 1);
+  if (id >= o.ovf_cap) { set_err(f.cnt, 4); return -2; }
+  OvfEnt* e = &o.ovf[id];
+  __stcg(&e->order_perf, (entry & kEntPerf) | ((entry >> 13) & ((1ull << kEntOrderBits) - 1)));
+  __stcg(&e->hi, (uint32_t)(entry & 0x1FFFull));
+  int old = ((volatile int*)o.head)[slot];
+  for (;;) {   // lock-free push that concurrent readers can always follow
+    __stcg(&e->next, old);
+    __threadfence();
+    const int seen = atomicCAS(&o.head[slot], old, id);
+    if (seen == old) break;
+    old = seen;
+  }
+  return -3 - id;
+}
+
+// latest performed visit of `slot` that precedes `my_order`: its (value >> 20), or -1
+__device__ __forceinline__ int latest_performed_before3(const Obs3& o, uint32_t slot, uint64_t my_order) {
+  const ulonglong2* b = (const ulonglong2*)(o.bkt + (size_t)slot * kBktK);
+  const int total = __ldcg(&o.slot_cnt[slot]);
+  const ulonglong2 v0 = __ldcg(b + 0), v1 = __ldcg(b + 1), v2 = __ldcg(b + 2), v3 = __ldcg(b + 3);
+  const int n = total < kBktK ? total : kBktK;
+  long long best = -1;
+  int best_hi = -1;
+  scan_entries(v0, 0, n, my_order, best, best_hi);
+  scan_entries(v1, 2, n, my_order, best, best_hi);
+  scan_entries(v2, 4, n, my_order, best, best_hi);
+  scan_entries(v3, 6, n, my_order, best, best_hi);
+  if (n > 8) {
+    const ulonglong2 v4 = __ldcg(b + 4), v5 = __ldcg(b + 5), v6 = __ldcg(b + 6), v7 = __ldcg(b + 7);
+    scan_entries(v4, 8, n, my_order, best, best_hi);
+    scan_entries(v5, 10, n, my_order, best, best_hi);
+    scan_entries(v6, 12, n, my_order, best, best_hi);
+    scan_entries(v7, 14, n, my_order, best, best_hi);
+  }
+  if (total > kBktK) {
+    int guard = total - kBktK + 8;
+    for (int id = __ldcg(&o.head[slot]); id >= 0 && id < o.ovf_cap && guard-- > 0; id = __ldcg(&o.ovf[id].next)) {
+      const uint64_t op = __ldcg(&o.ovf[id].order_perf);
+      const uint64_t eo = op & ~kEntPerf;
+      if ((op & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)__ldcg(&o.ovf[id].hi); }
+    }
+  }
+  return best_hi;
+}
+__device__ __forceinline__ bool later_performed_exists3(const Obs3& o, uint32_t slot, uint64_t my_order) {
+  const int total = __ldcg(&o.slot_cnt[slot]);
+  const int n = total < kBktK ? total : kBktK;
+  const uint64_t* b = o.bkt + (size_t)slot * kBktK;
+  bool later = false;
+  for (int j = 0; j < n; ++j) {
+    const uint64_t e = __ldcg(&b[j]);
+    if ((e & kEntPerf) && ((e >> 13) & ((1ull << kEntOrderBits) - 1)) > my_order) later = true;
+  }
+  if (total > kBktK) {
+    int guard = total - kBktK + 8;
+    for (int id = __ldcg(&o.head[slot]); id >= 0 && id < o.ovf_cap && !later && guard-- > 0; id = __ldcg(&o.ovf[id].next)) {
+      const uint64_t op = __ldcg(&o.ovf[id].order_perf);
+      if ((op & kEntPerf) && (op & ~kEntPerf) > my_order) later = true;
+    }
+  }
+  return later;
+}
+
+// single writer per candidate: the warp that owns the ray.  c.pos is updated when the candidate enters a bucket.
+__device__ __forceinline__ void set_performed3(const FastFrame& f, Cand& c, long long ci, uint32_t slot, uint64_t order, uint64_t v, bool on, int sweep) {
+  const Obs3& o = f.o3;
+  if (c.pos >= 0) __stcg(&o.bkt[c.pos], make_entry(on, order, v));
+  else if (c.pos <= -3) __stcg(&o.ovf[-3 - c.pos].order_perf, (on ? kEntPerf : 0ull) | order);
+  else if (on) c.pos = cand_insert3(f, slot, make_entry(true, order, v));
+  else return;                       // never entered a bucket and stays unperformed: invisible to every other ray
+  c.tog = sweep;
+  st_cand_state(&o.cand[ci], c.pos, c.tog);
+  __threadfence();
+  stamp_toggle(o.stamp, slot, sweep);
+}
+
+__device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n_cast) {
+  const DevCfg& cfg = f.cfg;
+  const Obs3& o = f.o3;
+  int h = 0;
+  if (r < n_cast) {
+    const int seq = f.cast_seq[r];
+    const float4 p = f.pt_pG[seq];
+    const uint8_t fl = f.pt_flags[seq];
+    f.ray_param[r] = p;
+    f.ray_label[r] = f.pt_label[seq];
+    f.ray_flags[r] = fl;
+    f.ray_color[r] = f.pt_color[seq];
+    Dda d;
+    raycaster_init(d, f3(f.T.tx, f.T.ty, f.T.tz), f3(p.x, p.y, p.z), (fl & 2) != 0, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc,
+                   /*cast_from_origin=*/false);
+    int n = d.length_in_steps + 1;
+    if (!d.in_range || n >= (1 << kOrderStepBits)) { set_err(f.cnt, 5); n = 0; }
+    h = n < kH0 ? n : kH0;
+    const int l0 = h < cfg.maxc ? h : cfg.maxc;   // a ray cannot break before `maxc` consecutive collisions
+    for (int s = 0; s < h; ++s) {
+      const I3 g = dda_next(d);
+      if (!key_in_range(g)) { set_err(f.cnt, 5); h = s; break; }
+      const uint64_t vkey = pack_key(g);
+      const long long ci = (long long)r * kH0 + s;
+      int pos = -2;
+      if (s < l0) {
+        const uint64_t v = (uint64_t)index_hash(g) + f.set_offset;
+        pos = cand_insert3(f, (uint32_t)v & kSetMask, make_entry(true, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, v));
+      }
+      st_cand(&o.cand[ci], vkey, pos, 0);
+    }
+    RayState st; save_state(st, d); f.ray_state[r] = st;
+    RayRec rr; rr.H = h; rr.L = (h < l0) ? h : l0; rr.nsteps = (h < kH0 && h < n) ? h : n; rr.eval_sweep = 0;
+    *(int4*)&f.rayrec[r] = make_int4(rr.H, rr.L, rr.nsteps, rr.eval_sweep);
+  }
+  warp_add(&f.cnt->ray_steps, (unsigned long long)h);
+}
+
+// One sweep over the rays [r_lo, r_hi): one warp per ray, one ray step per lane and chunk (chunks: [0,16), [16,32), then 32 at a time).
+__device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r_lo, int r_hi) {
+  const Obs3& o = f.o3;
+  const DevCfg& cfg = f.cfg;
+  Counters* cnt = f.cnt;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) cnt->changed[(sweep + 1) & 3] = 0;
+  for (int r = r_lo + (threadIdx.x >> 5) * gridDim.x + blockIdx.x; r < r_hi; r += warps_total) {
+    const int4 rr = __ldcg((const int4*)&f.rayrec[r]);
+    int h = rr.x;
+    const int old = rr.y, n = rr.z, last = rr.w;
+    bool need = last == 0;
+    if (!need) {
+      const int upto = (old < h - 1) ? old : h - 1;             // steps 0..upto were examined last time
+      bool dirty = false;
+      for (int s = lane; s <= upto; s += 32) {
+        const Cand c = ld_cand(&o.cand[cand_index3(o, f.ext_off, r, s)]);
+        const uint32_t slot = (uint32_t)cand_value(c.vkey, f.set_offset) & kSetMask;
+        const uint32_t w = __ldcg(&o.stamp[slot]);
+        const int sk = (int)(w >> 8);
+        if (sk > last || (sk == last && !((w & 255u) == 1u && c.tog == last))) dirty = true;
+      }
+      need = __ballot_sync(0xffffffffu, dirty) != 0u;
+    }
+    if (!need) continue;
+    int run = 0, U = -1;
+    for (int s0 = 0; s0 < n && U < 0;) {
+      const int len = (s0 < 32) ? kH0 : 32;
+      const int cend = (s0 + len < n) ? s0 + len : n;
+      if (s0 >= h) {   // materialise the next chunk: lane 0 continues the ray's DDA (A.7) from the saved state
+        if (lane == 0) {
+          bool ok = true;
+          if ((s0 & (s0 - 1)) == 0) {   // s0 = 16 << k: first chunk of storage segment k (steps [16<<k, 32<<k))
+            const int k = 31 - __clz(s0 >> 4);
+            const long long need_c = s0;
+            const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need_c);
+            if (o.ext_base + off + need_c > o.cand_cap) { set_err(cnt, 4); ok = false; }
+            else f.ext_off[(size_t)r * kExtSegs + k] = off;
+          }
+          if (ok) {
+            Dda d; load_state(d, f.ray_state[r]);
+            for (int s = s0; s < cend; ++s) {
+              const I3 g = dda_next(d);
+              if (!key_in_range(g)) { set_err(cnt, 5); ok = false; break; }
+              st_cand(&o.cand[cand_index3(o, f.ext_off, r, s)], pack_key(g), -2, 0);
+            }
+            if (ok) {
+              RayState st; save_state(st, d); f.ray_state[r] = st;
+              f.rayrec[r].H = cend;
+              atomicAdd(&cnt->ray_steps, (unsigned long long)(cend - s0));
+            }
+          }
+          h = ok ? cend : -1;
+        }
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (h < 0) { U = s0; break; }   // scratch exhausted / index range (flagged): stop here
+        __syncwarp();
+      }
+      const int s = s0 + lane;
+      bool coll = false;
+      long long ci = 0;
+      uint32_t slot = 0;
+      uint64_t v = 0;
+      Cand c; c.vkey = 0; c.pos = -2; c.tog = 0;
+      const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
+      if (s < cend) {
+        ci = cand_index3(o, f.ext_off, r, s);
+        c = ld_cand(&o.cand[ci]);
+        v = cand_value(c.vkey, f.set_offset);
+        slot = (uint32_t)v & kSetMask;
+        const uint32_t stale = o.table[slot];   // issued together with the bucket loads
+        const int hi = latest_performed_before3(o, slot, my_order);
+        coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (stale == (uint32_t)(v >> kSetBits));
+      }
+      const unsigned bits = __ballot_sync(0xffffffffu, coll);
+      int brk = -1;
+      for (int j = 0; s0 + j < cend; ++j) {
+        if ((bits >> j) & 1u) ++run; else run = 0;            // fast.cpp:115-119
+        if (run > cfg.maxc) { brk = s0 + j; break; }          // fast.cpp:120-122
+      }
+      const int perf_end = (brk >= 0) ? brk : cend;
+      if (s < perf_end && s >= old) set_performed3(f, c, ci, slot, my_order, v, true, sweep);   // newly performed steps of this chunk
+      __syncwarp();
+      if (brk >= 0) U = brk;
+      s0 = cend;
+    }
+    if (U < 0) U = n;   // the ray ran its full length
+    if (U < old) {      // steps [U, old) are no longer performed
+      for (int s = U + lane; s < old; s += 32) {
+        const long long ci = cand_index3(o, f.ext_off, r, s);
+        Cand c = ld_cand(&o.cand[ci]);
+        const uint64_t v = cand_value(c.vkey, f.set_offset);
+        set_performed3(f, c, ci, (uint32_t)v & kSetMask, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, v, false, sweep);
+      }
+    }
+    if (lane == 0) {
+      if (U != old) { f.rayrec[r].L = U; cnt->changed[sweep & 3] = 1; }
+      f.rayrec[r].eval_sweep = sweep;
+    }
+  }
+}
+
+// The performed candidates of every ray, 8 lanes per ray.  PASS 1: persistent table commit (the last performed visit of a slot
+// survives the frame), block allocation (base.cpp:205-254), records per tile.  PASS 2: (voxel, rank) key into the tile's segment.
+template <int PASS>
+__device__ __forceinline__ void fast3_walk_performed(const FastFrame& f, int n_cast, int n_tiles) {
+  constexpr int G = 8;
+  const Obs3& o = f.o3;
+  const DevCfg& cfg = f.cfg;
+  const int groups_total = (gridDim.x * blockDim.x) / G;
+  const int gl = threadIdx.x % G;
+  const int gt = ((((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | (threadIdx.x & 31));   // CTA-balanced
+  for (int r = gt / G; r < n_cast; r += groups_total) {
+    const int U = __ldcg(&f.rayrec[r].L);
+    for (int s = gl; s < U; s += G) {
+      const Cand c = ld_cand(&o.cand[cand_index3(o, f.ext_off, r, s)]);
+      const I3 g = unpack_key(c.vkey);
+      if (PASS == 1) {
+        const uint64_t v = (uint64_t)index_hash(g) + f.set_offset;
+        const uint32_t slot = (uint32_t)v & kSetMask;
+        if (!later_performed_exists3(o, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s)) o.table[slot] = (uint32_t)(v >> kSetBits);
+      }
+      const I3 b = block_of_voxel(g, cfg.vps_inv);
+      if (!key_in_range(b)) { set_err(f.cnt, 5); continue; }
+      const int htpos = ht_find_or_insert(f.map, pack_key(b), f.cnt);
+      if (htpos < 0) continue;
+      const uint64_t rec = make_record(cfg, htpos, g, (uint32_t)r);
+      const uint32_t tk = (uint32_t)(rec >> 32);
+      if (PASS == 1) {
+        if (atomicAdd(&f.tile_cnt[tk], 1) == 0) {
+          const int idx = atomicAdd(&f.fc->n_tile_list, 1);
+          if (idx < f.tile_cap) { f.tile_list[idx].tk = tk; f.tile_slot[tk] = idx; } else set_err(f.cnt, 4);
+        }
+      } else {
+        const int at = atomicSub(&f.tile_cnt[tk], 1) - 1;
+        const int idx = __ldcg(&f.tile_slot[tk]);
+        if (idx >= 0 && idx < n_tiles && at >= 0) f.keys[__ldcg(&f.tile_list[idx].off) + at] = (uint32_t)rec;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, int max_sweeps) {
+  unsigned int epoch = 0;
+  unsigned int* bar = &f.fc->gridbar;
+  const int lane = threadIdx.x & 31;
+  const int gtid = (((threadIdx.x >> 5) * gridDim.x + blockIdx.x) << 5) | lane;   // consecutive 32-item chunks go to different CTAs
+  const int gthreads = gridDim.x * blockDim.x;
+  Counters* cnt = f.cnt;
+  const int n_points = cnt->n_points;
+  const int n_cast = cnt->n_cast;
+  int tl = 0;
+  timeline_mark(f, tl++);
+  // ---- phase 0: compaction of the cast points, in sequence order (= ray rank order); stamp wrap-around
+  for (int base = (gtid & ~31); base < n_points; base += gthreads) {
+    const int seq = base + lane;
+    const bool c = seq < n_points && f.cast_flag[seq] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, c);
+    if (c) f.cast_seq[f.warp_off[seq >> 5] + __popc(m & ((1u << lane) - 1u))] = seq;
+  }
+  const int sweep_base0 = ((volatile int*)&f.fc->sweep_base)[0];
+  const bool wrap = sweep_base0 > (1 << 23);     // sweep ids live in 24 bits of the stamp word: restart them long before they overflow
+  if (wrap) for (int i = gtid; i < (int)kSetSize; i += gthreads) f.o3.stamp[i] = 0u;
+  solve_barrier(bar, epoch);
+  if (gtid == 0) f.fc->sweep_base = wrap ? 0 : sweep_base0;
+  timeline_mark(f, tl++);
+  // ---- phase 1: ray set-up (first kH0 steps of every ray)
+  for (int r0 = (gtid & ~31); r0 < n_cast; r0 += gthreads) fast3_ray_setup(f, r0 + lane, n_cast);
+  solve_barrier(bar, epoch);
+  timeline_mark(f, tl++);
+  // ---- phase 2: observed-set fixpoint, rank group by rank group
+  int sweep = (wrap ? 0 : sweep_base0);
+  sweep = (sweep + 4) & ~3;       // counter slot (sweep + 1) & 3 of the first sweep was zeroed by the frame reset
+  const int first_sweep = sweep + 1;
+  bool failed = false;
+  int g_lo = 0, g_size = kGroup0;
+  while (g_lo < n_cast && !failed) {
+    const int g_hi = (g_lo + g_size < n_cast) ? g_lo + g_size : n_cast;
+    bool converged = false;
+    for (int it = 0; it < max_sweeps; ++it) {
+      ++sweep;
+      fast3_sweep(f, sweep, g_lo, g_hi);
+      solve_barrier(bar, epoch);
+      if (tl < kTimelineSlots - 12) timeline_mark(f, tl++);
+      const int changed = ((volatile int*)cnt->changed)[sweep & 3];
+      const int err = ((volatile int*)&cnt->err)[0];
+      if (err) { failed = true; break; }
+      if (!changed) { converged = true; break; }
+    }
+    if (!converged) failed = true;
+    g_lo = g_hi;
+    g_size *= 4;
+  }
+  if (gtid == 0) {
+    cnt->last_sweep = sweep;
+    f.fc->sweep_base = sweep;
+    f.fc->sweeps_last = sweep - first_sweep + 1;
+    if (failed && !((volatile int*)&cnt->err)[0]) set_err(cnt, 2 /*KSG_ERR_CUDA: the solver did not converge*/);
+    if (f.profile) f.fc->timeline[kTimelineSlots - 1] = tl;
+  }
+  tl = kTimelineSlots - 12;
+  timeline_mark(f, tl++);
+  // ---- phase 3: table commit + block allocation + records per tile
+  if (!failed) fast3_walk_performed<1>(f, n_cast, 0);
+  solve_barrier(bar, epoch);
+  timeline_mark(f, tl++);
+  timeline_mark(f, tl++);     // (slot kept for the layout of k_fast_solve: there the per-tile count is a phase of its own)
+  const bool ok = ((volatile int*)&cnt->err)[0] == 0 && !failed;
+  const int n_new_all = ((volatile int*)&cnt->n_new_blocks)[0];
+  const int n_new = n_new_all < f.map.new_cap ? n_new_all : f.map.new_cap;
+  const int pool_base = ((volatile int*)&cnt->pool_count)[0];
+  // ---- phase 4: key segment per tile, updated() bookkeeping, ownership (spatial sharding), new blocks
+  const int n_tiles = (int)min((long long)((volatile int*)&f.fc->n_tile_list)[0], f.tile_cap);
+  for (int base = (gtid & ~31); base < n_tiles; base += gthreads) {
+    const int idx = base + lane;
+    int n = 0;
+    uint32_t tk = 0;
+    if (idx < n_tiles) { tk = f.tile_list[idx].tk; n = __ldcg(&f.tile_cnt[tk]); }
+    const long long off = (long long)warp_alloc(&f.fc->rec_cursor, (unsigned long long)n);
+    if (idx < n_tiles) {
+      const int pos = (int)(tk / (uint32_t)f.cfg.tiles_per_block);
+      const int old = atomicExch(&f.map.touched_stamp[pos], f.frame_stamp);
+      if (old != f.frame_stamp) f.map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
+      const bool owned = f.cfg.shard_count <= 1 ||
+                         tile_owner(f.map.ht_keys[pos], (int)(tk % (uint32_t)f.cfg.tiles_per_block), f.cfg.shard_count) == f.cfg.shard_rank;
+      if (off + n > f.rec_cap) { set_err(cnt, 4); n = 0; }
+      f.tile_list[idx].n = owned ? n : -n;
+      f.tile_list[idx].off = off;
+    }
+  }
+  if (ok) fast_block_init(f, n_new, pool_base);
+  solve_barrier(bar, epoch);
+  timeline_mark(f, tl++);
+  // ---- phase 5: keys into the tile segments (the per-tile counters run back to zero: nothing to clear for the next frame)
+  const bool ok2 = ((volatile int*)&cnt->err)[0] == 0 && !failed;
+  if (!failed) fast3_walk_performed<2>(f, n_cast, ok2 ? n_tiles : 0);
+  if (gtid == 0) {
+    int add = n_new;
+    if (pool_base + add > f.map.max_blocks) add = f.map.max_blocks - pool_base;
+    if (ok) cnt->pool_count = pool_base + (add > 0 ? add : 0);
+    cnt->n_tiles = ok2 ? n_tiles : 0;
+    cnt->n_records = ((volatile unsigned long long*)&f.fc->rec_cursor)[0];
+    f.fc->tile_cursor = 0;
+    f.fc->n_tile_list = 0;
+    f.fc->rec_cursor = 0;
+    f.fc->ovf_count = 0;
+  }
+  timeline_mark(f, tl++);
+}
+
+}  // namespace ksg

@@ -448,7 +448,7 @@ __device__ __forceinline__ void eval_sweep_body(const DevCfg& cfg, Counters* cnt
   const int n_cast = cnt->n_cast;
   if (blockIdx.x == 0 && threadIdx.x == 0) { const int nx = (sweep + 1) & 3; cnt->changed[nx] = 0; cnt->sum_updates[nx] = 0; }
   unsigned long long usum = 0;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_cast; r += warps_total) {
+  for (int r = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; r < n_cast; r += warps_total) {   // ray -> warp: round robin over the CTAs first
     int h = __ldcg(&H[r]);
     const int n = nsteps[r];
     const int old = ((volatile int*)L)[r];
@@ -541,8 +541,8 @@ __device__ __forceinline__ void eval_sweep_body(const DevCfg& cfg, Counters* cnt
     if (lane == 0) usum += (unsigned long long)U;
   }
   // one atomic per block (instead of per warp) on the sweep's counter
-  __shared__ unsigned long long s_part[8];
-  if (lane == 0) s_part[(threadIdx.x >> 5) & 7] = usum;
+  __shared__ unsigned long long s_part[32];
+  if (lane == 0) s_part[threadIdx.x >> 5] = usum;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long t = 0;

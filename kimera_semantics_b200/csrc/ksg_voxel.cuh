@@ -1,0 +1,307 @@
+// ksg_voxel.cuh — `merged`: per-VOXEL update kernels (round 2).
+//
+// Round 1 applied a frame's sorted update records with one CTA per touched 8^3 tile (k_tile_apply).  On the 2 cm workload
+// (31 M records, 4 690 tiles) that kernel ran 12.8 ms at 27 % SM-active: the tiles around the camera hold up to 1.1 M records each
+// and one CTA (8 warps) worked through such a tile alone while most SMs idled (profiles/r01/prof_apply_merged2.details.txt:
+// 2.28 G warp instructions = 1.9 ms of issue slots at full balance).  DRAM traffic was never the limit (0.7 %), so staging tiles in
+// shared memory bought nothing here.  This file drops the tile as the unit of work:
+//
+//   k_voxel_heads        one thread per sorted record: detects voxel-segment heads, measures the segment (galloping search), and
+//                        files it by length: `long` (>= kLongLen records, one item per role) or `short`; tile heads do the updated()
+//                        bookkeeping of the block (base.cpp:248)
+//   k_voxel_apply_long   warps take long segments from a queue (longest class first): the TSDF recurrence and the semantic
+//                        recurrence of a voxel are independent, so they are separate items; software-pipelined row gathers
+//   k_voxel_apply_short  warps take short segments (the bulk of the voxels: ~17 records each) - lean code, high occupancy; it runs
+//                        CONCURRENTLY with the long kernel on a second stream, filling the SMs the long tail leaves idle
+//
+// Per-voxel arithmetic and order are those of k_tile_apply (same device functions): results stay bit-identical.
+#pragma once
+#include "ksg_kernels.cuh"
+
+namespace ksg {
+
+static constexpr int kLongLen = 96;        // segments of at least this many records are split into a TSDF item and a semantic item
+static constexpr int kHotLen = 4096;       // ... and these are queued first
+static constexpr int kGrab = 8;            // short items fetched per queue access
+
+struct VoxelQueues {
+  unsigned long long* long_items;    // [begin:40][len:23][role:1], hot ones from the front, the others from the back
+  unsigned long long* short_items;   // [begin:40][len:24]
+  long long long_cap, short_cap;
+  int* counters;                     // [0] hot count (front), [1] other long count (back), [2] short count, [3] long cursor, [4] short cursor
+};
+
+__device__ __forceinline__ uint8_t* voxel_chunk(const DevCfg& cfg, const MapRef& map, uint32_t tk, int& pos, int& tile) {
+  pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
+  tile = (int)(tk % (uint32_t)cfg.tiles_per_block);
+  const int slot = map.ht_slot[pos];
+  if (slot < 0 || slot >= map.max_blocks) return nullptr;
+  return map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
+}
+
+__global__ void k_voxel_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64_t* __restrict__ rec, long long n, int stamp, VoxelQueues q) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = rec[i];
+  if (k == ~0ull) return;
+  const uint64_t vk = k >> kRecOrdBits;
+  if (i > 0 && (rec[i - 1] >> kRecOrdBits) == vk) return;
+  const uint32_t tk = (uint32_t)(k >> 32);
+  const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
+  if (i == 0 || (uint32_t)(rec[i - 1] >> 32) != tk) {   // tile head: updated() bookkeeping is replicated on every shard
+    const int old = atomicExch(&map.touched_stamp[pos], stamp);
+    if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
+    atomicAdd(&cnt->n_tiles, 1);
+  }
+  if (cfg.shard_count > 1 && tile_owner(map.ht_keys[pos], (int)(tk % (uint32_t)cfg.tiles_per_block), cfg.shard_count) != cfg.shard_rank) return;
+  // segment end: first j > i whose voxel differs (galloping, then bisection)
+  long long lo = i, hi;            // invariant: rec[lo] belongs to the segment
+  long long step = 1;
+  for (;;) {
+    const long long p = i + step;
+    if (p >= n) { hi = n; break; }
+    if ((rec[p] >> kRecOrdBits) != vk) { hi = p; break; }
+    lo = p;
+    step <<= 1;
+  }
+  while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if ((rec[mid] >> kRecOrdBits) == vk) lo = mid; else hi = mid; }
+  const long long len = hi - i;
+  if (len >= kLongLen) {
+    const bool hot = len >= kHotLen;
+    const int at = atomicAdd(&q.counters[hot ? 0 : 1], 2);
+    if (at + 2 > q.long_cap / 2) { set_err(cnt, 4); return; }   // cannot happen: long_cap >= 2 * (2 * records / kLongLen)
+    const unsigned long long item = ((unsigned long long)i << 24) | ((unsigned long long)len << 1);
+    if (hot) { q.long_items[at] = item; q.long_items[at + 1] = item | 1ull; }
+    else { q.long_items[q.long_cap - 1 - at] = item; q.long_items[q.long_cap - 2 - at] = item | 1ull; }
+  } else {
+    // one atomic per warp: the short segments are the bulk of the heads
+    const unsigned am = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(am) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&q.counters[2], __popc(am));
+    base = __shfl_sync(am, base, leader);
+    const int at = base + __popc(am & ((1u << lane) - 1u));
+    if (at >= q.short_cap) { set_err(cnt, 4); return; }
+    q.short_items[at] = ((unsigned long long)i << 24) | (unsigned long long)len;
+  }
+}
+
+struct VoxelCtx {
+  uint8_t* chunk;
+  int v;          // voxel inside the tile
+  F3 center;
+};
+__device__ __forceinline__ bool voxel_ctx(const DevCfg& cfg, const MapRef& map, uint64_t key, VoxelCtx& c) {
+  const uint32_t tk = (uint32_t)(key >> 32);
+  int pos, tile;
+  c.chunk = voxel_chunk(cfg, map, tk, pos, tile);
+  c.v = (int)((key >> kRecOrdBits) & ((1u << kRecVoxBits) - 1u));
+  if (!c.chunk) return false;
+  const I3 bi = unpack_key(map.ht_keys[pos]);
+  const int tps = cfg.tiles_per_side;
+  const int tx = tile % tps, ty = (tile / tps) % tps, tz = tile / (tps * tps);
+  const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1;
+  I3 g;
+  g.x = bi.x * cfg.vps + tx * cfg.tile_side + (c.v & tm);
+  g.y = bi.y * cfg.vps + ty * cfg.tile_side + ((c.v >> ts) & tm);
+  g.z = bi.z * cfg.vps + tz * cfg.tile_side + (c.v >> (2 * ts));
+  c.center = voxel_center(g, cfg.voxel_size);
+  return true;
+}
+
+// arg-max (first maximum wins, base.cpp:352-367) + colour hand-off (base.cpp:370-380, 172-191) of one voxel's finished row
+template <int NCH>
+__device__ __forceinline__ void voxel_finish_semantic(const DevCfg& cfg, const Luts* __restrict__ luts, const VoxelCtx& vc, int lane, const float (&p)[NCH]) {
+  const int C = cfg.C;
+  float best = -3.402823466e38f;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C && (p[q] > best || bi == 0x7fffffff)) { best = p[q]; bi = c; } }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_down_sync(0xffffffffu, best, o);
+    const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+  }
+  best = __shfl_sync(0xffffffffu, best, 0);
+  const int lab = __shfl_sync(0xffffffffu, bi, 0);
+  float* prow = (float*)(vc.chunk + cfg.head_bytes) + (size_t)vc.v * C;
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) prow[c] = p[q]; }
+  if (lane == 0) {
+    (vc.chunk + 4 * cfg.plane_f32)[vc.v] = (uint8_t)lab;
+    const uint32_t sc = luts->label_rgba[lab];
+    ((uint32_t*)(vc.chunk + 3 * cfg.plane_f32))[vc.v] = sc;
+    if (cfg.color_mode == 1) ((uint32_t*)(vc.chunk + 2 * cfg.plane_f32))[vc.v] = sc;                                        // kSemantic
+    else if (cfg.color_mode == 2) ((uint32_t*)(vc.chunk + 2 * cfg.plane_f32))[vc.v] = rainbow_color_map((double)expf(best));  // kSemanticProbability
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// long segments: one item per role
+// ---------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
+                                                            const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q) {
+  const int lane = threadIdx.x & 31;
+  const int C = cfg.C;
+  const int n_hot = q.counters[0], n_other = q.counters[1];
+  const int n_items = n_hot + n_other;
+  const F3 origin = f3(T.tx, T.ty, T.tz);
+  const bool keep_blend = cfg.color_mode == 0;
+  const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
+  const uint32_t zero_row = (uint32_t)cnt->n_cast;   // all-zero row behind the last bundle: padded lanes add +0.0f (exact)
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = atomicAdd(&q.counters[3], 1);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_items) break;
+    const unsigned long long item = (it < n_hot) ? q.long_items[it] : q.long_items[q.long_cap - 1 - (it - n_hot)];
+    const long long begin = (long long)(item >> 24);
+    const int len = (int)((item >> 1) & 0x7FFFFFu);
+    const int role = (int)(item & 1ull);       // 0: TSDF, 1: semantic
+    VoxelCtx vc;
+    if (!voxel_ctx(cfg, map, rec[begin], vc)) continue;
+    const uint64_t* r = rec + begin;
+    if (role == 0) {
+      float* pd = (float*)vc.chunk + vc.v;
+      float* pw = (float*)(vc.chunk + cfg.plane_f32) + vc.v;
+      uint32_t* pc = (uint32_t*)(vc.chunk + 2 * cfg.plane_f32) + vc.v;
+      float dist = *pd, wgt = *pw;
+      uint32_t rgba = *pc;
+      // parameters of the next batch are fetched one batch ahead
+      float4 pr_a = (lane < len) ? src.param[(uint32_t)r[lane] & ord_mask] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int base = 0; base < len; base += 32) {
+        const int nb = (len - base) < 32 ? (len - base) : 32;
+        float4 pr_b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (base + 32 + lane < len) pr_b = src.param[(uint32_t)r[base + 32 + lane] & ord_mask];
+        float sdf = 0.0f, uw = 0.0f;
+        if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), vc.center, pr_a.w, sdf, uw);
+        tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);   // merged: point colours are (0,0,0,0) (merged.cpp:70)
+        pr_a = pr_b;
+      }
+      if (lane == 0) { *pd = dist; *pw = wgt; if (keep_blend) *pc = rgba; }
+    } else {
+      const float* prow = (const float*)(vc.chunk + cfg.head_bytes) + (size_t)vc.v * C;
+      float p[NCH];
+#pragma unroll
+      for (int qq = 0; qq < NCH; ++qq) { const int c = qq * 32 + lane; p[qq] = (c < C) ? prow[c] : 0.0f; }
+      if (NCH == 1) {
+        // software pipeline over batches of 32 records: keys two batches ahead, the 32 (L * freq) row values one batch ahead
+        const float* lane_tmp = src.tmp + (lane < C ? lane : 0);
+        uint32_t ord_a = (lane < len) ? ((uint32_t)r[lane] & ord_mask) : zero_row;
+        uint32_t ord_b = (32 + lane < len) ? ((uint32_t)r[32 + lane] & ord_mask) : zero_row;
+        float rv_a[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) rv_a[u] = __ldg(lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_a, u) * C);
+        for (int base = 0; base < len; base += 32) {
+          const uint32_t ord_c = (base + 64 + lane < len) ? ((uint32_t)r[base + 64 + lane] & ord_mask) : zero_row;
+          float rv_b[32];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) rv_b[u] = __ldg(lane_tmp + (size_t)__shfl_sync(0xffffffffu, ord_b, u) * C);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) p[0] += rv_a[u];
+#pragma unroll
+          for (int u = 0; u < 32; ++u) rv_a[u] = rv_b[u];
+          ord_b = ord_c;
+        }
+        if (lane >= C) p[0] = 0.0f;
+      } else {
+        constexpr int kRowUnroll = (NCH <= 2) ? 8 : 2;
+        for (int base = 0; base < len; base += 32) {
+          const int nb = (len - base) < 32 ? (len - base) : 32;
+          const uint32_t ord = (lane < nb) ? ((uint32_t)r[base + lane] & ord_mask) : zero_row;
+          for (int j0 = 0; j0 < nb; j0 += kRowUnroll) {
+            float rv[kRowUnroll][NCH];
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+              const uint32_t o = __shfl_sync(0xffffffffu, ord, (j0 + u) & 31);
+              const float* row = src.tmp + (size_t)o * C;
+#pragma unroll
+              for (int qq = 0; qq < NCH; ++qq) { const int cc = qq * 32 + lane; rv[u][qq] = (j0 + u < nb && cc < C) ? __ldg(row + cc) : 0.0f; }
+            }
+#pragma unroll
+            for (int u = 0; u < kRowUnroll; ++u) {
+#pragma unroll
+              for (int qq = 0; qq < NCH; ++qq) p[qq] += rv[u][qq];
+            }
+          }
+        }
+      }
+      voxel_finish_semantic<NCH>(cfg, luts, vc, lane, p);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// short segments: both roles by one warp
+// ---------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256, 6) k_voxel_apply_short(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
+                                                             const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q) {
+  const int lane = threadIdx.x & 31;
+  const int C = cfg.C;
+  const int n_items = min((long long)q.counters[2], q.short_cap);
+  const F3 origin = f3(T.tx, T.ty, T.tz);
+  const bool keep_blend = cfg.color_mode == 0;
+  const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
+  for (;;) {
+    int it0 = 0;
+    if (lane == 0) it0 = atomicAdd(&q.counters[4], kGrab);
+    it0 = __shfl_sync(0xffffffffu, it0, 0);
+    if (it0 >= n_items) break;
+    // the kGrab items of this round: lane g holds item g's descriptor and first record (independent loads, one round trip)
+    unsigned long long my_item = 0, my_key = 0;
+    if (lane < kGrab && it0 + lane < n_items) { my_item = q.short_items[it0 + lane]; my_key = rec[my_item >> 24]; }
+    const int n_here = (n_items - it0) < kGrab ? (n_items - it0) : kGrab;
+    for (int gi = 0; gi < n_here; ++gi) {
+      const unsigned long long item = __shfl_sync(0xffffffffu, my_item, gi);
+      const uint64_t key0 = __shfl_sync(0xffffffffu, my_key, gi);
+      const long long begin = (long long)(item >> 24);
+      const int len = (int)(item & 0xFFFFFFu);
+      VoxelCtx vc;
+      if (!voxel_ctx(cfg, map, key0, vc)) continue;
+      const uint64_t* r = rec + begin;
+      float* pd = (float*)vc.chunk + vc.v;
+      float* pw = (float*)(vc.chunk + cfg.plane_f32) + vc.v;
+      uint32_t* pc = (uint32_t*)(vc.chunk + 2 * cfg.plane_f32) + vc.v;
+      float dist = *pd, wgt = *pw;
+      uint32_t rgba = *pc;
+      const float* prow = (const float*)(vc.chunk + cfg.head_bytes) + (size_t)vc.v * C;
+      float p[NCH];
+#pragma unroll
+      for (int qq = 0; qq < NCH; ++qq) { const int c = qq * 32 + lane; p[qq] = (c < C) ? prow[c] : 0.0f; }
+      for (int base = 0; base < len; base += 32) {
+        const int nb = (len - base) < 32 ? (len - base) : 32;
+        uint32_t ord = 0;
+        float sdf = 0.0f, uw = 0.0f;
+        if (lane < nb) {
+          ord = (uint32_t)r[base + lane] & ord_mask;
+          const float4 pr = src.param[ord];
+          tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), vc.center, pr.w, sdf, uw);
+        }
+        // (L * freq) rows in record order: lane c adds column c; four independent row loads in flight
+        for (int j0 = 0; j0 < nb; j0 += 4) {
+          float rv[4][NCH];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t o = __shfl_sync(0xffffffffu, ord, (j0 + u) & 31);
+            const float* row = src.tmp + (size_t)o * C;
+#pragma unroll
+            for (int qq = 0; qq < NCH; ++qq) { const int cc = qq * 32 + lane; rv[u][qq] = (j0 + u < nb && cc < C) ? __ldg(row + cc) : 0.0f; }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int qq = 0; qq < NCH; ++qq) p[qq] += rv[u][qq];   // + 0.0f is exact for the padded tail
+          }
+        }
+        tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
+      }
+      if (lane == 0) { *pd = dist; *pw = wgt; if (keep_blend) *pc = rgba; }
+      voxel_finish_semantic<NCH>(cfg, luts, vc, lane, p);
+    }
+  }
+}
+
+}  // namespace ksg

@@ -52,6 +52,9 @@ class FakeDeviceIntegrator:
     def num_blocks(self):
         return self.o.num_blocks()
 
+    def fast_timeline(self):
+        return {"sweeps": 6, "solve_kernel_us": 100.0}
+
     def sync(self):
         pass
 
@@ -63,7 +66,7 @@ class FakeEvent:
     def __init__(self, enable_timing=True):
         self.t = 0.0
 
-    def record(self):
+    def record(self, stream=None):
         import time
         self.t = time.perf_counter()
 
@@ -81,6 +84,8 @@ def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extr
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: types.SimpleNamespace(cuda_stream=0))
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=1))
+    monkeypatch.setattr(torch.cuda, "set_stream", lambda s: None)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     real_tensor = torch.tensor

@@ -3,11 +3,23 @@
 set -u
 O=gpurun_out/r02
 mkdir -p $O
-timeout 120 tools/ubench_launch > $O/ubench_launch.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_ref_golden.py tests/test_gpu_bundle_order.py tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -15 > $O/gpu_merged_order.log
-run() { name=$1; shift; timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline "$@" > $O/bench_${name}.json 2> $O/bench_${name}.err; }
-run merged2_reforder_v2 --workload merged2
-run merged5_reforder_v2 --workload merged5
-cat $O/ubench_launch.txt
-tail -8 $O/gpu_merged_order.log
-for f in $O/bench_*v2.json; do echo "$f: $(grep -o '"value": [0-9.]*' $f | head -1) $(grep -o '"phase_ms_per_frame": {[^}]*}' $f)"; done
+timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > $O/gpu_suite_v3.log
+tail -6 $O/gpu_suite_v3.log
+run() { name=$1; shift; timeout 400 python bench.py --no-cpu-baseline "$@" > $O/bench_${name}.json 2> $O/bench_${name}.err; }
+run merged2_voxel --workload merged2 --steps 30 --warmup 5
+run merged5_voxel --workload merged5 --steps 30 --warmup 5
+run fast5_v2b --steps 100 --warmup 10
+for f in $O/bench_merged2_voxel.json $O/bench_merged5_voxel.json $O/bench_fast5_v2b.json; do python - $f <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1])); r=d['roofline']
+    print(sys.argv[1], 'fps %.1f e2e %.1f mups %.0f frac %.3f'%(d['value'], d['e2e']['value'], d['mvoxel_updates_per_s'], r['frac']), {k:round(v,4) for k,v in r['phase_ms_per_frame'].items()})
+    print('  timeline', r.get('solve_kernel_timeline_last_profiled_frame'))
+except Exception as e:
+    print(sys.argv[1], 'ERR', e); print(open(sys.argv[1].replace('.json','.err')).read()[-1500:])
+PY
+done
+# launch lists (cold cache, serialised: shares only)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fast5_v2.csv python tools/run_frames.py fast5 14 > $O/ncu_fast5.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_merged2_voxel.csv python tools/run_frames.py merged2 5 > $O/ncu_merged2.log 2>&1
+tail -3 $O/ncu_fast5.log
