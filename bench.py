@@ -273,9 +273,9 @@ def main():
     ap.add_argument("--workload", default="fast5", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hot-voxels", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--hot-voxels", type=int, default=2, choices=[0, 1, 2],
                     help="merged workloads: ksg_config.hot_voxel_mode (1 = parallel pre-pass for the semantic rows of hot voxels, 2 = + TSDF fixed-point check)")
-    ap.add_argument("--merged-bundle-order", default="canonical", choices=["canonical", "libstdcxx"],
+    ap.add_argument("--merged-bundle-order", default="libstdcxx", choices=["canonical", "libstdcxx"],
                     help="merged workloads: bundle order (ksg_config.merged_bundle_order); libstdcxx = the reference's unordered_map order")
     ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial"],
                     help="N > 1: sequence = one stream + map per rank (weak scaling, default); spatial = ONE stream and map, every rank "

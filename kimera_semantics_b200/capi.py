@@ -142,7 +142,7 @@ def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float
     cfg.shard_rank = 0
     cfg.shard_count = 1
     cfg.merged_bundle_order = KSG_BUNDLE_ORDER_LIBSTDCXX   # the reference's order (merged.cpp:210-231)
-    cfg.hot_voxel_mode = 0
+    cfg.hot_voxel_mode = 2   # merged, C <= 32: exact parallel pre-pass for voxels with thousands of records per frame
     return cfg
 
 

@@ -156,6 +156,8 @@ struct ksg_integrator {
   OvfEnt* ovf = nullptr;
   RayRec* rayrec = nullptr;
   int ovf_cap = 0;
+  int *mixed_list = nullptr, *m_list = nullptr;
+  int solve_smem = 0;
   double clock_khz = 1965000.0;
   // frames whose counters have not been read back yet (at most two: the counter copies land in two pinned slots)
   Counters* h_cnt_base = nullptr;    // [2] pinned; h_cnt points at the slot read last
@@ -243,7 +245,7 @@ void free_all(ksg_integrator* h) {
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
-                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt_base) cudaFreeHost(h->h_cnt_base);
   if (h->h_fc_base) cudaFreeHost(h->h_fc_base);
@@ -486,10 +488,13 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   f.o3.cand = h->cand16; f.o3.ext_base = h->ob.ext_base; f.o3.cand_cap = h->ob.cand_cap; f.o3.slot_cnt = h->ob.slot_cnt; f.o3.bkt = h->ob.bkt;
   f.o3.head = h->ob.head; f.o3.ovf = h->ovf; f.o3.ovf_cap = h->ovf_cap; f.o3.stamp = (uint32_t*)h->ob.slot_stamp; f.o3.table = h->ob.table;
   f.rayrec = h->rayrec;
+  f.s_base = h->start_head; f.s_hmin = h->start_val; f.s_hmax = (uint32_t*)(h->clear_00 + (size_t)kSetSize * 5);
+  f.s_visits = (int*)(h->clear_00 + (size_t)kSetSize * 9); f.mixed_list = h->mixed_list; f.m_list = h->m_list;
+  const bool s3 = h->solver == 3;
 
   if (h->profiling) cudaEventRecord(h->ev[0], s);
   KSG_CUDA(cudaMemsetAsync(h->clear_ff, 0xFF, (size_t)kSetSize * 16, s));
-  KSG_CUDA(cudaMemsetAsync(h->clear_00, 0x00, (size_t)kSetSize * 5, s));
+  KSG_CUDA(cudaMemsetAsync(h->clear_00, 0x00, (size_t)kSetSize * (s3 ? 13 : 5), s));
   KSG_CUDA(cudaMemsetAsync(h->start_min, 0x7F, sizeof(int) * kSetSize, s));
   const int B = 256;
   ++h->n_launches;
@@ -506,18 +511,19 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
     k_fast_invert_perm<<<grid_for(cap, B), B, 0, s>>>(h->d_cnt, (const uint32_t*)h->point_of_seq, h->seq_of_i);
   }
   ++h->n_launches;
-  if (in.d_depth) k_fast_classify<true><<<f.n_count_blocks, 256, 0, s>>>(f);
-  else k_fast_classify<false><<<grid_for(cap, B), B, 0, s>>>(f);
+  if (in.d_depth) { if (s3) k_fast_classify<true, true><<<f.n_count_blocks, 256, 0, s>>>(f); else k_fast_classify<true, false><<<f.n_count_blocks, 256, 0, s>>>(f); }
+  else { if (s3) k_fast_classify<false, true><<<grid_for(cap, B), B, 0, s>>>(f); else k_fast_classify<false, false><<<grid_for(cap, B), B, 0, s>>>(f); }
   const int n_eval_blocks = (cap + kEvalBlock - 1) / kEvalBlock;
   ++h->n_launches;
-  k_fast_start_eval<<<n_eval_blocks, kEvalBlock, 0, s>>>(f, n_eval_blocks);
+  if (s3) k_fast_start_eval3<<<n_eval_blocks, kEvalBlock, 0, s>>>(f);
+  else k_fast_start_eval<<<n_eval_blocks, kEvalBlock, 0, s>>>(f, n_eval_blocks);
   if (h->profiling) cudaEventRecord(h->ev[1], s);
   {
     int max_sweeps = 4096;   // theory: <= rays + 1 sweeps, practice 6-8; the kernel flags an error rather than spin for ever
     void* args[] = {(void*)&f, (void*)&max_sweeps};
     ++h->n_launches;
-    KSG_CUDA(cudaLaunchCooperativeKernel(h->solver == 3 ? (const void*)k_fast_solve3 : (const void*)k_fast_solve, dim3(h->solve_grid),
-                                         dim3(kSolveThreads), args, 0, s));
+    KSG_CUDA(cudaLaunchCooperativeKernel(s3 ? (const void*)k_fast_solve3 : (const void*)k_fast_solve, dim3(h->solve_grid),
+                                         dim3(kSolveThreads), args, s3 ? (size_t)h->solve_smem : 0, s));
   }
   if (h->profiling) cudaEventRecord(h->ev[2], s);
   {
@@ -784,6 +790,14 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       k_voxel_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->vq);
       if (h->profiling) cudaEventRecord(h->ev[5], s);
       did_apply = true;
+      if (h->hot_enabled) {
+        int n_hot = 0;
+        const int rch = hot_voxel_prepass(h, s, T, src.param, n_records, &n_hot);
+        if (rch) return rch;
+        src.hot_segs = h->d_hot_segs; src.hot_prior = h->d_hot_prior; src.n_hot = n_hot; src.hot_thresh = kHotThresh;
+        src.hot_tsdf_same = (h->cfg.hot_voxel_mode == 2) ? h->d_hot_same : nullptr;
+        last_hot_voxels = n_hot;
+      }
       KSG_CUDA(cudaEventRecord(h->ev_fork, s));
       KSG_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
       h->n_launches += 2;
@@ -941,7 +955,7 @@ void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size
   c->shard_rank = 0;
   c->shard_count = 1;
   c->merged_bundle_order = KSG_BUNDLE_ORDER_LIBSTDCXX;   // the reference's unordered_map iteration order (merged.cpp:210-231)
-  c->hot_voxel_mode = 0;
+  c->hot_voxel_mode = 2;   // merged, C <= 32: exact parallel pre-pass for the voxels that receive thousands of records per frame
 }
 
 #define KSG_STR_(x) #x
@@ -1071,7 +1085,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     // per-frame cleared arrays live in two contiguous regions: [0xFF: start_head | start_max | start_val | ob.head] and
     // [0x00: ob.slot_cnt | start_mixed], so that a frame needs three memsets instead of seven
     KSG_CUDA(cudaMalloc((void**)&h->clear_ff, (size_t)kSetSize * 16));
-    KSG_CUDA(cudaMalloc((void**)&h->clear_00, (size_t)kSetSize * 5));
+    KSG_CUDA(cudaMalloc((void**)&h->clear_00, (size_t)kSetSize * 13));   // [ob.slot_cnt 4 | start_mixed 1 | s_hmax 4 | s_visits 4] bytes per slot
     h->start_head = (int*)h->clear_ff; h->start_max = h->start_head + kSetSize; h->start_val = (uint32_t*)(h->start_max + kSetSize);
     h->start_mixed = h->clear_00 + (size_t)kSetSize * 4;
     KSG_CUDA(dmalloc(&h->start_min, kSetSize));
@@ -1095,6 +1109,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
         h->ovf_cap = (int)std::min<long long>(std::max<long long>(1ll << 20, 4ll * (long long)N), 1ll << 28);
         KSG_CUDA(cudaMalloc((void**)&h->ovf, sizeof(OvfEnt) * (size_t)h->ovf_cap));
         KSG_CUDA(cudaMalloc((void**)&h->rayrec, sizeof(RayRec) * N));
+        KSG_CUDA(dmalloc(&h->mixed_list, N)); KSG_CUDA(dmalloc(&h->m_list, N));
       }
     }
     h->ob.slot_cnt = (int*)h->clear_00; KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));
@@ -1104,8 +1119,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
     KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
-    // per-voxel apply kernels (default); the tile kernel stays for hot_voxel_mode > 0, apply_mode 1 and KSG_MERGED_TILE_APPLY=1
-    h->voxel_apply = cfg->hot_voxel_mode == 0 && cfg->apply_mode == 0;
+    // per-voxel apply kernels (default); the tile kernel stays for apply_mode 1 and KSG_MERGED_TILE_APPLY=1
+    h->voxel_apply = cfg->apply_mode == 0;
     if (const char* e = std::getenv("KSG_MERGED_TILE_APPLY")) if (std::atoi(e) != 0) h->voxel_apply = false;
     if (h->voxel_apply) {
       h->vq.long_cap = 4 * (rec_cap / kLongLen) + 64;
@@ -1210,7 +1225,9 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       int per_sm = 0;
       KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_solve, kSolveThreads, 0));
       int per_sm3 = 0;
-      KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_fast_solve3, kSolveThreads, 0));
+      h->solve_smem = (int)(sizeof(int) * kSortPerWarp * (kSolveThreads / 32));
+      KSG_CUDA(cudaFuncSetAttribute(k_fast_solve3, cudaFuncAttributeMaxDynamicSharedMemorySize, h->solve_smem));
+      KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_fast_solve3, kSolveThreads, (size_t)h->solve_smem));
       if (h->solver == 3) per_sm = per_sm3;
       int coop = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
@@ -1222,7 +1239,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     }
     {
       const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
-      h->apply_fast_smem = (int)(stage + (size_t)dc.tile_voxels * 10 + 16 + sizeof(uint32_t) * kFastKeyCap + 64);
+      h->apply_fast_smem = (int)(stage + (size_t)dc.tile_voxels * 10 + 16 + sizeof(uint32_t) * kFastKeyCap + 64 + 16 + (size_t)kFastPref * 21);
 #define KSG_ATTRF(TMA, NCH) KSG_CUDA(cudaFuncSetAttribute(k_tile_apply_fast<TMA, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_fast_smem))
       KSG_ATTRF(true, 1); KSG_ATTRF(true, 2); KSG_ATTRF(true, 4); KSG_ATTRF(true, 8);
       KSG_ATTRF(false, 1); KSG_ATTRF(false, 2); KSG_ATTRF(false, 4); KSG_ATTRF(false, 8);

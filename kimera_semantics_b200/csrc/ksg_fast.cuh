@@ -27,6 +27,7 @@ static constexpr int kCountBlock = 1024;      // pixels per block of k_fast_coun
 static constexpr int kEvalBlock = 512;        // sequence positions per block of k_fast_start_eval
 static constexpr int kSolveThreads = 1024;     // one CTA per SM: a grid barrier is 148 arrivals
 static constexpr int kFastKeyCap = 4096;      // update records of one tile sorted in shared memory (more: sorted in place in global memory)
+static constexpr int kFastPref = 1024;        // ... and whose per-record operands (point, label, colour) are prefetched into shared memory
 static constexpr int kTimelineSlots = 64;
 
 struct FastCounters {      // device-resident state of the frame driver (persistent across frames)
@@ -39,6 +40,8 @@ struct FastCounters {      // device-resident state of the frame driver (persist
   int pool_base;                             // pool_count before this frame's new blocks
   unsigned long long rec_cursor;             // allocation cursor of the per-tile key segments
   int ovf_count;                             // overflow pool cursor (solver 3)
+  int n_mixed;                               // start-set slots visited by more than one start cell this frame
+  int m_cursor;                              // allocation cursor of their visitor lists
   int pad0;
   long long timeline[kTimelineSlots];        // clock64 of block 0 at the phase boundaries of k_fast_solve (profiling)
 };
@@ -96,6 +99,12 @@ struct FastFrame {
   // solver 3
   Obs3 o3;
   RayRec* rayrec;
+  // start set, third formulation: per-slot aggregates only (no linked lists)
+  int* s_visits;             // [2^20] visitors of the slot this frame (sb.next[seq] = arrival index of the point)
+  uint32_t *s_hmin, *s_hmax; // [2^20] smallest / largest (value >> 20) among the visitors: different <=> several cells share the slot
+  int* s_base;               // [2^20] start of the slot's visitor list in m_list (slots shared by several cells only)
+  int* mixed_list;           // such slots
+  int* m_list;               // their visitors (sequence positions), grouped by slot
 };
 
 __device__ __forceinline__ int inv_mixed_index(int i, int n) {   // inverse of mixed_index (voxblox MixedThreadSafeIndex, A.3)
@@ -171,6 +180,7 @@ __global__ void k_fast_reset(FastFrame f) { frame_counters_reset(f.cnt, f.capaci
 // ---------------------------------------------------------------------------------------------
 // k_fast_classify: per input point (image order) — fast.cpp:152-158, :75-81, :87-89 — + start-set push
 // ---------------------------------------------------------------------------------------------
+template <bool PUSH3>
 __device__ __forceinline__ void fast_classify_one(const FastFrame& f, int seq, F3 pC, uint8_t label, uint32_t color, bool& valid) {
   const DevCfg& cfg = f.cfg;
   if ((int)label >= cfg.C) { set_err(f.cnt, 1 /*CHECK_LT fast.cpp:134*/); label = 0; }
@@ -197,16 +207,24 @@ __device__ __forceinline__ void fast_classify_one(const FastFrame& f, int seq, F
     const I3 g = grid_index(pG, cfg.start_inv);              // fast.cpp:88-89
     key = (uint64_t)index_hash(g) + f.set_offset;            // ApproxHashSet value = hash + offset_
     const uint32_t slot = (uint32_t)key & kSetMask, hi = (uint32_t)(key >> kSetBits);
-    f.sb.next[seq] = atomicExch(&f.sb.head[slot], seq);
-    atomicMin(&f.sb.smin[slot], seq);
-    atomicMax(&f.sb.smax[slot], seq);
-    const uint32_t old = atomicCAS(&f.sb.sval[slot], 0xFFFFFFFFu, hi);
-    if (old != 0xFFFFFFFFu && old != hi) f.sb.mixed[slot] = 1;
+    if (PUSH3) {   // aggregates only: no result of these atomics steers the thread, so the four points of a thread overlap
+      f.sb.next[seq] = atomicAdd(&f.s_visits[slot], 1);
+      atomicMin(&f.sb.smin[slot], seq);
+      atomicMax(&f.sb.smax[slot], seq);
+      atomicMin(&f.s_hmin[slot], hi);
+      atomicMax(&f.s_hmax[slot], hi);
+    } else {
+      f.sb.next[seq] = atomicExch(&f.sb.head[slot], seq);
+      atomicMin(&f.sb.smin[slot], seq);
+      atomicMax(&f.sb.smax[slot], seq);
+      const uint32_t old = atomicCAS(&f.sb.sval[slot], 0xFFFFFFFFu, hi);
+      if (old != 0xFFFFFFFFu && old != hi) f.sb.mixed[slot] = 1;
+    }
   }
   f.pt_key[seq] = key;
 }
 
-template <bool DEPTH>
+template <bool DEPTH, bool PUSH3>
 __global__ void __launch_bounds__(256) k_fast_classify(FastFrame f) {
   __shared__ int s_w[8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -235,7 +253,7 @@ __global__ void __launch_bounds__(256) k_fast_classify(FastFrame f) {
       const F3 pC = f3(((float)u - f.in.cx) * d[k] * f.in.constant_x, ((float)v - f.in.cy) * d[k] * f.in.constant_y, d[k]);
       const int seq = f.seq_of_i ? f.seq_of_i[i] : inv_mixed_index(i, n);
       bool valid;
-      fast_classify_one(f, seq, pC, lab[k], f.luts->label_rgba[lab[k]], valid);
+      fast_classify_one<PUSH3>(f, seq, pC, lab[k], f.luts->label_rgba[lab[k]], valid);
       nvalid += valid ? 1 : 0;
       ++i;
     }
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(256) k_fast_classify(FastFrame f) {
       if (!in.rgba) color = f.luts->label_rgba[label];
       const int seq = f.seq_of_i ? f.seq_of_i[i] : inv_mixed_index(i, n);
       bool valid;
-      fast_classify_one(f, seq, pC, label, color, valid);
+      fast_classify_one<PUSH3>(f, seq, pC, label, color, valid);
       nvalid = valid ? 1 : 0;
     }
   }
@@ -349,6 +367,58 @@ __global__ void __launch_bounds__(kEvalBlock) k_fast_start_eval(FastFrame f, int
   const int n_warps = n_eval_blocks * (kEvalBlock / 32);
   const int total = block_scan_array(f.warp_cnt, f.warp_off, n_warps);
   if (threadIdx.x == 0) { f.cnt->n_cast = total; f.fc->ticket_eval = 0; f.fc->gridbar = 0; }
+}
+
+// Third formulation (solver 3): per-slot aggregates instead of linked lists.  Slots visited by ONE start cell (the normal case) are
+// decided here as above.  A slot shared by several cells (20-bit aliasing, a few hundred per frame) needs every visitor's predecessor in
+// sequence order: its first visitor reserves a list for it; the solve kernel fills, sorts and decides those lists with one warp per slot
+// (round 1 let every visitor walk the slot's linked list: the longest list was the critical path of the kernel, 88 us).
+__global__ void __launch_bounds__(kEvalBlock) k_fast_start_eval3(FastFrame f) {
+  const int seq = blockIdx.x * kEvalBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const StartBuf& sb = f.sb;
+  uint8_t cast = 0;
+  if (seq < f.cnt->n_points) {
+    const uint64_t v = f.pt_key[seq];
+    if (v != ~0ull) {
+      const uint32_t slot = (uint32_t)v & kSetMask, hi = (uint32_t)(v >> kSetBits);
+      if (sb.smin[slot] == seq) {
+        cast = sb.table[slot] != hi;
+        ((uint32_t*)sb.table)[slot] = (uint32_t)(f.pt_key[sb.smax[slot]] >> kSetBits);   // state after the frame = last visitor's value
+        if (f.s_hmin[slot] != f.s_hmax[slot]) {
+          f.s_base[slot] = atomicAdd(&f.fc->m_cursor, f.s_visits[slot]);
+          f.mixed_list[atomicAdd(&f.fc->n_mixed, 1)] = (int)slot;
+        }
+      }
+    }
+  }
+  if (seq < f.capacity) f.cast_flag[seq] = cast;
+  const unsigned m = __ballot_sync(0xffffffffu, cast != 0);
+  if (lane == 0) __stcg(&f.warp_cnt[seq >> 5], __popc(m));
+  if (blockIdx.x == 0 && threadIdx.x == 0) f.fc->gridbar = 0;
+}
+
+// ascending sort of a[0..n) by one warp (same network as cta_sort_u32 below)
+__device__ __forceinline__ void warp_sort_i32(int* a, int n, int lane) {
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  const int half = n2 >> 1;
+  for (int k = 2; k <= n2; k <<= 1) {
+    const int hk = k >> 1;
+    for (int t = lane; t < half; t += 32) {
+      const int blk = t / hk, o = t - blk * hk;
+      const int i = blk * k + o, p = blk * k + (k - 1 - o);
+      if (p < n) { const int x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+    }
+    __syncwarp();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int t = lane; t < half; t += 32) {
+        const int i = (t / j) * 2 * j + (t % j), p = i + j;
+        if (p < n) { const int x = a[i], y = a[p]; if (x > y) { a[i] = y; a[p] = x; } }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -658,6 +728,9 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
   uint64_t* s_bar = (uint64_t*)(s_seg_hi + V + (V & 1));
   uint32_t* s_keys = (uint32_t*)(s_bar + 2); // [kFastKeyCap]
   uint16_t* s_vox = (uint16_t*)(s_keys + kFastKeyCap);   // [V] touched voxels
+  float4* s_par = (float4*)(((uintptr_t)(s_vox + V) + 15) & ~(uintptr_t)15);   // [kFastPref] operands of the sorted records
+  uint32_t* s_col = (uint32_t*)(s_par + kFastPref);
+  uint8_t* s_lab = (uint8_t*)(s_col + kFastPref);
   __shared__ uint8_t* s_chunk;
   __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor, s_nvox, s_n;
   __shared__ long long s_off;
@@ -703,6 +776,13 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
     if (n <= kFastKeyCap) { for (int i = tid; i < n; i += nthreads) s_keys[i] = keys[i]; keys = s_keys; }
     __syncthreads();
     cta_sort_u32(keys, n);
+    const bool pref = n <= kFastPref;      // one parallel gather instead of a dependent L2 round trip per voxel
+    if (pref) for (int i = tid; i < n; i += nthreads) {
+      const uint32_t ord = keys[i] & ord_mask;
+      s_par[i] = src.param[ord];
+      s_lab[i] = src.label[ord];
+      if (keep_blend) s_col[i] = src.color[ord];
+    }
     for (int i = tid; i < n; i += nthreads) {
       const int vx = (int)(keys[i] >> kRecOrdBits);
       if (i == 0 || (int)(keys[i - 1] >> kRecOrdBits) != vx) { s_seg_lo[vx] = i; s_vox[atomicAdd(&s_nvox, 1)] = (uint16_t)vx; }
@@ -736,10 +816,10 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
         float sdf = 0.0f, uw = 0.0f;
         if (k < hi) {
           ord = keys[k] & ord_mask;
-          const float4 pr = src.param[ord];
+          const float4 pr = pref ? s_par[k] : src.param[ord];
           tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), center, pr.w, sdf, uw);
-          if (keep_blend) col = src.color[ord];
-          lab = src.label[ord];
+          if (keep_blend) col = pref ? s_col[k] : src.color[ord];
+          lab = pref ? (int)s_lab[k] : (int)src.label[ord];
         }
         const int nb = (hi - base) < 32 ? (hi - base) : 32;
         for (int jj = 0; jj < nb; ++jj) {      // semantic rows: lanes = classes, one-hot frequencies (fast.cpp:132-135)

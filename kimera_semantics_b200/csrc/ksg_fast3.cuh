@@ -26,6 +26,7 @@ namespace ksg {
 struct __align__(16) Cand { uint64_t vkey; int pos; int tog; };      // pos: >= 0 bucket entry, -2 not inserted, <= -3 overflow entry -3-pos
 struct __align__(16) OvfEnt { uint64_t order_perf; uint32_t hi; int next; };
 struct __align__(16) RayRec { int H, L, nsteps, eval_sweep; };
+static constexpr int kSortPerWarp = 1024;     // visitors of a shared start-set slot sorted in shared memory (more: in place in global memory)
 
 __device__ __forceinline__ Cand ld_cand(const Cand* p) {
   const int4 v = __ldcg((const int4*)p);
@@ -326,15 +327,51 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
   const int gthreads = gridDim.x * blockDim.x;
   Counters* cnt = f.cnt;
   const int n_points = cnt->n_points;
-  const int n_cast = cnt->n_cast;
   int tl = 0;
   timeline_mark(f, tl++);
-  // ---- phase 0: compaction of the cast points, in sequence order (= ray rank order); stamp wrap-around
+  extern __shared__ int s_sort[];            // kSortPerWarp ints per warp
+  // ---- phase 0a: start-set slots shared by several cells: every visitor files itself in the slot's list
+  const int n_mixed = ((volatile int*)&f.fc->n_mixed)[0];
+  if (n_mixed > 0) {
+    for (int seq = gtid; seq < n_points; seq += gthreads) {
+      const uint64_t v = f.pt_key[seq];
+      if (v == ~0ull) continue;
+      const uint32_t slot = (uint32_t)v & kSetMask;
+      if (f.s_hmin[slot] != f.s_hmax[slot]) f.m_list[f.s_base[slot] + f.sb.next[seq]] = seq;
+    }
+    solve_barrier(bar, epoch);
+    // ---- phase 0b: one warp per such slot: visitors in sequence order; a visitor is cast iff its predecessor carried another value
+    const int warps_total = gthreads >> 5;
+    int* scratch = s_sort + (threadIdx.x >> 5) * kSortPerWarp;
+    for (int mi = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; mi < n_mixed; mi += warps_total) {
+      const int slot = f.mixed_list[mi];
+      const int n = __ldcg(&f.s_visits[slot]);
+      int* seg = f.m_list + __ldcg(&f.s_base[slot]);
+      int* a = seg;
+      if (n <= kSortPerWarp) { for (int i = lane; i < n; i += 32) scratch[i] = __ldcg(&seg[i]); a = scratch; }
+      __syncwarp();
+      warp_sort_i32(a, n, lane);
+      for (int i = 1 + lane; i < n; i += 32) {
+        const int pa = a[i - 1], pb = a[i];
+        if (f.pt_key[pa] != f.pt_key[pb]) { f.cast_flag[pb] = 1; atomicAdd(&f.warp_cnt[pb >> 5], 1); }
+      }
+      __syncwarp();
+    }
+    solve_barrier(bar, epoch);
+  }
+  // ---- phase 0c: offsets of the cast points (block 0), then compaction in sequence order (= ray rank order)
+  if (blockIdx.x == 0) {
+    const int n_warps32 = (f.capacity + 31) >> 5;
+    const int total = block_scan_array(f.warp_cnt, f.warp_off, n_warps32);
+    if (threadIdx.x == 0) cnt->n_cast = total;
+  }
+  solve_barrier(bar, epoch);
+  const int n_cast = ((volatile int*)&cnt->n_cast)[0];
   for (int base = (gtid & ~31); base < n_points; base += gthreads) {
     const int seq = base + lane;
-    const bool c = seq < n_points && f.cast_flag[seq] != 0;
+    const bool c = seq < n_points && __ldcg(&f.cast_flag[seq]) != 0;
     const unsigned m = __ballot_sync(0xffffffffu, c);
-    if (c) f.cast_seq[f.warp_off[seq >> 5] + __popc(m & ((1u << lane) - 1u))] = seq;
+    if (c) f.cast_seq[__ldcg(&f.warp_off[seq >> 5]) + __popc(m & ((1u << lane) - 1u))] = seq;
   }
   const int sweep_base0 = ((volatile int*)&f.fc->sweep_base)[0];
   const bool wrap = sweep_base0 > (1 << 23);     // sweep ids live in 24 bits of the stamp word: restart them long before they overflow
@@ -422,6 +459,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     f.fc->n_tile_list = 0;
     f.fc->rec_cursor = 0;
     f.fc->ovf_count = 0;
+    f.fc->n_mixed = 0;
+    f.fc->m_cursor = 0;
   }
   timeline_mark(f, tl++);
 }

@@ -163,7 +163,16 @@ __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T
     VoxelCtx vc;
     if (!voxel_ctx(cfg, map, rec[begin], vc)) continue;
     const uint64_t* r = rec + begin;
+    // hot voxel (thousands of records): the pre-pass (ksg_hot.cuh) may have finished its semantic row with the exact parallel scan,
+    // and checked in parallel that the saturated TSDF state survives the frame; then there is nothing sequential left to do here
+    int hot = -1;
+    if (NCH == 1 && src.n_hot > 0 && len >= src.hot_thresh) {
+      int a = 0, b = src.n_hot;
+      while (a < b) { const int mid = (a + b) >> 1; if (src.hot_segs[mid].begin < begin) a = mid + 1; else b = mid; }
+      if (a < src.n_hot && src.hot_segs[a].begin == begin && src.hot_segs[a].end == begin + len) hot = a;
+    }
     if (role == 0) {
+      if (hot >= 0 && src.hot_tsdf_same != nullptr && src.hot_tsdf_same[hot] != 0) continue;
       float* pd = (float*)vc.chunk + vc.v;
       float* pw = (float*)(vc.chunk + cfg.plane_f32) + vc.v;
       uint32_t* pc = (uint32_t*)(vc.chunk + 2 * cfg.plane_f32) + vc.v;
@@ -186,7 +195,9 @@ __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T
       float p[NCH];
 #pragma unroll
       for (int qq = 0; qq < NCH; ++qq) { const int c = qq * 32 + lane; p[qq] = (c < C) ? prow[c] : 0.0f; }
-      if (NCH == 1) {
+      if (NCH == 1 && hot >= 0) {
+        p[0] = (lane < C) ? src.hot_prior[(size_t)hot * 32 + lane] : 0.0f;
+      } else if (NCH == 1) {
         // software pipeline over batches of 32 records: keys two batches ahead, the 32 (L * freq) row values one batch ahead
         const float* lane_tmp = src.tmp + (lane < C ? lane : 0);
         uint32_t ord_a = (lane < len) ? ((uint32_t)r[lane] & ord_mask) : zero_row;

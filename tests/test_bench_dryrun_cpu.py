@@ -104,6 +104,6 @@ def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extr
     assert line["e2e"]["d2h_bytes_per_step"] == (152 * 4 if workload == "fast10" else 152 * 3)
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"]) and line["roofline"]["bound"] == "hbm"
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"]) and line["cpu_baseline"]["value"] > 0
-    assert line["config"]["merged_bundle_order"] == ("libstdcxx" if extra else "canonical")
-    assert line["config"]["hot_voxel_mode"] == (2 if extra else 0)
+    assert line["config"]["merged_bundle_order"] == "libstdcxx"
+    assert line["config"]["hot_voxel_mode"] == 2
     assert line["gpu_launches"] > 0

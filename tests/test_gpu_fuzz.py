@@ -3,7 +3,7 @@ tests/fuzz_cases.py (the oracle itself is held to the reference's own sources on
 Block set, labels, colours, distances, weights and log-probabilities must all be bit-exact, and the per-frame counters equal.
 
 Status: the generator was written after round 1's GPU minutes were spent, so these cases (saturating max_weight, odd voxel sizes,
-points behind the camera, zero-weight points, random orientations, ...) have not yet run on a B200 - hence xfail(strict=False):
+points behind the camera, zero-weight points, random orientations, ...) first ran green on a B200 at the start of round 2 (profiles/r02/gpu_suite_start_of_round.log):
 XPASS once they do, and no effect on the rest of the suite (own process) if a corner case turns out to need work."""
 import json
 import os
@@ -16,7 +16,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="random corner-case configurations not yet run on a B200 (written after the round-1 GPU budget was spent)")
 def test_random_cases_cuda_path_equals_oracle_bit_for_bit():
     r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_fuzz_check.py"), "0", "24"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]

@@ -4,7 +4,7 @@ tens of thousands of semantic updates per frame; their per-class float32 additio
 pre-pass must actually engage.
 
 Status: algorithm proven on the CPU (tools/exact_float_chain.py, csrc/test/chain_host_test.cpp); the kernels were written after round
-1's GPU minutes were spent and have never run - xfail(strict=False), own process.  The default path is provably untouched: the SASS
+1's GPU minutes were spent; first green B200 run at the start of round 2 (own process).  The default path is provably untouched: the SASS
 of every existing k_tile_apply instantiation is identical up to one parameter offset."""
 import json
 import os
@@ -17,7 +17,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="hot_voxel_mode = 1: kernels written after the round-1 GPU budget was spent, first GPU run pending")
 def test_hot_voxel_prepass_keeps_the_map_bit_identical():
     r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_hot_voxel_check.py")], capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stderr[-2000:]

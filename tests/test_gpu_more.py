@@ -50,13 +50,11 @@ def read_shim_output(path, vps, C):
 REF_FACTORY_DEMO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "shim_demo_ref_factory")
 
 
-_REF_FACTORY_PENDING = pytest.mark.xfail(strict=False, reason="binary linked with the reference's factory.cpp: built and run up to ksg_create on the CPU, "
-                                                       "first GPU run pending (written after the round-1 GPU budget was spent)")
 
 
 @pytest.mark.parametrize("method,mode,factory", [("fast", "eager", "shim"), ("merged", "eager", "shim"), ("fast", "lazy", "shim"),
-                                                 pytest.param("fast", "eager", "reference", marks=_REF_FACTORY_PENDING),
-                                                 pytest.param("merged", "eager", "reference", marks=_REF_FACTORY_PENDING)])
+                                                 ("fast", "eager", "reference"),
+                                                 ("merged", "eager", "reference")])
 def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mode, factory):
     """SemanticTsdfIntegratorFactory::create(method, ...) + integratePointCloud(T_G_C, points_C, colors) through the C++ shim
     fill the host Layer<TsdfVoxel> / Layer<SemanticVoxel> exactly as the oracle's layers.
@@ -89,8 +87,6 @@ def test_cpp_shim_factory_and_integrate_match_oracle(demo, tmp_path, method, mod
     assert_parity(compare_maps(got, ora.export()))
 
 
-@pytest.mark.xfail(strict=False, reason="SemanticTsdfServer::saveMap / loadMap: host file round trip tested on the CPU, device upload goes through the "
-                                        "GPU-tested ksg_import_blocks, but this end-to-end path has not run on a B200 yet (written after the GPU budget was spent)")
 def test_checkpoint_and_resume_through_the_shim_continues_bit_exactly(demo, tmp_path):
     """merged has no cross-frame integrator state, so integrate(0..1) -> saveMap | new process: loadMap -> integrate(2..3) must
     equal integrate(0..3) in every voxel of both host layers."""
@@ -118,8 +114,6 @@ def test_checkpoint_and_resume_through_the_shim_continues_bit_exactly(demo, tmp_
 BINDING_CHECK = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "gpu_binding_check")
 
 
-@pytest.mark.xfail(strict=False, reason="INTEGRATION.md section B binding: built and link-checked against the reference's real headers on the CPU, "
-                                        "first GPU run pending (written after the round-1 GPU budget was spent)")
 @pytest.mark.parametrize("method", ["fast", "merged"])
 def test_integration_md_binding_against_reference_headers_matches_oracle(tmp_path, method):
     """integration/kimera_semantics/semantic_tsdf_integrator_gpu.h (what a kimera_semantics maintainer adds) compiled against the
@@ -305,8 +299,6 @@ def test_fast_sets_full_reset_after_10000_frames():
     gpu.close()
 
 
-@pytest.mark.xfail(strict=False, reason="ksg_integrate_depth_k64 (float64 intrinsics): host-side widening only, the float-K entries are unchanged; "
-                                        "first GPU run pending (written after the round-1 GPU budget was spent)")
 def test_depth_entry_with_float64_intrinsics_matches_oracle():
     """fx = 415.69219381653056 (60 degree FOV, 480 lines) is not representable in float; the k64 entry must reproduce the reference's
     float(1.0 / fx_double) exactly (depth_map_to_pointcloud.h:228-230)."""
@@ -321,8 +313,6 @@ def test_depth_entry_with_float64_intrinsics_matches_oracle():
     gpu.close()
 
 
-@pytest.mark.xfail(strict=False, reason="SemanticTsdfServer::processDepthFrame (shim-level depth entry): first GPU run pending "
-                                        "(written after the round-1 GPU budget was spent)")
 def test_shim_depth_frame_entry_matches_oracle(demo, tmp_path):
     C, w, h, vs = 21, 320, 240, 0.10
     cfg = make_config(KSG_INTEGRATOR_FAST, vs, C, max_points=w * h)
@@ -344,8 +334,6 @@ def test_shim_depth_frame_entry_matches_oracle(demo, tmp_path):
     assert_parity(compare_maps(read_shim_output(opath, 16, C), ora.export()))
 
 
-@pytest.mark.xfail(strict=False, reason="warp-level exact chain scan (ksg_chain.cuh): host-device primitives proven on the CPU, the shuffle wrapper has "
-                                        "not run on a B200 yet (written after the round-1 GPU budget was spent)")
 def test_warp_chain_scan_equals_sequential_float_loop():
     """ksg_debug_chain_sum: one warp, lanes = records, composition of two-entry tables over shuffles; must reproduce the sequential
     float32 recurrence of a hot `merged` voxel bit for bit (tests/test_exact_float_chain.py holds the same claim for the CPU model)."""

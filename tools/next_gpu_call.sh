@@ -3,13 +3,15 @@
 set -u
 O=gpurun_out/r02
 mkdir -p $O
-timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > $O/gpu_suite_v3.log
-tail -6 $O/gpu_suite_v3.log
+timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_s3.log 2>&1; echo "smoke rc=$?" >> $O/smoke_s3.log
+tail -4 $O/smoke_s3.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py tests/test_gpu_more.py tests/test_gpu_fuzz.py -q -m gpu -x -k "fast or fuzz or reset or shard or import or resume or shim" 2>&1 | tail -15 > $O/gpu_fast_s3.log
+tail -6 $O/gpu_fast_s3.log
 run() { name=$1; shift; timeout 400 python bench.py --no-cpu-baseline "$@" > $O/bench_${name}.json 2> $O/bench_${name}.err; }
-run merged2_voxel --workload merged2 --steps 30 --warmup 5
-run merged5_voxel --workload merged5 --steps 30 --warmup 5
-run fast5_v2b --steps 100 --warmup 10
-for f in $O/bench_merged2_voxel.json $O/bench_merged5_voxel.json $O/bench_fast5_v2b.json; do python - $f <<'PY'
+run fast5_s3 --steps 100 --warmup 10
+KSG_SOLVER=2 timeout 400 python bench.py --no-cpu-baseline --steps 100 --warmup 10 > $O/bench_fast5_s2.json 2> $O/bench_fast5_s2.err
+run merged2_voxel6 --workload merged2 --steps 30 --warmup 5
+for f in $O/bench_fast5_s3.json $O/bench_fast5_s2.json $O/bench_merged2_voxel6.json; do python - $f <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1])); r=d['roofline']
@@ -19,7 +21,3 @@ except Exception as e:
     print(sys.argv[1], 'ERR', e); print(open(sys.argv[1].replace('.json','.err')).read()[-1500:])
 PY
 done
-# launch lists (cold cache, serialised: shares only)
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fast5_v2.csv python tools/run_frames.py fast5 14 > $O/ncu_fast5.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_merged2_voxel.csv python tools/run_frames.py merged2 5 > $O/ncu_merged2.log 2>&1
-tail -3 $O/ncu_fast5.log
