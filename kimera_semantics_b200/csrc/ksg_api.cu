@@ -156,7 +156,8 @@ struct ksg_integrator {
   OvfEnt* ovf = nullptr;
   RayRec* rayrec = nullptr;
   int ovf_cap = 0;
-  int *mixed_list = nullptr, *m_list = nullptr;
+  int *mixed_list = nullptr, *m_list = nullptr, *blk_run = nullptr;
+  uint64_t* stamp64 = nullptr;       // [2][2^20] toggle stamps of solver 3
   int solve_smem = 0;
   double clock_khz = 1965000.0;
   // frames whose counters have not been read back yet (at most two: the counter copies land in two pinned slots)
@@ -245,7 +246,7 @@ void free_all(ksg_integrator* h) {
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
-                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->blk_run, h->stamp64, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt_base) cudaFreeHost(h->h_cnt_base);
   if (h->h_fc_base) cudaFreeHost(h->h_fc_base);
@@ -294,6 +295,10 @@ int reset_map(ksg_integrator* h, cudaStream_t s) {
   if (h->ob.table) KSG_CUDA(cudaMemsetAsync(h->ob.table, 0xFF, sizeof(uint32_t) * kSetSize, s));
   if (h->ob.slot_stamp) KSG_CUDA(cudaMemsetAsync(h->ob.slot_stamp, 0, sizeof(int) * kSetSize, s));
   if (h->d_fc) KSG_CUDA(cudaMemsetAsync(h->d_fc, 0, sizeof(FastCounters), s));
+  if (h->stamp64) {   // (sweep 0, nobody): max word 0, min word all ones
+    KSG_CUDA(cudaMemsetAsync(h->stamp64, 0x00, sizeof(uint64_t) * kSetSize, s));
+    KSG_CUDA(cudaMemsetAsync(h->stamp64 + kSetSize, 0xFF, sizeof(uint64_t) * kSetSize, s));
+  }
   if (h->tile_cnt) KSG_CUDA(cudaMemsetAsync(h->tile_cnt, 0, sizeof(int) * (size_t)h->ht_cap * h->dc.tiles_per_block, s));
   h->n_pend = 0; h->n_stash = 0;
   std::memset(h->h_cnt_base, 0, 2 * sizeof(Counters));
@@ -486,8 +491,8 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   f.rec = h->rec_a; f.rec_cap = h->rec_cap; f.keys = h->keys32;
   f.tile_cnt = h->tile_cnt; f.tile_slot = h->tile_slot; f.tile_list = h->tile_list; f.tile_cap = h->tile_cap;
   f.o3.cand = h->cand16; f.o3.ext_base = h->ob.ext_base; f.o3.cand_cap = h->ob.cand_cap; f.o3.slot_cnt = h->ob.slot_cnt; f.o3.bkt = h->ob.bkt;
-  f.o3.head = h->ob.head; f.o3.ovf = h->ovf; f.o3.ovf_cap = h->ovf_cap; f.o3.stamp = (uint32_t*)h->ob.slot_stamp; f.o3.table = h->ob.table;
-  f.rayrec = h->rayrec;
+  f.o3.head = h->ob.head; f.o3.ovf = h->ovf; f.o3.ovf_cap = h->ovf_cap; f.o3.stamp_max = h->stamp64; f.o3.stamp_min = h->stamp64 + kSetSize; f.o3.table = h->ob.table;
+  f.rayrec = h->rayrec; f.blk_run = h->blk_run;
   f.s_base = h->start_head; f.s_hmin = h->start_val; f.s_hmax = (uint32_t*)(h->clear_00 + (size_t)kSetSize * 5);
   f.s_visits = (int*)(h->clear_00 + (size_t)kSetSize * 9); f.mixed_list = h->mixed_list; f.m_list = h->m_list;
   const bool s3 = h->solver == 3;
@@ -1110,6 +1115,8 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
         KSG_CUDA(cudaMalloc((void**)&h->ovf, sizeof(OvfEnt) * (size_t)h->ovf_cap));
         KSG_CUDA(cudaMalloc((void**)&h->rayrec, sizeof(RayRec) * N));
         KSG_CUDA(dmalloc(&h->mixed_list, N)); KSG_CUDA(dmalloc(&h->m_list, N));
+        KSG_CUDA(dmalloc(&h->blk_run, (size_t)(h->ob.cand_cap / 16 + 16)));
+        KSG_CUDA(dmalloc(&h->stamp64, 2 * (size_t)kSetSize));
       }
     }
     h->ob.slot_cnt = (int*)h->clear_00; KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));

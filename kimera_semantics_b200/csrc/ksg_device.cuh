@@ -135,9 +135,11 @@ __host__ __device__ __forceinline__ void raycaster_init(Dda& d, F3 origin, F3 po
 // nextRayIndex: returns the current index, then advances along argmin(t_next) (first minimum wins)
 __host__ __device__ __forceinline__ I3 dda_next(Dda& d) {
   const I3 out = d.cur;
+  // argmin of t_to_next_boundary_, first minimum wins (written without a run-time array index: the state stays in registers)
   int k = 0;
-  if (d.tn[1] < d.tn[k]) k = 1;
-  if (d.tn[2] < d.tn[k]) k = 2;
+  float m = d.tn[0];
+  if (d.tn[1] < m) { k = 1; m = d.tn[1]; }
+  if (d.tn[2] < m) k = 2;
   if (k == 0) { d.cur.x += d.sg[0]; d.tn[0] += d.ts[0]; }
   else if (k == 1) { d.cur.y += d.sg[1]; d.tn[1] += d.ts[1]; }
   else { d.cur.z += d.sg[2]; d.tn[2] += d.ts[2]; }

@@ -61,7 +61,8 @@ struct Obs3 {
   int* head;               // [2^20] overflow list head (cleared to -1 per frame)
   OvfEnt* ovf;             // overflow pool (slots with more than kBktK performed-ever candidates)
   int ovf_cap;
-  uint32_t* stamp;         // [2^20] (sweep << 8) | toggles of the slot in that sweep
+  uint64_t* stamp_max;     // [2^20] max over the toggles of the slot of (sweep << 32 | ray)
+  uint64_t* stamp_min;     // [2^20] min over the toggles of ((~sweep) << 32 | ray)
   uint32_t* table;         // persistent compact table: value >> 20
 };
 
@@ -99,6 +100,7 @@ struct FastFrame {
   // solver 3
   Obs3 o3;
   RayRec* rayrec;
+  int* blk_run;              // consecutive-collision count at the start of every evaluation block (index: candidate index / 16)
   // start set, third formulation: per-slot aggregates only (no linked lists)
   int* s_visits;             // [2^20] visitors of the slot this frame (sb.next[seq] = arrival index of the point)
   uint32_t *s_hmin, *s_hmax; // [2^20] smallest / largest (value >> 20) among the visitors: different <=> several cells share the slot

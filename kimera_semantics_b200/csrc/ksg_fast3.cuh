@@ -45,15 +45,21 @@ __device__ __forceinline__ long long cand_index3(const Obs3& o, const long long*
   return o.ext_base + __ldcg(&ext_off[(size_t)r * kExtSegs + k]) + (s - (kH0 << k));
 }
 
-__device__ __forceinline__ void stamp_toggle(uint32_t* stamp, uint32_t slot, int sweep) {
-  uint32_t cur = __ldcg(&stamp[slot]);
-  for (;;) {
-    const uint32_t nw = ((int)(cur >> 8) < sweep) ? (((uint32_t)sweep << 8) | 1u) : (((cur & 255u) < 255u) ? cur + 1u : cur);
-    if (nw == cur) break;
-    const uint32_t old = atomicCAS(&stamp[slot], cur, nw);
-    if (old == cur) break;
-    cur = old;
-  }
+// A toggle of `slot` by ray r in sweep k leaves (k, r) in two monotonic words: smax = max (k << 32 | r), smin = min ((~k) << 32 | r).
+// Both are fire-and-forget reductions.  A ray evaluated last in sweep `last` is dirty iff the slot was toggled in a later sweep, or in
+// sweep `last` by a ray other than itself (smallest and largest toggler of that sweep are not both the ray).
+static constexpr uint32_t kSweepCap = 0x7FFFFFFFu;
+__device__ __forceinline__ void stamp_toggle(const Obs3& o, uint32_t slot, int sweep, int r) {
+  atomicMax((unsigned long long*)&o.stamp_max[slot], ((unsigned long long)(uint32_t)sweep << 32) | (uint32_t)r);
+  atomicMin((unsigned long long*)&o.stamp_min[slot], ((unsigned long long)(kSweepCap - (uint32_t)sweep) << 32) | (uint32_t)r);
+}
+__device__ __forceinline__ bool stamp_dirty(const Obs3& o, uint32_t slot, int last, int r) {
+  const unsigned long long a = __ldcg((const unsigned long long*)&o.stamp_max[slot]);
+  const unsigned long long b = __ldcg((const unsigned long long*)&o.stamp_min[slot]);
+  const int sk = (int)(a >> 32);
+  if (sk > last) return true;
+  if (sk < last) return false;
+  return !((uint32_t)(b >> 32) == kSweepCap - (uint32_t)sk && (uint32_t)a == (uint32_t)r && (uint32_t)b == (uint32_t)r);
 }
 
 // first time a candidate turns performed: it enters the slot's bucket (or the overflow pool); returns its position code
@@ -126,16 +132,86 @@ __device__ __forceinline__ bool later_performed_exists3(const Obs3& o, uint32_t 
 }
 
 // single writer per candidate: the warp that owns the ray.  c.pos is updated when the candidate enters a bucket.
-__device__ __forceinline__ void set_performed3(const FastFrame& f, Cand& c, long long ci, uint32_t slot, uint64_t order, uint64_t v, bool on, int sweep) {
+// No fence between the entry and the stamp: a reader of the same sweep that misses the entry is flagged by the stamp (another
+// ray toggled its slot in its own sweep), and every store is visible after the grid barrier that ends the sweep.
+__device__ __forceinline__ void set_performed3(const FastFrame& f, Cand& c, long long ci, uint32_t slot, uint64_t order, uint64_t v, bool on, int sweep, int r) {
   const Obs3& o = f.o3;
   if (c.pos >= 0) __stcg(&o.bkt[c.pos], make_entry(on, order, v));
   else if (c.pos <= -3) __stcg(&o.ovf[-3 - c.pos].order_perf, (on ? kEntPerf : 0ull) | order);
-  else if (on) c.pos = cand_insert3(f, slot, make_entry(true, order, v));
+  else if (on) { c.pos = cand_insert3(f, slot, make_entry(true, order, v)); st_cand_state(&o.cand[ci], c.pos, 0); }
   else return;                       // never entered a bucket and stays unperformed: invisible to every other ray
-  c.tog = sweep;
-  st_cand_state(&o.cand[ci], c.pos, c.tog);
-  __threadfence();
-  stamp_toggle(o.stamp, slot, sweep);
+  stamp_toggle(o, slot, sweep, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// RayCaster steps (A.7) of ONE ray by a whole warp.  The serial walk picks, at every step, the axis with the smallest
+// t_to_next_boundary_ (first minimum wins) and adds that axis' t_step_size_ to it: per axis the boundary times form the chain
+// a(j+1) = fl(a(j) + ts), independent of the other axes, and the walk is the merge of the three non-decreasing chains ordered by
+// (time, axis, index).  So: three lanes run the three chains (W dependent additions each instead of 3 W dependent steps), every
+// element finds its rank with two binary searches, and the element of rank s carries the per-axis step counts before step s,
+// i.e. the voxel emitted at step s.  Bit-identical to dda_next as long as every time and step is finite and every step positive
+// (else the caller walks serially: NaN / zero components follow the comparison semantics of the serial code).
+// ---------------------------------------------------------------------------------------------
+static constexpr int kWin = 64;               // steps per window (= the evaluation block)
+struct WarpDdaScratch { float a[3][kWin + 1]; int endc[4]; uint64_t out[kWin]; };
+
+__device__ __forceinline__ bool ray_state_parallel_ok(const RayState& st) {
+  const bool fin = isfinite(st.tn0) && isfinite(st.tn1) && isfinite(st.tn2) && isfinite(st.ts0) && isfinite(st.ts1) && isfinite(st.ts2);
+  return fin && st.ts0 > 0.0f && st.ts1 > 0.0f && st.ts2 > 0.0f;
+}
+// W <= kWin steps from `st`; sc->out[0..W) = packed voxel indices, st advanced by W steps.  Returns false if an index left the packed range.
+__device__ __forceinline__ bool warp_dda_window(RayState& st, int W, WarpDdaScratch* sc, int lane) {
+  if (lane < 3) {
+    float a = lane == 0 ? st.tn0 : (lane == 1 ? st.tn1 : st.tn2);
+    const float ts = lane == 0 ? st.ts0 : (lane == 1 ? st.ts1 : st.ts2);
+    sc->a[lane][0] = a;
+    for (int j = 1; j <= W; ++j) { a = a + ts; sc->a[lane][j] = a; }
+  }
+  __syncwarp();
+  const int sg0 = (st.sg & 3) - 1, sg1 = ((st.sg >> 2) & 3) - 1, sg2 = ((st.sg >> 4) & 3) - 1;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int j = lane; j <= W; j += 32) {
+      const float v = sc->a[k][j];
+      int cnt[3];
+      cnt[k] = j;
+#pragma unroll
+      for (int d = 1; d < 3; ++d) {
+        const int k2 = (k + d) % 3;
+        const float* b = sc->a[k2];
+        // elements of axis k2 that precede (v, k): value < v, or value == v when k2 < k
+        int lo = 0, hi = W + 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const float x = b[mid];
+          const bool before = (k2 < k) ? (x <= v) : (x < v);
+          if (before) lo = mid + 1; else hi = mid;
+        }
+        cnt[k2] = lo;
+      }
+      const int rank = cnt[0] + cnt[1] + cnt[2];
+      if (rank <= W) {
+        I3 g; g.x = st.cx + sg0 * cnt[0]; g.y = st.cy + sg1 * cnt[1]; g.z = st.cz + sg2 * cnt[2];
+        if (rank < W) { if (key_in_range(g)) sc->out[rank] = pack_key(g); else ok = false; }
+        else { sc->endc[0] = cnt[0]; sc->endc[1] = cnt[1]; sc->endc[2] = cnt[2]; }
+      }
+    }
+  }
+  __syncwarp();
+  const int e0 = sc->endc[0], e1 = sc->endc[1], e2 = sc->endc[2];
+  st.cx += sg0 * e0; st.cy += sg1 * e1; st.cz += sg2 * e2;
+  st.tn0 = sc->a[0][e0]; st.tn1 = sc->a[1][e1]; st.tn2 = sc->a[2][e2];
+  return __all_sync(0xffffffffu, ok);
+}
+
+// evaluation blocks: [0,16), [16,32), [32,64), then 64 steps at a time; a block never straddles a storage segment
+__device__ __forceinline__ void block_of_step(int s, int& s0, int& blen) {
+  if (s < kH0) { s0 = 0; blen = kH0; return; }
+  const int k = 31 - __clz(s >> 4);
+  const int seg = kH0 << k;
+  if (seg <= kWin) { s0 = seg; blen = seg; }
+  else { s0 = seg + ((s - seg) & ~(kWin - 1)); blen = kWin; }
 }
 
 __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n_cast) {
@@ -176,8 +252,10 @@ __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n
   warp_add(&f.cnt->ray_steps, (unsigned long long)h);
 }
 
-// One sweep over the rays [r_lo, r_hi): one warp per ray, one ray step per lane and chunk (chunks: [0,16), [16,32), then 32 at a time).
-__device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r_lo, int r_hi) {
+// One sweep over the rays [r_lo, r_hi): one warp per ray.  A ray is re-evaluated only from the first block that holds a dirty
+// step (the consecutive-collision count at every block start is kept), in blocks of up to 64 steps = two steps per lane; steps that
+// do not exist yet are produced by the warp-parallel ray walk.
+__device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r_lo, int r_hi, WarpDdaScratch* sc) {
   const Obs3& o = f.o3;
   const DevCfg& cfg = f.cfg;
   Counters* cnt = f.cnt;
@@ -188,80 +266,104 @@ __device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r
     const int4 rr = __ldcg((const int4*)&f.rayrec[r]);
     int h = rr.x;
     const int old = rr.y, n = rr.z, last = rr.w;
-    bool need = last == 0;
-    if (!need) {
+    int fd = 0x7fffffff;                                        // first dirty step
+    if (last == 0) fd = 0;
+    else {
       const int upto = (old < h - 1) ? old : h - 1;             // steps 0..upto were examined last time
-      bool dirty = false;
       for (int s = lane; s <= upto; s += 32) {
         const Cand c = ld_cand(&o.cand[cand_index3(o, f.ext_off, r, s)]);
         const uint32_t slot = (uint32_t)cand_value(c.vkey, f.set_offset) & kSetMask;
-        const uint32_t w = __ldcg(&o.stamp[slot]);
-        const int sk = (int)(w >> 8);
-        if (sk > last || (sk == last && !((w & 255u) == 1u && c.tog == last))) dirty = true;
+        if (stamp_dirty(o, slot, last, r)) { fd = s; break; }
       }
-      need = __ballot_sync(0xffffffffu, dirty) != 0u;
+      for (int d = 16; d > 0; d >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, fd, d); fd = t < fd ? t : fd; }
     }
-    if (!need) continue;
-    int run = 0, U = -1;
-    for (int s0 = 0; s0 < n && U < 0;) {
-      const int len = (s0 < 32) ? kH0 : 32;
-      const int cend = (s0 + len < n) ? s0 + len : n;
-      if (s0 >= h) {   // materialise the next chunk: lane 0 continues the ray's DDA (A.7) from the saved state
-        if (lane == 0) {
-          bool ok = true;
-          if ((s0 & (s0 - 1)) == 0) {   // s0 = 16 << k: first chunk of storage segment k (steps [16<<k, 32<<k))
-            const int k = 31 - __clz(s0 >> 4);
-            const long long need_c = s0;
-            const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need_c);
-            if (o.ext_base + off + need_c > o.cand_cap) { set_err(cnt, 4); ok = false; }
-            else f.ext_off[(size_t)r * kExtSegs + k] = off;
-          }
-          if (ok) {
-            Dda d; load_state(d, f.ray_state[r]);
-            for (int s = s0; s < cend; ++s) {
-              const I3 g = dda_next(d);
-              if (!key_in_range(g)) { set_err(cnt, 5); ok = false; break; }
-              st_cand(&o.cand[cand_index3(o, f.ext_off, r, s)], pack_key(g), -2, 0);
-            }
-            if (ok) {
-              RayState st; save_state(st, d); f.ray_state[r] = st;
-              f.rayrec[r].H = cend;
-              atomicAdd(&cnt->ray_steps, (unsigned long long)(cend - s0));
-            }
-          }
-          h = ok ? cend : -1;
+    if (fd == 0x7fffffff) continue;
+    int s0, blen;
+    block_of_step(fd, s0, blen);
+    long long base_ci = cand_index3(o, f.ext_off, r, s0);
+    int run = (s0 == 0) ? 0 : __ldcg(&f.blk_run[base_ci >> 4]);
+    int U = -1;
+    while (s0 < n && U < 0) {
+      const int cend = (s0 + blen < n) ? s0 + blen : n;
+      if (s0 >= h) {   // materialise the block: continue the ray walk (A.7) from the saved state
+        int ok = 1;
+        if (lane == 0 && s0 >= kH0 && (s0 & (s0 - 1)) == 0) {   // s0 = 16 << k: first block of storage segment k (steps [16<<k, 32<<k))
+          const int k = 31 - __clz(s0 >> 4);
+          const long long need_c = s0;
+          const long long off = (long long)atomicAdd(&cnt->n_cand_ext, (unsigned long long)need_c);
+          if (o.ext_base + off + need_c > o.cand_cap) { set_err(cnt, 4); ok = 0; }
+          else f.ext_off[(size_t)r * kExtSegs + k] = off;
         }
-        h = __shfl_sync(0xffffffffu, h, 0);
-        if (h < 0) { U = s0; break; }   // scratch exhausted / index range (flagged): stop here
-        __syncwarp();
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          __syncwarp();
+          base_ci = cand_index3(o, f.ext_off, r, s0);
+          RayState st = f.ray_state[r];
+          const int W = cend - s0;
+          if (ray_state_parallel_ok(st)) {
+            if (!warp_dda_window(st, W, sc, lane)) { set_err(cnt, 5); ok = 0; }
+            else {
+              for (int t = lane; t < W; t += 32) st_cand(&o.cand[base_ci + t], sc->out[t], -2, 0);
+              if (lane == 0) f.ray_state[r] = st;
+            }
+            __syncwarp();
+          } else {
+            if (lane == 0) {
+              Dda d; load_state(d, st);
+              for (int t = 0; t < W; ++t) {
+                const I3 g = dda_next(d);
+                if (!key_in_range(g)) { set_err(cnt, 5); ok = 0; break; }
+                st_cand(&o.cand[base_ci + t], pack_key(g), -2, 0);
+              }
+              if (ok) { save_state(st, d); f.ray_state[r] = st; }
+            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            __syncwarp();
+          }
+          if (ok && lane == 0) { f.rayrec[r].H = cend; atomicAdd(&cnt->ray_steps, (unsigned long long)W); }
+        }
+        if (!ok) { U = s0; break; }   // scratch exhausted / index range (flagged): stop here
+        h = cend;
       }
-      const int s = s0 + lane;
-      bool coll = false;
-      long long ci = 0;
-      uint32_t slot = 0;
-      uint64_t v = 0;
-      Cand c; c.vkey = 0; c.pos = -2; c.tog = 0;
-      const uint64_t my_order = ((uint64_t)r << kOrderStepBits) | (uint64_t)s;
-      if (s < cend) {
-        ci = cand_index3(o, f.ext_off, r, s);
-        c = ld_cand(&o.cand[ci]);
-        v = cand_value(c.vkey, f.set_offset);
-        slot = (uint32_t)v & kSetMask;
-        const uint32_t stale = o.table[slot];   // issued together with the bucket loads
-        const int hi = latest_performed_before3(o, slot, my_order);
-        coll = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v >> kSetBits)) : (stale == (uint32_t)(v >> kSetBits));
+      if (lane == 0 && s0 > 0) f.blk_run[base_ci >> 4] = run;
+      // ---- collisions of the block's steps: two per lane
+      Cand c[2];
+      uint64_t v[2];
+      bool coll[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int s = s0 + q * 32 + lane;
+        c[q].vkey = 0; c[q].pos = -2; c[q].tog = 0; v[q] = 0; coll[q] = false;
+        if (s < cend) { c[q] = ld_cand(&o.cand[base_ci + q * 32 + lane]); v[q] = cand_value(c[q].vkey, f.set_offset); }
       }
-      const unsigned bits = __ballot_sync(0xffffffffu, coll);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int s = s0 + q * 32 + lane;
+        if (s < cend) {
+          const uint32_t slot = (uint32_t)v[q] & kSetMask;
+          const uint32_t stale = o.table[slot];   // issued together with the bucket loads
+          const int hi = latest_performed_before3(o, slot, ((uint64_t)r << kOrderStepBits) | (uint64_t)s);
+          coll[q] = (hi >= 0) ? ((uint32_t)hi == (uint32_t)(v[q] >> kSetBits)) : (stale == (uint32_t)(v[q] >> kSetBits));
+        }
+      }
+      const unsigned bits0 = __ballot_sync(0xffffffffu, coll[0]), bits1 = __ballot_sync(0xffffffffu, coll[1]);
       int brk = -1;
-      for (int j = 0; s0 + j < cend; ++j) {
-        if ((bits >> j) & 1u) ++run; else run = 0;            // fast.cpp:115-119
-        if (run > cfg.maxc) { brk = s0 + j; break; }          // fast.cpp:120-122
+      for (int jj = 0; s0 + jj < cend; ++jj) {
+        const unsigned bit = (jj < 32) ? ((bits0 >> jj) & 1u) : ((bits1 >> (jj - 32)) & 1u);
+        if (bit) ++run; else run = 0;                          // fast.cpp:115-119
+        if (run > cfg.maxc) { brk = s0 + jj; break; }          // fast.cpp:120-122
       }
       const int perf_end = (brk >= 0) ? brk : cend;
-      if (s < perf_end && s >= old) set_performed3(f, c, ci, slot, my_order, v, true, sweep);   // newly performed steps of this chunk
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {                            // newly performed steps of this block
+        const int s = s0 + q * 32 + lane;
+        if (s < perf_end && s >= old)
+          set_performed3(f, c[q], base_ci + q * 32 + lane, (uint32_t)v[q] & kSetMask, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, v[q], true, sweep, r);
+      }
       __syncwarp();
-      if (brk >= 0) U = brk;
+      if (brk >= 0) { U = brk; break; }
       s0 = cend;
+      if (s0 < n) { int nb; block_of_step(s0, s0, nb); blen = nb; if (s0 < h) base_ci = cand_index3(o, f.ext_off, r, s0); }
     }
     if (U < 0) U = n;   // the ray ran its full length
     if (U < old) {      // steps [U, old) are no longer performed
@@ -269,7 +371,7 @@ __device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r
         const long long ci = cand_index3(o, f.ext_off, r, s);
         Cand c = ld_cand(&o.cand[ci]);
         const uint64_t v = cand_value(c.vkey, f.set_offset);
-        set_performed3(f, c, ci, (uint32_t)v & kSetMask, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, v, false, sweep);
+        set_performed3(f, c, ci, (uint32_t)v & kSetMask, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, v, false, sweep, r);
       }
     }
     if (lane == 0) {
@@ -373,11 +475,9 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     const unsigned m = __ballot_sync(0xffffffffu, c);
     if (c) f.cast_seq[__ldcg(&f.warp_off[seq >> 5]) + __popc(m & ((1u << lane) - 1u))] = seq;
   }
-  const int sweep_base0 = ((volatile int*)&f.fc->sweep_base)[0];
-  const bool wrap = sweep_base0 > (1 << 23);     // sweep ids live in 24 bits of the stamp word: restart them long before they overflow
-  if (wrap) for (int i = gtid; i < (int)kSetSize; i += gthreads) f.o3.stamp[i] = 0u;
+  const int sweep_base0 = ((volatile int*)&f.fc->sweep_base)[0];   // sweep ids are monotonic across frames (31 bits: never wraps in practice)
+  const bool wrap = false;
   solve_barrier(bar, epoch);
-  if (gtid == 0) f.fc->sweep_base = wrap ? 0 : sweep_base0;
   timeline_mark(f, tl++);
   // ---- phase 1: ray set-up (first kH0 steps of every ray)
   for (int r0 = (gtid & ~31); r0 < n_cast; r0 += gthreads) fast3_ray_setup(f, r0 + lane, n_cast);
@@ -394,7 +494,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     bool converged = false;
     for (int it = 0; it < max_sweeps; ++it) {
       ++sweep;
-      fast3_sweep(f, sweep, g_lo, g_hi);
+      fast3_sweep(f, sweep, g_lo, g_hi, (WarpDdaScratch*)(s_sort + (threadIdx.x >> 5) * kSortPerWarp));
       solve_barrier(bar, epoch);
       if (tl < kTimelineSlots - 12) timeline_mark(f, tl++);
       const int changed = ((volatile int*)cnt->changed)[sweep & 3];

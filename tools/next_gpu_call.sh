@@ -3,15 +3,15 @@
 set -u
 O=gpurun_out/r02
 mkdir -p $O
-timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_s3.log 2>&1; echo "smoke rc=$?" >> $O/smoke_s3.log
-tail -4 $O/smoke_s3.log
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py tests/test_gpu_more.py tests/test_gpu_fuzz.py -q -m gpu -x -k "fast or fuzz or reset or shard or import or resume or shim" 2>&1 | tail -15 > $O/gpu_fast_s3.log
-tail -6 $O/gpu_fast_s3.log
+timeout 180 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_s31.log 2>&1; echo "smoke rc=$?" >> $O/smoke_s31.log
+tail -4 $O/smoke_s31.log
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > $O/gpu_suite_s31.log
+tail -8 $O/gpu_suite_s31.log
 run() { name=$1; shift; timeout 400 python bench.py --no-cpu-baseline "$@" > $O/bench_${name}.json 2> $O/bench_${name}.err; }
-run fast5_s3 --steps 100 --warmup 10
-KSG_SOLVER=2 timeout 400 python bench.py --no-cpu-baseline --steps 100 --warmup 10 > $O/bench_fast5_s2.json 2> $O/bench_fast5_s2.err
-run merged2_voxel6 --workload merged2 --steps 30 --warmup 5
-for f in $O/bench_fast5_s3.json $O/bench_fast5_s2.json $O/bench_merged2_voxel6.json; do python - $f <<'PY'
+run fast5_s31 --steps 100 --warmup 10
+run merged2_hot --workload merged2 --steps 30 --warmup 5
+run merged5_hot --workload merged5 --steps 30 --warmup 5
+for f in $O/bench_fast5_s31.json $O/bench_merged2_hot.json $O/bench_merged5_hot.json; do python - $f <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1])); r=d['roofline']
@@ -21,3 +21,4 @@ except Exception as e:
     print(sys.argv[1], 'ERR', e); print(open(sys.argv[1].replace('.json','.err')).read()[-1500:])
 PY
 done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fast5_s31.csv python tools/run_frames.py fast5 14 > $O/ncu_fast5.log 2>&1
