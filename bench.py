@@ -196,23 +196,25 @@ def best_cpu_arm(workload, frames, cam):
 
 
 def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the tile-apply kernel, per launch, from the committed
-    `ncu --set full` capture of this workload (profiles/r01/prof_apply_<workload>.raw.csv); None when there is none."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's update kernel, from the newest committed `ncu --set full`
+    capture (profiles/r*/prof_apply_<workload>.raw.csv) -> (bytes or None, which capture).  A capture describes the kernel of the commit it
+    was taken at; the file name carries the round."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01", f"prof_apply_{workload}.raw.csv")
-    if not os.path.exists(path):
-        return None
-    try:
-        rows = list(csv.reader(open(path)))
-        hdr, units, vals = rows[0], rows[1], rows[-1]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(name)
-            tot += float(vals[i].replace(",", "")) * scale.get(units[i], 1.0)
-        return tot
-    except Exception:
-        return None
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"prof_apply_{workload}*.raw.csv")))
+    for path in reversed(cands):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units, vals = rows[0], rows[1], rows[-1]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            tot = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                k = hdr.index(name)
+                tot += float(vals[k].replace(",", "")) * scale.get(units[k], 1.0)
+            return tot, os.path.relpath(path, ROOT) + " (ncu --set full, one launch)"
+        except Exception:
+            continue
+    return None, None
 
 
 def peaks():
@@ -265,45 +267,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="fast5", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--hot-voxels", type=int, default=2, choices=[0, 1, 2],
-                    help="merged workloads: ksg_config.hot_voxel_mode (1 = parallel pre-pass for the semantic rows of hot voxels, 2 = + TSDF fixed-point check)")
-    ap.add_argument("--merged-bundle-order", default="libstdcxx", choices=["canonical", "libstdcxx"],
-                    help="merged workloads: bundle order (ksg_config.merged_bundle_order); libstdcxx = the reference's unordered_map order")
-    ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial"],
-                    help="N > 1: sequence = one stream + map per rank (weak scaling, default); spatial = ONE stream and map, every rank "
-                         "receives every frame (NCCL broadcast from rank 0) and applies only the tiles it owns (strong scaling)")
-    ap.add_argument("--profile-frames", type=int, default=20, help="frames of the separate per-phase profiling pass")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        return run_reference(args)
-
+def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
+    """Every leg of one workload on this rank; rank 0 gets the result dictionary (the others None)."""
     import torch
     import torch.distributed as dist
     from kimera_semantics_b200.capi import Integrator
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the integrator has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    itype, w, h, vs, C, _, _ = WORKLOADS[args.workload]
-    n = args.warmup + args.steps
+    world, rank, local_rank = ctx["world"], ctx["rank"], ctx["local_rank"]
+    itype, w, h, vs, C, _, _ = WORKLOADS[workload]
+    n = warmup + steps
     spatial = args.sharding == "spatial" and world > 1
-    cam, frames = gen_frames(args.workload, n, 0 if spatial else rank)
+    cam, frames = gen_frames(workload, n, 0 if spatial else rank)
     P = w * h
 
     def barrier():
@@ -316,7 +289,7 @@ def main():
     d_depth = [torch.from_numpy(f[0]).cuda() for f in frames]
     d_label = [torch.from_numpy(f[1]).cuda() for f in frames]
     total_in = sum(t.numel() * t.element_size() for t in d_depth + d_label)
-    cfg = make_cfg(args.workload, device=local_rank)
+    cfg = make_cfg(workload, device=local_rank)
     cfg.merged_bundle_order = 1 if args.merged_bundle_order == "libstdcxx" else 0
     cfg.hot_voxel_mode = int(args.hot_voxels)
     if spatial:
@@ -327,7 +300,7 @@ def main():
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    for i in range(args.warmup):
+    for i in range(warmup):
         integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -339,7 +312,7 @@ def main():
     # driver never blocks the host inside the region (its frame has no read-back); the voxel-update count of exactly these frames
     # is taken from an identical untimed replay below.
     ev0.record(tstream)
-    for i in range(args.warmup, n):
+    for i in range(warmup, n):
         integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream)
     ev1.record(tstream)
     barrier()
@@ -353,24 +326,22 @@ def main():
     # ---------------- per-phase profiling pass + untimed replay of the timed frames (separate map, not part of `value`) ----------------
     integ.close()
     integ = Integrator(cfg)
-    npf = min(args.profile_frames, args.steps)
-    for i in range(args.warmup):
+    npf = min(profile_frames, steps)
+    for i in range(warmup):
         integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream)
     integ.set_profiling(True)
     p_updates = 0
     timeline = None
-    for i in range(args.warmup, args.warmup + npf):
-        st = integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream,
-                                          want_stats=True)
+    for i in range(warmup, warmup + npf):
+        st = integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream, want_stats=True)
         p_updates += st.voxel_updates
     if itype == KSG_INTEGRATOR_FAST:
         timeline = integ.fast_timeline()
     prof = integ.get_profile()
     integ.set_profiling(False)
     updates = p_updates
-    for i in range(args.warmup + npf, n):       # rest of the replay: same frames as the timed region -> their voxel updates
-        st = integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream,
-                                          want_stats=True)
+    for i in range(warmup + npf, n):       # rest of the replay: same frames as the timed region -> their voxel updates
+        st = integ.integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, stream, want_stats=True)
         updates += st.voxel_updates
     integ.close()
     t = torch.tensor([ms, float(updates)], device="cuda", dtype=torch.float64)
@@ -385,100 +356,214 @@ def main():
     jobs = 1 if spatial else world          # spatial: every rank works on the same frames
     if spatial:
         updates_all = float(updates)
-    value = jobs * args.steps / (ms / 1e3)
+    value = jobs * steps / (ms / 1e3)
     mups = updates_all / (ms / 1e3) / 1e6
-    apply_ms = prof["tile_apply"] / max(1, prof["frames"])
+    nprof = max(1, prof["frames"])
+    phase_ms = {k: prof[k] / nprof for k in Integrator.PHASES}
     alg_bytes = (p_updates / max(1, npf)) * (34 + 8 * C) + P * 5
     peak, peak_kind = peaks()
-    achieved = alg_bytes / (apply_ms / 1e3) / 1e9 if apply_ms > 0 else 0.0
+    # the kernel that carries the roofline number: the phase with the largest share of the frame
+    kernel_of_phase = ({"classify+start_set": "k_fast_count + k_fast_classify + k_fast_start_eval (+ compaction / ray set-up inside k_fast_solve3)",
+                        "fixpoint|bundling": "k_fast_solve3 (observed-set sweeps)", "ray_emit": "k_fast_solve3 (table commit + block allocation)",
+                        "record_sort": "k_fast_solve3 (records -> tile segments)", "alloc+tile_heads": "-", "tile_apply": "k_tile_apply_fast"}
+                       if itype == KSG_INTEGRATOR_FAST else
+                       {"classify+start_set": "k_classify", "fixpoint|bundling": "bundle sort + k_bundle_order + k_bundle_merge", "ray_emit": "k_emit_merged",
+                        "record_sort": "cub::DeviceRadixSort (stable, voxel bits only)", "alloc+tile_heads": "k_block_init + k_voxel_heads",
+                        "tile_apply": "k_voxel_apply_long + k_voxel_apply_short (+ hot-voxel pre-pass)"})
+    shares = {k: v for k, v in phase_ms.items() if k != "frame"}
+    top_phase = max(shares, key=shares.get)
+    top_ms = shares[top_phase]
+    apply_ms = phase_ms["tile_apply"]
+    frame_ms = phase_ms["frame"] if phase_ms["frame"] > 0 else ms / steps
+    ach = lambda t_ms: alg_bytes / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0
 
-    # ---------------- end-to-end leg (host buffers through the C-ABI) ----------------
+    # ---------------- end-to-end legs (host buffers through the C-ABI) ----------------
     barrier()
     # the step's inputs live in page-locked host memory (the contract's "pinned host memory"); the library copies from it
     pin_d = [torch.from_numpy(f[0]).pin_memory() for f in frames]
     pin_l = [torch.from_numpy(f[1]).pin_memory() for f in frames]
     hd = [t.numpy() for t in pin_d]
     hl = [t.numpy() for t in pin_l]
-    e2e_passes = []
-    e2e_iters = []   # observed-set sweeps per timed frame: every sweep after the first batch costs one counter read-back
-    for _pass in range(2):   # two identical passes of exactly K timed steps each (fresh map); the faster one is reported:
-        integ = Integrator(cfg)   # the box is shared and a single ~70 ms host stall triples a 75 ms wall-clock region
+    e2e = {}
+    for mode in ("pipelined", "sync"):
+        passes = []
+        for _pass in range(2):   # two identical passes of exactly K timed steps each (fresh map); the faster one is reported:
+            integ = Integrator(cfg)   # the box is shared and a single ~70 ms host stall triples a 75 ms wall-clock region
+            got = []
+            if spatial:
+                # rank 0 owns the camera stream: H2D on rank 0, NCCL broadcast of depth + label to every rank, then all ranks integrate
+                buf_d = torch.empty((h, w), dtype=torch.float32, device="cuda")
+                buf_l = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+
+                def run(lo, hi):
+                    for i in range(lo, hi):
+                        if rank == 0:
+                            buf_d.copy_(pin_d[i], non_blocking=True)
+                            buf_l.copy_(pin_l[i], non_blocking=True)
+                        dist.broadcast(buf_d, 0)
+                        dist.broadcast(buf_l, 0)
+                        got.append(integ.integrate_depth_device(frames[i][2], buf_d.data_ptr(), buf_l.data_ptr(), w, h, cam.K, stream, want_stats=True))
+            elif mode == "sync":
+                def run(lo, hi):      # the reference's calling convention: the call returns when the frame is integrated
+                    for i in range(lo, hi):
+                        got.append(integ.integrate_depth(frames[i][2], hd[i], hl[i], cam.K))
+            else:
+                def run(lo, hi):      # camera-stream convention: submit frame i, then collect frame i-1 (its H2D overlaps frame i-1's kernels)
+                    for i in range(lo, hi):
+                        integ.integrate_depth_async(frames[i][2], hd[i], hl[i], cam.K)
+                        if i > lo:
+                            got.append(integ.wait_frame())
+                    got.append(integ.wait_frame())
+            run(0, warmup)
+            barrier()
+            t0 = time.perf_counter()
+            run(warmup, n)
+            integ.sync()
+            passes.append(time.perf_counter() - t0)
+            integ.close()
+        te = torch.tensor([min(passes)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e[mode] = {"value": jobs * steps / float(te[0]), "pass_seconds": passes}
         if spatial:
-            # rank 0 owns the camera stream: H2D on rank 0, NCCL broadcast of depth + label to every rank, then all ranks integrate
-            buf_d = torch.empty((h, w), dtype=torch.float32, device="cuda")
-            buf_l = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+            e2e["sync"] = e2e[mode]
+            break
 
-            def step(i):
-                if rank == 0:
-                    buf_d.copy_(pin_d[i], non_blocking=True)
-                    buf_l.copy_(pin_l[i], non_blocking=True)
-                dist.broadcast(buf_d, 0)
-                dist.broadcast(buf_l, 0)
-                st = integ.integrate_depth_device(frames[i][2], buf_d.data_ptr(), buf_l.data_ptr(), w, h, cam.K, stream, want_stats=True)
-                e2e_iters.append(int(st.fixpoint_iterations))
-        else:
-            def step(i):
-                st = integ.integrate_depth(frames[i][2], hd[i], hl[i], cam.K)
-                e2e_iters.append(int(st.fixpoint_iterations))
-        for i in range(args.warmup):
-            step(i)
-        barrier()
+    # ---------------- several independent sequences on ONE GPU (how far the machine is from full at this frame size) ----------------
+    multi = None
+    if world == 1 and args.sequences_per_gpu > 1 and itype == KSG_INTEGRATOR_FAST:
+        K = args.sequences_per_gpu
+        integs = [Integrator(cfg) for _ in range(K)]
+        streams = [torch.cuda.Stream() for _ in range(K)]
+        for i in range(warmup):
+            for k in range(K):
+                integs[k].integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, streams[k].cuda_stream)
+        torch.cuda.synchronize()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
         t0 = time.perf_counter()
-        for i in range(args.warmup, n):
-            step(i)
-        integ.sync()
-        e2e_passes.append(time.perf_counter() - t0)
-        integ.close()
-    e2e_s = min(e2e_passes)
-    te = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = jobs * args.steps / float(te[0])
+        for k in range(K):
+            e0[k].record(streams[k])
+        for i in range(warmup, n):
+            for k in range(K):
+                integs[k].integrate_depth_device(frames[i][2], d_depth[i].data_ptr(), d_label[i].data_ptr(), w, h, cam.K, streams[k].cuda_stream)
+        for k in range(K):
+            e1[k].record(streams[k])
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        span = max(e0[0].elapsed_time(e1[k]) for k in range(K))
+        for it in integs:
+            it.sync()
+            it.close()
+        multi = {"sequences": K, "value": K * steps / (span / 1e3), "unit": "frames/s", "wall_value": K * steps / wall,
+                 "note": "K integrators (own map each) fed round-robin on K streams of one GPU; device time from the first stream's start to the last stream's end"}
 
+    if rank != 0:
+        return None
+    cpu = None
+    if with_cpu:
+        cores = os.cpu_count() or 1
+        arm, threads, calib = best_cpu_arm(workload, frames[warmup:], cam)
+        c_all = cpu_baseline(workload, frames[warmup:], cam, threads, arm=arm)
+        cpu = {"value": c_all["fps"], "unit": "frames/s", "cores": threads, "kind": arm, "host_cores": cores,
+               "implementation": CPU_ARMS[arm],
+               "sample": f"{c_all['frames']} frames of the same stream (from the first timed frame, empty map); fastest (implementation, "
+                         f"integrator_threads) pair of the calibration = {arm} with {threads} threads",
+               "calibration_fps": calib}
+        if arm == "port":
+            cpu["mvoxel_updates_per_s"] = c_all["mupdates_per_s"]
+    head = e2e.get("pipelined", e2e["sync"])
+    traffic, traffic_src = ncu_traffic(workload)
+    return {
+        "metric": "depth_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if spatial else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mvoxel_updates_per_s": mups,
+        "config": {"workload": f"{w}x{h} depth+label stream, {vs * 100:.0f} cm voxels, {C} classes, "
+                               f"{'fast' if itype == KSG_INTEGRATOR_FAST else 'merged'} integrator (BASELINE.json configs)",
+                   "name": workload, "voxels_per_side": 16, "frames_distinct": n, "merged_bundle_order": args.merged_bundle_order,
+                   "hot_voxel_mode": int(args.hot_voxels),
+                   "l2_policy": f"every step reads a different frame ({total_in / 1e6:.0f} MB of inputs cycled, larger than the 126 MB L2 "
+                                "when steps >= 90) and a different part of the map; no explicit flush",
+                   "parallelism": ("one map spatially sharded by tile owner over the GPUs; frames broadcast from rank 0 with NCCL" if spatial
+                                   else "one sequence + map per GPU, no collective") if world > 1 else "single GPU",
+                   "map_blocks_after_run": blocks},
+        "clocks": clocks,
+        "e2e": {"value": head["value"], "unit": "frames/s", "h2d_bytes_per_step": P * 5,
+                # fast: one copy of the frame counters (152 B) + the driver state with the solve kernel's time marks (568 B) per frame;
+                # merged: the frame counters twice (record count for the sort, end of frame)
+                "d2h_bytes_per_step": 152 + 568 if itype == KSG_INTEGRATOR_FAST else 2 * 152,
+                "mode": "pipelined" if "pipelined" in e2e else "sync",
+                "sync_value": e2e["sync"]["value"],
+                "note": "host frames in page-locked memory through the C-ABI.  `value`: ksg_integrate_depth_async + ksg_wait_frame - frame i is "
+                        "submitted (H2D of depth+label on a copy stream, then its kernels), then the statistics of frame i-1 are read back "
+                        "(one D2H of the counter blocks per step); `sync_value`: ksg_integrate_depth, which returns when the frame is "
+                        "integrated (the reference's calling convention).  Wall clock, faster of two identical K-step passes",
+                "pass_seconds": head["pass_seconds"], "sync_pass_seconds": e2e["sync"]["pass_seconds"]},
+        "gpu_launches": int(launches),
+        "library_calls": int(libcalls),
+        "multi_sequence": multi,
+        "roofline": {"bound": "hbm", "achieved": ach(top_ms), "peak": peak, "unit": "GB/s", "frac": ach(top_ms) / peak if peak else None,
+                     "kernel": kernel_of_phase[top_phase], "phase": top_phase, "kernel_ms": top_ms,
+                     "frame_frac": ach(frame_ms) / peak if peak else None, "frame_ms": frame_ms,
+                     "tile_apply_frac": ach(apply_ms) / peak if peak and apply_ms > 0 else None, "tile_apply_ms": apply_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "algorithmic bytes of one frame = updates * (34 + 8 C) + pixels * 5 (SURVEY.md 8d); `frac` divides them by the duration of "
+                             "the phase with the largest share of the frame (`kernel`), `frame_frac` by the whole frame, `tile_apply_frac` by the update "
+                             "kernel alone; durations are device-timed inside the library (CUDA events; clock64 marks inside the persistent kernel)",
+                     "phase_ms_per_frame": phase_ms,
+                     "solve_kernel_timeline_last_profiled_frame": timeline},
+        "cpu_baseline": cpu,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="fast5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hot-voxels", type=int, default=0, choices=[0, 1, 2],
+                    help="merged workloads: ksg_config.hot_voxel_mode (1 = parallel pre-pass for the semantic rows of hot voxels, 2 = + TSDF fixed-point check)")
+    ap.add_argument("--merged-bundle-order", default="libstdcxx", choices=["canonical", "libstdcxx"],
+                    help="merged workloads: bundle order (ksg_config.merged_bundle_order); libstdcxx = the reference's unordered_map order")
+    ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial"],
+                    help="N > 1: sequence = one stream + map per rank (weak scaling, default); spatial = ONE stream and map, every rank "
+                         "receives every frame (NCCL broadcast from rank 0) and applies only the tiles it owns (strong scaling)")
+    ap.add_argument("--profile-frames", type=int, default=20, help="frames of the separate per-phase profiling pass")
+    ap.add_argument("--sequences-per-gpu", type=int, default=4, help="N = 1, fast: also measure K independent sequences on one GPU (0/1: skip)")
+    ap.add_argument("--extra-workloads", default="merged2", help="comma list of further workloads measured (briefly) into `workloads` at N = 1; '' = none")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the integrator has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = {"world": world, "rank": rank, "local_rank": local_rank}
+    line = measure(args, args.workload, args.steps, args.warmup, ctx, not args.no_cpu_baseline, args.profile_frames)
+    extra = {}
+    if world == 1 and args.extra_workloads:
+        for wl in [x for x in args.extra_workloads.split(",") if x and x != args.workload]:
+            # BASELINE.json configs[2] etc. in the same JSON line: a short run (frames are 10-100x heavier than the headline's)
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.sequences_per_gpu = 0
+            extra[wl] = measure(sub_args, wl, min(args.steps, 30), 5, ctx, not args.no_cpu_baseline, min(args.profile_frames, 10))
     if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            arm, threads, calib = best_cpu_arm(args.workload, frames[args.warmup:], cam)
-            c_all = cpu_baseline(args.workload, frames[args.warmup:], cam, threads, arm=arm)
-            cpu = {"value": c_all["fps"], "unit": "frames/s", "cores": threads, "kind": arm, "host_cores": cores,
-                   "implementation": CPU_ARMS[arm],
-                   "sample": f"{c_all['frames']} frames of the same stream (from the first timed frame, empty map); fastest (implementation, "
-                             f"integrator_threads) pair of the calibration = {arm} with {threads} threads",
-                   "calibration_fps": calib}
-            if arm == "port":
-                cpu["mvoxel_updates_per_s"] = c_all["mupdates_per_s"]
-        line = {
-            "metric": "depth_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if spatial else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "mvoxel_updates_per_s": mups,
-            "config": {"workload": f"{w}x{h} depth+label stream, {vs * 100:.0f} cm voxels, {C} classes, "
-                                   f"{'fast' if itype == KSG_INTEGRATOR_FAST else 'merged'} integrator (BASELINE.json configs)",
-                       "name": args.workload, "voxels_per_side": 16, "frames_distinct": n, "merged_bundle_order": args.merged_bundle_order, "hot_voxel_mode": int(args.hot_voxels),
-                       "l2_policy": f"every step reads a different frame ({total_in / 1e6:.0f} MB of inputs cycled, larger than the 126 MB L2 "
-                                    "when steps >= 90) and a different part of the map; no explicit flush",
-                       "parallelism": ("one map spatially sharded by tile owner over the GPUs; frames broadcast from rank 0 with NCCL" if spatial
-                                       else "one sequence + map per GPU, no collective") if world > 1 else "single GPU",
-                       "map_blocks_after_run": blocks},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": P * 5,
-                    # read-backs of the 152-byte counter block: fast = one after the first batch of 4 solver sweeps, one per further
-                    # sweep, one at frame end; merged = two (three in the reference bundle order)
-                    "d2h_bytes_per_step": int(round(152 * ((2 + max(0.0, float(np.mean(e2e_iters)) - 4.0)) if itype == KSG_INTEGRATOR_FAST
-                                                           else (3 if args.merged_bundle_order == "libstdcxx" else 2)))) if e2e_iters else 304,
-                    "note": "ksg_integrate_depth on page-locked host frames: H2D of depth+label + integrate + counter read-backs per step, wall clock; "
-                            "faster of two identical K-step passes", "pass_seconds": e2e_passes},
-            "gpu_launches": int(launches),
-            "library_calls": int(libcalls),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": ncu_traffic(args.workload), "traffic_source": "profiles/r01/prof_apply_%s.raw.csv (ncu --set full, one launch)" % args.workload,
-                         "kernel": "k_tile_apply", "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": apply_ms,
-                         "phase_ms_per_frame": {k: prof[k] / max(1, prof["frames"]) for k in Integrator.PHASES},
-                         "solve_kernel_timeline_last_profiled_frame": timeline},
-            "cpu_baseline": cpu,
-        }
+        line["workloads"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -189,6 +189,15 @@ int32_t ksg_integrate_depth_device_k64(ksg_integrator* h, const float* T_G_C_hos
                                        const uint8_t* d_label, int32_t width, int32_t height,
                                        const double* K_host, void* cuda_stream, ksg_frame_stats* stats);
 
+/* Pipelined variant of ksg_integrate_depth for a camera stream: enqueues the host->device copy of THIS frame on a copy stream (so it
+ * overlaps the kernels of the previous frame) and the frame's kernels behind it, and returns without waiting; at most two frames are in
+ * flight.  ksg_wait_frame completes the OLDEST outstanding frame and returns its statistics / status (the reference call is synchronous:
+ * a caller that needs those semantics calls ksg_wait_frame right after, or uses ksg_integrate_depth).  Page-locked caller buffers are read
+ * asynchronously and must stay unchanged until the frame's ksg_wait_frame returns; pageable buffers are staged before the call returns. */
+int32_t ksg_integrate_depth_async(ksg_integrator* h, const float* T_G_C, const float* depth, const uint8_t* label,
+                                  int32_t width, int32_t height, const float* K);
+int32_t ksg_wait_frame(ksg_integrator* h, ksg_frame_stats* stats);
+
 /* Colour -> label table: SemanticLabel2Color::getSemanticLabelFromColor (color.cpp:69-82). n entries
  * of (r,g,b) -> label (alpha is forced to 255 by the callers fast.cpp:157, merged.cpp:87). A colour
  * that is not in the table maps to label 0 (color.cpp:80). */
@@ -257,9 +266,10 @@ int64_t ksg_debug_tile_times(ksg_integrator* h, int32_t enable, int64_t capacity
 /* Debug aid (fast integrator, profiling enabled): SM-clock stamps that block 0 of the frame's persistent solve kernel took at its phase
  * boundaries during the LAST frame: out[0] kernel start, out[1] rays compacted, out[2] rays set up, out[3 .. 2+sweeps] end of each
  * observed-set sweep, out[52] sweeps done, out[53] table commit + ray emit done, out[54] records counted per tile, out[55] tile
- * segments allocated + new blocks constructed, out[56] records scattered (kernel end); *sweeps = sweeps of that frame, *clock_khz = SM
- * clock the stamps count in.  Returns the number of slots written (64) or 0. */
-int64_t ksg_debug_fast_timeline(ksg_integrator* h, int64_t* out64, int64_t* sweeps, double* clock_khz);
+ * segments allocated + new blocks constructed, out[56] records scattered (kernel end); out[64..79]: maxima / counts gathered inside the
+ * kernel (longest single ray set-up / evaluation in clocks, rays evaluated, blocks evaluated / materialised, ...); *sweeps = sweeps of that
+ * frame, *clock_khz = SM clock the stamps count in.  Returns the number of slots written (80) or 0. */
+int64_t ksg_debug_fast_timeline(ksg_integrator* h, int64_t* out80 /* 64 time marks + 16 debug maxima / counts */, int64_t* sweeps, double* clock_khz);
 
 /* Debug aid for the next optimisation (not on the integration path): evaluates  s <- fl(s + terms[k]), k = 0..n-1  (s0 < 0, terms <= 0,
  * float32, round to nearest even) with ONE warp as an exact associative scan (lanes = records, csrc/ksg_chain.cuh) and returns the

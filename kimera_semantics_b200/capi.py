@@ -142,7 +142,7 @@ def default_config(integrator_type: int = KSG_INTEGRATOR_FAST, voxel_size: float
     cfg.shard_rank = 0
     cfg.shard_count = 1
     cfg.merged_bundle_order = KSG_BUNDLE_ORDER_LIBSTDCXX   # the reference's order (merged.cpp:210-231)
-    cfg.hot_voxel_mode = 2   # merged, C <= 32: exact parallel pre-pass for voxels with thousands of records per frame
+    cfg.hot_voxel_mode = 0   # opt-in: measured slower than the per-voxel kernels alone (profiles/r02/bench_merged2_hot.json)
     return cfg
 
 
@@ -223,6 +223,10 @@ def load_library(path: Optional[str] = None):
     lib.ksg_unordered_map_schedule.restype = C.c_int64
     lib.ksg_debug_fast_timeline.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     lib.ksg_debug_fast_timeline.restype = C.c_int64
+    lib.ksg_integrate_depth_async.argtypes = [H, fp, fp, u8p, C.c_int32, C.c_int32, fp]
+    lib.ksg_integrate_depth_async.restype = C.c_int32
+    lib.ksg_wait_frame.argtypes = [H, sp]
+    lib.ksg_wait_frame.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -235,7 +239,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
-               "ksg_debug_chain_sum", "ksg_debug_fast_timeline"]
+               "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -365,6 +369,19 @@ class Integrator:
                                                  w, h, _ptr(K, C.c_float), C.byref(st)), "ksg_integrate_depth")
         return st
 
+    def integrate_depth_async(self, T_G_C, depth, label, K):
+        """Pipelined host-buffer entry: returns once the frame is enqueued; wait_frame() completes the oldest outstanding frame."""
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        K = np.ascontiguousarray(K, np.float32)
+        h, w = depth.shape
+        self._check(self.lib.ksg_integrate_depth_async(self.handle, _ptr(T, C.c_float), _ptr(depth, C.c_float), _ptr(label, C.c_uint8),
+                                                       w, h, _ptr(K, C.c_float)), "ksg_integrate_depth_async")
+
+    def wait_frame(self) -> KsgFrameStats:
+        st = KsgFrameStats()
+        self._check(self.lib.ksg_wait_frame(self.handle, C.byref(st)), "ksg_wait_frame")
+        return st
+
     def integrate_depth_k64(self, T_G_C, depth, label, K64) -> KsgFrameStats:
         """Depth entry with float64 intrinsics (fx fy cx cy), as sensor_msgs/CameraInfo holds them."""
         T = np.ascontiguousarray(T_G_C, np.float32)
@@ -416,7 +433,7 @@ class Integrator:
 
     def fast_timeline(self) -> Dict[str, object]:
         """Phase boundaries of the last frame's persistent solve kernel in microseconds from its start (fast integrator, profiling on)."""
-        out = (C.c_int64 * 64)()
+        out = (C.c_int64 * 80)()
         sweeps, khz = C.c_int64(), C.c_double()
         n = int(self.lib.ksg_debug_fast_timeline(self.handle, out, C.byref(sweeps), C.byref(khz)))
         if n == 0:
@@ -427,7 +444,13 @@ class Integrator:
         return {"sweeps": ns, "compact_us": us(0, 1), "ray_setup_us": us(1, 2),
                 "sweep_us": [us(2 + i, 3 + i) for i in range(max(0, min(ns, 48)))],
                 "commit_emit_us": us(52, 53), "tile_count_us": us(53, 54), "tile_alloc_block_init_us": us(54, 55), "scatter_us": us(55, 56),
-                "solve_kernel_us": us(0, 56)}
+                "solve_kernel_us": us(0, 56),
+                "phase0_us": {"file_shared_slot_visitors": us(0, 57) if t[57] else None, "sort_shared_slots": us(57, 58) if t[58] else None,
+                              "scan_cast_counts": us(58 if t[58] else 0, 59), "compaction": us(59, 1)},
+                "debug": {"max_ray_setup_us": t[64] / (khz.value / 1e3), "max_ray_setup_insert_us": t[65] / (khz.value / 1e3),
+                          "max_ray_eval_us": t[67] / (khz.value / 1e3), "ray_evals": t[68], "blocks_evaluated": t[69], "blocks_materialised": t[70],
+                          "ray_evals_that_changed": t[71], "max_shared_slot_visitors": t[72], "shared_slot_visitors": t[73],
+                          "shared_slots": t[74], "rays": t[75]}}
 
     def sync(self):
         self._check(self.lib.ksg_sync(self.handle), "ksg_sync")

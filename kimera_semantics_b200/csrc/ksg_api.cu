@@ -107,6 +107,7 @@ struct ksg_integrator {
   uint32_t* bord_hash = nullptr;
   int* bundle_f2 = nullptr;
   int* bord_scratch = nullptr;       // one allocation behind every array of BordBuf
+  unsigned long long* d_scan_tot = nullptr;   // per-CTA totals of k_bundle_scan
   BordBuf bord{};
 
   // merged, hot_voxel_mode = 1 (ksg_hot.cuh)
@@ -244,7 +245,7 @@ void free_all(ksg_integrator* h) {
                   h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
-                  h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
+                  h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->d_scan_tot, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
                   h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->blk_run, h->stamp64, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -497,7 +498,10 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   f.s_visits = (int*)(h->clear_00 + (size_t)kSetSize * 9); f.mixed_list = h->mixed_list; f.m_list = h->m_list;
   const bool s3 = h->solver == 3;
 
-  if (h->profiling) cudaEventRecord(h->ev[0], s);
+  if (h->profiling) {
+    cudaEventRecord(h->ev[0], s);
+    KSG_CUDA(cudaMemsetAsync(h->d_fc->dbg, 0, sizeof(h->d_fc->dbg), s));
+  }
   KSG_CUDA(cudaMemsetAsync(h->clear_ff, 0xFF, (size_t)kSetSize * 16, s));
   KSG_CUDA(cudaMemsetAsync(h->clear_00, 0x00, (size_t)kSetSize * (s3 ? 13 : 5), s));
   KSG_CUDA(cudaMemsetAsync(h->start_min, 0x7F, sizeof(int) * kSetSize, s));
@@ -758,7 +762,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     k_bundle_merge<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, bundle_heads, h->bstart, h->ks_sorted, h->seq_sorted, cap, h->pt_pC,
                                                    h->pt_label, h->hist, h->ray_param, h->ray_flags, h->b_key, h->nsteps);
     ++h->n_launches;
-    k_bundle_alloc<<<grid_for(cap, 256), 256, 0, s>>>(h->d_cnt, h->nsteps, h->b_base, h->rec_cap);
+    k_bundle_scan<<<kBordCluster, kBordThreads, 0, s>>>(h->d_cnt, h->nsteps, h->b_base, h->rec_cap, h->d_scan_tot);
     int rc = fetch_counters(h, s);
     if (rc) return rc;
     if (h->profiling) cudaEventRecord(h->ev[2], s);
@@ -784,7 +788,8 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
     // significant key bits: [order 23][voxel 9][tile key < ht_cap * tiles_per_block]
     int end_bit = 32;
     while (end_bit < 64 && (1ull << (end_bit - 32)) < (unsigned long long)h->ht_cap * (unsigned long long)dc.tiles_per_block) ++end_bit;
-    KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, 0, end_bit, s));
+    // merged: the records were laid out by (bundle rank, step), so a stable sort on the voxel bits [23, end) keeps the rank order
+    KSG_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_temp, tb, h->rec_a, h->rec_b, n_records, fast ? 0 : kRecOrdBits, end_bit, s));
     if (h->profiling) cudaEventRecord(h->ev[4], s);
     ++h->n_launches;
     k_block_init<<<h->sm_count * 4, 256, 0, s>>>(dc, h->d_cnt, h->map);
@@ -960,7 +965,7 @@ void ksg_default_config(ksg_config* c, int32_t integrator_type, float voxel_size
   c->shard_rank = 0;
   c->shard_count = 1;
   c->merged_bundle_order = KSG_BUNDLE_ORDER_LIBSTDCXX;   // the reference's unordered_map iteration order (merged.cpp:210-231)
-  c->hot_voxel_mode = 2;   // merged, C <= 32: exact parallel pre-pass for the voxels that receive thousands of records per frame
+  c->hot_voxel_mode = 0;   // opt-in (measured slower than the per-voxel kernels alone, profiles/r02/bench_merged2_hot.json)
 }
 
 #define KSG_STR_(x) #x
@@ -1126,6 +1131,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     KSG_CUDA(dmalloc(&h->bstart, 2 * N)); KSG_CUDA(dmalloc(&h->bundle_f, N));
     KSG_CUDA(dmalloc(&h->hist, N * dc.C)); KSG_CUDA(dmalloc(&h->tmp, (N + 1) * dc.C));  // + the all-zero row
     KSG_CUDA(dmalloc(&h->b_key, N)); KSG_CUDA(dmalloc(&h->b_base, N));
+    KSG_CUDA(dmalloc(&h->d_scan_tot, 16));
     // per-voxel apply kernels (default); the tile kernel stays for apply_mode 1 and KSG_MERGED_TILE_APPLY=1
     h->voxel_apply = cfg->apply_mode == 0;
     if (const char* e = std::getenv("KSG_MERGED_TILE_APPLY")) if (std::atoi(e) != 0) h->voxel_apply = false;
@@ -1367,6 +1373,69 @@ int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* dept
   if (!K) return KSG_ERR_INVALID_ARGUMENT;
   const double K64[4] = {K[0], K[1], K[2], K[3]};
   return ksg_integrate_depth_k64(h, T, depth, label, width, height, K64, stats);
+}
+
+// Pipelined host-buffer entry: the H2D copy of this frame runs on a copy stream into one of two device staging buffers, so it
+// overlaps the kernels of the previous frame; the frame's kernels wait for the copy with an event.  Returns without waiting.
+int32_t ksg_integrate_depth_async(ksg_integrator* h, const float* T, const float* depth, const uint8_t* label, int32_t width,
+                                  int32_t height, const float* K) {
+  if (!h || !T || !K || width <= 0 || height <= 0 || !depth || !label) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  const size_t P = (size_t)width * height;
+  if ((int64_t)P > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");
+  const size_t o_lab = (P * 4 + 255) / 256 * 256;
+  const size_t total = o_lab + (P + 255) / 256 * 256;
+  const int slot = h->in_slot;
+  h->in_slot ^= 1;
+  if (total > h->in2_bytes[slot]) {
+    if (h->in2_used[slot]) KSG_CUDA(cudaEventSynchronize(h->ev_free[slot]));
+    if (h->d_in2[slot]) cudaFree(h->d_in2[slot]);
+    if (h->h_stage2[slot]) cudaFreeHost(h->h_stage2[slot]);
+    h->d_in2[slot] = nullptr; h->h_stage2[slot] = nullptr;
+    KSG_CUDA(cudaMalloc((void**)&h->d_in2[slot], total));
+    KSG_CUDA(cudaMallocHost((void**)&h->h_stage2[slot], total));
+    h->in2_bytes[slot] = total;
+  }
+  // the slot's previous frame must have consumed the device buffer before it is overwritten
+  if (h->in2_used[slot]) KSG_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_free[slot], 0));
+  if (is_pinned_host(depth) && is_pinned_host(label)) {   // page-locked caller buffers: read asynchronously (keep them unchanged until ksg_wait_frame)
+    KSG_CUDA(cudaMemcpyAsync(h->d_in2[slot], depth, P * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    KSG_CUDA(cudaMemcpyAsync(h->d_in2[slot] + o_lab, label, P, cudaMemcpyHostToDevice, h->copy_stream));
+  } else {
+    if (h->in2_used[slot]) KSG_CUDA(cudaEventSynchronize(h->ev_copy[slot]));   // the staging buffer's previous copy has left the host
+    std::memcpy(h->h_stage2[slot], depth, P * 4);
+    std::memcpy(h->h_stage2[slot] + o_lab, label, P);
+    KSG_CUDA(cudaMemcpyAsync(h->d_in2[slot], h->h_stage2[slot], total, cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  KSG_CUDA(cudaEventRecord(h->ev_copy[slot], h->copy_stream));
+  KSG_CUDA(cudaStreamWaitEvent(h->own_stream, h->ev_copy[slot], 0));
+  InputDesc in; in.d_depth = (const float*)h->d_in2[slot]; in.d_label_img = h->d_in2[slot] + o_lab; in.width = width; in.height = height;
+  in.n = (int64_t)P;
+  in.K[0] = K[0]; in.K[1] = K[1]; in.K[2] = K[2]; in.K[3] = K[3];
+  const bool deferred = h->cfg.integrator_type == KSG_INTEGRATOR_FAST && h->fast_v2;
+  ksg_frame_stats st;
+  const int rc = integrate(h, in, T, h->own_stream, deferred ? nullptr : &st);
+  KSG_CUDA(cudaEventRecord(h->ev_free[slot], h->own_stream));
+  h->in2_used[slot] = true;
+  if (!deferred && h->n_stash < 4) h->stash[h->n_stash++] = st;   // drivers that complete inside the call: statistics are ready
+  return rc;
+}
+
+// Completes the oldest frame submitted with ksg_integrate_depth_async and returns its statistics.
+int32_t ksg_wait_frame(ksg_integrator* h, ksg_frame_stats* stats) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  if (h->n_stash > 0) {
+    if (stats) *stats = h->stash[0];
+    for (int i = 1; i < h->n_stash; ++i) h->stash[i - 1] = h->stash[i];
+    --h->n_stash;
+    if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
+    return KSG_OK;
+  }
+  if (h->n_pend > 0) return finish_oldest(h, stats);
+  if (stats) fill_stats(h, stats);
+  return h->deferred_status ? h->fail(h->deferred_status, err_text(h->deferred_status)) : KSG_OK;
 }
 
 int32_t ksg_sync(ksg_integrator* h) {
@@ -1711,9 +1780,10 @@ int64_t ksg_debug_fast_timeline(ksg_integrator* h, int64_t* out64, int64_t* swee
   cudaSetDevice(h->device);
   if (h->n_pend > 0) finish_frame(h, nullptr);
   for (int i = 0; i < kTimelineSlots; ++i) out64[i] = (int64_t)h->h_fc->timeline[i];
+  for (int i = 0; i < 16; ++i) out64[kTimelineSlots + i] = (int64_t)h->h_fc->dbg[i];
   if (sweeps) *sweeps = h->h_fc->sweeps_last;
   if (clock_khz) *clock_khz = h->clock_khz;
-  return kTimelineSlots;
+  return kTimelineSlots + 16;
 }
 
 int32_t ksg_reset(ksg_integrator* h) {

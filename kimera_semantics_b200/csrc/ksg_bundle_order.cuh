@@ -121,4 +121,44 @@ k_bundle_order(const Counters* __restrict__ cnt, BordBuf bb, const int* __restri
   for (int pos = gt; pos < n; pos += nthreads) bundle_f_out[off + pos] = bundle_f[off + __ldcg(&cur[pos])];
 }
 
+// Record ranges of the bundles: b_base[b] = sum of nsteps[b'] for b' < b, in RANK order (exclusive scan by one cluster).  The records
+// of a frame are therefore laid out by (bundle rank, ray step), and a STABLE sort on the voxel bits alone leaves every voxel's
+// records in rank order = the reference's per-voxel update order: four radix passes instead of seven.
+__global__ void __cluster_dims__(kBordCluster, 1, 1) __launch_bounds__(kBordThreads, 1)
+k_bundle_scan(Counters* cnt, int* __restrict__ nsteps, long long* __restrict__ b_base, long long rec_cap, unsigned long long* cta_tot) {
+  __shared__ unsigned long long s_warp[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int nthreads = kBordCluster * kBordThreads;
+  const int gt = crank * kBordThreads + threadIdx.x;
+  const int n = cnt->n_cast;
+  const int per = (n + nthreads - 1) / nthreads;
+  const int i0 = min(n, gt * per), i1 = min(n, i0 + per);
+  unsigned long long local = 0;
+  for (int i = i0; i < i1; ++i) local += (unsigned long long)nsteps[i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long incl = local;
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long w = s_warp[lane];
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const unsigned long long block_excl = incl - local + (wid > 0 ? s_warp[wid - 1] : 0ull);
+  if (threadIdx.x == 0) __stcg(&cta_tot[crank], s_warp[31]);
+  cluster.sync();
+  unsigned long long run = block_excl, total = 0;
+  for (int c = 0; c < kBordCluster; ++c) { const unsigned long long t = __ldcg(&cta_tot[c]); if (c < crank) run += t; total += t; }
+  const bool fits = total <= (unsigned long long)rec_cap;
+  for (int i = i0; i < i1; ++i) {
+    b_base[i] = (long long)run;
+    run += (unsigned long long)nsteps[i];
+    if (!fits) nsteps[i] = 0;
+  }
+  if (gt == 0) { if (fits) cnt->n_records = total; else { cnt->n_records = 0; set_err(cnt, 4); } }
+}
+
 }  // namespace ksg

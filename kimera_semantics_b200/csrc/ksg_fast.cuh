@@ -44,6 +44,7 @@ struct FastCounters {      // device-resident state of the frame driver (persist
   int m_cursor;                              // allocation cursor of their visitor lists
   int pad0;
   long long timeline[kTimelineSlots];        // clock64 of block 0 at the phase boundaries of k_fast_solve (profiling)
+  long long dbg[16];                         // profiling only: maxima / counts gathered inside the solve kernel (see ksg_debug_fast_timeline)
 };
 
 struct TileDesc { uint32_t tk; int n; long long off; };
@@ -437,6 +438,8 @@ __device__ __forceinline__ void solve_barrier(unsigned int* bar, unsigned int& e
   }
   __syncthreads();
 }
+__device__ __forceinline__ void dbg_max(const FastFrame& f, int k, long long v) { if (f.profile) atomicMax((unsigned long long*)&f.fc->dbg[k], (unsigned long long)v); }
+__device__ __forceinline__ void dbg_add(const FastFrame& f, int k, long long v) { if (f.profile) atomicAdd((unsigned long long*)&f.fc->dbg[k], (unsigned long long)v); }
 __device__ __forceinline__ void timeline_mark(const FastFrame& f, int slot) {
   if (f.profile && blockIdx.x == 0 && threadIdx.x == 0 && slot < kTimelineSlots) f.fc->timeline[slot] = clock64();
 }

@@ -218,6 +218,8 @@ __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n
   const DevCfg& cfg = f.cfg;
   const Obs3& o = f.o3;
   int h = 0;
+  const long long t_begin = f.profile ? clock64() : 0;
+  long long t_ins = 0;
   if (r < n_cast) {
     const int seq = f.cast_seq[r];
     const float4 p = f.pt_pG[seq];
@@ -240,8 +242,10 @@ __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n
       const long long ci = (long long)r * kH0 + s;
       int pos = -2;
       if (s < l0) {
+        const long long t0 = f.profile ? clock64() : 0;
         const uint64_t v = (uint64_t)index_hash(g) + f.set_offset;
         pos = cand_insert3(f, (uint32_t)v & kSetMask, make_entry(true, ((uint64_t)r << kOrderStepBits) | (uint64_t)s, v));
+        if (f.profile) t_ins += clock64() - t0;
       }
       st_cand(&o.cand[ci], vkey, pos, 0);
     }
@@ -250,6 +254,7 @@ __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n
     *(int4*)&f.rayrec[r] = make_int4(rr.H, rr.L, rr.nsteps, rr.eval_sweep);
   }
   warp_add(&f.cnt->ray_steps, (unsigned long long)h);
+  if (f.profile) { dbg_max(f, 0, clock64() - t_begin); dbg_max(f, 1, t_ins); }
 }
 
 // One sweep over the rays [r_lo, r_hi): one warp per ray.  A ray is re-evaluated only from the first block that holds a dirty
@@ -278,6 +283,8 @@ __device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r
       for (int d = 16; d > 0; d >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, fd, d); fd = t < fd ? t : fd; }
     }
     if (fd == 0x7fffffff) continue;
+    const long long t_eval = f.profile ? clock64() : 0;
+    int n_blocks_eval = 0, n_blocks_mat = 0;
     int s0, blen;
     block_of_step(fd, s0, blen);
     long long base_ci = cand_index3(o, f.ext_off, r, s0);
@@ -285,7 +292,9 @@ __device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r
     int U = -1;
     while (s0 < n && U < 0) {
       const int cend = (s0 + blen < n) ? s0 + blen : n;
+      ++n_blocks_eval;
       if (s0 >= h) {   // materialise the block: continue the ray walk (A.7) from the saved state
+        ++n_blocks_mat;
         int ok = 1;
         if (lane == 0 && s0 >= kH0 && (s0 & (s0 - 1)) == 0) {   // s0 = 16 << k: first block of storage segment k (steps [16<<k, 32<<k))
           const int k = 31 - __clz(s0 >> 4);
@@ -377,6 +386,7 @@ __device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r
     if (lane == 0) {
       if (U != old) { f.rayrec[r].L = U; cnt->changed[sweep & 3] = 1; }
       f.rayrec[r].eval_sweep = sweep;
+      if (f.profile) { dbg_max(f, 3, clock64() - t_eval); dbg_add(f, 4, 1); dbg_add(f, 5, n_blocks_eval); dbg_add(f, 6, n_blocks_mat); if (U != old) dbg_add(f, 7, 1); }
     }
   }
 }
@@ -442,6 +452,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
       if (f.s_hmin[slot] != f.s_hmax[slot]) f.m_list[f.s_base[slot] + f.sb.next[seq]] = seq;
     }
     solve_barrier(bar, epoch);
+    timeline_mark(f, 57);
     // ---- phase 0b: one warp per such slot: visitors in sequence order; a visitor is cast iff its predecessor carried another value
     const int warps_total = gthreads >> 5;
     int* scratch = s_sort + (threadIdx.x >> 5) * kSortPerWarp;
@@ -458,8 +469,10 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
         if (f.pt_key[pa] != f.pt_key[pb]) { f.cast_flag[pb] = 1; atomicAdd(&f.warp_cnt[pb >> 5], 1); }
       }
       __syncwarp();
+      if (f.profile && lane == 0) { dbg_max(f, 8, n); dbg_add(f, 9, n); }
     }
     solve_barrier(bar, epoch);
+    timeline_mark(f, 58);
   }
   // ---- phase 0c: offsets of the cast points (block 0), then compaction in sequence order (= ray rank order)
   if (blockIdx.x == 0) {
@@ -468,6 +481,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     if (threadIdx.x == 0) cnt->n_cast = total;
   }
   solve_barrier(bar, epoch);
+  timeline_mark(f, 59);
   const int n_cast = ((volatile int*)&cnt->n_cast)[0];
   for (int base = (gtid & ~31); base < n_points; base += gthreads) {
     const int seq = base + lane;
@@ -559,6 +573,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     f.fc->n_tile_list = 0;
     f.fc->rec_cursor = 0;
     f.fc->ovf_count = 0;
+    if (f.profile) { f.fc->dbg[10] = n_mixed; f.fc->dbg[11] = n_cast; }
     f.fc->n_mixed = 0;
     f.fc->m_cursor = 0;
   }

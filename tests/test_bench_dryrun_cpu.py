@@ -52,6 +52,13 @@ class FakeDeviceIntegrator:
     def num_blocks(self):
         return self.o.num_blocks()
 
+    def integrate_depth_async(self, T, depth, label, K):
+        self._pending = getattr(self, "_pending", [])
+        self._pending.append(self.integrate_depth(T, depth, label, K))
+
+    def wait_frame(self):
+        return self._pending.pop(0)
+
     def fast_timeline(self):
         return {"sweeps": 6, "solve_kernel_us": 100.0}
 
@@ -90,7 +97,8 @@ def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extr
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     real_tensor = torch.tensor
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", workload, "--steps", "4", "--warmup", "3", "--profile-frames", "2"] + extra)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", workload, "--steps", "4", "--warmup", "3", "--profile-frames", "2", "--sequences-per-gpu", "2",
+                                      "--extra-workloads", "fast10" if workload != "fast10" else "merged5"] + extra)
     monkeypatch.setattr(bench, "best_cpu_arm", lambda wl, fr, cam: ("port", 1, {"port@1": 1.0}))
     buf = io.StringIO()
     with redirect_stdout(buf):
@@ -101,9 +109,15 @@ def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extr
         assert key in line, key
     assert line["steps"] == 4 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["value"] > 0
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"]) and line["e2e"]["value"] > 0
-    assert line["e2e"]["d2h_bytes_per_step"] == (152 * 4 if workload == "fast10" else 152 * 3)
+    assert line["e2e"]["d2h_bytes_per_step"] == (152 + 568 if workload == "fast10" else 152 * 2)
+    assert line["e2e"]["sync_value"] > 0 and line["e2e"]["mode"] == "pipelined"
+    assert set(("frame_frac", "kernel", "phase", "tile_apply_frac")) <= set(line["roofline"])
+    other = "merged5" if workload == "fast10" else "fast10"
+    assert other in line["workloads"] and line["workloads"][other]["value"] > 0 and "roofline" in line["workloads"][other]
+    if workload == "fast10":
+        assert line["multi_sequence"]["sequences"] == 2 and line["multi_sequence"]["value"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"]) and line["roofline"]["bound"] == "hbm"
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"]) and line["cpu_baseline"]["value"] > 0
     assert line["config"]["merged_bundle_order"] == "libstdcxx"
-    assert line["config"]["hot_voxel_mode"] == 2
+    assert line["config"]["hot_voxel_mode"] == (2 if extra else 0)
     assert line["gpu_launches"] > 0
