@@ -1252,7 +1252,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     }
     {
       const size_t stage = dc.head_bytes + (dc.full_stage ? dc.prior_bytes : 0u);
-      h->apply_fast_smem = (int)(stage + (size_t)dc.tile_voxels * 10 + 16 + sizeof(uint32_t) * kFastKeyCap + 64 + 16 + (size_t)kFastPref * 21);
+      h->apply_fast_smem = (int)(stage + (size_t)dc.tile_voxels * 10 + 16 + 2 * sizeof(uint32_t) * kFastKeyCap + 64 + 32 + (size_t)kFastPref * 21);
 #define KSG_ATTRF(TMA, NCH) KSG_CUDA(cudaFuncSetAttribute(k_tile_apply_fast<TMA, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->apply_fast_smem))
       KSG_ATTRF(true, 1); KSG_ATTRF(true, 2); KSG_ATTRF(true, 4); KSG_ATTRF(true, 8);
       KSG_ATTRF(false, 1); KSG_ATTRF(false, 2); KSG_ATTRF(false, 4); KSG_ATTRF(false, 8);

@@ -736,6 +736,8 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
   float4* s_par = (float4*)(((uintptr_t)(s_vox + V) + 15) & ~(uintptr_t)15);   // [kFastPref] operands of the sorted records
   uint32_t* s_col = (uint32_t*)(s_par + kFastPref);
   uint8_t* s_lab = (uint8_t*)(s_col + kFastPref);
+  uint32_t* s_keys2 = (uint32_t*)(((uintptr_t)(s_lab + kFastPref) + 15) & ~(uintptr_t)15);   // [kFastKeyCap] records grouped by voxel
+  __shared__ uint8_t s_perm[16 * 32];
   __shared__ uint8_t* s_chunk;
   __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor, s_nvox, s_n;
   __shared__ long long s_off;
@@ -776,22 +778,52 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
     uint8_t* chunk = s_chunk;
     if (chunk == nullptr) continue;          // not owned by this shard / pool overflow already flagged
     const int n = s_n;
-    // the tile's records -> shared memory, sorted by (voxel, ray rank): the reference's per-voxel update order (overlaps the bulk load)
+    // The tile's records, grouped by voxel and, inside a voxel, in ray-rank order = the reference's per-voxel update order (overlaps
+    // the bulk load).  Usual case (n <= kFastKeyCap): counting sort by voxel in shared memory - histogram, scan, scatter: three barriers -
+    // and the few records of one voxel are ordered by the warp that applies them.  Oversized tiles: bitonic sort in global memory.
     uint32_t* keys = f.keys + s_off;
-    if (n <= kFastKeyCap) { for (int i = tid; i < n; i += nthreads) s_keys[i] = keys[i]; keys = s_keys; }
-    __syncthreads();
-    cta_sort_u32(keys, n);
-    const bool pref = n <= kFastPref;      // one parallel gather instead of a dependent L2 round trip per voxel
-    if (pref) for (int i = tid; i < n; i += nthreads) {
-      const uint32_t ord = keys[i] & ord_mask;
-      s_par[i] = src.param[ord];
-      s_lab[i] = src.label[ord];
-      if (keep_blend) s_col[i] = src.color[ord];
-    }
-    for (int i = tid; i < n; i += nthreads) {
-      const int vx = (int)(keys[i] >> kRecOrdBits);
-      if (i == 0 || (int)(keys[i - 1] >> kRecOrdBits) != vx) { s_seg_lo[vx] = i; s_vox[atomicAdd(&s_nvox, 1)] = (uint16_t)vx; }
-      if (i + 1 == n || (int)(keys[i + 1] >> kRecOrdBits) != vx) s_seg_hi[vx] = i + 1;
+    const bool grouped = n <= kFastKeyCap;
+    bool pref = false;
+    if (grouped) {
+      for (int v = tid; v < V; v += nthreads) s_seg_lo[v] = 0;
+      for (int i = tid; i < n; i += nthreads) s_keys[i] = keys[i];
+      __syncthreads();
+      for (int i = tid; i < n; i += nthreads) atomicAdd(&s_seg_lo[s_keys[i] >> kRecOrdBits], 1);
+      __syncthreads();
+      if (tid < 32) {        // exclusive scan of the V counts by one warp; the touched voxels are listed on the way
+        const int per = (V + 31) / 32;
+        const int v0 = lane * per, v1 = min(V, v0 + per);
+        int local = 0;
+        for (int v = v0; v < v1; ++v) local += s_seg_lo[v];
+        int incl = local;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        int run = incl - local;
+        for (int v = v0; v < v1; ++v) {
+          const int c = s_seg_lo[v];
+          s_seg_lo[v] = run; s_seg_hi[v] = run;
+          if (c > 0) s_vox[atomicAdd(&s_nvox, 1)] = (uint16_t)v;
+          run += c;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += nthreads) { const uint32_t k = s_keys[i]; s_keys2[atomicAdd(&s_seg_hi[k >> kRecOrdBits], 1)] = k; }
+      __syncthreads();
+      keys = s_keys2;
+      pref = n <= kFastPref;      // one parallel gather instead of a dependent L2 round trip per voxel
+      if (pref) for (int i = tid; i < n; i += nthreads) {
+        const uint32_t ord = keys[i] & ord_mask;
+        s_par[i] = src.param[ord];
+        s_lab[i] = src.label[ord];
+        if (keep_blend) s_col[i] = src.color[ord];
+      }
+    } else {
+      __syncthreads();
+      cta_sort_u32(keys, n);
+      for (int i = tid; i < n; i += nthreads) {
+        const int vx = (int)(keys[i] >> kRecOrdBits);
+        if (i == 0 || (int)(keys[i - 1] >> kRecOrdBits) != vx) { s_seg_lo[vx] = i; s_vox[atomicAdd(&s_nvox, 1)] = (uint16_t)vx; }
+        if (i + 1 == n || (int)(keys[i + 1] >> kRecOrdBits) != vx) s_seg_hi[vx] = i + 1;
+      }
     }
     if (USE_TMA) { mbar_wait(s_bar, phase); phase ^= 1; }
     else for (uint32_t t = tid; t < stage_bytes / 16; t += nthreads) ((uint4*)smem)[t] = ((const uint4*)chunk)[t];
@@ -814,17 +846,56 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
       float p[NCH];
 #pragma unroll
       for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; p[q] = (c < C) ? prow[c] : 0.0f; }
+      // order the voxel's records by ray rank (grouped tiles only; the bitonic path is sorted already)
+      bool vpref = pref;
+      int perm_src = lane;                        // position (relative to lo) of the record that lane handles
+      if (grouped && hi - lo > 1) {
+        if (hi - lo <= 32) {                      // rank sort inside the warp
+          const int len = hi - lo;
+          const uint32_t mine = (lane < len) ? keys[lo + lane] : 0xFFFFFFFFu;
+          int rank = 0;
+          for (int jj = 0; jj < len; ++jj) { const uint32_t kj = __shfl_sync(0xffffffffu, mine, jj); rank += (kj < mine) ? 1 : 0; }
+          uint8_t* perm = s_perm + (tid >> 5) * 32;
+          if (lane < len) perm[rank] = (uint8_t)lane;
+          __syncwarp();
+          if (lane < len) perm_src = perm[lane];
+          __syncwarp();
+        } else {                                  // long segment (rare in `fast`): in place, operands gathered from global memory
+          int n2 = 1;
+          const int len = hi - lo;
+          uint32_t* a = keys + lo;
+          while (n2 < len) n2 <<= 1;
+          const int half = n2 >> 1;
+          for (int k = 2; k <= n2; k <<= 1) {
+            const int hk = k >> 1;
+            for (int t = lane; t < half; t += 32) {
+              const int blk = t / hk, o = t - blk * hk;
+              const int i = blk * k + o, pp = blk * k + (k - 1 - o);
+              if (pp < len) { const uint32_t x = a[i], y = a[pp]; if (x > y) { a[i] = y; a[pp] = x; } }
+            }
+            __syncwarp();
+            for (int jx = k >> 2; jx > 0; jx >>= 1) {
+              for (int t = lane; t < half; t += 32) {
+                const int i = (t / jx) * 2 * jx + (t % jx), pp = i + jx;
+                if (pp < len) { const uint32_t x = a[i], y = a[pp]; if (x > y) { a[i] = y; a[pp] = x; } }
+              }
+              __syncwarp();
+            }
+          }
+          vpref = false;
+        }
+      }
       for (int base = lo; base < hi; base += 32) {
-        const int k = base + lane;
+        const int k = (hi - lo <= 32) ? lo + perm_src : base + lane;
         uint32_t ord = 0, col = 0;
         int lab = 0;
         float sdf = 0.0f, uw = 0.0f;
-        if (k < hi) {
+        if (base + lane < hi) {
           ord = keys[k] & ord_mask;
-          const float4 pr = pref ? s_par[k] : src.param[ord];
+          const float4 pr = vpref ? s_par[k] : src.param[ord];
           tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), center, pr.w, sdf, uw);
-          if (keep_blend) col = pref ? s_col[k] : src.color[ord];
-          lab = pref ? (int)s_lab[k] : (int)src.label[ord];
+          if (keep_blend) col = vpref ? s_col[k] : src.color[ord];
+          lab = vpref ? (int)s_lab[k] : (int)src.label[ord];
         }
         const int nb = (hi - base) < 32 ? (hi - base) : 32;
         for (int jj = 0; jj < nb; ++jj) {      // semantic rows: lanes = classes, one-hot frequencies (fast.cpp:132-135)
