@@ -43,6 +43,8 @@ WORKLOADS = {
     "merged2": (KSG_INTEGRATOR_MERGED, 640, 480, 0.02, 21, 80 << 20, 32768),  # configs[2]
     "merged5": (KSG_INTEGRATOR_MERGED, 640, 480, 0.05, 21, 16 << 20, 8192),
     "fast10": (KSG_INTEGRATOR_FAST, 320, 240, 0.10, 5, 0, 4096),        # configs[0] geometry
+    "fast5_720p_c150": (KSG_INTEGRATOR_FAST, 1280, 720, 0.05, 150, 0, 2048),   # configs[3]: ADE20K-size label set, frame-per-GPU batches
+    "merged1_4k_c40": (KSG_INTEGRATOR_MERGED, 3840, 2160, 0.01, 40, 400 << 20, 65536),   # configs[4]: 4K / 1 cm, spatially sharded
 }
 
 
@@ -518,6 +520,103 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
     }
 
 
+def measure_frame_batches(args, workload, steps, warmup, ctx):
+    """--sharding frames: ONE camera stream, batches of N frames, one frame per GPU (BASELINE configs[3]).  Every rank
+    holds a replica of the map; per batch it integrates its frame into an EMPTY delta map, the deltas (blocks in pool layout + block keys)
+    are all-gathered with NCCL, and every rank merges the N deltas into its replica in frame order (ksg_merge_blocks_device).  A step = one
+    batch = N frames."""
+    import torch
+    import torch.distributed as dist
+    from kimera_semantics_b200.capi import Integrator
+    world, rank, local_rank = ctx["world"], ctx["rank"], ctx["local_rank"]
+    itype, w, h, vs, C, _, _ = WORKLOADS[workload]
+    nb_batches = warmup + steps
+    cam = synth.make_camera(w, h)
+    mine = []
+    for k in range(nb_batches):                       # frame k * N + rank of the single trajectory
+        f = k * world + rank
+        depth, label, T = synth.frame(cam, f, C, seed=0, T_G_C=synth.pose(f, phase=-2.967))
+        mine.append((torch.from_numpy(depth).cuda(), torch.from_numpy(label).cuda(), T))
+    cfg = make_cfg(workload, device=local_rank)
+    base, delta = Integrator(cfg), Integrator(cfg)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    _, stride, _, _ = delta.device_map_view()
+    cap_blocks = 0
+    send_pool = recv_pool = send_keys = recv_keys = None
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+    t_int = t_xchg = t_merge = 0.0
+    bytes_moved = 0
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def one_batch(k, timed):
+        nonlocal cap_blocks, send_pool, recv_pool, send_keys, recv_keys, t_int, t_xchg, t_merge, bytes_moved
+        d, l, T = mine[k]
+        evs[0].record(tstream)
+        delta.reset()
+        delta.integrate_depth_device(T, d.data_ptr(), l.data_ptr(), w, h, cam.K, stream)
+        nb, _, _, _ = delta.device_map_view()
+        evs[1].record(tstream)
+        mine_n = torch.tensor([nb], dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(counts, mine_n)
+        cs = [int(x) for x in counts.tolist()]
+        mx = max(cs)
+        if mx > cap_blocks:
+            cap_blocks = int(mx * 1.25) + 8
+            send_pool = torch.empty(cap_blocks * stride, dtype=torch.uint8, device="cuda")
+            recv_pool = torch.empty(world * cap_blocks * stride, dtype=torch.uint8, device="cuda")
+            send_keys = torch.empty(cap_blocks, dtype=torch.int64, device="cuda")
+            recv_keys = torch.empty(world * cap_blocks, dtype=torch.int64, device="cuda")
+        delta.copy_map_device(send_pool.data_ptr(), send_keys.data_ptr(), stream)
+        sp, rp = send_pool[: mx * stride], recv_pool[: world * mx * stride]
+        sk, rk = send_keys[:mx], recv_keys[: world * mx]
+        dist.all_gather_into_tensor(rp, sp)
+        dist.all_gather_into_tensor(rk, sk)
+        evs[2].record(tstream)
+        for g in range(world):                      # frame order
+            base.merge_blocks_device(cs[g], rk[g * mx:].data_ptr(), rp[g * mx * stride:].data_ptr(), stream)
+        evs[3].record(tstream)
+        torch.cuda.synchronize()
+        if timed:
+            t_int += evs[0].elapsed_time(evs[1]); t_xchg += evs[1].elapsed_time(evs[2]); t_merge += evs[2].elapsed_time(evs[3])
+            bytes_moved += world * mx * (stride + 8)
+
+    for k in range(warmup):
+        one_batch(k, False)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(tstream)
+    for k in range(warmup, nb_batches):
+        one_batch(k, True)
+    e1.record(tstream)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, wall_ms = float(t[0]), float(t[1])
+    blocks = base.num_blocks()
+    base.close(); delta.close()
+    if rank != 0:
+        return None
+    frames_total = steps * world
+    return {
+        "metric": "depth_frames_per_s", "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w}x{h} depth+label stream, {vs * 100:.0f} cm voxels, {C} classes, "
+                               f"{'fast' if itype == KSG_INTEGRATOR_FAST else 'merged'} integrator, batches of {world} frames, one frame per GPU (BASELINE.json configs[3] shape)",
+                   "name": workload, "parallelism": "frame-per-GPU batches: delta maps all-gathered with NCCL, merged into every rank's replica in frame order",
+                   "map_blocks_after_run": blocks},
+        "e2e": {"value": frames_total / (wall_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 152 * (1 + world),
+                "note": "wall clock of the same loop (frames resident on the device; the per-batch host work - block counts, launches - is inside)"},
+        "collective": {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor) of block keys + blocks in pool layout",
+                       "bytes_per_step": bytes_moved / max(1, steps), "limiting": "the all-gather of whole blocks: block_stride = %d B at C = %d" % (stride, C)},
+        "phase_ms_per_step": {"integrate_own_frame": t_int / steps, "all_gather": t_xchg / steps, "merge_all_deltas": t_merge / steps},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -530,9 +629,11 @@ def main():
                     help="merged workloads: ksg_config.hot_voxel_mode (1 = parallel pre-pass for the semantic rows of hot voxels, 2 = + TSDF fixed-point check)")
     ap.add_argument("--merged-bundle-order", default="libstdcxx", choices=["canonical", "libstdcxx"],
                     help="merged workloads: bundle order (ksg_config.merged_bundle_order); libstdcxx = the reference's unordered_map order")
-    ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial"],
+    ap.add_argument("--sharding", default="sequence", choices=["sequence", "spatial", "frames"],
                     help="N > 1: sequence = one stream + map per rank (weak scaling, default); spatial = ONE stream and map, every rank "
-                         "receives every frame (NCCL broadcast from rank 0) and applies only the tiles it owns (strong scaling)")
+                         "receives every frame (NCCL broadcast from rank 0) and applies only the tiles it owns (strong scaling); frames = ONE "
+                         "stream, batches of N frames, one frame per GPU into an empty delta map, NCCL all-gather of the deltas, every rank "
+                         "merges them into its replica of the map in frame order (SURVEY.md 8e row 1, BASELINE configs[3])")
     ap.add_argument("--profile-frames", type=int, default=20, help="frames of the separate per-phase profiling pass")
     ap.add_argument("--sequences-per-gpu", type=int, default=4, help="N = 1, fast: also measure K independent sequences on one GPU (0/1: skip)")
     ap.add_argument("--extra-workloads", default="merged2", help="comma list of further workloads measured (briefly) into `workloads` at N = 1; '' = none")
@@ -554,6 +655,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = {"world": world, "rank": rank, "local_rank": local_rank}
+    if args.sharding == "frames" and world > 1:
+        line = measure_frame_batches(args, args.workload, args.steps, args.warmup, ctx)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
     line = measure(args, args.workload, args.steps, args.warmup, ctx, not args.no_cpu_baseline, args.profile_frames)
     extra = {}
     if world == 1 and args.extra_workloads:

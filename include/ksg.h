@@ -232,6 +232,19 @@ int32_t ksg_export_blocks_by_index(ksg_integrator* h, int64_t n, const int32_t* 
 int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_index, const float* tsdf_distance,
                           const float* tsdf_weight, const uint8_t* tsdf_rgba, const uint8_t* sem_label,
                           const float* sem_priors, const uint8_t* sem_rgba);
+/* Frame-per-GPU batch mode.  ksg_device_map_view exposes this integrator's map as device
+ * memory without a copy: its n_blocks blocks in pool layout (block_stride_bytes each, tiles of [distance | weight | rgba | sem rgba | label |
+ * log-probabilities]) and one packed 64-bit block key per block - the payload a rank sends to its peers.  ksg_merge_blocks_device merges such a
+ * payload (device memory of THIS device, e.g. the receive buffer of an all-gather) into this integrator's map voxel by voxel: TSDF by
+ * voxblox's mergeVoxelAIntoVoxelB (weighted mean, blended colour, weight capped at max_weight), labels by adding the payload's accumulated
+ * log-likelihoods (base.cpp:283-314) followed by arg-max and the colour hand-off; blocks the map does not hold yet are created.  Payloads are
+ * merged in the order of the calls.  Both integrators must share voxel size, voxels_per_side and num_labels. */
+int32_t ksg_device_map_view(ksg_integrator* h, int64_t* n_blocks, int64_t* block_stride_bytes, void** d_pool, void** d_block_keys);
+int32_t ksg_merge_blocks_device(ksg_integrator* h, int64_t n_blocks, const void* d_block_keys, const void* d_pool_src, void* cuda_stream);
+/* Copies the payload of ksg_device_map_view (n_blocks * block_stride_bytes, n_blocks keys) into caller-owned device buffers on `cuda_stream`
+ * (e.g. the send buffer of the all-gather). */
+int32_t ksg_copy_map_device(ksg_integrator* h, void* d_dst_pool, void* d_dst_keys, void* cuda_stream);
+
 /* Indices (nb*3 int32, sorted as above) of the blocks updated by the most recent integrate call:
  * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);

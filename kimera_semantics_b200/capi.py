@@ -227,6 +227,12 @@ def load_library(path: Optional[str] = None):
     lib.ksg_integrate_depth_async.restype = C.c_int32
     lib.ksg_wait_frame.argtypes = [H, sp]
     lib.ksg_wait_frame.restype = C.c_int32
+    lib.ksg_device_map_view.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.ksg_device_map_view.restype = C.c_int32
+    lib.ksg_merge_blocks_device.argtypes = [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ksg_merge_blocks_device.restype = C.c_int32
+    lib.ksg_copy_map_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ksg_copy_map_device.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -239,7 +245,8 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_set_color_to_label", "ksg_sync", "ksg_num_blocks", "ksg_export_blocks", "ksg_export_blocks_by_index", "ksg_import_blocks",
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
-               "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame"]
+               "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -471,6 +478,19 @@ class Integrator:
                                                _ptr(a["tsdf_distance"], C.c_float), _ptr(a["tsdf_weight"], C.c_float),
                                                _ptr(a["tsdf_rgba"], C.c_uint8), _ptr(a["sem_label"], C.c_uint8),
                                                _ptr(a["sem_priors"], C.c_float), _ptr(a["sem_rgba"], C.c_uint8)), "ksg_import_blocks")
+
+    def device_map_view(self):
+        """(n_blocks, block_stride_bytes, pool pointer, block-key pointer) of the device-resident map (frame-per-GPU batch mode)."""
+        nb, stride, pool, keys = C.c_int64(), C.c_int64(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.ksg_device_map_view(self.handle, C.byref(nb), C.byref(stride), C.byref(pool), C.byref(keys)), "ksg_device_map_view")
+        return int(nb.value), int(stride.value), int(pool.value or 0), int(keys.value or 0)
+
+    def copy_map_device(self, d_pool: int, d_keys: int, stream: int = 0):
+        self._check(self.lib.ksg_copy_map_device(self.handle, C.c_void_p(d_pool), C.c_void_p(d_keys), C.c_void_p(stream)), "ksg_copy_map_device")
+
+    def merge_blocks_device(self, n_blocks: int, d_keys: int, d_pool: int, stream: int = 0):
+        self._check(self.lib.ksg_merge_blocks_device(self.handle, n_blocks, C.c_void_p(d_keys), C.c_void_p(d_pool), C.c_void_p(stream)),
+                    "ksg_merge_blocks_device")
 
     def last_updated_blocks(self) -> np.ndarray:
         n = int(self.lib.ksg_last_updated_blocks(self.handle, 0, None))

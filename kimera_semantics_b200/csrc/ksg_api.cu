@@ -21,6 +21,7 @@
 #include "ksg_fast.cuh"
 #include "ksg_fast3.cuh"
 #include "ksg_voxel.cuh"
+#include "ksg_merge.cuh"
 
 using namespace ksg;
 
@@ -1664,6 +1665,64 @@ int32_t ksg_import_blocks(ksg_integrator* h, int64_t n, const int32_t* block_ind
                                                          sem_rgba ? i_srgba : nullptr);
     KSG_CUDA(cudaStreamSynchronize(h->own_stream));
   }
+  return KSG_OK;
+}
+
+int32_t ksg_device_map_view(ksg_integrator* h, int64_t* n_blocks, int64_t* block_stride_bytes, void** d_pool, void** d_block_keys) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  if (n_blocks) *n_blocks = h->num_blocks;
+  if (block_stride_bytes) *block_stride_bytes = (int64_t)h->dc.block_stride;
+  if (d_pool) *d_pool = h->map.pool;
+  if (d_block_keys) *d_block_keys = h->map.slot_key;
+  return KSG_OK;
+}
+
+int32_t ksg_copy_map_device(ksg_integrator* h, void* d_dst_pool, void* d_dst_keys, void* stream) {
+  if (!h || !d_dst_pool || !d_dst_keys) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+  if (h->num_blocks > 0) {
+    KSG_CUDA(cudaMemcpyAsync(d_dst_pool, h->map.pool, (size_t)h->num_blocks * (size_t)h->dc.block_stride, cudaMemcpyDeviceToDevice, s));
+    KSG_CUDA(cudaMemcpyAsync(d_dst_keys, h->map.slot_key, (size_t)h->num_blocks * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+  }
+  return KSG_OK;
+}
+
+int32_t ksg_merge_blocks_device(ksg_integrator* h, int64_t n_blocks, const void* d_block_keys, const void* d_pool_src, void* stream) {
+  if (!h || n_blocks < 0 || (n_blocks > 0 && (!d_block_keys || !d_pool_src))) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
+  if (n_blocks == 0) return KSG_OK;
+  KSG_CUDA(cudaSetDevice(h->device));
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+  if (h->exp_slots_cap < n_blocks) {
+    KSG_CUDA(cudaStreamSynchronize(s));
+    if (h->d_exp_slots) cudaFree(h->d_exp_slots);
+    h->d_exp_slots = nullptr;
+    KSG_CUDA(dmalloc(&h->d_exp_slots, (size_t)n_blocks));
+    h->exp_slots_cap = (int)n_blocks;
+  }
+  h->frame_stamp += 1;
+  h->n_launches += 5;
+  k_frame_reset<<<1, 1, 0, s>>>(h->d_cnt, 0);
+  k_merge_insert<<<grid_for(n_blocks, 256), 256, 0, s>>>(h->d_cnt, h->map, (const uint64_t*)d_block_keys, (int)n_blocks, h->d_exp_slots, h->frame_stamp);
+  k_block_init<<<h->sm_count * 4, 256, 0, s>>>(h->dc, h->d_cnt, h->map);
+  k_frame_finish<<<1, 1, 0, s>>>(h->d_cnt, h->map);
+  k_merge_tiles<<<h->sm_count * 8, 256, 0, s>>>(h->dc, h->d_cnt, h->map, h->d_luts, h->d_exp_slots, (const uint8_t*)d_pool_src, (int)n_blocks);
+  KSG_CUDA(cudaGetLastError());
+  int rc = fetch_counters(h, s);
+  if (rc) return rc;
+  h->num_blocks = h->h_cnt->pool_count;
+  h->last_blocks_touched = h->h_cnt->n_blocks_touched;
+  const int dev_err = h->h_cnt->err;
+  if (dev_err) { h->deferred_status = dev_err; return fail(dev_err, err_text(dev_err)); }
   return KSG_OK;
 }
 

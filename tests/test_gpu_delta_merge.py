@@ -1,0 +1,38 @@
+"""Frame-per-GPU batch mode on ONE device: every frame of a batch is integrated into an empty map (a "delta",
+what each GPU of the batch does) and the deltas are merged into the base map in frame order with ksg_merge_blocks_device.  The oracle runs
+the same schedule - one fresh oracle integrator per frame, merged with the numpy twin of the merge kernel (tests/delta_merge_ref.py) - and
+the maps must agree bit for bit."""
+import numpy as np
+import pytest
+
+from kimera_semantics_b200.capi import Integrator, KSG_INTEGRATOR_FAST, KSG_INTEGRATOR_MERGED, KSG_COLOR_MODE_COLOR
+from oracle.oracle_py import OracleIntegrator
+from parity_utils import assert_parity, compare_maps, frames, make_config
+import delta_merge_ref as dm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("itype,color_mode", [(KSG_INTEGRATOR_FAST, 1), (KSG_INTEGRATOR_MERGED, 1), (KSG_INTEGRATOR_FAST, KSG_COLOR_MODE_COLOR)])
+def test_batch_of_frames_then_merge_equals_the_same_schedule_on_the_oracle(itype, color_mode):
+    W, H, C, G = 320, 240, 21, 4
+    cfg = make_config(itype, 0.05, C, max_points=W * H, max_updates=16 << 20, color_mode=color_mode)
+    pal = np.array([[cfg.label_color[l][k] if cfg.label_color_known[l] else 0 for k in range(4)] for l in range(256)], np.uint8)
+    base = Integrator(cfg)
+    ref = dm.empty_map(cfg.voxels_per_side, C)
+    for batch in range(2):
+        for cam, depth, label, T in frames(W, H, C, G, start=batch * G):
+            d = Integrator(cfg)
+            d.integrate_depth(T, depth, label, cam.K)
+            nb, stride, pool, keys = d.device_map_view()
+            base.merge_blocks_device(nb, keys, pool)
+            base.sync()
+            d.close()
+            o = OracleIntegrator(cfg)
+            o.integrate_depth(T, depth, label, cam.K)
+            ref = dm.merge(ref, o.export(), pal, cfg.max_weight, color_mode)
+            o.close()
+    rep = compare_maps(base.export(), ref)
+    assert_parity(rep)
+    assert rep["tsdf_distance_bit_mismatch"] == 0 and rep["tsdf_weight_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0, rep
+    base.close()

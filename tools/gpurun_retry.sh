@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: tools/gpurun_retry.sh <logfile> <gpurun args...>   - retries while the pod answers "busy" (exit 3), up to 12 times
+log=$1; shift
+for i in $(seq 1 12); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ] && ! grep -q "status=transient" "$log"; then exit $rc; fi
+  sleep 120
+done

@@ -3,8 +3,8 @@
 set -u
 O=gpurun_out/r02
 mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py tests/test_gpu_bundle_order.py -q -m gpu -x 2>&1 | tail -8 > $O/gpu_quick_7.log
-tail -4 $O/gpu_quick_7.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py tests/test_gpu_bundle_order.py tests/test_gpu_delta_merge.py -q -m gpu -x 2>&1 | tail -12 > $O/gpu_quick_7.log
+tail -6 $O/gpu_quick_7.log
 timeout 900 python bench.py --no-cpu-baseline --steps 100 --warmup 10 > $O/bench_full_7.json 2> $O/bench_full_7.err
 python - $O/bench_full_7.json <<'PY'
 import json,sys
