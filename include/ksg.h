@@ -153,15 +153,20 @@ const char* ksg_last_error(const ksg_integrator* h);
  *   xyz        : n*3 floats, camera frame
  *   rgba       : n*4 bytes or NULL. When labels == NULL the label of a point is looked up from its
  *                colour through the table set with ksg_set_color_to_label (fast.cpp:152-158).
- *   labels     : n bytes or NULL. merged.h:82-86 label-explicit overload.
+ *   labels     : n bytes or NULL. merged.h:82-86 label-explicit overload.  With rgba AND labels the merged integrator keeps the colours out
+ *                of the TSDF layer (they are blended per bundle in the reference, merged.cpp:262-274): exact in ColorMode kSemantic /
+ *                kSemanticProbability, where the TSDF colour is overwritten anyway; in ColorMode::kColor that combination is rejected with
+ *                KSG_ERR_INVALID_ARGUMENT.
  * Host buffers; the call copies them to the device, integrates and returns after the device
  * finished (the reference call is synchronous, SURVEY.md 8b "Threading"). */
 int32_t ksg_integrate_points(ksg_integrator* h, const float* T_G_C, const float* xyz,
                              const uint8_t* rgba, const uint8_t* labels, int64_t n,
                              int32_t freespace_points, ksg_frame_stats* stats);
 
-/* Same call with DEVICE buffers, enqueued on `cuda_stream` (a cudaStream_t passed as void*); does not
- * synchronise unless stats != NULL. Used by bench.py's device-resident leg. */
+/* Same call with DEVICE buffers, enqueued on `cuda_stream` (a cudaStream_t passed as void*).  `fast`: the frame has no host read-back, the
+ * call returns as soon as it is enqueued unless stats != NULL (then it waits for the frame); a device-side error surfaces at the next call
+ * that completes a frame (ksg_sync, ksg_wait_frame, an export, ...).  `merged`: the call reads the record count back once and returns when
+ * the frame is enqueued behind it.  Used by bench.py's device-resident leg. */
 int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T_G_C_host, const float* d_xyz,
                                     const uint8_t* d_rgba, const uint8_t* d_labels, int64_t n,
                                     int32_t freespace_points, void* cuda_stream, ksg_frame_stats* stats);
@@ -188,6 +193,17 @@ int32_t ksg_integrate_depth_k64(ksg_integrator* h, const float* T_G_C, const flo
 int32_t ksg_integrate_depth_device_k64(ksg_integrator* h, const float* T_G_C_host, const float* d_depth,
                                        const uint8_t* d_label, int32_t width, int32_t height,
                                        const double* K_host, void* cuda_stream, ksg_frame_stats* stats);
+
+/* Generic image entry (host buffers): the two depth encodings and the two semantic encodings the reference's front end accepts
+ * (kimera_semantics_ros/include/kimera_semantics_ros/depth_map_to_pointcloud.h:183-193: TYPE_32FC1 / TYPE_16UC1; semantic image = RGB8 colour
+ * image whose colours name the labels, fast.cpp:152-158).  uint16 depth follows depth_image_proc::DepthTraits<uint16_t>: 0 = invalid,
+ * metres = depth * 0.001f, x = (u - cx) * depth * float(double(0.001f) / fx) (depth_map_to_pointcloud.h:222-230,259-265).  With an RGB
+ * semantic image every pixel's label comes from the table of ksg_set_color_to_label (unknown colour -> label 0) and the point carries the
+ * image colour, exactly as integratePointCloud(points_C, colors) receives it.  K = fx fy cx cy (float64). */
+enum { KSG_DEPTH_F32_METRES = 0, KSG_DEPTH_U16_MILLIMETRES = 1 };
+enum { KSG_SEMANTIC_LABEL_U8 = 0, KSG_SEMANTIC_RGB8 = 1 };
+int32_t ksg_integrate_image(ksg_integrator* h, const float* T_G_C, const void* depth, int32_t depth_type, const void* semantic,
+                            int32_t semantic_type, int32_t width, int32_t height, const double* K, ksg_frame_stats* stats);
 
 /* Pipelined variant of ksg_integrate_depth for a camera stream: enqueues the host->device copy of THIS frame on a copy stream (so it
  * overlaps the kernels of the previous frame) and the frame's kernels behind it, and returns without waiting; at most two frames are in

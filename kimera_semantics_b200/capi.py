@@ -233,6 +233,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_merge_blocks_device.restype = C.c_int32
     lib.ksg_copy_map_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ksg_copy_map_device.restype = C.c_int32
+    lib.ksg_integrate_image.argtypes = [H, fp, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, dp, sp]
+    lib.ksg_integrate_image.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -246,7 +248,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
                "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
-               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device"]
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -374,6 +376,20 @@ class Integrator:
         h, w = depth.shape
         self._check(self.lib.ksg_integrate_depth(self.handle, _ptr(T, C.c_float), _ptr(depth, C.c_float), _ptr(label, C.c_uint8),
                                                  w, h, _ptr(K, C.c_float), C.byref(st)), "ksg_integrate_depth")
+        return st
+
+    def integrate_image(self, T_G_C, depth, semantic, K64) -> KsgFrameStats:
+        """depth: float32 metres or uint16 millimetres [h, w]; semantic: uint8 labels [h, w] or RGB8 [h, w, 3] (ksg_integrate_image)."""
+        T = np.ascontiguousarray(T_G_C, np.float32)
+        K = np.ascontiguousarray(K64, np.float64)
+        depth = np.ascontiguousarray(depth)
+        semantic = np.ascontiguousarray(semantic, np.uint8)
+        assert depth.dtype in (np.float32, np.uint16)
+        h, w = depth.shape
+        st = KsgFrameStats()
+        self._check(self.lib.ksg_integrate_image(self.handle, _ptr(T, C.c_float), depth.ctypes.data_as(C.c_void_p), 1 if depth.dtype == np.uint16 else 0,
+                                                 semantic.ctypes.data_as(C.c_void_p), 1 if semantic.ndim == 3 else 0, w, h, _ptr(K, C.c_double), C.byref(st)),
+                    "ksg_integrate_image")
         return st
 
     def integrate_depth_async(self, T_G_C, depth, label, K):

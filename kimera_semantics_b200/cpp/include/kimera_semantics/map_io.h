@@ -95,9 +95,17 @@ inline bool loadLayers(const std::string& path, vxb::Layer<vxb::TsdfVoxel>* tsdf
   if (!f.good() || std::memcmp(magic, kMagic, 4) != 0 || version != kVersion) return false;
   if (voxel_size != tsdf->voxel_size() || vps != tsdf->voxels_per_side() || C != kTotalNumberOfLabels ||
       voxel_size != semantic->voxel_size() || vps != semantic->voxels_per_side()) return false;
+  const size_t V = (size_t)vps * vps * vps;
+  {   // nothing is touched unless the file holds exactly the nb blocks its header announces (truncated / corrupt files leave the layers as they are)
+    const std::streampos here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const uint64_t file_bytes = (uint64_t)f.tellg();
+    f.seekg(here);
+    const uint64_t per_block = 12ull + (uint64_t)V * (4ull + 4ull + 4ull + 1ull + 4ull * C + 4ull);
+    if (!f.good() || nb > (file_bytes / per_block) || (uint64_t)here + nb * per_block != file_bytes) return false;
+  }
   tsdf->removeAllBlocks();
   semantic->removeAllBlocks();
-  const size_t V = (size_t)vps * vps * vps;
   std::vector<float> dist(V), weight(V), priors(V * C);
   std::vector<uint8_t> rgba(4 * V), label(V), srgba(4 * V);
   for (uint64_t b = 0; b < nb; ++b) {

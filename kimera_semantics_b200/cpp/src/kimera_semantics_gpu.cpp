@@ -324,6 +324,10 @@ void MergedSemanticTsdfIntegrator::integratePointCloud(const vxb::Transformation
   KSG_CHECK(points_C.size() == colors.size());            // merged.cpp:103-105
   KSG_CHECK(points_C.size() == semantic_labels.size());
   for (const SemanticLabel l : semantic_labels) KSG_CHECK(l < kTotalNumberOfLabels);  // CHECK_LT merged.cpp:278
+  // the reference blends the explicit colours into the TSDF colour (merged.cpp:262-274); the device path keeps them out of it, which is
+  // exact for the colour modes that overwrite the TSDF colour with the semantic one
+  KSG_CHECK(semantic_config_.color_mode != ColorMode::kColor)
+      << "MergedSemanticTsdfIntegrator(GPU): the label-explicit overload is not supported in ColorMode::kColor";
   core_.integrate(T_G_C, points_C, nullptr, semantic_labels.data(), freespace_points);
 }
 

@@ -282,7 +282,7 @@ __global__ void k_sqnorm(FrameIn in, const Counters* cnt, int capacity, uint32_t
     const int pix = in.pix_list[i];
     const int v = pix / in.width, u = pix - v * in.width;
     const float d = in.depth[pix];
-    pC = f3(((float)u - in.cx) * d * in.constant_x, ((float)v - in.cy) * d * in.constant_y, d);
+    pC = f3(((float)u - in.cx) * d * in.constant_x, ((float)v - in.cy) * d * in.constant_y, d * in.z_scale);
   } else pC = f3(in.xyz[3 * i], in.xyz[3 * i + 1], in.xyz[3 * i + 2]);
   keys[i] = __float_as_uint(dot3(pC, pC));
 }
@@ -323,6 +323,9 @@ struct InputDesc {
   const uint8_t* d_label_img = nullptr;
   int width = 0, height = 0;
   double K[4] = {0, 0, 0, 0};   // fx fy cx cy as the reference holds them (sensor_msgs/CameraInfo: float64)
+  double unit_scaling = 1.0;    // DepthTraits<T>::toMeters(T(1)) as double: 1 (float32 metres) or double(0.001f) (uint16 millimetres)
+  float z_scale = 1.0f;
+  const uint32_t* d_color_img = nullptr;
   int64_t n = 0;  // points (points entry) or pixels (depth entry)
   int freespace = 0;
 };
@@ -606,9 +609,11 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
   fin.width = in.width;
   fin.cx = (float)in.K[2]; fin.cy = (float)in.K[3];   // depth_map_to_pointcloud.h:222-223 float center = model_.cx()
   if (in.d_depth) {  // depth_map_to_pointcloud.h:228-230: float constant = unit_scaling / f  (double division)
-    fin.constant_x = (float)(1.0 / in.K[0]);
-    fin.constant_y = (float)(1.0 / in.K[1]);
+    fin.constant_x = (float)(in.unit_scaling / in.K[0]);
+    fin.constant_y = (float)(in.unit_scaling / in.K[1]);
   }
+  fin.z_scale = in.z_scale;
+  fin.color_img = in.d_color_img;
   fin.freespace = in.freespace;
   if (fast && h->fast_v2) return integrate_fast_v2(h, in, fin, T, cap, s, stats);
 
@@ -1306,6 +1311,9 @@ int32_t ksg_set_color_to_label(ksg_integrator* h, const uint8_t* rgb, const uint
 int32_t ksg_integrate_points_device(ksg_integrator* h, const float* T, const float* d_xyz, const uint8_t* d_rgba,
                                     const uint8_t* d_labels, int64_t n, int32_t freespace, void* stream, ksg_frame_stats* stats) {
   if (!h || !T || n < 0 || (n > 0 && !d_xyz)) return KSG_ERR_INVALID_ARGUMENT;
+  if (h->cfg.integrator_type == KSG_INTEGRATOR_MERGED && d_rgba && d_labels && h->cfg.color_mode == KSG_COLOR_MODE_COLOR)
+    return h->fail(KSG_ERR_INVALID_ARGUMENT, "merged, ColorMode::kColor: explicit labels together with point colours (merged.h:82-86 blends the colours, "
+                                             "merged.cpp:262-274) are not supported - pass the colours alone (labels by colour) or choose another colour mode");
   InputDesc in; in.d_xyz = d_xyz; in.d_rgba = d_rgba; in.d_labels = d_labels; in.n = n; in.freespace = freespace;
   return integrate(h, in, T, stream ? (cudaStream_t)stream : h->own_stream, stats);
 }
@@ -1328,10 +1336,14 @@ int32_t ksg_integrate_points(ksg_integrator* h, const float* T, const float* xyz
                              int64_t n, int32_t freespace, ksg_frame_stats* stats) {
   if (!h || !T || n < 0 || (n > 0 && !xyz)) return KSG_ERR_INVALID_ARGUMENT;
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (n > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");   // before any staging copy
+  if (h->cfg.integrator_type == KSG_INTEGRATOR_MERGED && rgba && labels && h->cfg.color_mode == KSG_COLOR_MODE_COLOR)
+    return fail(KSG_ERR_INVALID_ARGUMENT, "merged, ColorMode::kColor: explicit labels together with point colours are not supported (see ksg.h)");
   KSG_CUDA(cudaSetDevice(h->device));
+  auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t b_xyz = (size_t)n * 12, b_rgba = rgba ? (size_t)n * 4 : 0, b_lab = labels ? (size_t)n : 0;
-  const size_t o_rgba = round_up((uint32_t)b_xyz, 256), o_lab = o_rgba + round_up((uint32_t)b_rgba, 256);
-  const size_t total = o_lab + round_up((uint32_t)b_lab, 256) + 256;
+  const size_t o_rgba = up256(b_xyz), o_lab = o_rgba + up256(b_rgba);
+  const size_t total = o_lab + up256(b_lab) + 256;
   int rc = ensure_input(h, total);
   if (rc) return rc;
   if (n > 0) {
@@ -1352,8 +1364,9 @@ int32_t ksg_integrate_depth_k64(ksg_integrator* h, const float* T, const float* 
   auto fail = [&](int c, const char* m) { return h->fail(c, m); };
   KSG_CUDA(cudaSetDevice(h->device));
   const size_t P = (size_t)width * height;
-  const size_t o_lab = round_up((uint32_t)(P * 4), 256);
-  const size_t total = o_lab + round_up((uint32_t)P, 256);
+  if ((int64_t)P > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");   // before any staging copy
+  const size_t o_lab = (P * 4 + 255) / 256 * 256;
+  const size_t total = o_lab + (P + 255) / 256 * 256;
   int rc = ensure_input(h, total);
   if (rc) return rc;
   if (is_pinned_host(depth) && is_pinned_host(label)) {   // caller's buffers are page-locked: copy straight from them
@@ -1369,6 +1382,64 @@ int32_t ksg_integrate_depth_k64(ksg_integrator* h, const float* T, const float* 
   ksg_frame_stats local;
   return integrate(h, in, T, h->own_stream, stats ? stats : &local);
 }
+namespace {
+// SemanticLabel2Color::getSemanticLabelFromColor per pixel (color.cpp:69-82, alpha forced to 255 as fast.cpp:157 / merged.cpp:87 do)
+__global__ void k_rgb_to_label(const uint8_t* __restrict__ rgb, int n, const Luts* __restrict__ luts, uint8_t* __restrict__ label, uint32_t* __restrict__ color) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t c = (uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16);
+  uint32_t hh = (c * 2654435761u) >> 22;
+  uint8_t l = 0;
+  for (int p = 0; p < 1024; ++p) {
+    const uint32_t k = luts->c2l_keys[hh];
+    if (k == c) { l = luts->c2l_vals[hh]; break; }
+    if (k == 0xFFFFFFFFu) break;
+    hh = (hh + 1) & 1023;
+  }
+  label[i] = l;
+  color[i] = c | 0xFF000000u;
+}
+}  // namespace
+
+int32_t ksg_integrate_image(ksg_integrator* h, const float* T, const void* depth, int32_t depth_type, const void* semantic, int32_t semantic_type,
+                            int32_t width, int32_t height, const double* K, ksg_frame_stats* stats) {
+  if (!h || !T || !K || width <= 0 || height <= 0 || !depth || !semantic) return KSG_ERR_INVALID_ARGUMENT;
+  if (depth_type != KSG_DEPTH_F32_METRES && depth_type != KSG_DEPTH_U16_MILLIMETRES) return KSG_ERR_INVALID_ARGUMENT;
+  if (semantic_type != KSG_SEMANTIC_LABEL_U8 && semantic_type != KSG_SEMANTIC_RGB8) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  const size_t P = (size_t)width * height;
+  if ((int64_t)P > h->cap_points) return fail(KSG_ERR_INVALID_ARGUMENT, "cloud / frame larger than ksg_config.max_points");
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t b_depth = P * (depth_type == KSG_DEPTH_U16_MILLIMETRES ? 2 : 4), b_sem = P * (semantic_type == KSG_SEMANTIC_RGB8 ? 3 : 1);
+  // device staging: [raw depth | raw semantic | float depth | label | colour]
+  const size_t o_sem = up(b_depth), o_f32 = o_sem + up(b_sem), o_lab = o_f32 + up(P * 4), o_col = o_lab + up(P), total = o_col + up(P * 4);
+  int rc = ensure_input(h, total);
+  if (rc) return rc;
+  std::memcpy(h->h_stage, depth, b_depth);
+  std::memcpy(h->h_stage + o_sem, semantic, b_sem);
+  cudaStream_t s = h->own_stream;
+  KSG_CUDA(cudaMemcpyAsync(h->d_in, h->h_stage, o_sem + b_sem, cudaMemcpyHostToDevice, s));
+  InputDesc in;
+  in.width = width; in.height = height; in.n = (int64_t)P;
+  std::memcpy(in.K, K, sizeof(in.K));
+  if (depth_type == KSG_DEPTH_U16_MILLIMETRES) {
+    ++h->n_launches;
+    k_u16_to_f32<<<grid_for((long long)P, 256), 256, 0, s>>>((const uint16_t*)h->d_in, (int)P, (float*)(h->d_in + o_f32));
+    in.d_depth = (const float*)(h->d_in + o_f32);
+    in.unit_scaling = (double)0.001f;          // double unit_scaling = DepthTraits<uint16_t>::toMeters(1) = 1 * 0.001f
+    in.z_scale = 0.001f;
+  } else in.d_depth = (const float*)h->d_in;
+  if (semantic_type == KSG_SEMANTIC_RGB8) {
+    ++h->n_launches;
+    k_rgb_to_label<<<grid_for((long long)P, 256), 256, 0, s>>>(h->d_in + o_sem, (int)P, h->d_luts, h->d_in + o_lab, (uint32_t*)(h->d_in + o_col));
+    in.d_label_img = h->d_in + o_lab;
+    in.d_color_img = (const uint32_t*)(h->d_in + o_col);
+  } else in.d_label_img = h->d_in + o_sem;
+  ksg_frame_stats local;
+  return integrate(h, in, T, s, stats ? stats : &local);
+}
+
 int32_t ksg_integrate_depth(ksg_integrator* h, const float* T, const float* depth, const uint8_t* label, int32_t width,
                             int32_t height, const float* K, ksg_frame_stats* stats) {
   if (!K) return KSG_ERR_INVALID_ARGUMENT;

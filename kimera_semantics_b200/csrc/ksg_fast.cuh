@@ -253,10 +253,10 @@ __global__ void __launch_bounds__(256) k_fast_classify(FastFrame f) {
       if (!isfinite(d[k])) continue;
       const int pix = p0 + k;
       const int v = pix / f.in.width, u = pix - v * f.in.width;
-      const F3 pC = f3(((float)u - f.in.cx) * d[k] * f.in.constant_x, ((float)v - f.in.cy) * d[k] * f.in.constant_y, d[k]);
+      const F3 pC = f3(((float)u - f.in.cx) * d[k] * f.in.constant_x, ((float)v - f.in.cy) * d[k] * f.in.constant_y, d[k] * f.in.z_scale);
       const int seq = f.seq_of_i ? f.seq_of_i[i] : inv_mixed_index(i, n);
       bool valid;
-      fast_classify_one<PUSH3>(f, seq, pC, lab[k], f.luts->label_rgba[lab[k]], valid);
+      fast_classify_one<PUSH3>(f, seq, pC, lab[k], f.in.color_img ? f.in.color_img[pix] : f.luts->label_rgba[lab[k]], valid);
       nvalid += valid ? 1 : 0;
       ++i;
     }
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) k_fast_sqnorm(FastFrame f, uint32_t* __re
     if (!isfinite(d[k])) continue;
     const int pix = p0 + k;
     const int v = pix / f.in.width, u = pix - v * f.in.width;
-    const F3 pC = f3(((float)u - f.in.cx) * d[k] * f.in.constant_x, ((float)v - f.in.cy) * d[k] * f.in.constant_y, d[k]);
+    const F3 pC = f3(((float)u - f.in.cx) * d[k] * f.in.constant_x, ((float)v - f.in.cy) * d[k] * f.in.constant_y, d[k] * f.in.z_scale);
     keys[i++] = __float_as_uint(dot3(pC, pC));
   }
 }

@@ -127,8 +127,17 @@ struct FrameIn {
   const int* point_of_seq;  // "sorted" order mode, else NULL
   int width;
   float cx, cy, constant_x, constant_y;
+  float z_scale;            // z = depth * z_scale: 1 for float32 metres, 0.001f for uint16 millimetres (DepthTraits<T>::toMeters)
+  const uint32_t* color_img; // per-pixel point colour (RGB semantic image entry) or NULL: colour of the label
   int freespace;
 };
+
+// depth_map_to_pointcloud.h:213-266 for uint16 depth (DepthTraits<uint16_t>: valid = depth != 0, metres = depth * 0.001f): the raw value as
+// float (exact), invalid -> NaN, so that the float pipeline (finite test, (u - cx) * depth * constant_x with constant_x = 0.001 / fx) applies
+__global__ void k_u16_to_f32(const uint16_t* __restrict__ raw, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const uint16_t d = raw[i]; out[i] = d ? (float)d : __int_as_float(0x7fc00000); }
+}
 
 // One thread per sequence position (the order in which the reference's ThreadSafeIndex hands out points).
 // Replaces fast.cpp:152-158 (colour->label), :75-81 (validity, dynamic filter, transform), :87-89 (start cell)
@@ -150,9 +159,9 @@ __global__ void k_classify(DevCfg cfg, Xform T, FrameIn in, const Luts* __restri
     const int pix = in.pix_list[i];
     const int v = pix / in.width, u = pix - v * in.width;
     const float d = in.depth[pix];
-    pC = f3(((float)u - in.cx) * d * in.constant_x, ((float)v - in.cy) * d * in.constant_y, d);
+    pC = f3(((float)u - in.cx) * d * in.constant_x, ((float)v - in.cy) * d * in.constant_y, d * in.z_scale);
     label = in.label_img[pix];
-    color = luts->label_rgba[label];
+    color = in.color_img ? in.color_img[pix] : luts->label_rgba[label];
   } else {
     pC = f3(in.xyz[3 * i], in.xyz[3 * i + 1], in.xyz[3 * i + 2]);
     if (in.rgba) color = (uint32_t)in.rgba[4 * i] | ((uint32_t)in.rgba[4 * i + 1] << 8) | ((uint32_t)in.rgba[4 * i + 2] << 16) | ((uint32_t)in.rgba[4 * i + 3] << 24);
