@@ -1130,7 +1130,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
         KSG_CUDA(dmalloc(&h->stamp64, 2 * (size_t)kSetSize));
       }
     }
-    h->ob.slot_cnt = (int*)h->clear_00; KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * kBktK));
+    h->ob.slot_cnt = (int*)h->clear_00; KSG_CUDA(dmalloc(&h->ob.bkt, (size_t)kSetSize * (kBkt3 > kBktK ? kBkt3 : kBktK)));
     h->ob.head = (int*)(h->clear_ff + (size_t)kSetSize * 12); KSG_CUDA(dmalloc(&h->ob.table, kSetSize));
   } else {
     KSG_CUDA(dmalloc(&h->ks_sorted, N)); KSG_CUDA(dmalloc(&h->seq_sorted, N));

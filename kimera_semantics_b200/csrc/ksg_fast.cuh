@@ -116,16 +116,21 @@ __device__ __forceinline__ int inv_mixed_index(int i, int n) {   // inverse of m
   return (i % 1024) * groups + i / 1024;
 }
 
-// exclusive scan of a[0..n) into out[0..n) by ONE block (every thread of the block calls it); returns the total
+// exclusive scan of a[0..n) into out[0..n) by ONE block (every thread of the block calls it); returns the total.  a and out are
+// 16-byte aligned; every thread owns a contiguous run whose length is a multiple of four (128-bit loads and stores, all independent).
 __device__ __forceinline__ int block_scan_array(const int* a, int* out, int n) {
   __shared__ int s_w[32];
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int per = (n + nthreads - 1) / nthreads;
+  const int per = (((n + nthreads - 1) / nthreads) + 3) & ~3;
   const int i0 = min(n, tid * per), i1 = min(n, i0 + per);
   int local = 0;
-  for (int i = i0; i < i1; ++i) local += __ldcg(&a[i]);
+  {
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) { const int4 v = __ldcg((const int4*)(a + i)); local += v.x + v.y + v.z + v.w; }
+    for (; i < i1; ++i) local += __ldcg(&a[i]);
+  }
   int incl = local;
   for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
   if (lane == 31) s_w[wid] = incl;
@@ -133,7 +138,16 @@ __device__ __forceinline__ int block_scan_array(const int* a, int* out, int n) {
   if (tid == 0) { int t = 0; for (int w = 0; w < nwarps; ++w) { const int v = s_w[w]; s_w[w] = t; t += v; } s_total = t; }
   __syncthreads();
   int run = s_w[wid] + incl - local;
-  for (int i = i0; i < i1; ++i) { const int v = __ldcg(&a[i]); out[i] = run; run += v; }
+  {
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) {
+      const int4 v = __ldcg((const int4*)(a + i));
+      int4 r; r.x = run; r.y = run + v.x; r.z = r.y + v.y; r.w = r.z + v.z;
+      *(int4*)(out + i) = r;
+      run = r.w + v.w;
+    }
+    for (; i < i1; ++i) { const int v = __ldcg(&a[i]); out[i] = run; run += v; }
+  }
   return s_total;
 }
 

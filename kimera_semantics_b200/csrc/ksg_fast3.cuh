@@ -26,6 +26,8 @@ namespace ksg {
 struct __align__(16) Cand { uint64_t vkey; int pos; int tog; };      // pos: >= 0 bucket entry, -2 not inserted, <= -3 overflow entry -3-pos
 struct __align__(16) OvfEnt { uint64_t order_perf; uint32_t hi; int next; };
 struct __align__(16) RayRec { int H, L, nsteps, eval_sweep; };
+static constexpr int kBkt3 = 32;              // bucket entries per approximate-set slot (256 B): systematic aliases of the index hash stack 2-3 voxels per slot
+static constexpr int kOvfPending = -2;        // overflow entry published, link not yet written
 static constexpr int kSortPerWarp = 1024;     // visitors of a shared start-set slot sorted in shared memory (more: in place in global memory)
 
 __device__ __forceinline__ Cand ld_cand(const Cand* p) {
@@ -62,48 +64,49 @@ __device__ __forceinline__ bool stamp_dirty(const Obs3& o, uint32_t slot, int la
   return !((uint32_t)(b >> 32) == kSweepCap - (uint32_t)sk && (uint32_t)a == (uint32_t)r && (uint32_t)b == (uint32_t)r);
 }
 
-// first time a candidate turns performed: it enters the slot's bucket (or the overflow pool); returns its position code
+// first time a candidate turns performed: it enters the slot's bucket (or the overflow pool); returns its position code.
+// The overflow push is one exchange, no retry loop and no fence: a reader that catches the entry half-written (pending link, fields of
+// an older frame) takes a wrong decision for this sweep only - the inserter stamps the slot afterwards, which marks that reader dirty.
 __device__ __forceinline__ int cand_insert3(const FastFrame& f, uint32_t slot, uint64_t entry) {
   const Obs3& o = f.o3;
   const int idx = atomicAdd(&o.slot_cnt[slot], 1);
-  if (idx < kBktK) { const int pos = (int)slot * kBktK + idx; __stcg(&o.bkt[pos], entry); return pos; }
+  if (idx < kBkt3) { const int pos = (int)slot * kBkt3 + idx; __stcg(&o.bkt[pos], entry); return pos; }
   const int id = atomicAdd(&f.fc->ovf_count, 1);
   if (id >= o.ovf_cap) { set_err(f.cnt, 4); return -2; }
   OvfEnt* e = &o.ovf[id];
+  __stcg(&e->next, kOvfPending);
   __stcg(&e->order_perf, (entry & kEntPerf) | ((entry >> 13) & ((1ull << kEntOrderBits) - 1)));
   __stcg(&e->hi, (uint32_t)(entry & 0x1FFFull));
-  int old = ((volatile int*)o.head)[slot];
-  for (;;) {   // lock-free push that concurrent readers can always follow
-    __stcg(&e->next, old);
-    __threadfence();
-    const int seen = atomicCAS(&o.head[slot], old, id);
-    if (seen == old) break;
-    old = seen;
-  }
+  const int old = atomicExch(&o.head[slot], id);
+  __stcg(&e->next, old);
   return -3 - id;
 }
 
+__device__ __forceinline__ void scan_bucket_before(const ulonglong2* b, int from, int to, int n, uint64_t my_order, long long& best, int& best_hi) {
+  for (int q = from; q < to; q += 4) {
+    const ulonglong2 a0 = __ldcg(b + q), a1 = __ldcg(b + q + 1), a2 = __ldcg(b + q + 2), a3 = __ldcg(b + q + 3);
+    scan_entries(a0, 2 * q, n, my_order, best, best_hi);
+    scan_entries(a1, 2 * q + 2, n, my_order, best, best_hi);
+    scan_entries(a2, 2 * q + 4, n, my_order, best, best_hi);
+    scan_entries(a3, 2 * q + 6, n, my_order, best, best_hi);
+  }
+}
 // latest performed visit of `slot` that precedes `my_order`: its (value >> 20), or -1
 __device__ __forceinline__ int latest_performed_before3(const Obs3& o, uint32_t slot, uint64_t my_order) {
-  const ulonglong2* b = (const ulonglong2*)(o.bkt + (size_t)slot * kBktK);
+  const ulonglong2* b = (const ulonglong2*)(o.bkt + (size_t)slot * kBkt3);
   const int total = __ldcg(&o.slot_cnt[slot]);
-  const ulonglong2 v0 = __ldcg(b + 0), v1 = __ldcg(b + 1), v2 = __ldcg(b + 2), v3 = __ldcg(b + 3);
-  const int n = total < kBktK ? total : kBktK;
+  const ulonglong2 v0 = __ldcg(b + 0), v1 = __ldcg(b + 1), v2 = __ldcg(b + 2), v3 = __ldcg(b + 3);   // independent of the count: one round trip
+  const int n = total < kBkt3 ? total : kBkt3;
   long long best = -1;
   int best_hi = -1;
   scan_entries(v0, 0, n, my_order, best, best_hi);
   scan_entries(v1, 2, n, my_order, best, best_hi);
   scan_entries(v2, 4, n, my_order, best, best_hi);
   scan_entries(v3, 6, n, my_order, best, best_hi);
-  if (n > 8) {
-    const ulonglong2 v4 = __ldcg(b + 4), v5 = __ldcg(b + 5), v6 = __ldcg(b + 6), v7 = __ldcg(b + 7);
-    scan_entries(v4, 8, n, my_order, best, best_hi);
-    scan_entries(v5, 10, n, my_order, best, best_hi);
-    scan_entries(v6, 12, n, my_order, best, best_hi);
-    scan_entries(v7, 14, n, my_order, best, best_hi);
-  }
-  if (total > kBktK) {
-    int guard = total - kBktK + 8;
+  if (n > 8) scan_bucket_before(b, 4, 8, n, my_order, best, best_hi);
+  if (n > 16) scan_bucket_before(b, 8, 16, n, my_order, best, best_hi);
+  if (total > kBkt3) {
+    int guard = total - kBkt3 + 8;
     for (int id = __ldcg(&o.head[slot]); id >= 0 && id < o.ovf_cap && guard-- > 0; id = __ldcg(&o.ovf[id].next)) {
       const uint64_t op = __ldcg(&o.ovf[id].order_perf);
       const uint64_t eo = op & ~kEntPerf;
@@ -114,15 +117,15 @@ __device__ __forceinline__ int latest_performed_before3(const Obs3& o, uint32_t 
 }
 __device__ __forceinline__ bool later_performed_exists3(const Obs3& o, uint32_t slot, uint64_t my_order) {
   const int total = __ldcg(&o.slot_cnt[slot]);
-  const int n = total < kBktK ? total : kBktK;
-  const uint64_t* b = o.bkt + (size_t)slot * kBktK;
+  const int n = total < kBkt3 ? total : kBkt3;
+  const uint64_t* b = o.bkt + (size_t)slot * kBkt3;
   bool later = false;
   for (int j = 0; j < n; ++j) {
     const uint64_t e = __ldcg(&b[j]);
     if ((e & kEntPerf) && ((e >> 13) & ((1ull << kEntOrderBits) - 1)) > my_order) later = true;
   }
-  if (total > kBktK) {
-    int guard = total - kBktK + 8;
+  if (total > kBkt3) {
+    int guard = total - kBkt3 + 8;
     for (int id = __ldcg(&o.head[slot]); id >= 0 && id < o.ovf_cap && !later && guard-- > 0; id = __ldcg(&o.ovf[id].next)) {
       const uint64_t op = __ldcg(&o.ovf[id].order_perf);
       if ((op & kEntPerf) && (op & ~kEntPerf) > my_order) later = true;
