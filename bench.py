@@ -269,6 +269,45 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def shim_e2e(workload, frames, cam, warmup=5, timed=30):
+    """Throughput through the drop-in C++ classes (SemanticTsdfIntegratorFactory::create + integratePointCloud on host std::vector clouds),
+    eager (the reference's contract: host layers updated when the call returns) and lazy layer sync - kimera_semantics_b200/cpp/shim_bench."""
+    import tempfile
+    exe = os.path.join(ROOT, "kimera_semantics_b200", "cpp", "shim_bench")
+    itype, w, h, vs, C, max_updates, max_blocks = WORKLOADS[workload]
+    if not os.path.exists(exe) or C != 21:       # the shim keeps the reference's compile-time label count (common.h:27)
+        return None
+    cfg = make_cfg(workload)
+    pal = np.array([[cfg.label_color[l][k] for k in range(4)] for l in range(C)], np.uint8)
+    n = min(len(frames), warmup + timed)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "frames.bin")
+        with open(path, "wb") as f:
+            f.write(np.int32(n).tobytes()); f.write(np.float32(vs).tobytes()); f.write(np.int32(16).tobytes())
+            f.write(np.int32(C).tobytes())
+            for l in range(C):
+                f.write(bytes([int(pal[l, 0]), int(pal[l, 1]), int(pal[l, 2]), int(pal[l, 3]), l]))
+            f.write(np.int32(1).tobytes()); f.write(bytes([C - 1]))
+            for depth, label, T in frames[:n]:
+                xyz, pix = synth.backproject(depth, cam)
+                f.write(np.int32(len(xyz)).tobytes())
+                f.write(np.ascontiguousarray(T, np.float32).tobytes())
+                f.write(np.ascontiguousarray(xyz, np.float32).tobytes())
+                f.write(np.ascontiguousarray(pal[label.reshape(-1)[pix]]).tobytes())
+        env = dict(os.environ, KSG_MAX_POINTS=str(w * h), KSG_MAX_BLOCKS=str(max_blocks))
+        if max_updates:
+            env["KSG_MAX_UPDATES"] = str(max_updates)
+        for mode in ("eager", "lazy"):
+            try:
+                r = subprocess.run([exe, "fast" if itype == KSG_INTEGRATOR_FAST else "merged", path, str(warmup), mode], capture_output=True, text=True,
+                                   env=env, timeout=600)
+                out[mode] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+            except Exception as e:      # noqa: BLE001
+                out[mode] = {"error": str(e)}
+    return out
+
+
 def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
     """Every leg of one workload on this rank; rank 0 gets the result dictionary (the others None)."""
     import torch
@@ -476,6 +515,7 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
             cpu["mvoxel_updates_per_s"] = c_all["mupdates_per_s"]
     head = e2e.get("pipelined", e2e["sync"])
     traffic, traffic_src = ncu_traffic(workload)
+    shim = shim_e2e(workload, frames[warmup:], cam) if (world == 1 and args.shim_e2e) else None
     return {
         "metric": "depth_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if spatial else "weak",
@@ -505,6 +545,11 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
         "gpu_launches": int(launches),
         "library_calls": int(libcalls),
         "multi_sequence": multi,
+        "e2e_shim": None if shim is None else {
+            "eager": shim.get("eager"), "lazy": shim.get("lazy"), "unit": "frames/s (field fps)",
+            "note": "the reference's own call: SemanticTsdfIntegratorFactory::create + integratePointCloud(T_G_C, points_C, colors) on host clouds "
+                    "through the C++ drop-in classes; eager = host Layer<TsdfVoxel> / Layer<SemanticVoxel> refreshed inside every call (the "
+                    "reference's contract), lazy = refreshed once at the end (inside the measured span); clouds are back-projected before timing"},
         "roofline": {"bound": "hbm", "achieved": ach(top_ms), "peak": peak, "unit": "GB/s", "frac": ach(top_ms) / peak if peak else None,
                      "kernel": kernel_of_phase[top_phase], "phase": top_phase, "kernel_ms": top_ms,
                      "frame_frac": ach(frame_ms) / peak if peak else None, "frame_ms": frame_ms,
@@ -636,6 +681,7 @@ def main():
                          "merges them into its replica of the map in frame order (SURVEY.md 8e row 1, BASELINE configs[3])")
     ap.add_argument("--profile-frames", type=int, default=20, help="frames of the separate per-phase profiling pass")
     ap.add_argument("--sequences-per-gpu", type=int, default=4, help="N = 1, fast: also measure K independent sequences on one GPU (0/1: skip)")
+    ap.add_argument("--shim-e2e", type=int, default=1, help="N = 1: also time the C++ drop-in classes end to end (eager / lazy layer sync); 0 = skip")
     ap.add_argument("--extra-workloads", default="merged2", help="comma list of further workloads measured (briefly) into `workloads` at N = 1; '' = none")
     args = ap.parse_args()
     if args.warmup < 3:

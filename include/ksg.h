@@ -261,6 +261,21 @@ int32_t ksg_merge_blocks_device(ksg_integrator* h, int64_t n_blocks, const void*
  * (e.g. the send buffer of the all-gather). */
 int32_t ksg_copy_map_device(ksg_integrator* h, void* d_dst_pool, void* d_dst_keys, void* cuda_stream);
 
+/* Update log: the cheap way to keep HOST layers in step with the device map after every call (the reference's contract, base.cpp:257-265:
+ * on return the caller reads the host Layer<> objects).  With a log of `capacity_voxels` entries switched on, every integrate call of the
+ * `fast` integrator leaves one entry per voxel it updated (final distance, weight, colours, label and log-probabilities): kilobytes to a
+ * few megabytes per frame instead of whole blocks.  ksg_fetch_update_log completes the last frame, copies its entries to page-locked host
+ * memory owned by the library (two DMA transfers) and returns pointers that stay valid until the next call on this handle; *n = -1 and
+ * KSG_ERR_SCRATCH_FULL when the frame updated more voxels than the log holds (use the block export then).  capacity 0 switches it off. */
+typedef struct ksg_voxel_update {
+  int32_t block_index[3];
+  uint32_t lin_label;       /* voxblox linear voxel index x + vps*(y + vps*z) in bits 0..23, semantic label in bits 24..31 */
+  float tsdf_distance, tsdf_weight;
+  uint8_t tsdf_rgba[4], sem_rgba[4];
+} ksg_voxel_update;
+int32_t ksg_set_update_log(ksg_integrator* h, int64_t capacity_voxels);
+int32_t ksg_fetch_update_log(ksg_integrator* h, int64_t* n, const ksg_voxel_update** updates, const float** sem_priors /* n * num_labels */);
+
 /* Indices (nb*3 int32, sorted as above) of the blocks updated by the most recent integrate call:
  * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);

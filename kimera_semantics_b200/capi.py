@@ -235,6 +235,10 @@ def load_library(path: Optional[str] = None):
     lib.ksg_copy_map_device.restype = C.c_int32
     lib.ksg_integrate_image.argtypes = [H, fp, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, dp, sp]
     lib.ksg_integrate_image.restype = C.c_int32
+    lib.ksg_set_update_log.argtypes = [H, C.c_int64]
+    lib.ksg_set_update_log.restype = C.c_int32
+    lib.ksg_fetch_update_log.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_float))]
+    lib.ksg_fetch_update_log.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -248,7 +252,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
                "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
-               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image"]
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -473,7 +477,9 @@ class Integrator:
                 "debug": {"max_ray_setup_us": t[64] / (khz.value / 1e3), "max_ray_setup_insert_us": t[65] / (khz.value / 1e3),
                           "max_ray_eval_us": t[67] / (khz.value / 1e3), "ray_evals": t[68], "blocks_evaluated": t[69], "blocks_materialised": t[70],
                           "ray_evals_that_changed": t[71], "max_shared_slot_visitors": t[72], "shared_slot_visitors": t[73],
-                          "shared_slots": t[74], "rays": t[75]}}
+                          "shared_slots": t[74], "rays": t[75],
+                          "max_setup_after_loads_us": t[76] / (khz.value / 1e3), "max_setup_after_init_us": t[77] / (khz.value / 1e3),
+                          "max_setup_after_loop_us": t[78] / (khz.value / 1e3), "max_eval_first_block_loads_us": t[79] / (khz.value / 1e3)}}
 
     def sync(self):
         self._check(self.lib.ksg_sync(self.handle), "ksg_sync")
@@ -507,6 +513,22 @@ class Integrator:
     def merge_blocks_device(self, n_blocks: int, d_keys: int, d_pool: int, stream: int = 0):
         self._check(self.lib.ksg_merge_blocks_device(self.handle, n_blocks, C.c_void_p(d_keys), C.c_void_p(d_pool), C.c_void_p(stream)),
                     "ksg_merge_blocks_device")
+
+    def set_update_log(self, capacity_voxels: int):
+        self._check(self.lib.ksg_set_update_log(self.handle, capacity_voxels), "ksg_set_update_log")
+
+    def fetch_update_log(self):
+        """(heads structured array [n], priors [n, C]) of the voxels the last frame updated (copies)."""
+        n, heads, pri = C.c_int64(), C.c_void_p(), C.POINTER(C.c_float)()
+        self._check(self.lib.ksg_fetch_update_log(self.handle, C.byref(n), C.byref(heads), C.byref(pri)), "ksg_fetch_update_log")
+        dt = np.dtype([("block_index", np.int32, 3), ("lin_label", np.uint32), ("tsdf_distance", np.float32), ("tsdf_weight", np.float32),
+                       ("tsdf_rgba", np.uint8, 4), ("sem_rgba", np.uint8, 4)])
+        k = int(n.value)
+        if k == 0:
+            return np.zeros(0, dt), np.zeros((0, self.cfg.num_labels), np.float32)
+        h = np.frombuffer((C.c_uint8 * (k * dt.itemsize)).from_address(heads.value), dtype=dt).copy()
+        p = np.ctypeslib.as_array(pri, shape=(k, self.cfg.num_labels)).copy()
+        return h, p
 
     def last_updated_blocks(self) -> np.ndarray:
         n = int(self.lib.ksg_last_updated_blocks(self.handle, 0, None))

@@ -38,6 +38,8 @@ class GpuIntegratorCore {
 
  private:
   void copyBlocks(const std::vector<int32_t>& idx);
+  void syncAfterCall();        // eager mode: update log (fast) or updated blocks (merged)
+  bool update_log_tried_ = false, update_log_on_ = false;
   ksg_integrator* handle_ = nullptr;
   vxb::Layer<vxb::TsdfVoxel>* tsdf_layer_;
   vxb::Layer<SemanticVoxel>* semantic_layer_;

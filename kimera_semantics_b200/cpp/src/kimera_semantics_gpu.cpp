@@ -177,6 +177,10 @@ GpuIntegratorCore::GpuIntegratorCore(int integrator_type, const vxb::TsdfIntegra
   if (const char* e = std::getenv("KSG_MERGED_BUNDLE_ORDER")) c.merged_bundle_order = std::atoi(e);
   const int rc = ksg_create(&c, &handle_);
   KSG_CHECK(rc == KSG_OK) << "ksg_create failed (" << rc << "): " << ksg_last_error(nullptr);
+  // eager layer sync of `fast` goes through the device-side update log (one entry per updated voxel); it must be on before the first frame
+  update_log_tried_ = true;
+  update_log_on_ = integrator_type == KSG_INTEGRATOR_FAST && std::getenv("KSG_NO_UPDATE_LOG") == nullptr &&
+                   ksg_set_update_log(handle_, 1 << 21) == KSG_OK;
   // colour -> label table (color.cpp:69-82); alpha is forced to 255 by the callers
   std::vector<uint8_t> rgb, lab;
   for (const auto& kv : sc.semantic_label_to_color_->color_to_semantic_label_) {
@@ -200,7 +204,43 @@ void GpuIntegratorCore::integrate(const vxb::Transformation& T_G_C, const vxb::P
                                       labels, (int64_t)points_C.size(), freespace_points ? 1 : 0, &st);
   KSG_CHECK(rc == KSG_OK) << "ksg_integrate_points failed (" << rc << "): " << ksg_last_error(handle_);
   last_voxel_updates_ = st.voxel_updates;
-  if (sync_mode_ == LayerSyncMode::kEager) syncUpdatedBlocks();
+  if (sync_mode_ == LayerSyncMode::kEager) syncAfterCall();
+}
+
+// Eager sync (the reference's contract: the host layers hold the frame's result when integratePointCloud returns).  `fast` keeps an update
+// log on the device: one entry per updated voxel, fetched with two DMA transfers and written into the layers here; `merged` (and a frame
+// that overflows the log) copies the updated blocks.
+void GpuIntegratorCore::syncAfterCall() {
+  if (!update_log_on_) { syncUpdatedBlocks(); return; }
+  int64_t n = 0;
+  const ksg_voxel_update* up = nullptr;
+  const float* priors = nullptr;
+  const int rc = ksg_fetch_update_log(handle_, &n, &up, &priors);
+  if (rc != KSG_OK || n < 0) { syncUpdatedBlocks(); return; }
+  const size_t C = kTotalNumberOfLabels;
+  vxb::BlockIndex last_bi(0x7fffffff, 0x7fffffff, 0x7fffffff);
+  vxb::Block<vxb::TsdfVoxel>::Ptr tb;
+  vxb::Block<SemanticVoxel>::Ptr sb;
+  for (int64_t i = 0; i < n; ++i) {
+    const ksg_voxel_update& u = up[i];
+    const vxb::BlockIndex bi(u.block_index[0], u.block_index[1], u.block_index[2]);
+    if (!(bi == last_bi)) {           // entries come tile by tile: the block changes rarely
+      last_bi = bi;
+      tb = tsdf_layer_->allocateBlockPtrByIndex(bi);        // base.cpp:257-265: new blocks appear in both layers
+      sb = semantic_layer_->allocateBlockPtrByIndex(bi);
+      tb->updated() = true; sb->updated() = true;           // base.cpp:248
+      tb->has_data() = true; sb->has_data() = true;
+    }
+    const size_t lin = u.lin_label & 0xFFFFFFu;
+    vxb::TsdfVoxel& tv = tb->getVoxelByLinearIndex(lin);
+    tv.distance = u.tsdf_distance;
+    tv.weight = u.tsdf_weight;
+    tv.color = vxb::Color(u.tsdf_rgba[0], u.tsdf_rgba[1], u.tsdf_rgba[2], u.tsdf_rgba[3]);
+    SemanticVoxel& sv = sb->getVoxelByLinearIndex(lin);
+    sv.semantic_label = (SemanticLabel)(u.lin_label >> 24);
+    std::memcpy(sv.semantic_priors.data(), priors + (size_t)i * C, C * sizeof(float));
+    sv.color = HashableColor(u.sem_rgba[0], u.sem_rgba[1], u.sem_rgba[2], u.sem_rgba[3]);
+  }
 }
 
 void GpuIntegratorCore::integrateDepth(const vxb::Transformation& T_G_C, const float* depth, const SemanticLabel* label, int width,
@@ -213,7 +253,7 @@ void GpuIntegratorCore::integrateDepth(const vxb::Transformation& T_G_C, const f
   const int rc = ksg_integrate_depth_k64(handle_, T, depth, label, width, height, K, &st);
   KSG_CHECK(rc == KSG_OK) << "ksg_integrate_depth_k64 failed (" << rc << "): " << ksg_last_error(handle_);
   last_voxel_updates_ = st.voxel_updates;
-  if (sync_mode_ == LayerSyncMode::kEager) syncUpdatedBlocks();
+  if (sync_mode_ == LayerSyncMode::kEager) syncAfterCall();
 }
 
 void GpuIntegratorCore::copyBlocks(const std::vector<int32_t>& idx) {

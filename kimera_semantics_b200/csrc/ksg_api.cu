@@ -159,6 +159,10 @@ struct ksg_integrator {
   RayRec* rayrec = nullptr;
   int ovf_cap = 0;
   int *mixed_list = nullptr, *m_list = nullptr, *blk_run = nullptr;
+  // update log (ksg_set_update_log): one entry per voxel the last frame updated
+  VoxelUpdate *d_log_head = nullptr, *h_log_head = nullptr;
+  float *d_log_prior = nullptr, *h_log_prior = nullptr;
+  int log_cap = 0;
   uint64_t* stamp64 = nullptr;       // [2][2^20] toggle stamps of solver 3
   int solve_smem = 0;
   double clock_khz = 1965000.0;
@@ -184,8 +188,10 @@ struct ksg_integrator {
   // merged, round-2 per-voxel apply (ksg_voxel.cuh)
   bool voxel_apply = false;
   VoxelQueues vq{};
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux_stream = nullptr, aux_stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  bool hot_kernel = true;
+  int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
   int sweeps_per_sync = 1;
@@ -248,9 +254,11 @@ void free_all(ksg_integrator* h) {
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
                   h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->d_scan_tot, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
-                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->blk_run, h->stamp64, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
+                  h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->blk_run, h->stamp64, h->d_log_head, h->d_log_prior, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_cnt_base) cudaFreeHost(h->h_cnt_base);
+  if (h->h_log_head) cudaFreeHost(h->h_log_head);
+  if (h->h_log_prior) cudaFreeHost(h->h_log_prior);
   if (h->h_fc_base) cudaFreeHost(h->h_fc_base);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_frame_s[i]) cudaEventDestroy(h->ev_frame_s[i]);
@@ -262,6 +270,8 @@ void free_all(ksg_integrator* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+  if (h->aux_stream2) cudaStreamDestroy(h->aux_stream2);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_hot_segs) cudaFreeHost(h->h_hot_segs);
@@ -498,6 +508,7 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   f.o3.cand = h->cand16; f.o3.ext_base = h->ob.ext_base; f.o3.cand_cap = h->ob.cand_cap; f.o3.slot_cnt = h->ob.slot_cnt; f.o3.bkt = h->ob.bkt;
   f.o3.head = h->ob.head; f.o3.ovf = h->ovf; f.o3.ovf_cap = h->ovf_cap; f.o3.stamp_max = h->stamp64; f.o3.stamp_min = h->stamp64 + kSetSize; f.o3.table = h->ob.table;
   f.rayrec = h->rayrec; f.blk_run = h->blk_run;
+  f.log_head = h->d_log_head; f.log_prior = h->d_log_prior; f.log_cap = h->log_cap;
   f.s_base = h->start_head; f.s_hmin = h->start_val; f.s_hmax = (uint32_t*)(h->clear_00 + (size_t)kSetSize * 5);
   f.s_visits = (int*)(h->clear_00 + (size_t)kSetSize * 9); f.mixed_list = h->mixed_list; f.m_list = h->m_list;
   const bool s3 = h->solver == 3;
@@ -816,16 +827,25 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       }
       KSG_CUDA(cudaEventRecord(h->ev_fork, s));
       KSG_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+      // C <= 32: the voxels with thousands of records get one CTA each (third stream, concurrent with the other two kernels)
+      const int use_hot = (h->apply_nch == 1 && !h->hot_enabled && h->hot_kernel) ? 1 : 0;
+      if (use_hot) {
+        KSG_CUDA(cudaStreamWaitEvent(h->aux_stream2, h->ev_fork, 0));
+        ++h->n_launches;
+        k_voxel_apply_hot<<<h->sm_count, 256, h->hot_smem, h->aux_stream2>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);
+        KSG_CUDA(cudaEventRecord(h->ev_join2, h->aux_stream2));
+      }
       h->n_launches += 2;
 #define KSG_LAUNCH_VOXEL(NCH)                                                                                                             \
       do {                                                                                                                                \
-        k_voxel_apply_long<NCH><<<h->sm_count, 256, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);          \
+        k_voxel_apply_long<NCH><<<h->sm_count, 256, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, use_hot);  \
         k_voxel_apply_short<NCH><<<h->sm_count * 6, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);                 \
       } while (0)
       switch (h->apply_nch) { case 1: KSG_LAUNCH_VOXEL(1); break; case 2: KSG_LAUNCH_VOXEL(2); break; case 4: KSG_LAUNCH_VOXEL(4); break; default: KSG_LAUNCH_VOXEL(8); break; }
 #undef KSG_LAUNCH_VOXEL
       KSG_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
       KSG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+      if (use_hot) KSG_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
     } else {
     ++h->n_launches;
     k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
@@ -1149,6 +1169,11 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       KSG_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      KSG_CUDA(cudaStreamCreateWithFlags(&h->aux_stream2, cudaStreamNonBlocking));
+      KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+      h->hot_smem = 2 * kHotChunkRecs * (32 * (int)sizeof(float) + (int)sizeof(float4));
+      KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, h->hot_smem));
+      if (const char* e = std::getenv("KSG_HOT_KERNEL")) h->hot_kernel = std::atoi(e) != 0;
     }
     if (cfg->hot_voxel_mode >= 1 && dc.C <= 32 && cfg->apply_mode == 0) {
       h->hot_enabled = true;
@@ -1508,6 +1533,49 @@ int32_t ksg_wait_frame(ksg_integrator* h, ksg_frame_stats* stats) {
   if (h->n_pend > 0) return finish_oldest(h, stats);
   if (stats) fill_stats(h, stats);
   return h->deferred_status ? h->fail(h->deferred_status, err_text(h->deferred_status)) : KSG_OK;
+}
+
+int32_t ksg_set_update_log(ksg_integrator* h, int64_t capacity_voxels) {
+  if (!h || capacity_voxels < 0 || capacity_voxels > (1ll << 30)) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  if (h->d_log_head) cudaFree(h->d_log_head);
+  if (h->d_log_prior) cudaFree(h->d_log_prior);
+  if (h->h_log_head) cudaFreeHost(h->h_log_head);
+  if (h->h_log_prior) cudaFreeHost(h->h_log_prior);
+  h->d_log_head = nullptr; h->d_log_prior = nullptr; h->h_log_head = nullptr; h->h_log_prior = nullptr; h->log_cap = 0;
+  if (capacity_voxels == 0) return KSG_OK;
+  if (!(h->cfg.integrator_type == KSG_INTEGRATOR_FAST && h->fast_v2 && h->solver == 3))
+    return fail(KSG_ERR_INVALID_ARGUMENT, "the update log is kept by the fast integrator's tile kernel only (merged: use ksg_export_blocks_by_index)");
+  const size_t n = (size_t)capacity_voxels;
+  KSG_CUDA(cudaMalloc((void**)&h->d_log_head, n * sizeof(VoxelUpdate)));
+  KSG_CUDA(cudaMalloc((void**)&h->d_log_prior, n * sizeof(float) * h->dc.C));
+  KSG_CUDA(cudaMallocHost((void**)&h->h_log_head, n * sizeof(VoxelUpdate)));
+  KSG_CUDA(cudaMallocHost((void**)&h->h_log_prior, n * sizeof(float) * h->dc.C));
+  h->log_cap = (int)capacity_voxels;
+  return KSG_OK;
+}
+
+int32_t ksg_fetch_update_log(ksg_integrator* h, int64_t* n_out, const ksg_voxel_update** heads, const float** priors) {
+  if (!h || !n_out) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  *n_out = 0;
+  if (!h->d_log_head) return fail(KSG_ERR_INVALID_ARGUMENT, "update log is off (ksg_set_update_log)");
+  KSG_CUDA(cudaSetDevice(h->device));
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  const int64_t n = h->h_fc ? h->h_fc->log_count : 0;
+  if (n > h->log_cap) { *n_out = -1; return fail(KSG_ERR_SCRATCH_FULL, "update log too small for this frame: fall back to ksg_last_updated_blocks / ksg_export_blocks_by_index"); }
+  if (n > 0) {
+    KSG_CUDA(cudaMemcpyAsync(h->h_log_head, h->d_log_head, (size_t)n * sizeof(VoxelUpdate), cudaMemcpyDeviceToHost, h->own_stream));
+    KSG_CUDA(cudaMemcpyAsync(h->h_log_prior, h->d_log_prior, (size_t)n * sizeof(float) * h->dc.C, cudaMemcpyDeviceToHost, h->own_stream));
+    KSG_CUDA(cudaStreamSynchronize(h->own_stream));
+  }
+  *n_out = n;
+  if (heads) *heads = reinterpret_cast<const ksg_voxel_update*>(h->h_log_head);
+  if (priors) *priors = h->h_log_prior;
+  return KSG_OK;
 }
 
 int32_t ksg_sync(ksg_integrator* h) {

@@ -42,12 +42,15 @@ struct FastCounters {      // device-resident state of the frame driver (persist
   int ovf_count;                             // overflow pool cursor (solver 3)
   int n_mixed;                               // start-set slots visited by more than one start cell this frame
   int m_cursor;                              // allocation cursor of their visitor lists
-  int pad0;
+  int log_count;                             // update-log entries written by the frame (may exceed the capacity: then the log is incomplete)
   long long timeline[kTimelineSlots];        // clock64 of block 0 at the phase boundaries of k_fast_solve (profiling)
   long long dbg[16];                         // profiling only: maxima / counts gathered inside the solve kernel (see ksg_debug_fast_timeline)
 };
 
 struct TileDesc { uint32_t tk; int n; long long off; };
+
+// update log (eager host-layer sync of the C++ drop-in classes): one entry per voxel the frame updated, its final state
+struct VoxelUpdate { int bx, by, bz; uint32_t lin_label; float dist, wgt; uint32_t rgba, srgba; };   // lin_label = linear voxel index | label << 24
 
 // observed-set solver, third formulation (ksg_fast3.cuh)
 static constexpr int kGroup0 = 512;           // first rank group; the following groups are 4x larger each
@@ -102,6 +105,8 @@ struct FastFrame {
   Obs3 o3;
   RayRec* rayrec;
   int* blk_run;              // consecutive-collision count at the start of every evaluation block (index: candidate index / 16)
+  // update log (NULL: off)
+  VoxelUpdate* log_head; float* log_prior; int log_cap;
   // start set, third formulation: per-slot aggregates only (no linked lists)
   int* s_visits;             // [2^20] visitors of the slot this frame (sb.next[seq] = arrival index of the point)
   uint32_t *s_hmin, *s_hmax; // [2^20] smallest / largest (value >> 20) among the visitors: different <=> several cells share the slot
@@ -753,7 +758,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
   uint32_t* s_keys2 = (uint32_t*)(((uintptr_t)(s_lab + kFastPref) + 15) & ~(uintptr_t)15);   // [kFastKeyCap] records grouped by voxel
   __shared__ uint8_t s_perm[16 * 32];
   __shared__ uint8_t* s_chunk;
-  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor, s_nvox, s_n;
+  __shared__ int s_g0x, s_g0y, s_g0z, s_tile, s_vox_cursor, s_nvox, s_n, s_bx, s_by, s_bz, s_log_base;
   __shared__ long long s_off;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -785,6 +790,7 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
       s_g0x = bi.x * cfg.vps + tx * cfg.tile_side;
       s_g0y = bi.y * cfg.vps + ty * cfg.tile_side;
       s_g0z = bi.z * cfg.vps + tz * cfg.tile_side;
+      s_bx = bi.x; s_by = bi.y; s_bz = bi.z;
       s_vox_cursor = 0; s_nvox = 0;
       if (USE_TMA && chunk) { mbar_expect_tx(s_bar, stage_bytes); tma_load_1d(smem, chunk, stage_bytes, s_bar); }
     }
@@ -844,6 +850,10 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
     __syncthreads();
     float* g_prior = (float*)(chunk + cfg.head_bytes);
     const int nvox = s_nvox;
+    if (f.log_head != nullptr) {   // one range of the update log per tile
+      if (tid == 0) s_log_base = atomicAdd(&f.fc->log_count, nvox);
+      __syncthreads();
+    }
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&s_vox_cursor, 1);
@@ -943,6 +953,21 @@ __global__ void __launch_bounds__(512, 1) k_tile_apply_fast(FastFrame f, ApplySr
         if (cfg.color_mode == 1) s_rgba[v] = sc;                 // kSemantic (base.cpp:177-180)
         else if (cfg.color_mode == 2) s_rgba[v] = rainbow_color_map((double)expf(best));  // base.cpp:181-185
         else s_rgba[v] = rgba;                                   // kColor: the blended colour is the result
+      }
+      if (f.log_head != nullptr) {
+        const int at = s_log_base + item;
+        if (at < f.log_cap) {
+          if (lane == 0) {
+            const int m = cfg.vps - 1;
+            VoxelUpdate u;
+            u.bx = s_bx; u.by = s_by; u.bz = s_bz;
+            u.lin_label = (uint32_t)((g.x & m) + cfg.vps * ((g.y & m) + cfg.vps * (g.z & m))) | ((uint32_t)bi_lab << 24);
+            u.dist = dist; u.wgt = wgt; u.rgba = s_rgba[v]; u.srgba = s_srgba[v];
+            f.log_head[at] = u;
+          }
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) { const int c = q * 32 + lane; if (c < C) f.log_prior[(size_t)at * C + c] = p[q]; }
+        }
       }
     }
     if (USE_TMA) {

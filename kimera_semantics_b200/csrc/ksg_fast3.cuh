@@ -231,11 +231,13 @@ __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n
     f.ray_label[r] = f.pt_label[seq];
     f.ray_flags[r] = fl;
     f.ray_color[r] = f.pt_color[seq];
+    if (f.profile) dbg_max(f, 12, clock64() - t_begin);
     Dda d;
     raycaster_init(d, f3(f.T.tx, f.T.ty, f.T.tz), f3(p.x, p.y, p.z), (fl & 2) != 0, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc,
                    /*cast_from_origin=*/false);
     int n = d.length_in_steps + 1;
     if (!d.in_range || n >= (1 << kOrderStepBits)) { set_err(f.cnt, 5); n = 0; }
+    if (f.profile) dbg_max(f, 13, clock64() - t_begin);
     h = n < kH0 ? n : kH0;
     const int l0 = h < cfg.maxc ? h : cfg.maxc;   // a ray cannot break before `maxc` consecutive collisions
     for (int s = 0; s < h; ++s) {
@@ -252,6 +254,7 @@ __device__ __forceinline__ void fast3_ray_setup(const FastFrame& f, int r, int n
       }
       st_cand(&o.cand[ci], vkey, pos, 0);
     }
+    if (f.profile) dbg_max(f, 14, clock64() - t_begin);
     RayState st; save_state(st, d); f.ray_state[r] = st;
     RayRec rr; rr.H = h; rr.L = (h < l0) ? h : l0; rr.nsteps = (h < kH0 && h < n) ? h : n; rr.eval_sweep = 0;
     *(int4*)&f.rayrec[r] = make_int4(rr.H, rr.L, rr.nsteps, rr.eval_sweep);
@@ -359,6 +362,7 @@ __device__ __forceinline__ void fast3_sweep(const FastFrame& f, int sweep, int r
         }
       }
       const unsigned bits0 = __ballot_sync(0xffffffffu, coll[0]), bits1 = __ballot_sync(0xffffffffu, coll[1]);
+      if (f.profile && lane == 0 && n_blocks_eval == 1) dbg_max(f, 15, clock64() - t_eval);
       int brk = -1;
       for (int jj = 0; s0 + jj < cend; ++jj) {
         const unsigned bit = (jj < 32) ? ((bits0 >> jj) & 1u) : ((bits1 >> (jj - 32)) & 1u);
@@ -579,6 +583,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     if (f.profile) { f.fc->dbg[10] = n_mixed; f.fc->dbg[11] = n_cast; }
     f.fc->n_mixed = 0;
     f.fc->m_cursor = 0;
+    f.fc->log_count = 0;
   }
   timeline_mark(f, tl++);
 }

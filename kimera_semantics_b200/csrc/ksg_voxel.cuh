@@ -28,7 +28,7 @@ struct VoxelQueues {
   unsigned long long* long_items;    // [begin:40][len:23][role:1], hot ones from the front, the others from the back
   unsigned long long* short_items;   // [begin:40][len:24]
   long long long_cap, short_cap;
-  int* counters;                     // [0] hot count (front), [1] other long count (back), [2] short count, [3] long cursor, [4] short cursor
+  int* counters;                     // [0] hot count (front), [1] other long count (back), [2] short count, [3] long cursor, [4] short cursor, [5] hot cursor
 };
 
 __device__ __forceinline__ uint8_t* voxel_chunk(const DevCfg& cfg, const MapRef& map, uint32_t tk, int& pos, int& tile) {
@@ -142,18 +142,19 @@ __device__ __forceinline__ void voxel_finish_semantic(const DevCfg& cfg, const L
 // ---------------------------------------------------------------------------------------------
 template <int NCH>
 __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
-                                                            const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q) {
+                                                            const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q, int skip_hot) {
   const int lane = threadIdx.x & 31;
   const int C = cfg.C;
   const int n_hot = q.counters[0], n_other = q.counters[1];
   const int n_items = n_hot + n_other;
+  const int first_item = skip_hot ? n_hot : 0;      // the hot voxels are taken by k_voxel_apply_hot
   const F3 origin = f3(T.tx, T.ty, T.tz);
   const bool keep_blend = cfg.color_mode == 0;
   const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
   const uint32_t zero_row = (uint32_t)cnt->n_cast;   // all-zero row behind the last bundle: padded lanes add +0.0f (exact)
   for (;;) {
     int it = 0;
-    if (lane == 0) it = atomicAdd(&q.counters[3], 1);
+    if (lane == 0) it = first_item + atomicAdd(&q.counters[3], 1);
     it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= n_items) break;
     const unsigned long long item = (it < n_hot) ? q.long_items[it] : q.long_items[q.long_cap - 1 - (it - n_hot)];
@@ -240,6 +241,99 @@ __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T
         }
       }
       voxel_finish_semantic<NCH>(cfg, luts, vc, lane, p);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot voxels (>= kHotLen records in the frame: the voxels next to the camera, crossed by almost every bundle; up to ~10^5 records):
+// one CTA per voxel.  Both recurrences are sequential by definition of the reference (p <- fl(p + a_k); the running mean / clamp of
+// updateTsdfVoxel), so what can be taken off their critical path is everything else: six producer warps gather the records' operands
+// (bundle point, (L * freq) row) into a double-buffered shared-memory ring, one warp does nothing but the log-probability additions in
+// record order out of shared memory (one FADD per record per class), one warp the TSDF recurrence.  C <= 32.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kHotChunkRecs = 256;
+__global__ void __launch_bounds__(256, 2) k_voxel_apply_hot(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
+                                                           const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q) {
+  extern __shared__ __align__(16) uint8_t hot_smem[];
+  float* s_rows = (float*)hot_smem;                                        // [2][kHotChunkRecs][32]
+  float4* s_par = (float4*)(s_rows + 2 * kHotChunkRecs * 32);               // [2][kHotChunkRecs]
+  __shared__ int s_item;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = cfg.C;
+  const int n_hot_vox = q.counters[0] >> 1;
+  const F3 origin = f3(T.tx, T.ty, T.tz);
+  const bool keep_blend = cfg.color_mode == 0;
+  const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(&q.counters[5], 1);
+    __syncthreads();
+    const int it = s_item;
+    if (it >= n_hot_vox) break;
+    const unsigned long long item = q.long_items[2 * it];
+    const long long begin = (long long)(item >> 24);
+    const int len = (int)((item >> 1) & 0x7FFFFFu);
+    VoxelCtx vc;
+    if (!voxel_ctx(cfg, map, rec[begin], vc)) continue;
+    const uint64_t* r = rec + begin;
+    const int nchunks = (len + kHotChunkRecs - 1) / kHotChunkRecs;
+    // consumer state
+    float p = 0.0f, dist = 0.0f, wgt = 0.0f;
+    uint32_t rgba = 0;
+    if (warp == 0) { const float* prow = (const float*)(vc.chunk + cfg.head_bytes) + (size_t)vc.v * C; p = (lane < C) ? prow[lane] : 0.0f; }
+    if (warp == 1) {
+      dist = ((const float*)vc.chunk)[vc.v]; wgt = ((const float*)(vc.chunk + cfg.plane_f32))[vc.v];
+      rgba = ((const uint32_t*)(vc.chunk + 2 * cfg.plane_f32))[vc.v];
+    }
+    // producer: rows j = w, w + nw, ... of chunk c into buffer b (lanes = classes; lane 0 also fetches the bundle's point)
+    auto produce = [&](int c, int b, int w, int nw) {
+      const int base = c * kHotChunkRecs;
+      const int nrec = (len - base) < kHotChunkRecs ? (len - base) : kHotChunkRecs;
+      float* rows = s_rows + (size_t)b * kHotChunkRecs * 32;
+      float4* par = s_par + (size_t)b * kHotChunkRecs;
+      for (int j0 = w * 32; j0 < nrec; j0 += nw * 32) {      // 32 keys per warp and round, then one row per key
+        const uint32_t ord_l = (j0 + lane < nrec) ? ((uint32_t)r[base + j0 + lane] & ord_mask) : 0u;
+        if (j0 + lane < nrec) par[j0 + lane] = src.param[ord_l];
+        const int m = (nrec - j0) < 32 ? (nrec - j0) : 32;
+#pragma unroll 8
+        for (int u = 0; u < m; ++u) {
+          const uint32_t o = __shfl_sync(0xffffffffu, ord_l, u);
+          rows[(j0 + u) * 32 + lane] = (lane < C) ? __ldg(src.tmp + (size_t)o * C + lane) : 0.0f;
+        }
+      }
+    };
+    produce(0, 0, warp, 8);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+      const int b = c & 1;
+      const int base = c * kHotChunkRecs;
+      const int nrec = (len - base) < kHotChunkRecs ? (len - base) : kHotChunkRecs;
+      if (warp >= 2) { if (c + 1 < nchunks) produce(c + 1, b ^ 1, warp - 2, 6); }
+      else if (warp == 0) {
+        const float* rows = s_rows + (size_t)b * kHotChunkRecs * 32 + lane;
+        int j = 0;
+        for (; j + 8 <= nrec; j += 8) {      // loads run ahead, the additions stay in record order
+          const float a0 = rows[(j + 0) * 32], a1 = rows[(j + 1) * 32], a2 = rows[(j + 2) * 32], a3 = rows[(j + 3) * 32];
+          const float a4 = rows[(j + 4) * 32], a5 = rows[(j + 5) * 32], a6 = rows[(j + 6) * 32], a7 = rows[(j + 7) * 32];
+          p += a0; p += a1; p += a2; p += a3; p += a4; p += a5; p += a6; p += a7;
+        }
+        for (; j < nrec; ++j) p += rows[j * 32];
+      } else {
+        const float4* par = s_par + (size_t)b * kHotChunkRecs;
+        for (int j0 = 0; j0 < nrec; j0 += 32) {
+          const int nb = (nrec - j0) < 32 ? (nrec - j0) : 32;
+          float sdf = 0.0f, uw = 0.0f;
+          if (lane < nb) { const float4 pr = par[j0 + lane]; tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), vc.center, pr.w, sdf, uw); }
+          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0) { float pp[1]; pp[0] = (lane < C) ? p : 0.0f; voxel_finish_semantic<1>(cfg, luts, vc, lane, pp); }
+    if (warp == 1 && lane == 0) {
+      ((float*)vc.chunk)[vc.v] = dist; ((float*)(vc.chunk + cfg.plane_f32))[vc.v] = wgt;
+      if (keep_blend) ((uint32_t*)(vc.chunk + 2 * cfg.plane_f32))[vc.v] = rgba;
     }
   }
 }

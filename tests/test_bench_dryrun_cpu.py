@@ -97,7 +97,7 @@ def test_bench_main_dry_run_produces_a_complete_line(monkeypatch, workload, extr
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     real_tensor = torch.tensor
     monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", workload, "--steps", "4", "--warmup", "3", "--profile-frames", "2", "--sequences-per-gpu", "2",
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", workload, "--steps", "4", "--warmup", "3", "--profile-frames", "2", "--sequences-per-gpu", "2", "--shim-e2e", "0",
                                       "--extra-workloads", "fast10" if workload != "fast10" else "merged5"] + extra)
     monkeypatch.setattr(bench, "best_cpu_arm", lambda wl, fr, cam: ("port", 1, {"port@1": 1.0}))
     buf = io.StringIO()
