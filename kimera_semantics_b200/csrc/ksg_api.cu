@@ -191,6 +191,7 @@ struct ksg_integrator {
   cudaStream_t aux_stream = nullptr, aux_stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   bool hot_kernel = true;
+  bool emit_warp = true;             // one warp per bundle ray (KSG_EMIT_WARP=0: one thread per bundle, round 1)
   int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
@@ -789,6 +790,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       ++h->n_launches;
       k_bundle_loglik<<<grid_for((long long)(nb + 1) * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp);
       ++h->n_launches;
+      if (h->emit_warp)
+        k_emit_merged_warp<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps, h->b_base,
+                                                           h->ks_sorted, cap, h->rec_a);
+      else
       k_emit_merged<<<grid_for(nb, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps,
                                                       h->b_base, h->ks_sorted, cap, h->rec_a);
     }
@@ -814,7 +819,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       // per-voxel update (ksg_voxel.cuh): segment heads -> two queues; the long and the short kernel run concurrently
       KSG_CUDA(cudaMemsetAsync(h->vq.counters, 0, sizeof(int) * 8, s));
       ++h->n_launches;
-      k_voxel_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->vq);
+      k_voxel_heads<<<grid_for(n_records, kHeadsBlock), 256, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->vq);
       if (h->profiling) cudaEventRecord(h->ev[5], s);
       did_apply = true;
       if (h->hot_enabled) {
@@ -1174,6 +1179,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       h->hot_smem = 2 * kHotChunkRecs * (32 * (int)sizeof(float) + (int)sizeof(float4));
       KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, h->hot_smem));
       if (const char* e = std::getenv("KSG_HOT_KERNEL")) h->hot_kernel = std::atoi(e) != 0;
+      if (const char* e = std::getenv("KSG_EMIT_WARP")) h->emit_warp = std::atoi(e) != 0;
     }
     if (cfg->hot_voxel_mode >= 1 && dc.C <= 32 && cfg->apply_mode == 0) {
       h->hot_enabled = true;

@@ -67,71 +67,82 @@ __device__ __forceinline__ bool stamp_dirty(const Obs3& o, uint32_t slot, int la
 // first time a candidate turns performed: it enters the slot's bucket (or the overflow pool); returns its position code.
 // The overflow push is one exchange, no retry loop and no fence: a reader that catches the entry half-written (pending link, fields of
 // an older frame) takes a wrong decision for this sweep only - the inserter stamps the slot afterwards, which marks that reader dirty.
-__device__ __forceinline__ int cand_insert3(const FastFrame& f, uint32_t slot, uint64_t entry) {
-  const Obs3& o = f.o3;
-  const int idx = atomicAdd(&o.slot_cnt[slot], 1);
-  if (idx < kBkt3) { const int pos = (int)slot * kBkt3 + idx; __stcg(&o.bkt[pos], entry); return pos; }
-  const int id = atomicAdd(&f.fc->ovf_count, 1);
-  if (id >= o.ovf_cap) { set_err(f.cnt, 4); return -2; }
-  OvfEnt* e = &o.ovf[id];
+__device__ __noinline__ int cand_insert_raw(int* slot_cnt, uint64_t* bkt, int* head, OvfEnt* ovf, int ovf_cap, int* ovf_count, Counters* cnt,
+                                            uint32_t slot, uint64_t entry) {
+  const int idx = atomicAdd(&slot_cnt[slot], 1);
+  if (idx < kBkt3) { const int pos = (int)slot * kBkt3 + idx; __stcg(&bkt[pos], entry); return pos; }
+  const int id = atomicAdd(ovf_count, 1);
+  if (id >= ovf_cap) { set_err(cnt, 4); return -2; }
+  OvfEnt* e = &ovf[id];
   __stcg(&e->next, kOvfPending);
   __stcg(&e->order_perf, (entry & kEntPerf) | ((entry >> 13) & ((1ull << kEntOrderBits) - 1)));
   __stcg(&e->hi, (uint32_t)(entry & 0x1FFFull));
-  const int old = atomicExch(&o.head[slot], id);
+  const int old = atomicExch(&head[slot], id);
   __stcg(&e->next, old);
   return -3 - id;
 }
-
-__device__ __forceinline__ void scan_bucket_before(const ulonglong2* b, int from, int to, int n, uint64_t my_order, long long& best, int& best_hi) {
-  for (int q = from; q < to; q += 4) {
-    const ulonglong2 a0 = __ldcg(b + q), a1 = __ldcg(b + q + 1), a2 = __ldcg(b + q + 2), a3 = __ldcg(b + q + 3);
-    scan_entries(a0, 2 * q, n, my_order, best, best_hi);
-    scan_entries(a1, 2 * q + 2, n, my_order, best, best_hi);
-    scan_entries(a2, 2 * q + 4, n, my_order, best, best_hi);
-    scan_entries(a3, 2 * q + 6, n, my_order, best, best_hi);
-  }
+__device__ __forceinline__ int cand_insert3(const FastFrame& f, uint32_t slot, uint64_t entry) {
+  return cand_insert_raw(f.o3.slot_cnt, f.o3.bkt, f.o3.head, f.o3.ovf, f.o3.ovf_cap, &f.fc->ovf_count, f.cnt, slot, entry);
 }
-// latest performed visit of `slot` that precedes `my_order`: its (value >> 20), or -1
-__device__ __forceinline__ int latest_performed_before3(const Obs3& o, uint32_t slot, uint64_t my_order) {
-  const ulonglong2* b = (const ulonglong2*)(o.bkt + (size_t)slot * kBkt3);
-  const int total = __ldcg(&o.slot_cnt[slot]);
-  const ulonglong2 v0 = __ldcg(b + 0), v1 = __ldcg(b + 1), v2 = __ldcg(b + 2), v3 = __ldcg(b + 3);   // independent of the count: one round trip
+
+// latest performed visit of `slot` that precedes `my_order`: its (value >> 20), or -1.  Deliberately NOT inlined and with rolled loops:
+// the persistent kernel is instruction-cache bound otherwise (the fully unrolled scan alone was ~13 KB of SASS per call site).
+__device__ __noinline__ int latest_performed_before_raw(const uint64_t* bkt, const int* slot_cnt, const int* head, const OvfEnt* ovf, int ovf_cap,
+                                                        uint32_t slot, uint64_t my_order) {
+  const ulonglong2* b = (const ulonglong2*)(bkt + (size_t)slot * kBkt3);
+  const int total = __ldcg(&slot_cnt[slot]);
+  ulonglong2 v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = __ldcg(b + q);      // independent of the count: one round trip for the usual <= 8 entries
   const int n = total < kBkt3 ? total : kBkt3;
   long long best = -1;
   int best_hi = -1;
-  scan_entries(v0, 0, n, my_order, best, best_hi);
-  scan_entries(v1, 2, n, my_order, best, best_hi);
-  scan_entries(v2, 4, n, my_order, best, best_hi);
-  scan_entries(v3, 6, n, my_order, best, best_hi);
-  if (n > 8) scan_bucket_before(b, 4, 8, n, my_order, best, best_hi);
-  if (n > 16) scan_bucket_before(b, 8, 16, n, my_order, best, best_hi);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) scan_entries(v[q], 2 * q, n, my_order, best, best_hi);
+#pragma unroll 1
+  for (int q0 = 4; 2 * q0 < n; q0 += 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __ldcg(b + q0 + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) scan_entries(v[q], 2 * (q0 + q), n, my_order, best, best_hi);
+  }
   if (total > kBkt3) {
     int guard = total - kBkt3 + 8;
-    for (int id = __ldcg(&o.head[slot]); id >= 0 && id < o.ovf_cap && guard-- > 0; id = __ldcg(&o.ovf[id].next)) {
-      const uint64_t op = __ldcg(&o.ovf[id].order_perf);
+#pragma unroll 1
+    for (int id = __ldcg(&head[slot]); id >= 0 && id < ovf_cap && guard-- > 0; id = __ldcg(&ovf[id].next)) {
+      const uint64_t op = __ldcg(&ovf[id].order_perf);
       const uint64_t eo = op & ~kEntPerf;
-      if ((op & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)__ldcg(&o.ovf[id].hi); }
+      if ((op & kEntPerf) && eo < my_order && (long long)eo > best) { best = (long long)eo; best_hi = (int)__ldcg(&ovf[id].hi); }
     }
   }
   return best_hi;
 }
-__device__ __forceinline__ bool later_performed_exists3(const Obs3& o, uint32_t slot, uint64_t my_order) {
-  const int total = __ldcg(&o.slot_cnt[slot]);
+__device__ __forceinline__ int latest_performed_before3(const Obs3& o, uint32_t slot, uint64_t my_order) {
+  return latest_performed_before_raw(o.bkt, o.slot_cnt, o.head, o.ovf, o.ovf_cap, slot, my_order);
+}
+__device__ __noinline__ bool later_performed_exists_raw(const uint64_t* bkt, const int* slot_cnt, const int* head, const OvfEnt* ovf, int ovf_cap,
+                                                        uint32_t slot, uint64_t my_order) {
+  const int total = __ldcg(&slot_cnt[slot]);
   const int n = total < kBkt3 ? total : kBkt3;
-  const uint64_t* b = o.bkt + (size_t)slot * kBkt3;
+  const uint64_t* b = bkt + (size_t)slot * kBkt3;
   bool later = false;
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
     const uint64_t e = __ldcg(&b[j]);
     if ((e & kEntPerf) && ((e >> 13) & ((1ull << kEntOrderBits) - 1)) > my_order) later = true;
   }
   if (total > kBkt3) {
     int guard = total - kBkt3 + 8;
-    for (int id = __ldcg(&o.head[slot]); id >= 0 && id < o.ovf_cap && !later && guard-- > 0; id = __ldcg(&o.ovf[id].next)) {
-      const uint64_t op = __ldcg(&o.ovf[id].order_perf);
+#pragma unroll 1
+    for (int id = __ldcg(&head[slot]); id >= 0 && id < ovf_cap && !later && guard-- > 0; id = __ldcg(&ovf[id].next)) {
+      const uint64_t op = __ldcg(&ovf[id].order_perf);
       if ((op & kEntPerf) && (op & ~kEntPerf) > my_order) later = true;
     }
   }
   return later;
+}
+__device__ __forceinline__ bool later_performed_exists3(const Obs3& o, uint32_t slot, uint64_t my_order) {
+  return later_performed_exists_raw(o.bkt, o.slot_cnt, o.head, o.ovf, o.ovf_cap, slot, my_order);
 }
 
 // single writer per candidate: the warp that owns the ray.  c.pos is updated when the candidate enters a bucket.
@@ -163,7 +174,7 @@ __device__ __forceinline__ bool ray_state_parallel_ok(const RayState& st) {
   return fin && st.ts0 > 0.0f && st.ts1 > 0.0f && st.ts2 > 0.0f;
 }
 // W <= kWin steps from `st`; sc->out[0..W) = packed voxel indices, st advanced by W steps.  Returns false if an index left the packed range.
-__device__ __forceinline__ bool warp_dda_window(RayState& st, int W, WarpDdaScratch* sc, int lane) {
+__device__ __noinline__ bool warp_dda_window(RayState& st, int W, WarpDdaScratch* sc, int lane) {
   if (lane < 3) {
     float a = lane == 0 ? st.tn0 : (lane == 1 ? st.tn1 : st.tn2);
     const float ts = lane == 0 ? st.ts0 : (lane == 1 ? st.ts1 : st.ts2);

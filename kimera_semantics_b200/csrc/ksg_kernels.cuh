@@ -640,24 +640,27 @@ struct MapRef {
   int* touched_list;
 };
 
-__device__ __forceinline__ int ht_find_or_insert(const MapRef& m, uint64_t key, Counters* cnt) {
-  uint32_t pos = mix64(key) & m.ht_mask;
-  for (uint32_t probe = 0; probe <= m.ht_mask; ++probe) {
-    const uint64_t k = ((volatile uint64_t*)m.ht_keys)[pos];
+__device__ __noinline__ int ht_find_or_insert_raw(uint64_t* ht_keys, uint32_t ht_mask, int* new_list, int new_cap, uint64_t key, Counters* cnt) {
+  uint32_t pos = mix64(key) & ht_mask;
+  for (uint32_t probe = 0; probe <= ht_mask; ++probe) {
+    const uint64_t k = ((volatile uint64_t*)ht_keys)[pos];
     if (k == key) return (int)pos;
     if (k == kEmptyKey) {
-      const uint64_t old = atomicCAS((unsigned long long*)&m.ht_keys[pos], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      const uint64_t old = atomicCAS((unsigned long long*)&ht_keys[pos], (unsigned long long)kEmptyKey, (unsigned long long)key);
       if (old == kEmptyKey) {
         const int i = atomicAdd(&cnt->n_new_blocks, 1);
-        if (i < m.new_cap) m.new_list[i] = (int)pos; else set_err(cnt, 3);
+        if (i < new_cap) new_list[i] = (int)pos; else set_err(cnt, 3);
         return (int)pos;
       }
       if (old == key) return (int)pos;
     }
-    pos = (pos + 1) & m.ht_mask;
+    pos = (pos + 1) & ht_mask;
   }
   set_err(cnt, 3);
   return -1;
+}
+__device__ __forceinline__ int ht_find_or_insert(const MapRef& m, uint64_t key, Counters* cnt) {
+  return ht_find_or_insert_raw(m.ht_keys, m.ht_mask, m.new_list, m.new_cap, key, cnt);
 }
 
 // update record: [hash position * tiles_per_block + tile : 32][voxel in tile : 9][order : 23]

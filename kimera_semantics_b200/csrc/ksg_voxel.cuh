@@ -16,7 +16,7 @@
 //
 // Per-voxel arithmetic and order are those of k_tile_apply (same device functions): results stay bit-identical.
 #pragma once
-#include "ksg_kernels.cuh"
+#include "ksg_fast3.cuh"
 
 namespace ksg {
 
@@ -39,51 +39,151 @@ __device__ __forceinline__ uint8_t* voxel_chunk(const DevCfg& cfg, const MapRef&
   return map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
 }
 
-__global__ void k_voxel_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64_t* __restrict__ rec, long long n, int stamp, VoxelQueues q) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t k = rec[i];
-  if (k == ~0ull) return;
-  const uint64_t vk = k >> kRecOrdBits;
-  if (i > 0 && (rec[i - 1] >> kRecOrdBits) == vk) return;
-  const uint32_t tk = (uint32_t)(k >> 32);
-  const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
-  if (i == 0 || (uint32_t)(rec[i - 1] >> 32) != tk) {   // tile head: updated() bookkeeping is replicated on every shard
-    const int old = atomicExch(&map.touched_stamp[pos], stamp);
-    if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
-    atomicAdd(&cnt->n_tiles, 1);
+// ---------------------------------------------------------------------------------------------
+// merged ray emit, one WARP per bundle (round 1: one thread per bundle - 31 M scattered 8-byte stores, 0.47 ms on the 2 cm workload).
+// The ray is walked 64 steps at a time by the whole warp (warp_dda_window, ksg_fast3.cuh: bit-identical to the serial RayCaster), the
+// block lookup is done once per run of steps in the same block, and a window's records leave as two coalesced 256-byte stores.
+// merged.cpp:305-328, anti-grazing :306-313, allocateStorageAndGet*VoxelPtr base.cpp:205-254.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_emit_merged_warp(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const float4* __restrict__ b_param,
+                                                          const uint8_t* __restrict__ b_flags, const uint64_t* __restrict__ b_key,
+                                                          const int* __restrict__ b_nsteps, const long long* __restrict__ b_base,
+                                                          const uint64_t* __restrict__ ks, int capacity, uint64_t* __restrict__ records) {
+  __shared__ WarpDdaScratch s_sc[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpDdaScratch* sc = &s_sc[warp];
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int n_bundles = cnt->n_cast;
+  unsigned long long skipped = 0;
+  for (int b = blockIdx.x * (blockDim.x >> 5) + warp; b < n_bundles; b += warps_total) {
+    const int n = b_nsteps[b];
+    if (n <= 0) continue;
+    const float4 p = b_param[b];
+    const bool clearing = (b_flags[b] & 2) != 0;
+    Dda d;
+    raycaster_init(d, f3(T.tx, T.ty, T.tz), f3(p.x, p.y, p.z), clearing, cfg.carving != 0, cfg.max_ray, cfg.vsi, cfg.tp.trunc, true);
+    RayState st;
+    save_state(st, d);
+    const long long base = b_base[b];
+    const uint64_t own = b_key[b];
+    for (int s0 = 0; s0 < n; s0 += kWin) {
+      const int W = (n - s0) < kWin ? (n - s0) : kWin;
+      bool ok = true;
+      if (ray_state_parallel_ok(st)) ok = warp_dda_window(st, W, sc, lane);
+      else {
+        if (lane == 0) {
+          Dda dd; load_state(dd, st);
+          for (int t = 0; t < W; ++t) { const I3 g = dda_next(dd); if (key_in_range(g)) sc->out[t] = pack_key(g); else ok = false; }
+          save_state(st, dd);
+          sc->endc[0] = st.cx; sc->endc[1] = st.cy; sc->endc[2] = st.cz; sc->endc[3] = st.sg;
+          sc->a[0][0] = st.tn0; sc->a[1][0] = st.tn1; sc->a[2][0] = st.tn2;
+        }
+        __syncwarp();
+        st.cx = sc->endc[0]; st.cy = sc->endc[1]; st.cz = sc->endc[2];
+        st.tn0 = sc->a[0][0]; st.tn1 = sc->a[1][0]; st.tn2 = sc->a[2][0];
+        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+        __syncwarp();
+      }
+      if (!ok) { if (lane == 0) set_err(cnt, 5); for (int t = lane; t < W; t += 32) records[base + s0 + t] = ~0ull; continue; }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int t = half * 32 + lane;
+        const bool live = t < W;
+        const uint64_t vkey = live ? sc->out[t] : 0ull;
+        const I3 g = unpack_key(vkey);
+        bool skip = false;
+        if (live && cfg.anti_grazing && (clearing || vkey != own)) {   // merged.cpp:306-313: skip voxels that are some bundle's end voxel
+          int lo = 0, hi = capacity;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] < vkey) lo = mid + 1; else hi = mid; }
+          skip = (lo < capacity && ks[lo] == vkey);
+        }
+        // one block lookup per run of steps inside the same block
+        const I3 bi = block_of_voxel(g, cfg.vps_inv);
+        const uint64_t bk = (live && !skip) ? pack_key(bi) : ~0ull;
+        const uint64_t prev = __shfl_up_sync(0xffffffffu, bk, 1);
+        const bool leader = bk != ~0ull && (lane == 0 || prev != bk);
+        int htpos = -1;
+        if (leader) { if (!key_in_range(bi)) set_err(cnt, 5); else htpos = ht_find_or_insert(map, bk, cnt); }
+        const unsigned lm = __ballot_sync(0xffffffffu, leader);
+        const unsigned below = lm & (0xffffffffu >> (31 - lane));
+        const int src = below ? (31 - __clz(below)) : lane;
+        htpos = __shfl_sync(0xffffffffu, htpos, src);
+        if (live) {
+          uint64_t r = ~0ull;
+          if (skip) ++skipped;
+          else if (htpos >= 0) r = make_record(cfg, htpos, g, (uint32_t)b);
+          records[base + s0 + t] = r;
+        }
+      }
+      __syncwarp();
+    }
   }
-  if (cfg.shard_count > 1 && tile_owner(map.ht_keys[pos], (int)(tk % (uint32_t)cfg.tiles_per_block), cfg.shard_count) != cfg.shard_rank) return;
-  // segment end: first j > i whose voxel differs (galloping, then bisection)
-  long long lo = i, hi;            // invariant: rec[lo] belongs to the segment
-  long long step = 1;
-  for (;;) {
-    const long long p = i + step;
-    if (p >= n) { hi = n; break; }
-    if ((rec[p] >> kRecOrdBits) != vk) { hi = p; break; }
-    lo = p;
-    step <<= 1;
+  warp_add(&cnt->n_skipped, skipped);
+}
+
+static constexpr int kHeadsBlock = 1024;      // records per CTA of k_voxel_heads (256 threads x 4)
+__global__ void __launch_bounds__(256) k_voxel_heads(DevCfg cfg, Counters* cnt, MapRef map, const uint64_t* __restrict__ rec, long long n, int stamp, VoxelQueues q) {
+  // the CTA's 1024 voxel keys (+ the predecessor's) in shared memory: a head finds the end of its segment by scanning shared memory
+  // (segments average ~17 records); only a segment that runs past the CTA's range continues with a galloping search in global memory
+  __shared__ uint64_t s_vk[kHeadsBlock + 1];
+  const long long base = (long long)blockIdx.x * kHeadsBlock;
+  const uint64_t kNone = ~0ull;                     // no record here (beyond n)
+  for (int t = threadIdx.x; t < kHeadsBlock; t += blockDim.x) {
+    const long long i = base + t;
+    s_vk[1 + t] = (i < n) ? (rec[i] >> kRecOrdBits) : kNone;
   }
-  while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if ((rec[mid] >> kRecOrdBits) == vk) lo = mid; else hi = mid; }
-  const long long len = hi - i;
-  if (len >= kLongLen) {
-    const bool hot = len >= kHotLen;
-    const int at = atomicAdd(&q.counters[hot ? 0 : 1], 2);
-    if (at + 2 > q.long_cap / 2) { set_err(cnt, 4); return; }   // cannot happen: long_cap >= 2 * (2 * records / kLongLen)
-    const unsigned long long item = ((unsigned long long)i << 24) | ((unsigned long long)len << 1);
-    if (hot) { q.long_items[at] = item; q.long_items[at + 1] = item | 1ull; }
-    else { q.long_items[q.long_cap - 1 - at] = item; q.long_items[q.long_cap - 2 - at] = item | 1ull; }
-  } else {
-    // one atomic per warp: the short segments are the bulk of the heads
-    const unsigned am = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(am) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&q.counters[2], __popc(am));
-    base = __shfl_sync(am, base, leader);
-    const int at = base + __popc(am & ((1u << lane) - 1u));
-    if (at >= q.short_cap) { set_err(cnt, 4); return; }
-    q.short_items[at] = ((unsigned long long)i << 24) | (unsigned long long)len;
+  if (threadIdx.x == 0) s_vk[0] = (base > 0) ? (rec[base - 1] >> kRecOrdBits) : kNone;
+  __syncthreads();
+  const uint64_t kSkipped = ~0ull >> kRecOrdBits;   // records dropped by anti-grazing sort last (key ~0)
+  for (int t = threadIdx.x; t < kHeadsBlock; t += blockDim.x) {
+    const long long i = base + t;
+    if (i >= n) break;
+    const uint64_t vk = s_vk[1 + t];
+    if (vk == kSkipped) continue;
+    if (s_vk[t] == vk && !(base == 0 && t == 0)) continue;                    // not the first record of its voxel
+    const uint32_t tk = (uint32_t)(vk >> kRecVoxBits);
+    const int pos = (int)(tk / (uint32_t)cfg.tiles_per_block);
+    if ((base == 0 && t == 0) || (uint32_t)(s_vk[t] >> kRecVoxBits) != tk) {   // tile head: updated() bookkeeping is replicated on every shard
+      const int old = atomicExch(&map.touched_stamp[pos], stamp);
+      if (old != stamp) map.touched_list[atomicAdd(&cnt->n_blocks_touched, 1)] = pos;
+      atomicAdd(&cnt->n_tiles, 1);
+    }
+    if (cfg.shard_count > 1 && tile_owner(map.ht_keys[pos], (int)(tk % (uint32_t)cfg.tiles_per_block), cfg.shard_count) != cfg.shard_rank) continue;
+    int j = t + 1;
+    while (j < kHeadsBlock && s_vk[1 + j] == vk) ++j;
+    long long len = j - t;
+    if (j == kHeadsBlock && base + kHeadsBlock < n) {   // the segment reaches the end of the CTA's range: gallop on in global memory
+      long long lo = base + kHeadsBlock - 1, hi;       // invariant: rec[lo] belongs to the segment
+      long long step = 1;
+      for (;;) {
+        const long long p = base + kHeadsBlock - 1 + step;
+        if (p >= n) { hi = n; break; }
+        if ((rec[p] >> kRecOrdBits) != vk) { hi = p; break; }
+        lo = p;
+        step <<= 1;
+      }
+      while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if ((rec[mid] >> kRecOrdBits) == vk) lo = mid; else hi = mid; }
+      len = hi - i;
+    }
+    if (len >= kLongLen) {
+      const bool hot = len >= kHotLen;
+      const int at = atomicAdd(&q.counters[hot ? 0 : 1], 2);
+      if (at + 2 > q.long_cap / 2) { set_err(cnt, 4); continue; }   // cannot happen: long_cap >= 2 * (2 * records / kLongLen)
+      const unsigned long long item = ((unsigned long long)i << 24) | ((unsigned long long)len << 1);
+      if (hot) { q.long_items[at] = item; q.long_items[at + 1] = item | 1ull; }
+      else { q.long_items[q.long_cap - 1 - at] = item; q.long_items[q.long_cap - 2 - at] = item | 1ull; }
+    } else {
+      // one atomic per warp and round: the short segments are the bulk of the heads
+      const unsigned am = __activemask();
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(am) - 1;
+      int cbase = 0;
+      if (lane == leader) cbase = atomicAdd(&q.counters[2], __popc(am));
+      cbase = __shfl_sync(am, cbase, leader);
+      const int at = cbase + __popc(am & ((1u << lane) - 1u));
+      if (at >= q.short_cap) { set_err(cnt, 4); continue; }
+      q.short_items[at] = ((unsigned long long)i << 24) | (unsigned long long)len;
+    }
   }
 }
 

@@ -3,8 +3,17 @@
 set -u
 O=gpurun_out/r02
 mkdir -p $O
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ref_golden.py tests/test_gpu_more.py -q -m gpu -x 2>&1 | tail -8 > $O/gpu_quick_9.log
+T="tests/test_gpu_parity.py tests/test_gpu_ref_golden.py"
+timeout 900 python -m pytest $T tests/test_gpu_more.py -q -m gpu -x 2>&1 | tail -8 > $O/gpu_quick_9.log
 tail -4 $O/gpu_quick_9.log
+if ! grep -q " passed" $O/gpu_quick_9.log || grep -q "failed" $O/gpu_quick_9.log; then
+  # which of the new pieces breaks parity?
+  for v in "KSG_EMIT_WARP=0" "KSG_HOT_KERNEL=0" "KSG_EMIT_WARP=0 KSG_HOT_KERNEL=0" "KSG_NO_UPDATE_LOG=1"; do
+    echo "== $v" >> $O/gpu_bisect_9.log
+    env $v timeout 600 python -m pytest $T tests/test_gpu_more.py -q -m gpu -x 2>&1 | tail -4 >> $O/gpu_bisect_9.log
+  done
+  cat $O/gpu_bisect_9.log
+fi
 timeout 1200 python bench.py --no-cpu-baseline --steps 100 --warmup 10 > $O/bench_full_9.json 2> $O/bench_full_9.err
 python - $O/bench_full_9.json <<'PY'
 import json,sys
@@ -21,6 +30,6 @@ try:
 except Exception as e:
     print('ERR', e); print(open(sys.argv[1].replace('.json','.err')).read()[-2500:])
 PY
-KSG_HOT_KERNEL=0 timeout 600 python bench.py --no-cpu-baseline --workload merged2 --steps 30 --warmup 5 --extra-workloads "" --shim-e2e 0 > $O/bench_merged2_nohotk.json 2>/dev/null
+KSG_HOT_KERNEL=0 KSG_EMIT_WARP=0 timeout 600 python bench.py --no-cpu-baseline --workload merged2 --steps 30 --warmup 5 --extra-workloads "" --shim-e2e 0 > $O/bench_merged2_nohotk.json 2>/dev/null
 python -c "
-import json; d=json.load(open('$O/bench_merged2_nohotk.json')); print('merged2 without hot kernel: fps %.1f'%d['value'], {k:round(v,3) for k,v in d['roofline']['phase_ms_per_frame'].items()})"
+import json; d=json.load(open('$O/bench_merged2_nohotk.json')); print('merged2 without hot kernel / warp emit: fps %.1f'%d['value'], {k:round(v,3) for k,v in d['roofline']['phase_ms_per_frame'].items()})"
