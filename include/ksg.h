@@ -280,6 +280,20 @@ int32_t ksg_fetch_update_log(ksg_integrator* h, int64_t* n, const ksg_voxel_upda
  * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);
 
+/* Ground-truth label accuracy of the map against an analytic world (SURVEY.md 8f NEXT-4), computed on the device.  The ground truth
+ * follows SemanticSimulationWorld::generateSemanticSdfFromWorld (kimera_semantics/src/simulation/semantic_simulation_world.cpp:35-97): the
+ * label of a voxel is the label of the world object closest to its centre (voxblox simulation objects; distances below max_dist only).
+ * Evaluated over the voxels with weight > 0 and |distance| <= band.  checker_size > 0 selects the labelling of the synthetic benchmark
+ * scene instead: label = 1 + ((floor(x/s) + floor(y/s) + floor(z/s) + object label) mod (num_labels - 1)), leaving out voxels closer than
+ * checker_margin to a checker boundary.  Outputs: voxels evaluated, voxels whose stored label equals the ground truth, observed voxels. */
+typedef struct ksg_world_object {
+  int32_t type;      /* 0 sphere: a = centre, b[0] = radius;  1 plane: a = point, b = normal;  2 axis-aligned cube: a = centre, b = size */
+  float a[3], b[3];
+  int32_t label;
+} ksg_world_object;
+int32_t ksg_evaluate_labels(ksg_integrator* h, const ksg_world_object* objects, int32_t n_objects, float max_dist, float band,
+                            float checker_size, float checker_margin, int64_t* evaluated, int64_t* correct, int64_t* observed);
+
 /* Remove every block and reset the fast integrator's two approximate sets. */
 int32_t ksg_reset(ksg_integrator* h);
 

@@ -239,6 +239,9 @@ def load_library(path: Optional[str] = None):
     lib.ksg_set_update_log.restype = C.c_int32
     lib.ksg_fetch_update_log.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_float))]
     lib.ksg_fetch_update_log.restype = C.c_int32
+    lib.ksg_evaluate_labels.argtypes = [H, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64)]
+    lib.ksg_evaluate_labels.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -252,7 +255,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
                "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
-               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log"]
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -529,6 +532,16 @@ class Integrator:
         h = np.frombuffer((C.c_uint8 * (k * dt.itemsize)).from_address(heads.value), dtype=dt).copy()
         p = np.ctypeslib.as_array(pri, shape=(k, self.cfg.num_labels)).copy()
         return h, p
+
+    WORLD_DTYPE = np.dtype([("type", np.int32), ("a", np.float32, 3), ("b", np.float32, 3), ("label", np.int32)])
+
+    def evaluate_labels(self, objects: np.ndarray, max_dist: float, band: float, checker_size: float = 0.0, checker_margin: float = 0.0):
+        """(evaluated, correct, observed) voxel counts of the map's labels against an analytic world (ksg_evaluate_labels)."""
+        objs = np.ascontiguousarray(objects, self.WORLD_DTYPE)
+        ev, ok, ob = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.ksg_evaluate_labels(self.handle, objs.ctypes.data_as(C.c_void_p), len(objs), max_dist, band, checker_size, checker_margin,
+                                                 C.byref(ev), C.byref(ok), C.byref(ob)), "ksg_evaluate_labels")
+        return int(ev.value), int(ok.value), int(ob.value)
 
     def last_updated_blocks(self) -> np.ndarray:
         n = int(self.lib.ksg_last_updated_blocks(self.handle, 0, None))

@@ -22,6 +22,7 @@
 #include "ksg_fast3.cuh"
 #include "ksg_voxel.cuh"
 #include "ksg_merge.cuh"
+#include "ksg_eval.cuh"
 
 using namespace ksg;
 
@@ -1581,6 +1582,35 @@ int32_t ksg_fetch_update_log(ksg_integrator* h, int64_t* n_out, const ksg_voxel_
   *n_out = n;
   if (heads) *heads = reinterpret_cast<const ksg_voxel_update*>(h->h_log_head);
   if (priors) *priors = h->h_log_prior;
+  return KSG_OK;
+}
+
+int32_t ksg_evaluate_labels(ksg_integrator* h, const ksg_world_object* objects, int32_t n_objects, float max_dist, float band, float checker_size,
+                            float checker_margin, int64_t* evaluated, int64_t* correct, int64_t* observed) {
+  if (!h || n_objects < 0 || (n_objects > 0 && !objects) || n_objects > 4096) return KSG_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(ksg_world_object) == sizeof(WorldObject), "ksg_world_object layout");
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  unsigned long long res[3] = {0, 0, 0};
+  if (h->num_blocks > 0 && n_objects > 0) {
+    WorldObject* d_objs = nullptr;
+    unsigned long long* d_out = nullptr;
+    KSG_CUDA(cudaMalloc((void**)&d_objs, sizeof(WorldObject) * (size_t)n_objects));
+    KSG_CUDA(cudaMalloc((void**)&d_out, sizeof(res)));
+    KSG_CUDA(cudaMemcpy(d_objs, objects, sizeof(WorldObject) * (size_t)n_objects, cudaMemcpyHostToDevice));
+    KSG_CUDA(cudaMemset(d_out, 0, sizeof(res)));
+    ++h->n_launches;
+    k_eval_labels<<<h->sm_count * 4, 256, 0, h->own_stream>>>(h->dc, h->map, (int)h->num_blocks, d_objs, n_objects, max_dist, band, checker_size,
+                                                              checker_margin, d_out);
+    KSG_CUDA(cudaMemcpyAsync(res, d_out, sizeof(res), cudaMemcpyDeviceToHost, h->own_stream));
+    KSG_CUDA(cudaStreamSynchronize(h->own_stream));
+    cudaFree(d_objs); cudaFree(d_out);
+  }
+  if (evaluated) *evaluated = (int64_t)res[0];
+  if (correct) *correct = (int64_t)res[1];
+  if (observed) *observed = (int64_t)res[2];
   return KSG_OK;
 }
 
