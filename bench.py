@@ -363,6 +363,10 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
     launches, libcalls = prof["kernel_launches"], prof["library_calls"]
     clocks = sampler.stop() if rank == 0 else None
     blocks = integ.num_blocks()
+    if args.quick:
+        integ.close()
+        return {"workload": workload, "value": steps / (ms / 1e3), "ms_per_step": ms / steps, "quick": True,
+                "env": {k: v for k, v in os.environ.items() if k.startswith("KSG_")}}
 
     # ---------------- per-phase profiling pass + untimed replay of the timed frames (separate map, not part of `value`) ----------------
     integ.close()
@@ -681,6 +685,7 @@ def main():
                          "merges them into its replica of the map in frame order (SURVEY.md 8e row 1, BASELINE configs[3])")
     ap.add_argument("--profile-frames", type=int, default=20, help="frames of the separate per-phase profiling pass")
     ap.add_argument("--sequences-per-gpu", type=int, default=4, help="N = 1, fast: also measure K independent sequences on one GPU (0/1: skip)")
+    ap.add_argument("--quick", action="store_true", help="development aid: only the device-resident `value` leg, printed as a short line")
     ap.add_argument("--shim-e2e", type=int, default=1, help="N = 1: also time the C++ drop-in classes end to end (eager / lazy layer sync); 0 = skip")
     ap.add_argument("--extra-workloads", default="merged2", help="comma list of further workloads measured (briefly) into `workloads` at N = 1; '' = none")
     args = ap.parse_args()
@@ -708,6 +713,10 @@ def main():
         dist.destroy_process_group()
         return
     line = measure(args, args.workload, args.steps, args.warmup, ctx, not args.no_cpu_baseline, args.profile_frames)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
     extra = {}
     if world == 1 and args.extra_workloads:
         for wl in [x for x in args.extra_workloads.split(",") if x and x != args.workload]:

@@ -155,6 +155,8 @@ struct ksg_integrator {
   TileDesc* tile_list = nullptr;
   int solve_grid = 0, apply_fast_smem = 0;
   int solver = 3;                    // 3: rank-group solver (ksg_fast3.cuh), 2: first persistent formulation (k_fast_solve)
+  int solve_threads = kSolveThreads; // tuning knobs (environment): KSG_SOLVE_THREADS, KSG_SOLVE_CTAS_PER_SM, KSG_GROUP0, KSG_GROUP_MUL
+  int group0 = kGroup0, group_mul = 4;
   Cand* cand16 = nullptr;
   OvfEnt* ovf = nullptr;
   RayRec* rayrec = nullptr;
@@ -511,6 +513,7 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
   f.o3.head = h->ob.head; f.o3.ovf = h->ovf; f.o3.ovf_cap = h->ovf_cap; f.o3.stamp_max = h->stamp64; f.o3.stamp_min = h->stamp64 + kSetSize; f.o3.table = h->ob.table;
   f.rayrec = h->rayrec; f.blk_run = h->blk_run;
   f.log_head = h->d_log_head; f.log_prior = h->d_log_prior; f.log_cap = h->log_cap;
+  f.group0 = h->group0; f.group_mul = h->group_mul;
   f.s_base = h->start_head; f.s_hmin = h->start_val; f.s_hmax = (uint32_t*)(h->clear_00 + (size_t)kSetSize * 5);
   f.s_visits = (int*)(h->clear_00 + (size_t)kSetSize * 9); f.mixed_list = h->mixed_list; f.m_list = h->m_list;
   const bool s3 = h->solver == 3;
@@ -549,7 +552,7 @@ int integrate_fast_v2(ksg_integrator* h, const InputDesc& in, const FrameIn& fin
     void* args[] = {(void*)&f, (void*)&max_sweeps};
     ++h->n_launches;
     KSG_CUDA(cudaLaunchCooperativeKernel(s3 ? (const void*)k_fast_solve3 : (const void*)k_fast_solve, dim3(h->solve_grid),
-                                         dim3(kSolveThreads), args, s3 ? (size_t)h->solve_smem : 0, s));
+                                         dim3(s3 ? h->solve_threads : kSolveThreads), args, s3 ? (size_t)h->solve_smem : 0, s));
   }
   if (h->profiling) cudaEventRecord(h->ev[2], s);
   {
@@ -1276,9 +1279,12 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       int per_sm = 0;
       KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_solve, kSolveThreads, 0));
       int per_sm3 = 0;
-      h->solve_smem = (int)(sizeof(int) * kSortPerWarp * (kSolveThreads / 32));
+      if (const char* e = std::getenv("KSG_SOLVE_THREADS")) { const int t = std::atoi(e); if (t == 256 || t == 512 || t == 1024) h->solve_threads = t; }
+      if (const char* e = std::getenv("KSG_GROUP0")) h->group0 = std::max(32, std::atoi(e));
+      if (const char* e = std::getenv("KSG_GROUP_MUL")) h->group_mul = std::max(2, std::atoi(e));
+      h->solve_smem = (int)(sizeof(int) * kSortPerWarp * (h->solve_threads / 32));
       KSG_CUDA(cudaFuncSetAttribute(k_fast_solve3, cudaFuncAttributeMaxDynamicSharedMemorySize, h->solve_smem));
-      KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_fast_solve3, kSolveThreads, (size_t)h->solve_smem));
+      KSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_fast_solve3, h->solve_threads, (size_t)h->solve_smem));
       if (h->solver == 3) per_sm = per_sm3;
       int coop = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);

@@ -105,6 +105,7 @@ struct FastFrame {
   Obs3 o3;
   RayRec* rayrec;
   int* blk_run;              // consecutive-collision count at the start of every evaluation block (index: candidate index / 16)
+  int group0, group_mul;     // rank groups of the solver: first group, growth factor
   // update log (NULL: off)
   VoxelUpdate* log_head; float* log_prior; int log_cap;
   // start set, third formulation: per-slot aggregates only (no linked lists)

@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
   sweep = (sweep + 4) & ~3;       // counter slot (sweep + 1) & 3 of the first sweep was zeroed by the frame reset
   const int first_sweep = sweep + 1;
   bool failed = false;
-  int g_lo = 0, g_size = kGroup0;
+  int g_lo = 0, g_size = f.group0 > 0 ? f.group0 : kGroup0;
   while (g_lo < n_cast && !failed) {
     const int g_hi = (g_lo + g_size < n_cast) ? g_lo + g_size : n_cast;
     bool converged = false;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) k_fast_solve3(FastFrame f, i
     }
     if (!converged) failed = true;
     g_lo = g_hi;
-    g_size *= 4;
+    g_size = (g_size < (1 << 28)) ? g_size * (f.group_mul > 1 ? f.group_mul : 4) : g_size;
   }
   if (gtid == 0) {
     cnt->last_sweep = sweep;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/gpurun_retry.sh <logfile> <gpurun args...>   - retries while the pod answers "busy" (exit 3), up to 12 times
 log=$1; shift
-for i in $(seq 1 12); do
+for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
   rc=$?
   if [ $rc -ne 3 ] && ! grep -q "status=transient" "$log"; then exit $rc; fi

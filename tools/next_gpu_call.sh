@@ -33,3 +33,7 @@ PY
 KSG_HOT_KERNEL=0 KSG_EMIT_WARP=0 timeout 600 python bench.py --no-cpu-baseline --workload merged2 --steps 30 --warmup 5 --extra-workloads "" --shim-e2e 0 > $O/bench_merged2_nohotk.json 2>/dev/null
 python -c "
 import json; d=json.load(open('$O/bench_merged2_nohotk.json')); print('merged2 without hot kernel / warp emit: fps %.1f'%d['value'], {k:round(v,3) for k,v in d['roofline']['phase_ms_per_frame'].items()})"
+# tuning sweep of the solve kernel (quick legs only)
+for v in "KSG_GROUP0=512" "KSG_GROUP0=2048" "KSG_GROUP0=8192" "KSG_GROUP0=1000000" "KSG_GROUP0=512 KSG_GROUP_MUL=8" "KSG_GROUP0=128 KSG_GROUP_MUL=2" "KSG_SOLVE_THREADS=512" "KSG_SOLVE_THREADS=256" "KSG_SOLVE_THREADS=512 KSG_SOLVE_CTAS_PER_SM=1"; do
+  echo "== $v: $(env $v timeout 300 python bench.py --quick --steps 100 --warmup 10 2>/dev/null | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print("%.1f fps %.4f ms" % (d["value"], d["ms_per_step"]))')" | tee -a $O/tuning_9.log
+done
