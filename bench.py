@@ -197,23 +197,25 @@ def best_cpu_arm(workload, frames, cam):
     return best[0], best[1], {f"{a}@{t}": v for (a, t), v in res.items()}
 
 
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's update kernel, from the newest committed `ncu --set full`
-    capture (profiles/r*/prof_apply_<workload>.raw.csv) -> (bytes or None, which capture).  A capture describes the kernel of the commit it
-    was taken at; the file name carries the round."""
+def ncu_traffic(workload, tag="apply"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one frame's launches of the phase `tag` ("apply": the update kernel(s), "solve3": the
+    persistent solve kernel of `fast`, "sort": the radix sort passes of `merged`), from the newest committed `ncu --set full` capture
+    (profiles/r*/prof_<tag>_<workload>*.raw.csv; one row per launch, summed) -> (bytes or None, which capture).  A capture describes the
+    kernels of the commit it was taken at; the directory carries the round."""
     import csv
     import glob
-    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"prof_apply_{workload}*.raw.csv")))
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", f"prof_{tag}_{workload}*.raw.csv")))
     for path in reversed(cands):
         try:
-            rows = list(csv.reader(open(path)))
-            hdr, units, vals = rows[0], rows[1], rows[-1]
+            rows = [r for r in csv.reader(open(path)) if r]
+            hdr, units, launches = rows[0], rows[1], rows[2:]
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot = 0.0
-            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                k = hdr.index(name)
-                tot += float(vals[k].replace(",", "")) * scale.get(units[k], 1.0)
-            return tot, os.path.relpath(path, ROOT) + " (ncu --set full, one launch)"
+            for vals in launches:
+                for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    k = hdr.index(name)
+                    tot += float(vals[k].replace(",", "")) * scale.get(units[k], 1.0)
+            return tot, os.path.relpath(path, ROOT) + f" (ncu --set full, {len(launches)} launch(es) of one frame)"
         except Exception:
             continue
     return None, None
@@ -518,7 +520,8 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
         if arm == "port":
             cpu["mvoxel_updates_per_s"] = c_all["mupdates_per_s"]
     head = e2e.get("pipelined", e2e["sync"])
-    traffic, traffic_src = ncu_traffic(workload)
+    tag_of_phase = ({"tile_apply": "apply"} if itype == KSG_INTEGRATOR_FAST else {"tile_apply": "apply", "record_sort": "sort"})
+    traffic, traffic_src = ncu_traffic(workload, tag_of_phase.get(top_phase, "solve3" if itype == KSG_INTEGRATOR_FAST else top_phase))
     shim = shim_e2e(workload, frames[warmup:], cam) if (world == 1 and args.shim_e2e) else None
     return {
         "metric": "depth_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps,

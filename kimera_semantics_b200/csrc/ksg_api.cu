@@ -193,8 +193,15 @@ struct ksg_integrator {
   VoxelQueues vq{};
   cudaStream_t aux_stream = nullptr, aux_stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
-  bool hot_kernel = true;
-  bool emit_warp = true;             // one warp per bundle ray (KSG_EMIT_WARP=0: one thread per bundle, round 1)
+  // both measured SLOWER than what they were meant to replace (profiles/r02/bench_full_9.json vs bench_merged2_nohotk.json: the hot
+  // voxels' critical path is the TSDF weight recurrence, which a producer / consumer ring does not shorten; the warp-wide ray walk costs
+  // more in rank searches than the scattered stores it saves) - kept as opt-in experiments: KSG_HOT_KERNEL=1, KSG_EMIT_WARP=1
+  bool hot_kernel = false;
+  bool emit_warp = false;
+  // shape of the two per-voxel kernels (environment: KSG_LONG_THREADS, KSG_LONG_GRID, KSG_SHORT_CTAS): the short-segment kernel is
+  // capped at short_ctas CTAs per SM through a dynamic shared-memory reservation so that a CTA of the long-segment kernel (128
+  // registers per thread) always finds room beside it - otherwise the two kernels run back to back
+  int long_threads = 256, long_grid = 0, short_ctas = 6, short_smem = 0;
   int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
@@ -847,8 +854,8 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       h->n_launches += 2;
 #define KSG_LAUNCH_VOXEL(NCH)                                                                                                             \
       do {                                                                                                                                \
-        k_voxel_apply_long<NCH><<<h->sm_count, 256, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, use_hot);  \
-        k_voxel_apply_short<NCH><<<h->sm_count * 6, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);                 \
+        k_voxel_apply_long<NCH><<<h->long_grid, h->long_threads, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, use_hot);  \
+        k_voxel_apply_short<NCH><<<h->sm_count * h->short_ctas, 256, h->short_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);        \
       } while (0)
       switch (h->apply_nch) { case 1: KSG_LAUNCH_VOXEL(1); break; case 2: KSG_LAUNCH_VOXEL(2); break; case 4: KSG_LAUNCH_VOXEL(4); break; default: KSG_LAUNCH_VOXEL(8); break; }
 #undef KSG_LAUNCH_VOXEL
@@ -1175,7 +1182,11 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       h->vq.short_cap = rec_cap;
       KSG_CUDA(dmalloc(&h->vq.long_items, (size_t)h->vq.long_cap));
       KSG_CUDA(dmalloc(&h->vq.counters, 8));
-      KSG_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+      {   // the long-segment kernel must get its CTAs placed before the short-segment kernel fills the register files: its stream has priority
+        int lo_p = 0, hi_p = 0;
+        KSG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        KSG_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi_p));
+      }
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
       KSG_CUDA(cudaStreamCreateWithFlags(&h->aux_stream2, cudaStreamNonBlocking));
@@ -1183,6 +1194,17 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       h->hot_smem = 2 * kHotChunkRecs * (32 * (int)sizeof(float) + (int)sizeof(float4));
       KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, h->hot_smem));
       if (const char* e = std::getenv("KSG_HOT_KERNEL")) h->hot_kernel = std::atoi(e) != 0;
+      h->long_grid = h->sm_count;
+      if (const char* e = std::getenv("KSG_LONG_THREADS")) { const int t = std::atoi(e); if (t == 64 || t == 128 || t == 256) h->long_threads = t; }
+      if (const char* e = std::getenv("KSG_LONG_GRID")) h->long_grid = std::max(1, std::atoi(e));
+      if (const char* e = std::getenv("KSG_SHORT_CTAS")) h->short_ctas = std::max(1, std::min(6, std::atoi(e)));
+      if (h->short_ctas < 6) {
+        h->short_smem = std::min(200 * 1024, (220 * 1024) / h->short_ctas - 2048);
+        KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_short<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->short_smem));
+        KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_short<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->short_smem));
+        KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_short<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->short_smem));
+        KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_short<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->short_smem));
+      }
       if (const char* e = std::getenv("KSG_EMIT_WARP")) h->emit_warp = std::atoi(e) != 0;
     }
     if (cfg->hot_voxel_mode >= 1 && dc.C <= 32 && cfg->apply_mode == 0) {

@@ -67,7 +67,7 @@ __device__ __forceinline__ bool stamp_dirty(const Obs3& o, uint32_t slot, int la
 // first time a candidate turns performed: it enters the slot's bucket (or the overflow pool); returns its position code.
 // The overflow push is one exchange, no retry loop and no fence: a reader that catches the entry half-written (pending link, fields of
 // an older frame) takes a wrong decision for this sweep only - the inserter stamps the slot afterwards, which marks that reader dirty.
-__device__ __noinline__ int cand_insert_raw(int* slot_cnt, uint64_t* bkt, int* head, OvfEnt* ovf, int ovf_cap, int* ovf_count, Counters* cnt,
+__device__ __forceinline__ int cand_insert_raw(int* slot_cnt, uint64_t* bkt, int* head, OvfEnt* ovf, int ovf_cap, int* ovf_count, Counters* cnt,
                                             uint32_t slot, uint64_t entry) {
   const int idx = atomicAdd(&slot_cnt[slot], 1);
   if (idx < kBkt3) { const int pos = (int)slot * kBkt3 + idx; __stcg(&bkt[pos], entry); return pos; }
@@ -85,9 +85,9 @@ __device__ __forceinline__ int cand_insert3(const FastFrame& f, uint32_t slot, u
   return cand_insert_raw(f.o3.slot_cnt, f.o3.bkt, f.o3.head, f.o3.ovf, f.o3.ovf_cap, &f.fc->ovf_count, f.cnt, slot, entry);
 }
 
-// latest performed visit of `slot` that precedes `my_order`: its (value >> 20), or -1.  Deliberately NOT inlined and with rolled loops:
-// the persistent kernel is instruction-cache bound otherwise (the fully unrolled scan alone was ~13 KB of SASS per call site).
-__device__ __noinline__ int latest_performed_before_raw(const uint64_t* bkt, const int* slot_cnt, const int* head, const OvfEnt* ovf, int ovf_cap,
+// latest performed visit of `slot` that precedes `my_order`: its (value >> 20), or -1.  (A non-inlined variant of these helpers was measured
+// 20 % slower on the whole frame - profiles/r02/bench_full_9.json - so they stay inline; the loops past the first 8 entries are rolled.)
+__device__ __forceinline__ int latest_performed_before_raw(const uint64_t* bkt, const int* slot_cnt, const int* head, const OvfEnt* ovf, int ovf_cap,
                                                         uint32_t slot, uint64_t my_order) {
   const ulonglong2* b = (const ulonglong2*)(bkt + (size_t)slot * kBkt3);
   const int total = __ldcg(&slot_cnt[slot]);
@@ -120,7 +120,7 @@ __device__ __noinline__ int latest_performed_before_raw(const uint64_t* bkt, con
 __device__ __forceinline__ int latest_performed_before3(const Obs3& o, uint32_t slot, uint64_t my_order) {
   return latest_performed_before_raw(o.bkt, o.slot_cnt, o.head, o.ovf, o.ovf_cap, slot, my_order);
 }
-__device__ __noinline__ bool later_performed_exists_raw(const uint64_t* bkt, const int* slot_cnt, const int* head, const OvfEnt* ovf, int ovf_cap,
+__device__ __forceinline__ bool later_performed_exists_raw(const uint64_t* bkt, const int* slot_cnt, const int* head, const OvfEnt* ovf, int ovf_cap,
                                                         uint32_t slot, uint64_t my_order) {
   const int total = __ldcg(&slot_cnt[slot]);
   const int n = total < kBkt3 ? total : kBkt3;
@@ -174,7 +174,7 @@ __device__ __forceinline__ bool ray_state_parallel_ok(const RayState& st) {
   return fin && st.ts0 > 0.0f && st.ts1 > 0.0f && st.ts2 > 0.0f;
 }
 // W <= kWin steps from `st`; sc->out[0..W) = packed voxel indices, st advanced by W steps.  Returns false if an index left the packed range.
-__device__ __noinline__ bool warp_dda_window(RayState& st, int W, WarpDdaScratch* sc, int lane) {
+__device__ __forceinline__ bool warp_dda_window(RayState& st, int W, WarpDdaScratch* sc, int lane) {
   if (lane < 3) {
     float a = lane == 0 ? st.tn0 : (lane == 1 ? st.tn1 : st.tn2);
     const float ts = lane == 0 ? st.ts0 : (lane == 1 ? st.ts1 : st.ts2);

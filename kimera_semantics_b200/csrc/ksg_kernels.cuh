@@ -640,7 +640,7 @@ struct MapRef {
   int* touched_list;
 };
 
-__device__ __noinline__ int ht_find_or_insert_raw(uint64_t* ht_keys, uint32_t ht_mask, int* new_list, int new_cap, uint64_t key, Counters* cnt) {
+__device__ __forceinline__ int ht_find_or_insert_raw(uint64_t* ht_keys, uint32_t ht_mask, int* new_list, int new_cap, uint64_t key, Counters* cnt) {
   uint32_t pos = mix64(key) & ht_mask;
   for (uint32_t probe = 0; probe <= ht_mask; ++probe) {
     const uint64_t k = ((volatile uint64_t*)ht_keys)[pos];
