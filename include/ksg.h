@@ -294,6 +294,18 @@ typedef struct ksg_world_object {
 int32_t ksg_evaluate_labels(ksg_integrator* h, const ksg_world_object* objects, int32_t n_objects, float max_dist, float band,
                             float checker_size, float checker_margin, int64_t* evaluated, int64_t* correct, int64_t* observed);
 
+/* Semantic mesh of the map (SURVEY.md 8f NEXT-4), extracted on the device: marching cubes over the TSDF, every vertex carrying
+ * TsdfVoxel.color (which the semantic integrators overwrite with the label colour, semantic_integrator_base.cpp:172-191 - the mesh the
+ * reference displays, launch/kimera_semantics.launch:130-132) and the semantic label of the voxel that contains it.  Restates voxblox's
+ * MeshIntegrator / MarchingCubes (not under the reference tree: unpinned; csrc/ksg_mesh.cuh lists the conventions and the two deliberate
+ * differences).  min_weight: voxels with weight <= min_weight are unobserved (voxblox default 1e-4).  Triangles are 3 consecutive vertices.
+ * Blocks are listed in (z, y, x) order like ksg_export_blocks; block_first_vertex (block_capacity + 1 entries) holds the first vertex of
+ * every block and, last, the total.  A call with vertices = rgba = labels = NULL only counts (n_vertices, n_blocks, block tables);
+ * KSG_ERR_INVALID_ARGUMENT if a capacity is too small (n_vertices / n_blocks still report the need). */
+int32_t ksg_extract_mesh(ksg_integrator* h, float min_weight, int64_t vertex_capacity, float* vertices /* 3 per vertex */,
+                         uint8_t* rgba /* 4 per vertex */, uint8_t* labels /* 1 per vertex */, int64_t block_capacity,
+                         int32_t* block_index /* 3 per block */, int64_t* block_first_vertex, int64_t* n_vertices, int64_t* n_blocks);
+
 /* Remove every block and reset the fast integrator's two approximate sets. */
 int32_t ksg_reset(ksg_integrator* h);
 

@@ -242,6 +242,9 @@ def load_library(path: Optional[str] = None):
     lib.ksg_evaluate_labels.argtypes = [H, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int64)]
     lib.ksg_evaluate_labels.restype = C.c_int32
+    lib.ksg_extract_mesh.argtypes = [H, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ksg_extract_mesh.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -255,7 +258,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
                "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
-               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels"]
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels", "ksg_extract_mesh"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -542,6 +545,19 @@ class Integrator:
         self._check(self.lib.ksg_evaluate_labels(self.handle, objs.ctypes.data_as(C.c_void_p), len(objs), max_dist, band, checker_size, checker_margin,
                                                  C.byref(ev), C.byref(ok), C.byref(ob)), "ksg_evaluate_labels")
         return int(ev.value), int(ok.value), int(ob.value)
+
+    def extract_mesh(self, min_weight: float = 1e-4):
+        """Semantic mesh of the map (ksg_extract_mesh): dict(vertices [n, 3] f32 - three consecutive vertices per triangle, rgba [n, 4] u8,
+        labels [n] u8, block_index [nb, 3] i32 in (z, y, x) order, block_first [nb + 1] i64)."""
+        nv, nb = C.c_int64(), C.c_int64()
+        self._check(self.lib.ksg_extract_mesh(self.handle, min_weight, 0, None, None, None, 0, None, None, C.byref(nv), C.byref(nb)), "ksg_extract_mesh")
+        n, b = int(nv.value), int(nb.value)
+        vtx = np.zeros((n, 3), np.float32); rgba = np.zeros((n, 4), np.uint8); lab = np.zeros(n, np.uint8)
+        bidx = np.zeros((b, 3), np.int32); first = np.zeros(b + 1, np.int64)
+        self._check(self.lib.ksg_extract_mesh(self.handle, min_weight, n, vtx.ctypes.data_as(C.c_void_p), rgba.ctypes.data_as(C.c_void_p),
+                                              lab.ctypes.data_as(C.c_void_p), b, bidx.ctypes.data_as(C.c_void_p), first.ctypes.data_as(C.c_void_p),
+                                              C.byref(nv), C.byref(nb)), "ksg_extract_mesh")
+        return {"vertices": vtx, "rgba": rgba, "labels": lab, "block_index": bidx, "block_first": first}
 
     def last_updated_blocks(self) -> np.ndarray:
         n = int(self.lib.ksg_last_updated_blocks(self.handle, 0, None))

@@ -23,6 +23,7 @@
 #include "ksg_voxel.cuh"
 #include "ksg_merge.cuh"
 #include "ksg_eval.cuh"
+#include "ksg_mesh.cuh"
 
 using namespace ksg;
 
@@ -1639,6 +1640,74 @@ int32_t ksg_evaluate_labels(ksg_integrator* h, const ksg_world_object* objects, 
   if (evaluated) *evaluated = (int64_t)res[0];
   if (correct) *correct = (int64_t)res[1];
   if (observed) *observed = (int64_t)res[2];
+  return KSG_OK;
+}
+
+static bool key_less_zyx(uint64_t a, uint64_t b);
+
+int32_t ksg_extract_mesh(ksg_integrator* h, float min_weight, int64_t vertex_capacity, float* vertices, uint8_t* rgba, uint8_t* labels,
+                         int64_t block_capacity, int32_t* block_index, int64_t* block_first_vertex, int64_t* n_vertices, int64_t* n_blocks) {
+  if (!h || vertex_capacity < 0 || block_capacity < 0) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  const int64_t nb = h->num_blocks;
+  if (n_blocks) *n_blocks = nb;
+  if (n_vertices) *n_vertices = 0;
+  if (nb == 0) { if (block_first_vertex && block_capacity >= 0) block_first_vertex[0] = 0; return KSG_OK; }
+  if ((block_index || block_first_vertex) && nb > block_capacity) return fail(KSG_ERR_INVALID_ARGUMENT, "mesh: block capacity too small");
+  // blocks in (z, y, x) order, as ksg_export_blocks lists them
+  std::vector<uint64_t> keys((size_t)nb);
+  KSG_CUDA(cudaMemcpy(keys.data(), h->map.slot_key, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost));
+  std::vector<int> order((size_t)nb);
+  for (int64_t i = 0; i < nb; ++i) order[i] = (int)i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return key_less_zyx(keys[a], keys[b]); });
+  int* d_slots = nullptr; int* d_count = nullptr; long long* d_first = nullptr;
+  float* d_vtx = nullptr; uint32_t* d_rgba = nullptr; uint8_t* d_label = nullptr;
+  auto release = [&]() { cudaFree(d_slots); cudaFree(d_count); cudaFree(d_first); cudaFree(d_vtx); cudaFree(d_rgba); cudaFree(d_label); };
+#define KSG_MESH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); return fail(KSG_ERR_CUDA, cudaGetErrorString(e_)); } } while (0)
+  KSG_MESH(cudaMalloc((void**)&d_slots, sizeof(int) * nb));
+  KSG_MESH(cudaMalloc((void**)&d_count, sizeof(int) * nb));
+  KSG_MESH(cudaMalloc((void**)&d_first, sizeof(long long) * nb));
+  KSG_MESH(cudaMemcpy(d_slots, order.data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
+  cudaStream_t s = h->own_stream;
+  const int grid = (int)std::min<int64_t>(nb, (int64_t)h->sm_count * 8);
+  MeshBuf none{nullptr, nullptr, nullptr};
+  ++h->n_launches;
+  k_mesh_blocks<false><<<grid, kMeshThreads, 0, s>>>(h->dc, h->map, d_slots, (int)nb, min_weight, nullptr, d_count, none);
+  std::vector<int> count((size_t)nb);
+  KSG_MESH(cudaMemcpyAsync(count.data(), d_count, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+  KSG_MESH(cudaStreamSynchronize(s));
+  std::vector<long long> first((size_t)nb + 1);
+  first[0] = 0;
+  for (int64_t i = 0; i < nb; ++i) first[i + 1] = first[i] + count[i];
+  const int64_t total = first[nb];
+  if (n_vertices) *n_vertices = total;
+  if (block_index)
+    for (int64_t i = 0; i < nb; ++i) {
+      const I3 b = unpack_key(keys[order[i]]);
+      block_index[3 * i] = b.x; block_index[3 * i + 1] = b.y; block_index[3 * i + 2] = b.z;
+    }
+  if (block_first_vertex) for (int64_t i = 0; i <= nb && i <= block_capacity; ++i) block_first_vertex[i] = first[i];
+  if (!vertices && !rgba && !labels) { release(); return KSG_OK; }                 // counting call
+  if (total > vertex_capacity) { release(); return fail(KSG_ERR_INVALID_ARGUMENT, "mesh: vertex capacity too small (n_vertices holds the need)"); }
+  if (total > 0) {
+    KSG_MESH(cudaMalloc((void**)&d_vtx, sizeof(float) * 3 * total));
+    KSG_MESH(cudaMalloc((void**)&d_rgba, sizeof(uint32_t) * total));
+    KSG_MESH(cudaMalloc((void**)&d_label, (size_t)total));
+    KSG_MESH(cudaMemcpyAsync(d_first, first.data(), sizeof(long long) * nb, cudaMemcpyHostToDevice, s));
+    MeshBuf mb{d_vtx, d_rgba, d_label};
+    ++h->n_launches;
+    k_mesh_blocks<true><<<grid, kMeshThreads, 0, s>>>(h->dc, h->map, d_slots, (int)nb, min_weight, d_first, nullptr, mb);
+    if (vertices) KSG_MESH(cudaMemcpyAsync(vertices, d_vtx, sizeof(float) * 3 * total, cudaMemcpyDeviceToHost, s));
+    if (rgba) KSG_MESH(cudaMemcpyAsync(rgba, d_rgba, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, s));
+    if (labels) KSG_MESH(cudaMemcpyAsync(labels, d_label, (size_t)total, cudaMemcpyDeviceToHost, s));
+    KSG_MESH(cudaStreamSynchronize(s));
+    KSG_MESH(cudaGetLastError());
+  }
+#undef KSG_MESH
+  release();
   return KSG_OK;
 }
 

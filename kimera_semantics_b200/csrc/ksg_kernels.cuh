@@ -812,9 +812,9 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
                               const int* __restrict__ b_nsteps, const long long* __restrict__ b_base,
                               const uint64_t* __restrict__ ks, int capacity, uint64_t* __restrict__ records) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= cnt->n_cast) return;
-  const int n = b_nsteps[b];
-  if (n <= 0) return;
+  const int n = (b < cnt->n_cast) ? b_nsteps[b] : 0;
+  unsigned long long skipped = 0;      // one atomic per warp at the end (one per skipped record was ~5 x 10^5 same-address atomics per frame)
+  if (n > 0) {
   const float4 p = b_param[b];
   const bool clearing = (b_flags[b] & 2) != 0;
   Dda d;
@@ -837,7 +837,7 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
         }
       }
     }
-    if (skip) { records[base + s] = ~0ull; atomicAdd(&cnt->n_skipped, 1ull); continue; }
+    if (skip) { records[base + s] = ~0ull; ++skipped; continue; }
     const I3 bi = block_of_voxel(g, cfg.vps_inv);
     if (bi.x != last_b.x || bi.y != last_b.y || bi.z != last_b.z) {
       last_b = bi;
@@ -846,6 +846,8 @@ __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, co
     }
     records[base + s] = (htpos >= 0) ? make_record(cfg, htpos, g, (uint32_t)b) : ~0ull;
   }
+  }
+  warp_add(&cnt->n_skipped, skipped);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -135,9 +135,17 @@ __global__ void __launch_bounds__(256) k_voxel_heads(DevCfg cfg, Counters* cnt, 
   if (threadIdx.x == 0) s_vk[0] = (base > 0) ? (rec[base - 1] >> kRecOrdBits) : kNone;
   __syncthreads();
   const uint64_t kSkipped = ~0ull >> kRecOrdBits;   // records dropped by anti-grazing sort last (key ~0)
-  for (int t = threadIdx.x; t < kHeadsBlock; t += blockDim.x) {
+  // short segments are the bulk of the heads (~1.8 M per 640x480 / 2 cm frame): their queue slots are handed out with ONE atomic per
+  // CTA (block scan of the per-thread counts) - one atomic per warp and round was ~10^6 same-address atomics = the kernel's whole 0.5 ms
+  constexpr int kPerThread = kHeadsBlock / 256;
+  unsigned long long mine[kPerThread];
+  int n_mine = 0;
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    mine[k] = 0ull;
+    const int t = (int)threadIdx.x + k * 256;
     const long long i = base + t;
-    if (i >= n) break;
+    if (i >= n) continue;
     const uint64_t vk = s_vk[1 + t];
     if (vk == kSkipped) continue;
     if (s_vk[t] == vk && !(base == 0 && t == 0)) continue;                    // not the first record of its voxel
@@ -173,16 +181,29 @@ __global__ void __launch_bounds__(256) k_voxel_heads(DevCfg cfg, Counters* cnt, 
       if (hot) { q.long_items[at] = item; q.long_items[at + 1] = item | 1ull; }
       else { q.long_items[q.long_cap - 1 - at] = item; q.long_items[q.long_cap - 2 - at] = item | 1ull; }
     } else {
-      // one atomic per warp and round: the short segments are the bulk of the heads
-      const unsigned am = __activemask();
-      const int lane = threadIdx.x & 31;
-      const int leader = __ffs(am) - 1;
-      int cbase = 0;
-      if (lane == leader) cbase = atomicAdd(&q.counters[2], __popc(am));
-      cbase = __shfl_sync(am, cbase, leader);
-      const int at = cbase + __popc(am & ((1u << lane) - 1u));
-      if (at >= q.short_cap) { set_err(cnt, 4); continue; }
-      q.short_items[at] = ((unsigned long long)i << 24) | (unsigned long long)len;
+      mine[k] = ((unsigned long long)i << 24) | (unsigned long long)len;   // never 0: len >= 1
+      ++n_mine;
+    }
+  }
+  __shared__ int s_wsum[8];
+  __shared__ int s_cta_base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = n_mine;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_wsum[wid] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) { const int v = s_wsum[w]; s_wsum[w] = tot; tot += v; }
+    s_cta_base = tot > 0 ? atomicAdd(&q.counters[2], tot) : 0;
+  }
+  __syncthreads();
+  int at = s_cta_base + s_wsum[wid] + incl - n_mine;
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    if (mine[k] != 0ull) {
+      if (at >= q.short_cap) { set_err(cnt, 4); break; }
+      q.short_items[at++] = mine[k];
     }
   }
 }
