@@ -727,6 +727,24 @@ def main():
             sub_args = argparse.Namespace(**vars(args))
             sub_args.sequences_per_gpu = 0
             extra[wl] = measure(sub_args, wl, min(args.steps, 30), 5, ctx, not args.no_cpu_baseline, min(args.profile_frames, 10))
+    if world > 1 and args.sharding == "sequence" and args.extra_workloads:
+        # N > 1: the headline above is N independent sequences (replicas, no collective on the data path).  The two modes that share ONE
+        # sequence over the GPUs are measured briefly into the same line: the spatially sharded map (NCCL broadcast of the frame, strong
+        # scaling, on the workload where the per-voxel update dominates) and frame-per-GPU batches with the NCCL all-gather + delta merge.
+        def guarded(fn):
+            try:
+                return fn()
+            except Exception as e:          # a failing extra must not cost the headline line
+                return {"error": f"{type(e).__name__}: {e}"}
+        sub = argparse.Namespace(**vars(args))
+        sub.sequences_per_gpu = 0
+        sub.sharding = "spatial"
+        r1 = guarded(lambda: measure(sub, "merged2", 10, 3, ctx, False, 5))
+        sub2 = argparse.Namespace(**vars(args))
+        sub2.sharding = "frames"
+        r2 = guarded(lambda: measure_frame_batches(sub2, args.workload, 10, 3, ctx))
+        extra["merged2_spatial"] = r1
+        extra[f"{args.workload}_frame_batches"] = r2
     if rank == 0:
         line["workloads"] = extra
         print(json.dumps(line), flush=True)

@@ -202,7 +202,8 @@ struct ksg_integrator {
   // shape of the two per-voxel kernels (environment: KSG_LONG_THREADS, KSG_LONG_GRID, KSG_SHORT_CTAS): the short-segment kernel is
   // capped at short_ctas CTAs per SM through a dynamic shared-memory reservation so that a CTA of the long-segment kernel (128
   // registers per thread) always finds room beside it - otherwise the two kernels run back to back
-  int long_threads = 256, long_grid = 0, short_ctas = 6, short_smem = 0;
+  // (measured on merged2, profiles/r02/tuning_10.log: 6 CTAs/SM -> 148 fps, 4 + long 128 x 296 -> 163, 3 -> 166)
+  int long_threads = 256, long_grid = 0, short_ctas = 3, short_smem = 0;
   int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace

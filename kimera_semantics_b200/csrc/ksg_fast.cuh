@@ -53,7 +53,11 @@ struct TileDesc { uint32_t tk; int n; long long off; };
 struct VoxelUpdate { int bx, by, bz; uint32_t lin_label; float dist, wgt; uint32_t rgba, srgba; };   // lin_label = linear voxel index | label << 24
 
 // observed-set solver, third formulation (ksg_fast3.cuh)
-static constexpr int kGroup0 = 512;           // first rank group; the following groups are 4x larger each
+// Rank groups (ranks [0, n) are final once converged, so the solver can finish a prefix of the rays before it starts the rest; the
+// following groups are group_mul x larger each).  Measured (profiles/r02/tuning_10.log, fast5): 512 -> 2047 fps, 2048 -> 2207, 8192 -> 2393,
+// one group for all rays -> 2494: every extra group costs more grid barriers than it saves work, so the default is ONE group
+// (KSG_GROUP0 / KSG_GROUP_MUL keep the mechanism reachable).
+static constexpr int kGroup0 = 1 << 30;
 struct Cand;
 struct OvfEnt;
 struct RayRec;
