@@ -1,6 +1,6 @@
 // Checkpoint / resume of the two host layers (SURVEY.md 8f NEXT-3: "a simple binary for the semantic layer - the reference has
-// none"; the reference saves only the TSDF layer, through voxblox's .vxblx writer, kimera_semantics_rosbag.cpp:148-166, and that
-// format stays voxblox's).  One self-describing little-endian file for BOTH layers:
+// none"; the reference saves only the TSDF layer, through voxblox's .vxblx writer, kimera_semantics_rosbag.cpp:148-166 - that
+// format is in vxblx_io.h).  One self-describing little-endian file for BOTH layers:
 //   "KSGM", u32 version = 1, f32 voxel_size, u32 voxels_per_side, u32 num_labels, u64 num_blocks, then per block (sorted z,y,x):
 //   i32 index[3], f32 distance[V], f32 weight[V], u8 tsdf_rgba[4V], u8 label[V], f32 priors[V*C], u8 semantic_rgba[4V]
 // Host-only code; SemanticTsdfServer::loadMap() pushes the loaded layers to the device map through ksg_import_blocks.

@@ -6,6 +6,7 @@
 #include <memory>
 #include <string>
 #include "kimera_semantics/map_io.h"
+#include "kimera_semantics/vxblx_io.h"
 #include "kimera_semantics/semantic_tsdf_integrator_factory.h"
 #include "kimera_semantics/semantic_tsdf_integrator_fast.h"
 #include "kimera_semantics/semantic_tsdf_integrator_merged.h"
@@ -78,6 +79,13 @@ class SemanticTsdfServer {
     if (!map_io::loadLayers(path, tsdf_layer_.get(), semantic_layer_.get())) return false;
     gpu().uploadLayers();
     return true;
+  }
+
+  // The reference's own output file: the TSDF layer as a voxblox .vxblx (TsdfServer::saveMap -> voxblox::io::SaveLayer,
+  // kimera_semantics_rosbag.cpp:148-166), readable by voxblox tools; see vxblx_io.h for the (restated, unpinned) format.
+  bool saveTsdfVxblx(const std::string& path) {
+    updateLayers();
+    return vxblx_io::saveTsdfLayer(path, *tsdf_layer_);
   }
 
   vxb::Layer<vxb::TsdfVoxel>* getTsdfLayerPtr() { return tsdf_layer_.get(); }

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <string>
 #include "kimera_semantics/map_io.h"
+#include "kimera_semantics/vxblx_io.h"
 
 using namespace kimera;
 
@@ -75,6 +76,31 @@ int main(int argc, char** argv) {
     o.write(all.data(), (std::streamsize)(all.size() / 2));
   }
   KSG_CHECK(!map_io::loadLayers(dir + "/cut", &tsdf2, &sem2));
+  {  // voxblox .vxblx file of the TSDF layer: round trip, refusals
+    const std::string vx = dir + "/tsdf.vxblx";
+    tsdf.getBlockPtrByIndex(vxb::BlockIndex(0, 0, 0))->has_data() = true;
+    KSG_CHECK(vxblx_io::saveTsdfLayer(vx, tsdf));
+    vxb::Layer<vxb::TsdfVoxel> back(0.05f, 16u);
+    back.allocateBlockPtrByIndex(vxb::BlockIndex(7, 7, 7));              // replaced, not merged
+    KSG_CHECK(vxblx_io::loadTsdfLayer(vx, &back));
+    KSG_CHECK(back.getNumberOfAllocatedBlocks() == tsdf.getNumberOfAllocatedBlocks());
+    for (const vxb::BlockIndex& bi : map_io::sortedBlocks(tsdf)) {
+      auto a = tsdf.getBlockPtrByIndex(bi);
+      auto b = back.getBlockPtrByIndex(bi);
+      KSG_CHECK(b) << "block lost";
+      KSG_CHECK(a->has_data() == b->has_data());
+      for (size_t v = 0; v < a->num_voxels(); ++v) {
+        const vxb::TsdfVoxel &x = a->getVoxelByLinearIndex(v), &y = b->getVoxelByLinearIndex(v);
+        KSG_CHECK(!std::memcmp(&x.distance, &y.distance, 4) && !std::memcmp(&x.weight, &y.weight, 4) && x.color.r == y.color.r &&
+                  x.color.g == y.color.g && x.color.b == y.color.b && x.color.a == y.color.a);
+      }
+    }
+    KSG_CHECK(!vxblx_io::loadTsdfLayer(vx, &tsdf_other)) << "voxel size mismatch must be refused";
+    KSG_CHECK(!vxblx_io::loadTsdfLayer(vx, &tsdf_vps8));
+    KSG_CHECK(!vxblx_io::loadTsdfLayer(dir + "/junk", &back));
+    KSG_CHECK(!vxblx_io::loadTsdfLayer(dir + "/cut", &back));
+    KSG_CHECK(back.getNumberOfAllocatedBlocks() == tsdf.getNumberOfAllocatedBlocks()) << "a refused file must leave the layer untouched";
+  }
   std::printf("map io ok\n");
   return 0;
 }

@@ -207,6 +207,58 @@ def test_map_checkpoint_file_round_trip_on_the_host(demo, tmp_path):
     assert r.returncode == 0 and "map io ok" in r.stdout, r.stderr
     raw = open(tmp_path / "map.ksgm", "rb").read()
     assert raw[:4] == b"KSGM" and len(raw) == 28 + 4 * (12 + 16 ** 3 * (4 + 4 + 4 + 1 + 4 * 21 + 4))
+    _check_vxblx(tmp_path / "tsdf.vxblx")
+
+
+def _check_vxblx(path):
+    """The .vxblx file written by vxblx_io.h parses with google.protobuf against voxblox's schema (Layer.proto / Block.proto, restated in
+    the header) in voxblox's framing: varint32 message count, then length-delimited LayerProto + BlockProto messages."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name="vxblx_restated.proto", package="voxblox", syntax="proto2")
+    T = descriptor_pb2.FieldDescriptorProto
+    lay = fd.message_type.add(name="LayerProto")
+    for name, num, typ in (("voxel_size", 1, T.TYPE_DOUBLE), ("voxels_per_side", 2, T.TYPE_UINT32), ("type", 3, T.TYPE_STRING)):
+        lay.field.add(name=name, number=num, type=typ, label=T.LABEL_OPTIONAL)
+    blk = fd.message_type.add(name="BlockProto")
+    for name, num, typ in (("voxels_per_side", 1, T.TYPE_INT32), ("voxel_size", 2, T.TYPE_DOUBLE), ("origin_x", 3, T.TYPE_DOUBLE),
+                           ("origin_y", 4, T.TYPE_DOUBLE), ("origin_z", 5, T.TYPE_DOUBLE), ("has_data", 6, T.TYPE_BOOL)):
+        blk.field.add(name=name, number=num, type=typ, label=T.LABEL_OPTIONAL)
+    f = blk.field.add(name="voxel_data", number=7, type=T.TYPE_UINT32, label=T.LABEL_REPEATED)
+    f.options.packed = True
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    Layer = message_factory.GetMessageClass(pool.FindMessageTypeByName("voxblox.LayerProto"))
+    Block = message_factory.GetMessageClass(pool.FindMessageTypeByName("voxblox.BlockProto"))
+    raw = open(path, "rb").read()
+
+    def varint(pos):
+        v = shift = 0
+        while True:
+            c = raw[pos]
+            pos += 1
+            v |= (c & 0x7F) << shift
+            shift += 7
+            if not c & 0x80:
+                return v, pos
+    n, pos = varint(0)
+    assert n == 5                                    # layer header + the four blocks of the C++ test
+    size, pos = varint(pos)
+    layer = Layer()
+    layer.ParseFromString(raw[pos:pos + size])
+    pos += size
+    assert layer.type == "tsdf" and layer.voxels_per_side == 16 and abs(layer.voxel_size - 0.05) < 1e-7
+    origins = []
+    for _ in range(n - 1):
+        size, pos = varint(pos)
+        b = Block()
+        b.ParseFromString(raw[pos:pos + size])
+        pos += size
+        assert b.voxels_per_side == 16 and len(b.voxel_data) == 3 * 16 ** 3 and abs(b.voxel_size - 0.05) < 1e-7
+        origins.append(tuple(round(o / (16 * 0.05)) for o in (b.origin_x, b.origin_y, b.origin_z)))
+        if origins[-1] == (0, 0, 0):
+            assert b.has_data
+    assert pos == len(raw)
+    assert sorted(origins) == sorted([(0, 0, 0), (-1, 2, 3), (5, -7, 1), (-100000, 99999, -3)])
 
 
 LAUNCH_PARAMS = """# kimera_semantics_ros/launch/kimera_semantics.launch:98-122 as key: value lines
