@@ -102,7 +102,7 @@ struct ksg_integrator {
   uint64_t* ks_sorted = nullptr;
   uint32_t* seq_sorted = nullptr;
   int *bstart = nullptr, *bundle_f = nullptr;
-  float *hist = nullptr, *tmp = nullptr;
+  float *hist = nullptr, *tmp = nullptr, *tmp4 = nullptr;   // tmp4: rows of tmp at a 4-float stride (k_voxel_apply_short_t)
   uint64_t* b_key = nullptr;
   long long* b_base = nullptr;
   // merged, KSG_BUNDLE_ORDER_LIBSTDCXX
@@ -204,6 +204,8 @@ struct ksg_integrator {
   // registers per thread) always finds room beside it - otherwise the two kernels run back to back
   // (measured on merged2, profiles/r02/tuning_10.log: 6 CTAs/SM -> 148 fps, 4 + long 128 x 296 -> 163, 3 -> 166)
   int long_threads = 256, long_grid = 0, short_ctas = 3, short_smem = 0;
+  bool short_thread = false;         // merged, C <= 32: k_voxel_apply_short_t
+  int short_t_ctas = 2;              // its CTAs per SM (KSG_SHORT_T_CTAS); 2 x 256 threads leave the registers of one long-segment CTA free
   int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
@@ -265,7 +267,7 @@ void free_all(ksg_integrator* h) {
                   h->start_next, h->start_min, h->clear_ff, h->clear_00, h->start_table, h->cast_seq, h->ray_param, h->ray_label, h->ray_flags,
                   h->ray_color, h->nsteps, h->H, h->L, h->ray_state, h->ext_off, h->eval_sweep, h->ob.slot_stamp, h->ob.cand_pos, h->ob.bkt, h->ob.cand_val, h->ob.cand_order,
                   h->ob.cand_next, h->ob.table, h->ks_sorted, h->seq_sorted, h->bstart, h->bundle_f, h->hist,
-                  h->tmp, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->d_scan_tot, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
+                  h->tmp, h->tmp4, h->b_key, h->b_base, h->bord_hash, h->bord_scratch, h->d_scan_tot, h->bundle_f2, h->d_hot_segs, h->d_hot_counts, h->d_hot_chunk_seg, h->d_hot_guess, h->d_hot_sums,
                   h->d_hot_tables, h->d_hot_prior, h->d_hot_same, h->tile_debug, h->d_gridbar, h->d_fc, h->blk_cnt, h->blk_off, h->warp_cnt, h->warp_off, h->seq_of_i, h->keys32,
                   h->tile_cnt, h->tile_slot, h->tile_list, h->cand16, h->ovf, h->rayrec, h->mixed_list, h->m_list, h->blk_run, h->stamp64, h->d_log_head, h->d_log_prior, h->vq.long_items, h->vq.counters, h->rec_a, h->rec_b, h->tile_begin, h->cub_temp, h->d_in, h->d_exp, h->d_exp_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -801,7 +803,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       const int nb = std::max(1, h->h_cnt->n_cast);
       n_records = (long long)h->h_cnt->n_records;
       ++h->n_launches;
-      k_bundle_loglik<<<grid_for((long long)(nb + 1) * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp);
+      k_bundle_loglik<<<grid_for((long long)(nb + 1) * dc.C, B), B, 0, s>>>(dc, h->d_cnt, h->hist, h->tmp, h->tmp4);
       ++h->n_launches;
       if (h->emit_warp)
         k_emit_merged_warp<<<h->sm_count * 8, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps, h->b_base,
@@ -810,7 +812,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       k_emit_merged<<<grid_for(nb, 128), 128, 0, s>>>(dc, T, h->d_cnt, h->map, h->ray_param, h->ray_flags, h->b_key, h->nsteps,
                                                       h->b_base, h->ks_sorted, cap, h->rec_a);
     }
-    src.param = h->ray_param; src.label = nullptr; src.color = nullptr; src.tmp = h->tmp;
+    src.param = h->ray_param; src.label = nullptr; src.color = nullptr; src.tmp = h->tmp; src.tmp4 = h->tmp4;
   }
 
   if (h->profiling) cudaEventRecord(h->ev[3], s);
@@ -859,6 +861,10 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
         k_voxel_apply_long<NCH><<<h->long_grid, h->long_threads, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, use_hot);  \
         k_voxel_apply_short<NCH><<<h->sm_count * h->short_ctas, 256, h->short_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);        \
       } while (0)
+      if (h->short_thread && h->apply_nch == 1) {
+        k_voxel_apply_long<1><<<h->long_grid, h->long_threads, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, use_hot);
+        k_voxel_apply_short_t<<<h->sm_count * h->short_t_ctas, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);
+      } else
       switch (h->apply_nch) { case 1: KSG_LAUNCH_VOXEL(1); break; case 2: KSG_LAUNCH_VOXEL(2); break; case 4: KSG_LAUNCH_VOXEL(4); break; default: KSG_LAUNCH_VOXEL(8); break; }
 #undef KSG_LAUNCH_VOXEL
       KSG_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
@@ -1181,6 +1187,16 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
     if (const char* e = std::getenv("KSG_MERGED_TILE_APPLY")) if (std::atoi(e) != 0) h->voxel_apply = false;
     if (h->voxel_apply) {
       h->vq.long_cap = 4 * (rec_cap / kLongLen) + 64;
+      h->vq.long_len = kLongLen;
+      if (dc.C <= 32) {   // one thread per short voxel (ksg_voxel.cuh); KSG_SHORT_THREAD=0 selects the warp-per-voxel kernel, KSG_LONG_LEN the split
+        h->short_thread = true;
+        if (const char* e = std::getenv("KSG_SHORT_THREAD")) h->short_thread = std::atoi(e) != 0;
+        if (h->short_thread) {
+          KSG_CUDA(dmalloc(&h->tmp4, (N + 1) * (size_t)((dc.C + 3) & ~3)));
+          h->vq.long_len = kLongLenThread;
+          if (const char* e = std::getenv("KSG_LONG_LEN")) h->vq.long_len = std::max(kLongLen, std::min(1 << 20, std::atoi(e)));
+        }
+      }
       h->vq.short_cap = rec_cap;
       KSG_CUDA(dmalloc(&h->vq.long_items, (size_t)h->vq.long_cap));
       KSG_CUDA(dmalloc(&h->vq.counters, 8));
@@ -1199,6 +1215,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       h->long_grid = h->sm_count;
       if (const char* e = std::getenv("KSG_LONG_THREADS")) { const int t = std::atoi(e); if (t == 64 || t == 128 || t == 256) h->long_threads = t; }
       if (const char* e = std::getenv("KSG_LONG_GRID")) h->long_grid = std::max(1, std::atoi(e));
+      if (const char* e = std::getenv("KSG_SHORT_T_CTAS")) h->short_t_ctas = std::max(1, std::min(8, std::atoi(e)));
       if (const char* e = std::getenv("KSG_SHORT_CTAS")) h->short_ctas = std::max(1, std::min(6, std::atoi(e)));
       if (h->short_ctas < 6) {
         h->short_smem = std::min(200 * 1024, (220 * 1024) / h->short_ctas - 2048);

@@ -796,15 +796,25 @@ __global__ void k_bundle_alloc(Counters* cnt, int* __restrict__ b_nsteps, long l
 
 // tmp[b][i] = sum_j L[i][j] * freq[j]  (base.cpp:306-307) with L[i][j] = log_match on the diagonal, log_non_match
 // elsewhere, column 0 zero (base.cpp:108-127); summation fixed as j ascending, one multiply + one add per term (A.9).
-__global__ void k_bundle_loglik(DevCfg cfg, const Counters* cnt, const float* __restrict__ hist, float* __restrict__ tmp) {
+// tmp4 (optional): the same rows at a stride of C rounded up to a multiple of 4, padded with zeros, for 128-bit row loads.
+__global__ void k_bundle_loglik(DevCfg cfg, const Counters* cnt, const float* __restrict__ hist, float* __restrict__ tmp, float* __restrict__ tmp4) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)cnt->n_cast * cfg.C;
-  if (t >= total) { if (t < total + cfg.C) tmp[t] = 0.0f; return; }   // row n_cast = zeros: target of padded row loads
+  const int C4 = (cfg.C + 3) & ~3;
+  if (t >= total) {   // row n_cast = zeros: target of padded row loads
+    if (t < total + cfg.C) { tmp[t] = 0.0f; if (tmp4) { const long long b = t / cfg.C; const int i = (int)(t % cfg.C); tmp4[b * C4 + i] = 0.0f; if (i == 0) for (int k = cfg.C; k < C4; ++k) tmp4[b * C4 + k] = 0.0f; } }
+    return;
+  }
   const int i = (int)(t % cfg.C);
   const float* h = hist + (t - i);
   float acc = 0.0f;
   for (int j = 1; j < cfg.C; ++j) acc = acc + ((i == j) ? cfg.lm : cfg.ln) * h[j];
   tmp[t] = acc;
+  if (tmp4) {
+    const long long b = t / cfg.C;
+    tmp4[b * C4 + i] = acc;
+    if (i == 0) for (int k = cfg.C; k < C4; ++k) tmp4[b * C4 + k] = 0.0f;
+  }
 }
 
 __global__ void k_emit_merged(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const float4* __restrict__ b_param,
@@ -981,6 +991,7 @@ struct ApplySrc {
   const uint8_t* label;  // fast: measured label (one-hot frequencies, fast.cpp:132-135); NULL for merged
   const uint32_t* color; // fast: point colour; NULL -> (0,0,0,0) (merged.cpp:70 unfilled hash_colors)
   const float* tmp;      // merged: C floats per bundle = L * freq; NULL for fast
+  const float* tmp4;     // merged, C <= 32: the same rows at stride ((C + 3) & ~3), zero padded (128-bit loads of k_voxel_apply_short_t)
   // HOTSEM instantiation only: segments sorted by begin, and their finished rows (32 floats per segment)
   const HotSeg* hot_segs;
   const float* hot_prior;

@@ -21,6 +21,7 @@
 namespace ksg {
 
 static constexpr int kLongLen = 96;        // segments of at least this many records are split into a TSDF item and a semantic item
+static constexpr int kLongLenThread = 256; // the same split when the short segments go to the thread-per-voxel kernel (C <= 32)
 static constexpr int kHotLen = 4096;       // ... and these are queued first
 static constexpr int kGrab = 8;            // short items fetched per queue access
 
@@ -28,6 +29,7 @@ struct VoxelQueues {
   unsigned long long* long_items;    // [begin:40][len:23][role:1], hot ones from the front, the others from the back
   unsigned long long* short_items;   // [begin:40][len:24]
   long long long_cap, short_cap;
+  int long_len;                      // segments of at least this many records are `long` (>= kLongLen, which sizes long_items)
   int* counters;                     // [0] hot count (front), [1] other long count (back), [2] short count, [3] long cursor, [4] short cursor, [5] hot cursor
 };
 
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) k_voxel_heads(DevCfg cfg, Counters* cnt, 
       while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if ((rec[mid] >> kRecOrdBits) == vk) lo = mid; else hi = mid; }
       len = hi - i;
     }
-    if (len >= kLongLen) {
+    if (len >= q.long_len) {
       const bool hot = len >= kHotLen;
       const int at = atomicAdd(&q.counters[hot ? 0 : 1], 2);
       if (at + 2 > q.long_cap / 2) { set_err(cnt, 4); continue; }   // cannot happen: long_cap >= 2 * (2 * records / kLongLen)
@@ -527,6 +529,84 @@ __global__ void __launch_bounds__(256, 6) k_voxel_apply_short(DevCfg cfg, Xform 
       if (lane == 0) { *pd = dist; *pw = wgt; if (keep_blend) *pc = rgba; }
       voxel_finish_semantic<NCH>(cfg, luts, vc, lane, p);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// short segments, C <= 32: one THREAD per voxel.
+// The warp-per-voxel kernel above spends ~900 warp instructions on a voxel that has ~11 records (ncu, profiles/r02/prof_apply_merged2:
+// 1.6 G warp instructions per frame, ALU pipe 63 % busy, 84 % of the SM's issue slots - compute bound on bookkeeping: the 32-lane weight
+// recurrence, the warp arg-max, per-voxel index arithmetic, a third of the lanes idle at C = 21).  Here a thread walks its voxel's records
+// alone - the recurrences ARE sequential - and 32 voxels share every issued instruction.  Same operations in the same order per voxel as the
+// warp kernels (tsdf_measure + tsdf_chain_step per record, p[c] += row[c] in record order, first maximum wins), hence the same bits.
+// Rows of (L * freq) are read as 128-bit words from the zero-padded table tmp4.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) k_voxel_apply_short_t(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
+                                                               const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q) {
+  const int C = cfg.C;
+  const int C4 = (C + 3) & ~3;
+  const int n_items = (int)min((long long)q.counters[2], q.short_cap);
+  const F3 origin = f3(T.tx, T.ty, T.tz);
+  const bool keep_blend = cfg.color_mode == 0;
+  const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
+  const int tpb_log2 = __ffs(cfg.tiles_per_block) - 1, tps_log2 = __ffs(cfg.tiles_per_side) - 1;   // powers of two (tile_side_log2, vps - 1 masks)
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+    const unsigned long long item = q.short_items[it];
+    const uint64_t* r = rec + (long long)(item >> 24);
+    const int len = (int)(item & 0xFFFFFFu);
+    uint64_t key = r[0];
+    const uint32_t tk = (uint32_t)(key >> 32);
+    const int pos = (int)(tk >> tpb_log2), tile = (int)(tk & (uint32_t)(cfg.tiles_per_block - 1));
+    const int slot = map.ht_slot[pos];
+    if (slot < 0 || slot >= map.max_blocks) continue;
+    uint8_t* chunk = map.pool + (uint64_t)slot * cfg.block_stride + (uint64_t)tile * cfg.tile_stride;
+    const int v = (int)((key >> kRecOrdBits) & ((1u << kRecVoxBits) - 1u));
+    const I3 bi = unpack_key(map.ht_keys[pos]);
+    const int ts = cfg.tile_side_log2, tm = cfg.tile_side - 1, tpm = cfg.tiles_per_side - 1;
+    I3 g;
+    g.x = bi.x * cfg.vps + ((tile & tpm) << ts) + (v & tm);
+    g.y = bi.y * cfg.vps + (((tile >> tps_log2) & tpm) << ts) + ((v >> ts) & tm);
+    g.z = bi.z * cfg.vps + ((tile >> (2 * tps_log2)) << ts) + (v >> (2 * ts));
+    const F3 center = voxel_center(g, cfg.voxel_size);
+    float* pd = (float*)chunk + v;
+    float* pw = (float*)(chunk + cfg.plane_f32) + v;
+    uint32_t* pc = (uint32_t*)(chunk + 2 * cfg.plane_f32) + v;
+    float dist = *pd, wgt = *pw;
+    uint32_t rgba = *pc;
+    float* prow = (float*)(chunk + cfg.head_bytes) + (size_t)v * C;
+    float p[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) p[c] = (c < C) ? prow[c] : 0.0f;
+    for (int k = 0; k < len; ++k) {
+      const uint32_t ord = (uint32_t)key & ord_mask;
+      if (k + 1 < len) key = r[k + 1];                   // next key one record ahead of its use
+      const float4 pr = src.param[ord];
+      const float4* row = (const float4*)(src.tmp4 + (size_t)ord * C4);
+      float4 rv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rv[j] = (4 * j < C) ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float sdf, uw;
+      tsdf_measure(cfg.tp, origin, f3(pr.x, pr.y, pr.z), center, pr.w, sdf, uw);
+      tsdf_chain_step(cfg.tp, sdf, uw, 0u, keep_blend, dist, wgt, rgba);   // merged: point colours are (0,0,0,0) (merged.cpp:70)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (4 * j < C) { p[4 * j] += rv[j].x; p[4 * j + 1] += rv[j].y; p[4 * j + 2] += rv[j].z; p[4 * j + 3] += rv[j].w; }   // pads add +0.0f
+      }
+    }
+    *pd = dist; *pw = wgt;
+    if (keep_blend) *pc = rgba;
+    // arg-max, first maximum wins (base.cpp:352-367) + colour hand-off (base.cpp:370-380, 172-191)
+    float best = p[0];
+    int lab = 0;
+#pragma unroll
+    for (int c = 1; c < 32; ++c) if (c < C && p[c] > best) { best = p[c]; lab = c; }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) if (c < C) prow[c] = p[c];
+    (chunk + 4 * cfg.plane_f32)[v] = (uint8_t)lab;
+    const uint32_t sc = luts->label_rgba[lab];
+    ((uint32_t*)(chunk + 3 * cfg.plane_f32))[v] = sc;
+    if (cfg.color_mode == 1) *pc = sc;                                                        // kSemantic
+    else if (cfg.color_mode == 2) *pc = rainbow_color_map((double)expf(best));              // kSemanticProbability
   }
 }
 
