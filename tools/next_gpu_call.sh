@@ -39,7 +39,7 @@ except Exception as e:
 PY
 NCU="ncu --clock-control none"
 timeout 900 $NCU --set full --import-source on -k regex:k_voxel_apply -s 6 -c 2 -o $O/prof_apply_merged2_12 -f python tools/run_frames.py merged2 5 > $O/ncu_apply2_12.log 2>&1
-timeout 900 $NCU --set full -k regex:Onesweep -s 40 -c 4 -o $O/prof_sort_merged2_12 -f python tools/run_frames.py merged2 5 > $O/ncu_sort2_12.log 2>&1
+timeout 900 $NCU --set full -k regex:Onesweep -s 44 -c 4 -o $O/prof_sort_merged2_12 -f python tools/run_frames.py merged2 5 > $O/ncu_sort2_12.log 2>&1
 for f in apply_merged2_12 sort_merged2_12; do
   if [ -f $O/prof_$f.ncu-rep ]; then
     ncu -i $O/prof_$f.ncu-rep --page raw --csv > $O/prof_$f.raw.csv 2>/dev/null
