@@ -44,7 +44,7 @@ WORKLOADS = {
     "merged5": (KSG_INTEGRATOR_MERGED, 640, 480, 0.05, 21, 16 << 20, 8192),
     "fast10": (KSG_INTEGRATOR_FAST, 320, 240, 0.10, 5, 0, 4096),        # configs[0] geometry
     "fast5_720p_c150": (KSG_INTEGRATOR_FAST, 1280, 720, 0.05, 150, 0, 2048),   # configs[3]: ADE20K-size label set, frame-per-GPU batches
-    "merged1_4k_c40": (KSG_INTEGRATOR_MERGED, 3840, 2160, 0.01, 40, 400 << 20, 65536),   # configs[4]: 4K / 1 cm, spatially sharded
+    "merged1_4k_c40": (KSG_INTEGRATOR_MERGED, 3840, 2160, 0.01, 40, 700 << 20, 65536),   # configs[4]: 4K / 1 cm, spatially sharded
 }
 
 
@@ -576,7 +576,8 @@ def measure_frame_batches(args, workload, steps, warmup, ctx):
     """--sharding frames: ONE camera stream, batches of N frames, one frame per GPU (BASELINE configs[3]).  Every rank
     holds a replica of the map; per batch it integrates its frame into an EMPTY delta map, the deltas (blocks in pool layout + block keys)
     are all-gathered with NCCL, and every rank merges the N deltas into its replica in frame order (ksg_merge_blocks_device).  A step = one
-    batch = N frames."""
+    batch = N frames.  Rank r's delta integrator is ONE integrator object for the whole run (frames r, r + N, ...) whose layers are emptied
+    between its frames (ksg_clear_map = Layer::removeAllBlocks on a live reference integrator)."""
     import torch
     import torch.distributed as dist
     from kimera_semantics_b200.capi import Integrator
@@ -606,7 +607,7 @@ def measure_frame_batches(args, workload, steps, warmup, ctx):
         nonlocal cap_blocks, send_pool, recv_pool, send_keys, recv_keys, t_int, t_xchg, t_merge, bytes_moved
         d, l, T = mine[k]
         evs[0].record(tstream)
-        delta.reset()
+        delta.clear_map()       # empties the delta map, keeps the integrator (its per-scan approximate sets) - see ksg_clear_map
         delta.integrate_depth_device(T, d.data_ptr(), l.data_ptr(), w, h, cam.K, stream)
         nb, _, _, _ = delta.device_map_view()
         evs[1].record(tstream)

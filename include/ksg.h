@@ -306,6 +306,12 @@ int32_t ksg_extract_mesh(ksg_integrator* h, float min_weight, int64_t vertex_cap
                          uint8_t* rgba /* 4 per vertex */, uint8_t* labels /* 1 per vertex */, int64_t block_capacity,
                          int32_t* block_index /* 3 per block */, int64_t* block_first_vertex, int64_t* n_vertices, int64_t* n_blocks);
 
+/* Remove every block but keep the integrator: what Layer::removeAllBlocks() on both layers does to a live reference integrator.  The
+ * fast integrator's two per-scan approximate sets (members of the integrator, fast.h:114-130) keep their contents and offsets, so the
+ * next frame is integrated exactly as the reference integrator object would integrate it into its emptied layers.  Used by the
+ * frame-per-GPU batch mode (the per-GPU "delta" map is emptied between batches). */
+int32_t ksg_clear_map(ksg_integrator* h);
+
 /* Remove every block and reset the fast integrator's two approximate sets. */
 int32_t ksg_reset(ksg_integrator* h);
 

@@ -245,6 +245,8 @@ def load_library(path: Optional[str] = None):
     lib.ksg_extract_mesh.argtypes = [H, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.ksg_extract_mesh.restype = C.c_int32
+    lib.ksg_clear_map.argtypes = [H]
+    lib.ksg_clear_map.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
     lib.ksg_build_info.restype = C.c_char_p
     if path is None:
@@ -258,7 +260,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
                "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
-               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels", "ksg_extract_mesh"]
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels", "ksg_extract_mesh", "ksg_clear_map"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -545,6 +547,10 @@ class Integrator:
         self._check(self.lib.ksg_evaluate_labels(self.handle, objs.ctypes.data_as(C.c_void_p), len(objs), max_dist, band, checker_size, checker_margin,
                                                  C.byref(ev), C.byref(ok), C.byref(ob)), "ksg_evaluate_labels")
         return int(ev.value), int(ok.value), int(ob.value)
+
+    def clear_map(self):
+        """Remove every block, keep the integrator state (ksg_clear_map)."""
+        self._check(self.lib.ksg_clear_map(self.handle), "ksg_clear_map")
 
     def extract_mesh(self, min_weight: float = 1e-4):
         """Semantic mesh of the map (ksg_extract_mesh): dict(vertices [n, 3] f32 - three consecutive vertices per triangle, rgba [n, 4] u8,

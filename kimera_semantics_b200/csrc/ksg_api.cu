@@ -205,7 +205,10 @@ struct ksg_integrator {
   // (measured on merged2, profiles/r02/tuning_10.log: 6 CTAs/SM -> 148 fps, 4 + long 128 x 296 -> 163, 3 -> 166)
   int long_threads = 256, long_grid = 0, short_ctas = 3, short_smem = 0;
   bool short_thread = false;         // merged, C <= 32: k_voxel_apply_short_t
-  int short_t_ctas = 2;              // its CTAs per SM (KSG_SHORT_T_CTAS); 2 x 256 threads leave the registers of one long-segment CTA free
+  // its CTAs per SM (KSG_SHORT_T_CTAS).  The frame is bound by the long-segment kernel (1184 warps, 128 registers each); whatever the
+  // short kernel takes from it costs more than it gains: merged2 1 -> 178 fps, 2 -> 166, 3 -> 166, 4 -> 170, warp-per-voxel kernel 170
+  // (profiles/r02/tuning_12.log)
+  int short_t_ctas = 1;
   int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace
@@ -2133,6 +2136,28 @@ int64_t ksg_debug_fast_timeline(ksg_integrator* h, int64_t* out64, int64_t* swee
   if (sweeps) *sweeps = h->h_fc->sweeps_last;
   if (clock_khz) *clock_khz = h->clock_khz;
   return kTimelineSlots + 16;
+}
+
+int32_t ksg_clear_map(ksg_integrator* h) {
+  if (!h) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  KSG_CUDA(cudaSetDevice(h->device));
+  KSG_CUDA(cudaDeviceSynchronize());
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  cudaStream_t s = h->own_stream;
+  KSG_CUDA(cudaMemsetAsync(h->map.ht_keys, 0xFF, sizeof(uint64_t) * h->ht_cap, s));
+  KSG_CUDA(cudaMemsetAsync(h->map.ht_slot, 0xFF, sizeof(int) * h->ht_cap, s));
+  KSG_CUDA(cudaMemsetAsync(h->map.touched_stamp, 0, sizeof(int) * h->ht_cap, s));
+  if (h->tile_cnt) KSG_CUDA(cudaMemsetAsync(h->tile_cnt, 0, sizeof(int) * (size_t)h->ht_cap * h->dc.tiles_per_block, s));
+  // the block pool restarts at slot 0; everything else in the counter block is per frame (rewritten by the next frame's first kernel)
+  // or belongs to the integrator (sweep ids of the observed-set solver, which the slot stamps refer to) and stays
+  KSG_CUDA(cudaMemsetAsync(&h->d_cnt->pool_count, 0, sizeof(int), s));
+  KSG_CUDA(cudaMemsetAsync(&h->d_cnt->n_blocks_touched, 0, sizeof(int), s));
+  KSG_CUDA(cudaMemsetAsync(&h->d_cnt->n_new_blocks, 0, sizeof(int), s));
+  h->num_blocks = 0;
+  h->last_blocks_touched = 0;
+  KSG_CUDA(cudaStreamSynchronize(s));
+  return KSG_OK;
 }
 
 int32_t ksg_reset(ksg_integrator* h) {

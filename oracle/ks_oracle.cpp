@@ -785,6 +785,15 @@ int kso_integrate_depth(void* hh, const float* T_G_C, const float* depth, const 
 
 int64_t kso_num_blocks(void* hh) { return (int64_t)((Integrator*)hh)->layer.size(); }
 
+// Layer::removeAllBlocks() on both layers while the integrator object lives on: the fast integrator's two approximate sets keep their
+// contents and offsets (fast.h:114-130 - they are members of the integrator, not of the layers).  Twin of ksg_clear_map.
+void kso_clear_map(void* hh) {
+  Integrator* in = (Integrator*)hh;
+  in->layer.clear();
+  in->temp_block_map.clear();
+  in->last_updated.clear();
+}
+
 int kso_export_blocks(void* hh, int64_t capacity, int32_t* block_index, float* tsdf_distance, float* tsdf_weight,
                       uint8_t* tsdf_rgba, uint8_t* sem_label, float* sem_priors, uint8_t* sem_rgba) {
   Integrator* h = (Integrator*)hh;

@@ -50,6 +50,8 @@ def load(fast_build: bool = False) -> C.CDLL:
     lib.kso_backproject_k64.restype = C.c_int64
     lib.kso_backproject.argtypes = [fp, C.c_int, C.c_int, fp, fp, i32p]
     lib.kso_backproject.restype = C.c_int64
+    lib.kso_clear_map.argtypes = [H]
+    lib.kso_clear_map.restype = None
     lib.kso_num_blocks.argtypes = [H]
     lib.kso_num_blocks.restype = C.c_int64
     lib.kso_export_blocks.argtypes = [H, C.c_int64, i32p, fp, fp, u8p, u8p, fp, u8p]
@@ -154,6 +156,10 @@ class OracleIntegrator:
 
     def export(self) -> Dict[str, np.ndarray]:
         return export_arrays(self.lib, self.handle, "kso", self.cfg.voxels_per_side, self.cfg.num_labels)
+
+    def clear_map(self):
+        """Remove every block, keep the integrator (its per-scan approximate sets) - Layer::removeAllBlocks on a live integrator."""
+        self.lib.kso_clear_map(self.handle)
 
     def last_updated_blocks(self) -> np.ndarray:
         n = int(self.lib.kso_last_updated_blocks(self.handle, 0, None))

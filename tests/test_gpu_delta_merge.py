@@ -36,3 +36,44 @@ def test_batch_of_frames_then_merge_equals_the_same_schedule_on_the_oracle(itype
     assert_parity(rep)
     assert rep["tsdf_distance_bit_mismatch"] == 0 and rep["tsdf_weight_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0, rep
     base.close()
+
+
+def test_round_robin_integrators_with_emptied_layers_equal_the_same_schedule_on_the_oracle():
+    """What bench.py --sharding frames runs: integrator r lives for the whole run, sees frames r, r + G, ..., and its layers are emptied
+    between its frames (ksg_clear_map / Layer::removeAllBlocks) - the fast integrator's approximate sets carry over, which changes which
+    rays are cast (the sets are only re-offset per scan, fast.cpp:165-171), so this is NOT the fresh-integrator schedule of the test above."""
+    W, H, C, G, rounds = 320, 240, 21, 2, 3
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.05, C, max_points=W * H, max_updates=16 << 20)
+    pal = np.array([[cfg.label_color[l][k] if cfg.label_color_known[l] else 0 for k in range(4)] for l in range(256)], np.uint8)
+    base = Integrator(cfg)
+    gpus = [Integrator(cfg) for _ in range(G)]
+    oracles = [OracleIntegrator(cfg) for _ in range(G)]
+    ref = dm.empty_map(cfg.voxels_per_side, C)
+    fr = list(frames(W, H, C, G * rounds))
+    fresh_differs = False
+    for k, (cam, depth, label, T) in enumerate(fr):
+        r = k % G
+        gpus[r].clear_map()
+        oracles[r].clear_map()
+        gpus[r].integrate_depth(T, depth, label, cam.K)
+        oracles[r].integrate_depth(T, depth, label, cam.K)
+        delta, want = gpus[r].export(), oracles[r].export()
+        rep = compare_maps(delta, want)
+        assert_parity(rep)
+        assert rep["tsdf_distance_bit_mismatch"] == 0 and rep["tsdf_weight_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0, (k, rep)
+        if k >= G:      # a live integrator's second scan differs from a fresh integrator's: the emptied-layers semantics is observable
+            f = OracleIntegrator(cfg)
+            f.integrate_depth(T, depth, label, cam.K)
+            e = f.export()
+            fresh_differs |= (len(e["block_index"]) != len(want["block_index"])) or not np.array_equal(e["tsdf_weight"], want["tsdf_weight"])
+            f.close()
+        nb, stride, pool, keys = gpus[r].device_map_view()
+        base.merge_blocks_device(nb, keys, pool)
+        base.sync()
+        ref = dm.merge(ref, want, pal, cfg.max_weight, 1)
+    assert fresh_differs
+    rep = compare_maps(base.export(), ref)
+    assert_parity(rep)
+    assert rep["tsdf_distance_bit_mismatch"] == 0 and rep["tsdf_weight_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0, rep
+    for x in gpus + oracles + [base]:
+        x.close()
