@@ -596,6 +596,12 @@ def measure_frame_batches(args, workload, steps, warmup, ctx):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     _, stride, _, _ = delta.device_map_view()
+    # `fast`: voxel-granular deltas (the update log of the frame = exactly the voxels of the delta map: 32 + 4 C bytes per touched voxel);
+    # `merged` (no update log): whole blocks in pool layout
+    by_voxels = itype == KSG_INTEGRATOR_FAST and not os.environ.get("KSG_FRAMES_BY_BLOCKS")
+    if by_voxels:
+        delta.set_update_log(max(1 << 18, w * h))
+        stride = 32 + 4 * C
     cap_blocks = 0
     send_pool = recv_pool = send_keys = recv_keys = None
     counts = torch.zeros(world, dtype=torch.int64, device="cuda")
@@ -609,7 +615,7 @@ def measure_frame_batches(args, workload, steps, warmup, ctx):
         evs[0].record(tstream)
         delta.clear_map()       # empties the delta map, keeps the integrator (its per-scan approximate sets) - see ksg_clear_map
         delta.integrate_depth_device(T, d.data_ptr(), l.data_ptr(), w, h, cam.K, stream)
-        nb, _, _, _ = delta.device_map_view()
+        nb = delta.update_log_size() if by_voxels else delta.device_map_view()[0]
         evs[1].record(tstream)
         mine_n = torch.tensor([nb], dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(counts, mine_n)
@@ -621,14 +627,25 @@ def measure_frame_batches(args, workload, steps, warmup, ctx):
             recv_pool = torch.empty(world * cap_blocks * stride, dtype=torch.uint8, device="cuda")
             send_keys = torch.empty(cap_blocks, dtype=torch.int64, device="cuda")
             recv_keys = torch.empty(world * cap_blocks, dtype=torch.int64, device="cuda")
-        delta.copy_map_device(send_pool.data_ptr(), send_keys.data_ptr(), stream)
-        sp, rp = send_pool[: mx * stride], recv_pool[: world * mx * stride]
-        sk, rk = send_keys[:mx], recv_keys[: world * mx]
-        dist.all_gather_into_tensor(rp, sp)
-        dist.all_gather_into_tensor(rk, sk)
-        evs[2].record(tstream)
-        for g in range(world):                      # frame order
-            base.merge_blocks_device(cs[g], rk[g * mx:].data_ptr(), rp[g * mx * stride:].data_ptr(), stream)
+        if by_voxels:
+            # send_pool = [mx entries of 32 B | mx rows of C floats]; the gathered buffer keeps that layout per rank, so entries and rows of
+            # rank g start at g * mx * stride and g * mx * stride + mx * 32: two all-gathers keep both arrays dense for the merge
+            heads_s, rows_s = send_pool[: mx * 32], send_pool[cap_blocks * 32: cap_blocks * 32 + mx * 4 * C]
+            heads_r, rows_r = recv_pool[: world * mx * 32], recv_pool[world * cap_blocks * 32: world * cap_blocks * 32 + world * mx * 4 * C]
+            delta.copy_update_log_device(heads_s.data_ptr(), rows_s.data_ptr(), mx, stream)
+            dist.all_gather_into_tensor(heads_r, heads_s)
+            dist.all_gather_into_tensor(rows_r, rows_s)
+            evs[2].record(tstream)
+            base.merge_voxels_device(cs, mx, heads_r.data_ptr(), rows_r.data_ptr(), stream)      # the N deltas in frame order, one call
+        else:
+            delta.copy_map_device(send_pool.data_ptr(), send_keys.data_ptr(), stream)
+            sp, rp = send_pool[: mx * stride], recv_pool[: world * mx * stride]
+            sk, rk = send_keys[:mx], recv_keys[: world * mx]
+            dist.all_gather_into_tensor(rp, sp)
+            dist.all_gather_into_tensor(rk, sk)
+            evs[2].record(tstream)
+            for g in range(world):                      # frame order
+                base.merge_blocks_device(cs[g], rk[g * mx:].data_ptr(), rp[g * mx * stride:].data_ptr(), stream)
         evs[3].record(tstream)
         torch.cuda.synchronize()
         if timed:
@@ -664,8 +681,11 @@ def measure_frame_batches(args, workload, steps, warmup, ctx):
                    "map_blocks_after_run": blocks},
         "e2e": {"value": frames_total / (wall_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 152 * (1 + world),
                 "note": "wall clock of the same loop (frames resident on the device; the per-batch host work - block counts, launches - is inside)"},
-        "collective": {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor) of block keys + blocks in pool layout",
-                       "bytes_per_step": bytes_moved / max(1, steps), "limiting": "the all-gather of whole blocks: block_stride = %d B at C = %d" % (stride, C)},
+        "collective": {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor) of " +
+                               ("the frames' update logs: one 32-byte entry + C floats per touched voxel" if by_voxels else "block keys + blocks in pool layout"),
+                       "bytes_per_step": bytes_moved / max(1, steps),
+                       "limiting": ("integration of the own frame; the exchange is %d B per touched voxel" % stride) if by_voxels
+                                   else "the all-gather of whole blocks: block_stride = %d B at C = %d" % (stride, C)},
         "phase_ms_per_step": {"integrate_own_frame": t_int / steps, "all_gather": t_xchg / steps, "merge_all_deltas": t_merge / steps},
     }
 

@@ -276,6 +276,16 @@ typedef struct ksg_voxel_update {
 int32_t ksg_set_update_log(ksg_integrator* h, int64_t capacity_voxels);
 int32_t ksg_fetch_update_log(ksg_integrator* h, int64_t* n, const ksg_voxel_update** updates, const float** sem_priors /* n * num_labels */);
 
+/* Voxel-granular deltas for the frame-per-GPU batch mode: the update log of a frame integrated into EMPTIED layers
+ * (ksg_clear_map) lists exactly the voxels of that delta map with their final state.  ksg_copy_update_log_device copies the last frame's
+ * log (n entries of ksg_voxel_update + n * num_labels floats) into caller-owned device buffers - the payload of an ncclAllGather; both
+ * destinations NULL = size query.  ksg_merge_voxels_device merges n_deltas (<= 16) such logs, delta g at entry offset g * stride with
+ * counts[g] valid entries (counts on the host), into this map in delta order with the arithmetic of ksg_merge_blocks_device: the two
+ * give identical maps (tests/test_gpu_delta_merge.py).  One synchronisation per call. */
+int32_t ksg_copy_update_log_device(ksg_integrator* h, int64_t* n, void* d_dst_updates, void* d_dst_priors, int64_t capacity_entries, void* stream);
+int32_t ksg_merge_voxels_device(ksg_integrator* h, int32_t n_deltas, const int64_t* counts, int64_t stride_entries, const void* d_updates,
+                                const void* d_priors, void* stream);
+
 /* Indices (nb*3 int32, sorted as above) of the blocks updated by the most recent integrate call:
  * the blocks whose updated() flag the reference sets (base.cpp:248). Returns the count. */
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index);

@@ -245,6 +245,10 @@ def load_library(path: Optional[str] = None):
     lib.ksg_extract_mesh.argtypes = [H, C.c_float, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.ksg_extract_mesh.restype = C.c_int32
+    lib.ksg_copy_update_log_device.argtypes = [H, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.ksg_copy_update_log_device.restype = C.c_int32
+    lib.ksg_merge_voxels_device.argtypes = [H, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ksg_merge_voxels_device.restype = C.c_int32
     lib.ksg_clear_map.argtypes = [H]
     lib.ksg_clear_map.restype = C.c_int32
     lib.ksg_build_info.argtypes = []
@@ -260,7 +264,7 @@ KSG_SYMBOLS = ["ksg_default_config", "ksg_create", "ksg_destroy", "ksg_last_erro
                "ksg_last_updated_blocks", "ksg_reset", "ksg_build_info", "ksg_set_profiling", "ksg_get_profile", "ksg_debug_tile_times", "ksg_owner_mask",
                "ksg_unordered_map_schedule", "ksg_integrate_depth_k64", "ksg_integrate_depth_device_k64",
                "ksg_debug_chain_sum", "ksg_debug_fast_timeline", "ksg_integrate_depth_async", "ksg_wait_frame",
-               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels", "ksg_extract_mesh", "ksg_clear_map"]
+               "ksg_device_map_view", "ksg_merge_blocks_device", "ksg_copy_map_device", "ksg_integrate_image", "ksg_set_update_log", "ksg_fetch_update_log", "ksg_evaluate_labels", "ksg_extract_mesh", "ksg_clear_map", "ksg_copy_update_log_device", "ksg_merge_voxels_device"]
 
 
 def debug_chain_sum(terms: np.ndarray, s0: float, lib=None) -> np.float32:
@@ -547,6 +551,24 @@ class Integrator:
         self._check(self.lib.ksg_evaluate_labels(self.handle, objs.ctypes.data_as(C.c_void_p), len(objs), max_dist, band, checker_size, checker_margin,
                                                  C.byref(ev), C.byref(ok), C.byref(ob)), "ksg_evaluate_labels")
         return int(ev.value), int(ok.value), int(ob.value)
+
+    def update_log_size(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.ksg_copy_update_log_device(self.handle, C.byref(n), None, None, 0, None), "ksg_copy_update_log_device")
+        return int(n.value)
+
+    def copy_update_log_device(self, d_updates: int, d_priors: int, capacity: int, stream: int = 0) -> int:
+        """Copy the last frame's update log (32-byte entries, num_labels floats each) into device buffers; returns the entry count."""
+        n = C.c_int64()
+        self._check(self.lib.ksg_copy_update_log_device(self.handle, C.byref(n), C.c_void_p(d_updates), C.c_void_p(d_priors), capacity, C.c_void_p(stream)),
+                    "ksg_copy_update_log_device")
+        return int(n.value)
+
+    def merge_voxels_device(self, counts, stride: int, d_updates: int, d_priors: int, stream: int = 0):
+        """Merge len(counts) voxel-granular deltas (delta g at entry offset g * stride) into this map, in order (ksg_merge_voxels_device)."""
+        arr = (C.c_int64 * len(counts))(*[int(c) for c in counts])
+        self._check(self.lib.ksg_merge_voxels_device(self.handle, len(counts), arr, stride, C.c_void_p(d_updates), C.c_void_p(d_priors), C.c_void_p(stream)),
+                    "ksg_merge_voxels_device")
 
     def clear_map(self):
         """Remove every block, keep the integrator state (ksg_clear_map)."""

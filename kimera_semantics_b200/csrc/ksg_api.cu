@@ -2019,6 +2019,74 @@ int32_t ksg_merge_blocks_device(ksg_integrator* h, int64_t n_blocks, const void*
   return KSG_OK;
 }
 
+int32_t ksg_copy_update_log_device(ksg_integrator* h, int64_t* n_out, void* d_dst_updates, void* d_dst_priors, int64_t capacity, void* stream) {
+  if (!h || !n_out) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  *n_out = 0;
+  if (!h->d_log_head) return fail(KSG_ERR_INVALID_ARGUMENT, "update log is off (ksg_set_update_log)");
+  KSG_CUDA(cudaSetDevice(h->device));
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  const int64_t n = h->h_fc ? h->h_fc->log_count : 0;
+  if (n > h->log_cap) { *n_out = -1; return fail(KSG_ERR_SCRATCH_FULL, "update log too small for this frame"); }
+  *n_out = n;
+  if (!d_dst_updates && !d_dst_priors) return KSG_OK;                 // size query
+  if (n > capacity) return fail(KSG_ERR_INVALID_ARGUMENT, "update log copy: capacity too small");
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+  if (n > 0) {
+    if (d_dst_updates) KSG_CUDA(cudaMemcpyAsync(d_dst_updates, h->d_log_head, (size_t)n * sizeof(VoxelUpdate), cudaMemcpyDeviceToDevice, s));
+    if (d_dst_priors) KSG_CUDA(cudaMemcpyAsync(d_dst_priors, h->d_log_prior, (size_t)n * sizeof(float) * h->dc.C, cudaMemcpyDeviceToDevice, s));
+  }
+  return KSG_OK;
+}
+
+int32_t ksg_merge_voxels_device(ksg_integrator* h, int32_t n_deltas, const int64_t* counts, int64_t stride, const void* d_updates, const void* d_priors,
+                                void* stream) {
+  if (!h || n_deltas < 0 || n_deltas > 16 || stride < 0 || (n_deltas > 0 && (!counts || !d_updates || !d_priors))) return KSG_ERR_INVALID_ARGUMENT;
+  auto fail = [&](int c, const char* m) { return h->fail(c, m); };
+  if (h->deferred_status) return h->fail(h->deferred_status, err_text(h->deferred_status));
+  MergeCounts mc{};
+  int64_t any = 0;
+  for (int g = 0; g < n_deltas; ++g) {
+    if (counts[g] < 0 || counts[g] > stride || counts[g] > 0x7fffffff) return KSG_ERR_INVALID_ARGUMENT;
+    mc.n[g] = (int)counts[g];
+    any += counts[g];
+  }
+  if (any == 0) return KSG_OK;
+  KSG_CUDA(cudaSetDevice(h->device));
+  { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+  const int64_t total = (int64_t)n_deltas * stride;
+  if (h->exp_slots_cap < total) {
+    KSG_CUDA(cudaStreamSynchronize(s));
+    if (h->d_exp_slots) cudaFree(h->d_exp_slots);
+    h->d_exp_slots = nullptr;
+    KSG_CUDA(dmalloc(&h->d_exp_slots, (size_t)total));
+    h->exp_slots_cap = (int)total;
+  }
+  h->frame_stamp += 1;
+  h->n_launches += 4 + n_deltas;
+  const VoxelUpdate* upd = (const VoxelUpdate*)d_updates;
+  const float* pri = (const float*)d_priors;
+  k_frame_reset<<<1, 1, 0, s>>>(h->d_cnt, 0);
+  k_mergev_insert<<<grid_for(total, 256), 256, 0, s>>>(h->d_cnt, h->map, upd, mc, n_deltas, (long long)stride, h->d_exp_slots, h->frame_stamp);
+  k_block_init<<<h->sm_count * 4, 256, 0, s>>>(h->dc, h->d_cnt, h->map);
+  k_frame_finish<<<1, 1, 0, s>>>(h->d_cnt, h->map);
+  for (int g = 0; g < n_deltas; ++g) {      // frame order: a voxel that several deltas touched is merged delta by delta
+    if (mc.n[g] == 0) continue;
+    const int grid = (int)std::min<int64_t>((int64_t)h->sm_count * 16, (mc.n[g] + 7) / 8);
+    k_mergev_apply<<<std::max(1, grid), 256, 0, s>>>(h->dc, h->map, h->d_luts, upd + (size_t)g * stride, pri + (size_t)g * stride * h->dc.C,
+                                                    h->d_exp_slots + (size_t)g * stride, mc.n[g]);
+  }
+  KSG_CUDA(cudaGetLastError());
+  int rc = fetch_counters(h, s);
+  if (rc) return rc;
+  h->num_blocks = h->h_cnt->pool_count;
+  h->last_blocks_touched = h->h_cnt->n_blocks_touched;
+  const int dev_err = h->h_cnt->err;
+  if (dev_err) { h->deferred_status = dev_err; return fail(dev_err, err_text(dev_err)); }
+  return KSG_OK;
+}
+
 int64_t ksg_last_updated_blocks(ksg_integrator* h, int64_t capacity_blocks, int32_t* block_index) {
   if (!h) return 0;
   cudaSetDevice(h->device);

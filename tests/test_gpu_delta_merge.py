@@ -77,3 +77,50 @@ def test_round_robin_integrators_with_emptied_layers_equal_the_same_schedule_on_
     assert rep["tsdf_distance_bit_mismatch"] == 0 and rep["tsdf_weight_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0, rep
     for x in gpus + oracles + [base]:
         x.close()
+
+
+def test_voxel_granular_deltas_merge_to_the_same_map_as_whole_block_deltas():
+    """ksg_copy_update_log_device + ksg_merge_voxels_device (what bench.py --sharding frames exchanges for `fast`): per batch, the update
+    logs of the G live integrators are stacked into one buffer and merged with ONE call; the result equals merging the same deltas block
+    by block (ksg_merge_blocks_device), bit for bit, including the updated() list."""
+    import torch
+    W, H, C, G, rounds = 320, 240, 21, 3, 2
+    cfg = make_config(KSG_INTEGRATOR_FAST, 0.05, C, max_points=W * H, max_updates=16 << 20)
+    by_blocks, by_voxels = Integrator(cfg), Integrator(cfg)
+    gpus = [Integrator(cfg) for _ in range(G)]
+    for g in gpus:
+        g.set_update_log(1 << 20)
+    fr = list(frames(W, H, C, G * rounds))
+    for b in range(rounds):
+        sizes = []
+        for r in range(G):
+            cam, depth, label, T = fr[b * G + r]
+            gpus[r].clear_map()
+            gpus[r].integrate_depth(T, depth, label, cam.K)
+            sizes.append(gpus[r].update_log_size())
+        assert min(sizes) > 1000
+        stride = max(sizes) + 5
+        upd = torch.zeros(G * stride * 32, dtype=torch.uint8, device="cuda")
+        pri = torch.zeros(G * stride * C, dtype=torch.float32, device="cuda")
+        for r in range(G):
+            n = gpus[r].copy_update_log_device(upd[r * stride * 32:].data_ptr(), pri[r * stride * C:].data_ptr(), stride)
+            assert n == sizes[r]
+        torch.cuda.synchronize()
+        by_voxels.merge_voxels_device(sizes, stride, upd.data_ptr(), pri.data_ptr())
+        touched_v = by_voxels.last_updated_blocks()
+        touched_b = []
+        for r in range(G):
+            nb, _, pool, keys = gpus[r].device_map_view()
+            by_blocks.merge_blocks_device(nb, keys, pool)
+            by_blocks.sync()
+            touched_b.append(by_blocks.last_updated_blocks())
+        want = np.unique(np.concatenate(touched_b), axis=0)
+        got = np.unique(touched_v, axis=0)
+        assert np.array_equal(got, want)
+    a, b = by_voxels.export(), by_blocks.export()
+    rep = compare_maps(a, b)
+    assert_parity(rep)
+    assert rep["tsdf_distance_bit_mismatch"] == 0 and rep["tsdf_weight_bit_mismatch"] == 0 and rep["sem_priors_bit_mismatch"] == 0, rep
+    assert np.array_equal(a["tsdf_rgba"], b["tsdf_rgba"]) and np.array_equal(a["sem_label"], b["sem_label"]) and np.array_equal(a["sem_rgba"], b["sem_rgba"])
+    for x in gpus + [by_blocks, by_voxels]:
+        x.close()
