@@ -44,7 +44,7 @@ WORKLOADS = {
     "merged5": (KSG_INTEGRATOR_MERGED, 640, 480, 0.05, 21, 16 << 20, 8192),
     "fast10": (KSG_INTEGRATOR_FAST, 320, 240, 0.10, 5, 0, 4096),        # configs[0] geometry
     "fast5_720p_c150": (KSG_INTEGRATOR_FAST, 1280, 720, 0.05, 150, 0, 2048),   # configs[3]: ADE20K-size label set, frame-per-GPU batches
-    "merged1_4k_c40": (KSG_INTEGRATOR_MERGED, 3840, 2160, 0.01, 40, 700 << 20, 65536),   # configs[4]: 4K / 1 cm, spatially sharded
+    "merged1_4k_c40": (KSG_INTEGRATOR_MERGED, 3840, 2160, 0.01, 40, 1500 << 20, 65536),   # configs[4]: 4K / 1 cm, spatially sharded
 }
 
 
