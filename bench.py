@@ -728,7 +728,18 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device: the integrator has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on the process's stdout when the communicator is created: keep stdout = the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     ctx = {"world": world, "rank": rank, "local_rank": local_rank}
     if args.sharding == "frames" and world > 1:
         line = measure_frame_batches(args, args.workload, args.steps, args.warmup, ctx)
