@@ -319,7 +319,10 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
     itype, w, h, vs, C, _, _ = WORKLOADS[workload]
     n = warmup + steps
     spatial = args.sharding == "spatial" and world > 1
-    cam, frames = gen_frames(workload, n, 0 if spatial else rank)
+    # sequence mode (replicas): every rank integrates the SAME synthetic stream into its own map - weak scaling means fixed work per GPU
+    # (rank-specific trajectories differ by up to 10 % in voxel updates per frame, which the max over ranks then reports as lost efficiency:
+    # profiles/r02/bench_seq_fast5_n8.json, 18.4 K frames/s = 0.92 x 8 x the 1-GPU rate); KSG_BENCH_RANK_STREAMS=1 restores one trajectory per rank
+    cam, frames = gen_frames(workload, n, rank if (not spatial and os.environ.get("KSG_BENCH_RANK_STREAMS")) else 0)
     P = w * h
 
     def barrier():
@@ -535,7 +538,7 @@ def measure(args, workload, steps, warmup, ctx, with_cpu, profile_frames):
                    "l2_policy": f"every step reads a different frame ({total_in / 1e6:.0f} MB of inputs cycled, larger than the 126 MB L2 "
                                 "when steps >= 90) and a different part of the map; no explicit flush",
                    "parallelism": ("one map spatially sharded by tile owner over the GPUs; frames broadcast from rank 0 with NCCL" if spatial
-                                   else "one sequence + map per GPU, no collective") if world > 1 else "single GPU",
+                                   else "one sequence + map per GPU (the same synthetic stream on every rank), no collective") if world > 1 else "single GPU",
                    "map_blocks_after_run": blocks},
         "clocks": clocks,
         "e2e": {"value": head["value"], "unit": "frames/s", "h2d_bytes_per_step": P * 5,

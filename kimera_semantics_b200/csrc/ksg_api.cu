@@ -205,6 +205,7 @@ struct ksg_integrator {
   // (measured on merged2, profiles/r02/tuning_10.log: 6 CTAs/SM -> 148 fps, 4 + long 128 x 296 -> 163, 3 -> 166)
   int long_threads = 256, long_grid = 0, short_ctas = 3, short_smem = 0;
   bool short_thread = false;         // merged, C <= 32: k_voxel_apply_short_t
+  bool deep_hot = true;              // merged, C <= 32: the hot voxels go to the deep-pipeline instance of k_voxel_apply_long (KSG_DEEP_HOT=0: off)
   // its CTAs per SM (KSG_SHORT_T_CTAS).  The frame is bound by the long-segment kernel (1184 warps, 128 registers each); whatever the
   // short kernel takes from it costs more than it gains: merged2 1 -> 178 fps, 2 -> 166, 3 -> 166, 4 -> 170, warp-per-voxel kernel 170
   // (profiles/r02/tuning_12.log)
@@ -852,6 +853,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
       KSG_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
       // C <= 32: the voxels with thousands of records get one CTA each (third stream, concurrent with the other two kernels)
       const int use_hot = (h->apply_nch == 1 && !h->hot_enabled && h->hot_kernel) ? 1 : 0;
+      bool deep_launched = false;
       if (use_hot) {
         KSG_CUDA(cudaStreamWaitEvent(h->aux_stream2, h->ev_fork, 0));
         ++h->n_launches;
@@ -865,14 +867,22 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
         k_voxel_apply_short<NCH><<<h->sm_count * h->short_ctas, 256, h->short_smem, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);        \
       } while (0)
       if (h->short_thread && h->apply_nch == 1) {
-        k_voxel_apply_long<1><<<h->long_grid, h->long_threads, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, use_hot);
+        int skip = use_hot;
+        if (h->deep_hot && !use_hot) {   // the hot voxels' chains first, on their own high-priority stream (one warp per chain)
+          KSG_CUDA(cudaStreamWaitEvent(h->aux_stream2, h->ev_fork, 0));
+          ++h->n_launches;
+          k_voxel_apply_long<1, true><<<h->sm_count, 64, 0, h->aux_stream2>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, 0);
+          KSG_CUDA(cudaEventRecord(h->ev_join2, h->aux_stream2));
+          skip = 1; deep_launched = true;
+        }
+        k_voxel_apply_long<1><<<h->long_grid, h->long_threads, 0, h->aux_stream>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, skip);
         k_voxel_apply_short_t<<<h->sm_count * h->short_t_ctas, 256, 0, s>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq);
       } else
       switch (h->apply_nch) { case 1: KSG_LAUNCH_VOXEL(1); break; case 2: KSG_LAUNCH_VOXEL(2); break; case 4: KSG_LAUNCH_VOXEL(4); break; default: KSG_LAUNCH_VOXEL(8); break; }
 #undef KSG_LAUNCH_VOXEL
       KSG_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
       KSG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-      if (use_hot) KSG_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
+      if (use_hot || deep_launched) KSG_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
     } else {
     ++h->n_launches;
     k_tile_heads<<<grid_for(n_records, B), B, 0, s>>>(dc, h->d_cnt, h->map, h->rec_b, n_records, h->frame_stamp, h->tile_begin,
@@ -1210,7 +1220,11 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       }
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-      KSG_CUDA(cudaStreamCreateWithFlags(&h->aux_stream2, cudaStreamNonBlocking));
+      {
+        int lo_p = 0, hi_p = 0;
+        KSG_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        KSG_CUDA(cudaStreamCreateWithPriority(&h->aux_stream2, cudaStreamNonBlocking, hi_p));
+      }
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
       h->hot_smem = 2 * kHotChunkRecs * (32 * (int)sizeof(float) + (int)sizeof(float4));
       KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, h->hot_smem));
@@ -1218,6 +1232,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       h->long_grid = h->sm_count;
       if (const char* e = std::getenv("KSG_LONG_THREADS")) { const int t = std::atoi(e); if (t == 64 || t == 128 || t == 256) h->long_threads = t; }
       if (const char* e = std::getenv("KSG_LONG_GRID")) h->long_grid = std::max(1, std::atoi(e));
+      if (const char* e = std::getenv("KSG_DEEP_HOT")) h->deep_hot = std::atoi(e) != 0;
       if (const char* e = std::getenv("KSG_SHORT_T_CTAS")) h->short_t_ctas = std::max(1, std::min(8, std::atoi(e)));
       if (const char* e = std::getenv("KSG_SHORT_CTAS")) h->short_ctas = std::max(1, std::min(6, std::atoi(e)));
       if (h->short_ctas < 6) {

@@ -263,21 +263,26 @@ __device__ __forceinline__ void voxel_finish_semantic(const DevCfg& cfg, const L
 // ---------------------------------------------------------------------------------------------
 // long segments: one item per role
 // ---------------------------------------------------------------------------------------------
-template <int NCH>
-__global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
+// DEEP == true: the instance for the HOT voxels only (>= kHotLen records; the voxel next to the camera has ~10^5) - their two chains are the
+// critical path of the frame, and each record costs a key load -> operand load round trip, so the pipelines are twice as deep (keys 4-6
+// batches ahead, operands of two batches in flight; 186 registers) and the kernel is small (one warp per chain) so that it fits beside the
+// other two update kernels.  DEEP == false: everything else (skip_hot = 1 when the DEEP instance runs).
+template <int NCH, bool DEEP = false>
+__global__ void __launch_bounds__(256, DEEP ? 1 : 2) k_voxel_apply_long(DevCfg cfg, Xform T, Counters* cnt, MapRef map, const Luts* __restrict__ luts,
                                                             const uint64_t* __restrict__ rec, ApplySrc src, VoxelQueues q, int skip_hot) {
+  __shared__ uint32_t s_ring[DEEP ? 8 : 1][128];      // DEEP: per warp, the record keys of four batches (semantic role)
   const int lane = threadIdx.x & 31;
   const int C = cfg.C;
   const int n_hot = q.counters[0], n_other = q.counters[1];
-  const int n_items = n_hot + n_other;
-  const int first_item = skip_hot ? n_hot : 0;      // the hot voxels are taken by k_voxel_apply_hot
+  const int n_items = DEEP ? n_hot : n_hot + n_other;
+  const int first_item = (!DEEP && skip_hot) ? n_hot : 0;      // skip_hot: the hot voxels are taken by the DEEP instance (or k_voxel_apply_hot)
   const F3 origin = f3(T.tx, T.ty, T.tz);
   const bool keep_blend = cfg.color_mode == 0;
   const uint32_t ord_mask = (1u << kRecOrdBits) - 1u;
   const uint32_t zero_row = (uint32_t)cnt->n_cast;   // all-zero row behind the last bundle: padded lanes add +0.0f (exact)
   for (;;) {
     int it = 0;
-    if (lane == 0) it = first_item + atomicAdd(&q.counters[3], 1);
+    if (lane == 0) it = first_item + atomicAdd(&q.counters[DEEP ? 5 : 3], 1);
     it = __shfl_sync(0xffffffffu, it, 0);
     if (it >= n_items) break;
     const unsigned long long item = (it < n_hot) ? q.long_items[it] : q.long_items[q.long_cap - 1 - (it - n_hot)];
@@ -302,6 +307,24 @@ __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T
       uint32_t* pc = (uint32_t*)(vc.chunk + 2 * cfg.plane_f32) + vc.v;
       float dist = *pd, wgt = *pw;
       uint32_t rgba = *pc;
+      if (DEEP) {
+        // record keys four batches ahead, their bundle parameters two batches ahead
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pr_a = (lane < len) ? src.param[(uint32_t)r[lane] & ord_mask] : z4;
+        float4 pr_b = (32 + lane < len) ? src.param[(uint32_t)r[32 + lane] & ord_mask] : z4;
+        uint32_t key_c = (64 + lane < len) ? ((uint32_t)r[64 + lane] & ord_mask) : 0u;
+        uint32_t key_d = (96 + lane < len) ? ((uint32_t)r[96 + lane] & ord_mask) : 0u;
+        for (int base = 0; base < len; base += 32) {
+          const int nb = (len - base) < 32 ? (len - base) : 32;
+          const float4 pr_c = (base + 64 + lane < len) ? src.param[key_c] : z4;
+          const uint32_t key_e = (base + 128 + lane < len) ? ((uint32_t)r[base + 128 + lane] & ord_mask) : 0u;
+          float sdf = 0.0f, uw = 0.0f;
+          if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), vc.center, pr_a.w, sdf, uw);
+          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
+          pr_a = pr_b; pr_b = pr_c;
+          key_c = key_d; key_d = key_e;
+        }
+      } else {
       // parameters of the next batch are fetched one batch ahead
       float4 pr_a = (lane < len) ? src.param[(uint32_t)r[lane] & ord_mask] : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int base = 0; base < len; base += 32) {
@@ -313,6 +336,7 @@ __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T
         tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);   // merged: point colours are (0,0,0,0) (merged.cpp:70)
         pr_a = pr_b;
       }
+      }
       if (lane == 0) { *pd = dist; *pw = wgt; if (keep_blend) *pc = rgba; }
     } else {
       const float* prow = (const float*)(vc.chunk + cfg.head_bytes) + (size_t)vc.v * C;
@@ -321,6 +345,39 @@ __global__ void __launch_bounds__(256, 2) k_voxel_apply_long(DevCfg cfg, Xform T
       for (int qq = 0; qq < NCH; ++qq) { const int c = qq * 32 + lane; p[qq] = (c < C) ? prow[c] : 0.0f; }
       if (NCH == 1 && hot >= 0) {
         p[0] = (lane < C) ? src.hot_prior[(size_t)hot * 32 + lane] : 0.0f;
+      } else if (NCH == 1 && DEEP) {
+        // the (L * freq) rows of TWO batches are in flight while a third is added (three register buffers, loop unrolled by three so that no
+        // buffer is copied); record keys are loaded six batches ahead into registers and handed to a per-warp shared-memory ring three
+        // batches ahead (broadcast reads replace the 32 shuffles per batch).  The adds stay in record order; batches past the end read the
+        // all-zero row: + 0.0f is exact.
+        const float* lane_tmp = src.tmp + (lane < C ? lane : 0);
+        uint32_t* ring = s_ring[(threadIdx.x >> 5) & 7];
+        auto key_at = [&](int idx) -> uint32_t { return (idx < len) ? ((uint32_t)r[idx] & ord_mask) : zero_row; };
+        __syncwarp();
+        ring[lane] = key_at(lane); ring[32 + lane] = key_at(32 + lane); ring[64 + lane] = key_at(64 + lane);
+        uint32_t k0 = key_at(96 + lane), k1 = key_at(128 + lane), k2 = key_at(160 + lane);
+        __syncwarp();
+        float ra[32], rb[32], rc[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) ra[u] = __ldg(lane_tmp + (size_t)ring[u] * C);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) rb[u] = __ldg(lane_tmp + (size_t)ring[32 + u] * C);
+        const int nbatch = (len + 31) >> 5;
+#define KSG_SEM_STEP(S, KREG, LOADBUF, ADDBUF)                                                                                     \
+        {                                                                                                                          \
+          ring[(((S) + 3) & 3) * 32 + lane] = KREG;                          /* keys of batch S + 3 */                             \
+          KREG = key_at(((S) + 6) * 32 + lane);                                                                                    \
+          __syncwarp();                                                                                                            \
+          _Pragma("unroll") for (int u = 0; u < 32; ++u) LOADBUF[u] = __ldg(lane_tmp + (size_t)ring[(((S) + 2) & 3) * 32 + u] * C);  \
+          _Pragma("unroll") for (int u = 0; u < 32; ++u) p[0] += ADDBUF[u];                                                        \
+        }
+        for (int j = 0; j < nbatch; j += 3) {
+          KSG_SEM_STEP(j, k0, rc, ra)
+          KSG_SEM_STEP(j + 1, k1, ra, rb)
+          KSG_SEM_STEP(j + 2, k2, rb, rc)
+        }
+#undef KSG_SEM_STEP
+        if (lane >= C) p[0] = 0.0f;
       } else if (NCH == 1) {
         // software pipeline over batches of 32 records: keys two batches ahead, the 32 (L * freq) row values one batch ahead
         const float* lane_tmp = src.tmp + (lane < C ? lane : 0);

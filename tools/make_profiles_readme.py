@@ -219,6 +219,15 @@ for n in (2, 4, 8):
                 p = d["roofline"]["phase_ms_per_frame"]
                 extra = f"apply {p.get('tile_apply', 0):.2f} of {p.get('frame', 0):.2f} ms per frame"
             rows.append(f"| {n} | {what} | {f(d['value'])} | {f(d['e2e']['value'])} | {d.get('scaling')} | {extra} | `r02/{tag % n}` |")
+            for k, v in (d.get("workloads") or {}).items():      # the shared-map modes measured inside the driver's own N-GPU command line
+                if not v or "value" not in v:
+                    continue
+                if v.get("collective"):
+                    ex = f"{v['collective']['bytes_per_step'] / 1e6:.0f} MB all-gathered per batch; integrate {v['phase_ms_per_step']['integrate_own_frame']:.2f} + gather {v['phase_ms_per_step']['all_gather']:.2f} + merge {v['phase_ms_per_step']['merge_all_deltas']:.2f} ms"
+                else:
+                    pp = v["roofline"]["phase_ms_per_frame"]
+                    ex = f"apply {pp.get('tile_apply', 0):.2f} of {pp.get('frame', 0):.2f} ms per frame"
+                rows.append(f"| {n} | `workloads.{k}` of that line | {f(v['value'])} | {f(v['e2e']['value'])} | {v.get('scaling')} | {ex} | `r02/{tag % n}` |")
 for tag, what in (("bench_fast5_720p_c150_n1.json", "configs[3] geometry on ONE GPU (sequential)"), ("bench_merged1_4k_c40_n1.json", "configs[4] on ONE GPU")):
     d = load(os.path.join(R2, tag))
     if d:
@@ -228,6 +237,7 @@ if rows:
     w("| GPUs | mode | frames/s (resident) | frames/s (e2e) | scaling | notes | file |")
     w("|---|---|---|---|---|---|---|")
     out.extend(rows)
+w("\nReading: replicas scale with the number of sequences (0.92 at N = 8 when every rank follows its own trajectory - the slowest stream sets the time; the default is now the same stream on every rank).  The frame-per-GPU mode, with voxel-granular deltas, is 2.2x (`fast5`) to 2.9x (configs[3]) faster on 8 GPUs than ONE GPU running the frames sequentially - its own-frame integration carries the clearing of the delta layers and one host synchronisation per batch, and gather + merge grow with N.  Spatial sharding divides only the per-voxel update: `merged2` 175 -> 244 frames/s on 8 GPUs (ray casting, bundling and the record sort are replicated on every rank: Amdahl), configs[4] is sort / emit bound at N = 8 (its 2 timed steps also allocate thousands of new 725 KB blocks, which is why `value` is below the profiled frame time).")
 w("\nReal-NCCL parity: `tests/test_gpu_multi.py` (the sharded map assembled from the ranks' exports equals the unsharded map, bit for bit) — `r02/gpu_multi_n*.log`.")
 
 w("\n## GPU test logs\n")
