@@ -70,8 +70,8 @@ def ncu_rows(path):
         return []
 
 
-fin, fin_src = first("bench_final_13.json", "bench_full_12.json", "bench_full_10.json")
-ref, ref_src = first("bench_fast5_reference_13.json", "bench_fast5_reference_10.json")
+fin, fin_src = first("bench_final_17.json", "bench_final_13.json", "bench_full_12.json", "bench_full_10.json")
+ref, ref_src = first("bench_fast5_reference_17.json", "bench_fast5_reference_13.json", "bench_fast5_reference_10.json")
 r1 = load(os.path.join(R1, "bench_fast5.json"))
 r1m = load(os.path.join(R1, "bench_merged2.json"))
 m2 = (fin or {}).get("workloads", {}).get("merged2")
@@ -132,10 +132,10 @@ if tl:
       f"scan {f((tl.get('phase0_us') or {}).get('scan_cast_counts'))} + compaction {f((tl.get('phase0_us') or {}).get('compaction'))}; ray set-up {f(tl.get('ray_setup_us'))}; "
       f"{tl.get('sweeps')} sweeps {[round(x) for x in tl.get('sweep_us', [])]}; commit {f(tl.get('commit_emit_us'))}; tile alloc + block init {f(tl.get('tile_alloc_block_init_us'))}; scatter {f(tl.get('scatter_us'))}; "
       f"kernel {f(tl.get('solve_kernel_us'))}.  {(tl.get('debug') or {}).get('rays')} rays, {(tl.get('debug') or {}).get('ray_evals')} ray evaluations, {(tl.get('debug') or {}).get('ray_evals_that_changed')} of them changed something.")
-sh, tot = launch_shares(os.path.join(R2, "launches_fast5_13.csv"))
-src_l = "r02/launches_fast5_13.csv"
+sh, tot = launch_shares(os.path.join(R2, "launches_fast5_17.csv"))
+src_l = "r02/launches_fast5_17.csv"
 if not sh:
-    sh, tot = launch_shares(os.path.join(R2, "launches_fast5_10.csv")); src_l = "r02/launches_fast5_10.csv"
+    sh, tot = launch_shares(os.path.join(R2, "launches_fast5_13.csv")); src_l = "r02/launches_fast5_13.csv"
 if sh:
     w(f"\nncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold caches, serialised - shares only) `{src_l}`: " +
       ", ".join(f"`{k}` {p:.0f} %" for k, p, _ in sh[:6] if k) + ".  The solve kernel's share agrees with the event-timed phases (everything but the pre-kernels and the tile apply).")
@@ -153,18 +153,18 @@ if m2:
     r1pm = (r1m or {}).get("roofline", {}).get("phase_ms_per_frame", {})
     descm = {"classify+start_set": "`k_classify`", "fixpoint|bundling": "bundle sort (CUB pairs), `k_bundle_heads/merge`, `k_bord_hash`, `k_bundle_order` (all rehash phases of the reference's `unordered_map` in ONE cluster launch), `k_bundle_scan`, `k_bundle_loglik`",
              "ray_emit": "`k_emit_merged` (records laid out by (bundle rank, step))", "record_sort": "CUB `DeviceRadixSort::SortKeys` on the voxel bits only: 4 stable passes (round 1: 7-8 over all bits)",
-             "alloc+tile_heads": "`k_block_init`, `k_voxel_heads` (segments -> long / short queues)", "tile_apply": "`k_voxel_apply_long` (warp per role of a voxel with >= 256 records) || `k_voxel_apply_short_t` (thread per voxel) on two streams", "frame": ""}
+             "alloc+tile_heads": "`k_block_init`, `k_voxel_heads` (segments -> long / short queues)", "tile_apply": "`k_voxel_apply_long<1,DEEP>` (the hot voxels' chains, one warp each) || `k_voxel_apply_long` (warp per role of a voxel with >= 256 records) || `k_voxel_apply_short_t` (thread per voxel) on three streams", "frame": ""}
     w("| phase | ms (r02) | ms (r01) | what runs (r02) |")
     w("|---|---|---|---|")
     for k in ("classify+start_set", "fixpoint|bundling", "ray_emit", "record_sort", "alloc+tile_heads", "tile_apply", "frame"):
         w(f"| {k} | {f(pm.get(k), '{:.3f}')} | {f(r1pm.get(k), '{:.3f}')} | {descm[k]} |")
-    sh, tot = launch_shares(os.path.join(R2, "launches_merged2_13.csv"))
-    src_l = "r02/launches_merged2_13.csv"
+    sh, tot = launch_shares(os.path.join(R2, "launches_merged2_17.csv"))
+    src_l = "r02/launches_merged2_17.csv"
     if not sh:
-        sh, tot = launch_shares(os.path.join(R2, "launches_merged2_10.csv")); src_l = "r02/launches_merged2_10.csv"
+        sh, tot = launch_shares(os.path.join(R2, "launches_merged2_13.csv")); src_l = "r02/launches_merged2_13.csv"
     if sh:
         w(f"\nncu launch list `{src_l}` (serialised, so the two apply kernels ADD here while they overlap in the bench): " + ", ".join(f"`{k}` {p:.0f} %" for k, p, _ in sh[:7]) + ".")
-    for tag, label in (("prof_apply_merged2_12", "apply kernels (thread-per-voxel short kernel at 2 CTAs/SM)"), ("prof_apply_merged2", "apply kernels of the previous commit (warp-per-voxel short kernel)"), ("prof_sort_merged2", "the four record-sort passes")):
+    for tag, label in (("prof_apply_merged2_17", "the three update kernels of the final commit"), ("prof_apply_merged2_12", "apply kernels two commits earlier (no deep instance, thread-per-voxel short kernel at 2 CTAs/SM)"), ("prof_apply_merged2", "apply kernels of the previous commit (warp-per-voxel short kernel)"), ("prof_sort_merged2", "the four record-sort passes")):
         nr = ncu_rows(os.path.join(R2, tag + ".raw.csv"))
         if nr:
             w(f"\n`ncu --set full`, {label} — `r02/{tag}.details.txt`:")
@@ -188,7 +188,7 @@ w("\nReading: neither workload is bandwidth bound.  `fast5` moves ≈15 MB per f
 w("`merged2`'s update kernels run sequential per-voxel recurrences (they must, for bit-identical results) and are bound by instruction issue and L2 latency of a few thousand warps.")
 
 w("\n## Tuning sweeps and experiments that lost (all on the B200 box, `bench.py --quick`)\n")
-for fn in ("tuning_10.log", "tuning_12.log", "tuning_13.log"):
+for fn in ("tuning_10.log", "tuning_12.log", "tuning_13.log", "tuning_16.log", "tuning_17.log"):
     p = os.path.join(R2, fn)
     if os.path.exists(p):
         w(f"`r02/{fn}`:\n```")
