@@ -205,12 +205,14 @@ struct ksg_integrator {
   // (measured on merged2, profiles/r02/tuning_10.log: 6 CTAs/SM -> 148 fps, 4 + long 128 x 296 -> 163, 3 -> 166)
   int long_threads = 256, long_grid = 0, short_ctas = 3, short_smem = 0;
   bool short_thread = false;         // merged, C <= 32: k_voxel_apply_short_t
-  bool long_serial = false;          // KSG_LONG_SERIAL=1: the non-hot long segments run behind the short kernel instead of beside it
+  // the non-hot long segments (0.3 ms standalone) run behind the short kernel on its stream instead of beside it (KSG_LONG_SERIAL=0:
+  // beside it): 202 against 199 frames/s with two short-kernel CTAs per SM (profiles/r02/tuning_18.log)
+  bool long_serial = true;
   bool deep_hot = true;              // merged, C <= 32: the hot voxels go to the deep-pipeline instance of k_voxel_apply_long (KSG_DEEP_HOT=0: off)
   // its CTAs per SM (KSG_SHORT_T_CTAS).  The frame is bound by the long-segment kernel (1184 warps, 128 registers each); whatever the
   // short kernel takes from it costs more than it gains: merged2 1 -> 178 fps, 2 -> 166, 3 -> 166, 4 -> 170, warp-per-voxel kernel 170
   // (profiles/r02/tuning_12.log)
-  int short_t_ctas = 1;
+  int short_t_ctas = 2;              // (1 while the hot chains ran inside the long-segment kernel: tuning_12.log; 2 with the deep instance: tuning_18.log)
   int hot_smem = 0;
 
   long long* tile_debug = nullptr;  // optional per-tile (records, cycles) trace

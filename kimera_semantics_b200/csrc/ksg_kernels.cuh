@@ -1023,7 +1023,14 @@ __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int n
     for (int o = 16; o > 0; o >>= 1) usum += __shfl_xor_sync(0xffffffffu, usum, o);
     // sequential partial sums <= (1 + 2^-24)^32 x the exact sum; the tree sum >= (1 - 2^-24)^6 x it: a 0.1 % margin is ample
     const bool plain = negative == 0u && wgt >= kEps && (wgt + usum) * 1.001f < tp.max_weight;
-    if (plain) {
+    if (plain && nb == 32) {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {     // no loop overhead: shuffle, select, one dependent FADD per record
+        const float uj = __shfl_sync(0xffffffffu, uw, jj);
+        w_before = (jj == lane) ? wc : w_before;
+        wc = wc + uj;
+      }
+    } else if (plain) {
       for (int jj = 0; jj < nb; ++jj) {
         const float uj = __shfl_sync(0xffffffffu, uw, jj);
         if (jj == lane) w_before = wc;

@@ -308,22 +308,31 @@ __global__ void __launch_bounds__(256, DEEP ? 1 : 2) k_voxel_apply_long(DevCfg c
       float dist = *pd, wgt = *pw;
       uint32_t rgba = *pc;
       if (DEEP) {
-        // record keys four batches ahead, their bundle parameters two batches ahead
+        // record keys five batches ahead, their bundle parameters two batches ahead.  Three parameter and three key registers, the loop
+        // unrolled by three: a rotation by register moves (a = b; b = c) would wait for the load issued in the same iteration and undo
+        // the prefetch; the keys stay raw until they are used (masking at load time waits for the load, too).
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pr_a = (lane < len) ? src.param[(uint32_t)r[lane] & ord_mask] : z4;
-        float4 pr_b = (32 + lane < len) ? src.param[(uint32_t)r[32 + lane] & ord_mask] : z4;
-        uint32_t key_c = (64 + lane < len) ? ((uint32_t)r[64 + lane] & ord_mask) : 0u;
-        uint32_t key_d = (96 + lane < len) ? ((uint32_t)r[96 + lane] & ord_mask) : 0u;
-        for (int base = 0; base < len; base += 32) {
-          const int nb = (len - base) < 32 ? (len - base) : 32;
-          const float4 pr_c = (base + 64 + lane < len) ? src.param[key_c] : z4;
-          const uint32_t key_e = (base + 128 + lane < len) ? ((uint32_t)r[base + 128 + lane] & ord_mask) : 0u;
-          float sdf = 0.0f, uw = 0.0f;
-          if (lane < nb) tsdf_measure(cfg.tp, origin, f3(pr_a.x, pr_a.y, pr_a.z), vc.center, pr_a.w, sdf, uw);
-          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);
-          pr_a = pr_b; pr_b = pr_c;
-          key_c = key_d; key_d = key_e;
+        auto raw_key = [&](int idx) -> uint32_t { return (idx < len) ? (uint32_t)r[idx] : 0u; };
+        float4 pr0 = (lane < len) ? src.param[raw_key(lane) & ord_mask] : z4;
+        float4 pr1 = (32 + lane < len) ? src.param[raw_key(32 + lane) & ord_mask] : z4;
+        float4 pr2 = z4;
+        uint32_t kx2 = raw_key(64 + lane), kx0 = raw_key(96 + lane), kx1 = raw_key(128 + lane);
+        const int nbatch_t = (len + 31) >> 5;
+#define KSG_TSDF_STEP(S, PRU, PRL, KX)                                                                                             \
+        if ((S) < nbatch_t) {                                                                                                      \
+          PRL = (((S) + 2) * 32 + lane < len) ? src.param[KX & ord_mask] : z4;     /* parameters of batch S + 2 */                  \
+          KX = raw_key(((S) + 5) * 32 + lane);                                                                                      \
+          const int nb = (len - (S) * 32) < 32 ? (len - (S) * 32) : 32;                                                            \
+          float sdf = 0.0f, uw = 0.0f;                                                                                             \
+          if (lane < nb) tsdf_measure(cfg.tp, origin, f3(PRU.x, PRU.y, PRU.z), vc.center, PRU.w, sdf, uw);                         \
+          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);                                                  \
         }
+        for (int j = 0; j < nbatch_t; j += 3) {
+          KSG_TSDF_STEP(j, pr0, pr2, kx2)
+          KSG_TSDF_STEP(j + 1, pr1, pr0, kx0)
+          KSG_TSDF_STEP(j + 2, pr2, pr1, kx1)
+        }
+#undef KSG_TSDF_STEP
       } else {
       // parameters of the next batch are fetched one batch ahead
       float4 pr_a = (lane < len) ? src.param[(uint32_t)r[lane] & ord_mask] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -352,9 +361,10 @@ __global__ void __launch_bounds__(256, DEEP ? 1 : 2) k_voxel_apply_long(DevCfg c
         // all-zero row: + 0.0f is exact.
         const float* lane_tmp = src.tmp + (lane < C ? lane : 0);
         uint32_t* ring = s_ring[(threadIdx.x >> 5) & 7];
-        auto key_at = [&](int idx) -> uint32_t { return (idx < len) ? ((uint32_t)r[idx] & ord_mask) : zero_row; };
+        // raw keys: the order bits are masked when the key is handed to the ring, three batches after its load (zero_row < 2^23 survives the mask)
+        auto key_at = [&](int idx) -> uint32_t { return (idx < len) ? (uint32_t)r[idx] : zero_row; };
         __syncwarp();
-        ring[lane] = key_at(lane); ring[32 + lane] = key_at(32 + lane); ring[64 + lane] = key_at(64 + lane);
+        ring[lane] = key_at(lane) & ord_mask; ring[32 + lane] = key_at(32 + lane) & ord_mask; ring[64 + lane] = key_at(64 + lane) & ord_mask;
         uint32_t k0 = key_at(96 + lane), k1 = key_at(128 + lane), k2 = key_at(160 + lane);
         __syncwarp();
         float ra[32], rb[32], rc[32];
@@ -365,7 +375,7 @@ __global__ void __launch_bounds__(256, DEEP ? 1 : 2) k_voxel_apply_long(DevCfg c
         const int nbatch = (len + 31) >> 5;
 #define KSG_SEM_STEP(S, KREG, LOADBUF, ADDBUF)                                                                                     \
         {                                                                                                                          \
-          ring[(((S) + 3) & 3) * 32 + lane] = KREG;                          /* keys of batch S + 3 */                             \
+          ring[(((S) + 3) & 3) * 32 + lane] = KREG & ord_mask;               /* keys of batch S + 3 */                             \
           KREG = key_at(((S) + 6) * 32 + lane);                                                                                    \
           __syncwarp();                                                                                                            \
           _Pragma("unroll") for (int u = 0; u < 32; ++u) LOADBUF[u] = __ldg(lane_tmp + (size_t)ring[(((S) + 2) & 3) * 32 + u] * C);  \
