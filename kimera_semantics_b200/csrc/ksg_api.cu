@@ -208,6 +208,7 @@ struct ksg_integrator {
   // the non-hot long segments (0.3 ms standalone) run behind the short kernel on its stream instead of beside it (KSG_LONG_SERIAL=0:
   // beside it): 202 against 199 frames/s with two short-kernel CTAs per SM (profiles/r02/tuning_18.log)
   bool long_serial = true;
+  int deep_threads = 128;            // block size of the hot-voxel instance (KSG_DEEP_THREADS): one warp per chain, 148 x 4 warps
   bool deep_hot = true;              // merged, C <= 32: the hot voxels go to the deep-pipeline instance of k_voxel_apply_long (KSG_DEEP_HOT=0: off)
   // its CTAs per SM (KSG_SHORT_T_CTAS).  The frame is bound by the long-segment kernel (1184 warps, 128 registers each); whatever the
   // short kernel takes from it costs more than it gains: merged2 1 -> 178 fps, 2 -> 166, 3 -> 166, 4 -> 170, warp-per-voxel kernel 170
@@ -874,7 +875,7 @@ int integrate(ksg_integrator* h, const InputDesc& in, const float* T_host, cudaS
         if (h->deep_hot && !use_hot) {   // the hot voxels' chains first, on their own high-priority stream (one warp per chain)
           KSG_CUDA(cudaStreamWaitEvent(h->aux_stream2, h->ev_fork, 0));
           ++h->n_launches;
-          k_voxel_apply_long<1, true><<<h->sm_count, 64, 0, h->aux_stream2>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, 0);
+          k_voxel_apply_long<1, true><<<h->sm_count, h->deep_threads, 0, h->aux_stream2>>>(dc, T, h->d_cnt, h->map, h->d_luts, h->rec_b, src, h->vq, 0);
           KSG_CUDA(cudaEventRecord(h->ev_join2, h->aux_stream2));
           skip = 1; deep_launched = true;
         }
@@ -1242,6 +1243,7 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
       if (const char* e = std::getenv("KSG_LONG_GRID")) h->long_grid = std::max(1, std::atoi(e));
       if (const char* e = std::getenv("KSG_DEEP_HOT")) h->deep_hot = std::atoi(e) != 0;
       if (const char* e = std::getenv("KSG_LONG_SERIAL")) h->long_serial = std::atoi(e) != 0;
+      if (const char* e = std::getenv("KSG_DEEP_THREADS")) { const int t = std::atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) h->deep_threads = t; }
       if (const char* e = std::getenv("KSG_SHORT_T_CTAS")) h->short_t_ctas = std::max(1, std::min(8, std::atoi(e)));
       if (const char* e = std::getenv("KSG_SHORT_CTAS")) h->short_ctas = std::max(1, std::min(6, std::atoi(e)));
       if (h->short_ctas < 6) {
