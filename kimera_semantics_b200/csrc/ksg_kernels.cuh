@@ -1009,6 +1009,10 @@ static constexpr int kApplyThreads = 256;
 // uw >= 0); then every lane evaluates its record assuming the distance did not change before it.  Free-space voxels stay
 // pinned at +truncation, so whole batches commit without a sequential pass; the first record that moves the distance ends
 // the speculation and the rest of the batch is replayed in order.
+// WIDE (the hot-voxel kernel only, it has the registers): all 32 weights are shuffled into registers BEFORE the addition chain starts -
+// interleaved, every FADD of the chain waits ~23 cycles for its own shuffle (ncu: 1972 of 2183 samples on that FADD were short-scoreboard
+// stalls), 4x the latency of the addition itself.
+template <bool WIDE = false>
 __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int nb, float sdf, float uw, uint32_t col, bool keep_blend,
                                            float& dist, float& wgt, uint32_t& rgba) {
   float w_before = wgt, wc = wgt;
@@ -1023,7 +1027,16 @@ __device__ __forceinline__ void tsdf_batch(const TsdfParams& tp, int lane, int n
     for (int o = 16; o > 0; o >>= 1) usum += __shfl_xor_sync(0xffffffffu, usum, o);
     // sequential partial sums <= (1 + 2^-24)^32 x the exact sum; the tree sum >= (1 - 2^-24)^6 x it: a 0.1 % margin is ample
     const bool plain = negative == 0u && wgt >= kEps && (wgt + usum) * 1.001f < tp.max_weight;
-    if (plain && nb == 32) {
+    if (WIDE && plain && nb == 32) {
+      float u[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) u[jj] = __shfl_sync(0xffffffffu, uw, jj);
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {     // one dependent FADD per record
+        w_before = (jj == lane) ? wc : w_before;
+        wc = wc + u[jj];
+      }
+    } else if (plain && nb == 32) {
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) {     // no loop overhead: shuffle, select, one dependent FADD per record
         const float uj = __shfl_sync(0xffffffffu, uw, jj);

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256, DEEP ? 1 : 2) k_voxel_apply_long(DevCfg c
           const int nb = (len - (S) * 32) < 32 ? (len - (S) * 32) : 32;                                                            \
           float sdf = 0.0f, uw = 0.0f;                                                                                             \
           if (lane < nb) tsdf_measure(cfg.tp, origin, f3(PRU.x, PRU.y, PRU.z), vc.center, PRU.w, sdf, uw);                         \
-          tsdf_batch(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);                                                  \
+          tsdf_batch<true>(cfg.tp, lane, nb, sdf, uw, 0u, keep_blend, dist, wgt, rgba);                                            \
         }
         for (int j = 0; j < nbatch_t; j += 3) {
           KSG_TSDF_STEP(j, pr0, pr2, kx2)
