@@ -70,8 +70,8 @@ def ncu_rows(path):
         return []
 
 
-fin, fin_src = first("bench_final_17.json", "bench_final_13.json", "bench_full_12.json", "bench_full_10.json")
-ref, ref_src = first("bench_fast5_reference_17.json", "bench_fast5_reference_13.json", "bench_fast5_reference_10.json")
+fin, fin_src = first("bench_final_21.json", "bench_final_17.json", "bench_final_13.json", "bench_full_12.json", "bench_full_10.json")
+ref, ref_src = first("bench_fast5_reference_21.json", "bench_fast5_reference_17.json", "bench_fast5_reference_13.json", "bench_fast5_reference_10.json")
 r1 = load(os.path.join(R1, "bench_fast5.json"))
 r1m = load(os.path.join(R1, "bench_merged2.json"))
 m2 = (fin or {}).get("workloads", {}).get("merged2")
@@ -158,13 +158,13 @@ if m2:
     w("|---|---|---|---|")
     for k in ("classify+start_set", "fixpoint|bundling", "ray_emit", "record_sort", "alloc+tile_heads", "tile_apply", "frame"):
         w(f"| {k} | {f(pm.get(k), '{:.3f}')} | {f(r1pm.get(k), '{:.3f}')} | {descm[k]} |")
-    sh, tot = launch_shares(os.path.join(R2, "launches_merged2_17.csv"))
-    src_l = "r02/launches_merged2_17.csv"
+    sh, tot = launch_shares(os.path.join(R2, "launches_merged2_21.csv"))
+    src_l = "r02/launches_merged2_21.csv"
     if not sh:
-        sh, tot = launch_shares(os.path.join(R2, "launches_merged2_13.csv")); src_l = "r02/launches_merged2_13.csv"
+        sh, tot = launch_shares(os.path.join(R2, "launches_merged2_17.csv")); src_l = "r02/launches_merged2_17.csv"
     if sh:
         w(f"\nncu launch list `{src_l}` (serialised, so the two apply kernels ADD here while they overlap in the bench): " + ", ".join(f"`{k}` {p:.0f} %" for k, p, _ in sh[:7]) + ".")
-    for tag, label in (("prof_apply_merged2_17", "the three update kernels of the final commit"), ("prof_apply_merged2_12", "apply kernels two commits earlier (no deep instance, thread-per-voxel short kernel at 2 CTAs/SM)"), ("prof_apply_merged2", "apply kernels of the previous commit (warp-per-voxel short kernel)"), ("prof_sort_merged2", "the four record-sort passes")):
+    for tag, label in (("prof_apply_merged2_21", "the three update kernels of the final commit"), ("prof_apply_merged2_17", "the three update kernels before the hot-voxel pipelines were unrolled (deep instance 1.53 ms)"), ("prof_apply_merged2_12", "apply kernels two commits earlier (no deep instance, thread-per-voxel short kernel at 2 CTAs/SM)"), ("prof_apply_merged2", "apply kernels of the previous commit (warp-per-voxel short kernel)"), ("prof_sort_merged2", "the four record-sort passes")):
         nr = ncu_rows(os.path.join(R2, tag + ".raw.csv"))
         if nr:
             w(f"\n`ncu --set full`, {label} — `r02/{tag}.details.txt`:")
@@ -188,7 +188,7 @@ w("\nReading: neither workload is bandwidth bound.  `fast5` moves ≈15 MB per f
 w("`merged2`'s update kernels run sequential per-voxel recurrences (they must, for bit-identical results) and are bound by instruction issue and L2 latency of a few thousand warps.")
 
 w("\n## Tuning sweeps and experiments that lost (all on the B200 box, `bench.py --quick`)\n")
-for fn in ("tuning_10.log", "tuning_12.log", "tuning_13.log", "tuning_16.log", "tuning_17.log"):
+for fn in ("tuning_10.log", "tuning_12.log", "tuning_13.log", "tuning_16.log", "tuning_17.log", "tuning_18.log", "tuning_19.log", "tuning_20.log", "tuning_21.log"):
     p = os.path.join(R2, fn)
     if os.path.exists(p):
         w(f"`r02/{fn}`:\n```")
@@ -199,6 +199,7 @@ w("""
 * `__noinline__` helpers / rolled loops in the solve kernel (instruction-cache theory): 20 % slower (`r02/bench_full_9.json`) - reverted.
 * one CTA per hot voxel with a producer / consumer shared-memory ring (`k_voxel_apply_hot`, `KSG_HOT_KERNEL=1`) and a warp-wide ray walk for the `merged` emit (`KSG_EMIT_WARP=1`): 100 and 132 frames/s against 148 (`r02/tuning_10.log`) - kept as opt-in.
 * exact parallel scan of the hot voxels' float chains (`hot_voxel_mode` 1 / 2, `csrc/ksg_hot.cuh`, parity green): slower than the per-voxel kernels it feeds (`r02/bench_merged2_hot*.json`) - off by default.
+* what DID pay for `merged`, in order: per-voxel work items instead of per-tile CTAs (62 -> 141 frames/s), capping the short kernel's residency so that the long one runs beside it (148 -> 166), the thread-per-voxel short kernel (-> 178), a separate deep-pipeline instance for the hot voxels' chains (-> 194), the bare-addition weight chain (-> 200), loop unrolling instead of register rotation in those pipelines and running the small long-segment kernel behind the short one (-> 209), and issuing a batch's 32 shuffles ahead of the weight chain (final number above).  The lesson of the last three: a software pipeline written as `a = b; b = load()` waits for the load it has just issued, and a chain whose every link waits for its own shuffle runs at the shuffle's latency, not the adder's.
 * thread-per-voxel kernel for the short segments: 20x fewer warp instructions than the warp-per-voxel kernel (ncu: 1.6 G -> see above) but no faster standalone (dependent gathers at low occupancy); it wins by leaving the SMs to the long-segment kernel (1 CTA/SM: 178 frames/s against 170).
 """)
 
