@@ -1235,6 +1235,25 @@ int32_t ksg_create(const ksg_config* cfg, ksg_integrator** out) {
         KSG_CUDA(cudaStreamCreateWithPriority(&h->aux_stream2, cudaStreamNonBlocking, hi_p));
       }
       KSG_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+      if (const char* e = std::getenv("KSG_L2_PERSIST")) {
+        // experiment: keep the (L * freq) rows resident in L2 while the update kernels stream records and voxel data through it
+        if (std::atoi(e) != 0) {
+          cudaDeviceProp prop{};
+          KSG_CUDA(cudaGetDeviceProperties(&prop, h->device));
+          const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, 32u << 20);
+          if (want > 0) {
+            KSG_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = h->tmp;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)(N + 1) * dc.C * sizeof(float), (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            KSG_CUDA(cudaStreamSetAttribute(h->aux_stream2, cudaStreamAttributeAccessPolicyWindow, &attr));
+            KSG_CUDA(cudaStreamSetAttribute(h->aux_stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+          }
+        }
+      }
       h->hot_smem = 2 * kHotChunkRecs * (32 * (int)sizeof(float) + (int)sizeof(float4));
       KSG_CUDA(cudaFuncSetAttribute(k_voxel_apply_hot, cudaFuncAttributeMaxDynamicSharedMemorySize, h->hot_smem));
       if (const char* e = std::getenv("KSG_HOT_KERNEL")) h->hot_kernel = std::atoi(e) != 0;
