@@ -188,7 +188,7 @@ w("\nReading: neither workload is bandwidth bound.  `fast5` moves ≈15 MB per f
 w("`merged2`'s update kernels run sequential per-voxel recurrences (they must, for bit-identical results) and are bound by instruction issue and L2 latency of a few thousand warps.")
 
 w("\n## Tuning sweeps and experiments that lost (all on the B200 box, `bench.py --quick`)\n")
-for fn in ("tuning_10.log", "tuning_12.log", "tuning_13.log", "tuning_16.log", "tuning_17.log", "tuning_18.log", "tuning_19.log", "tuning_20.log", "tuning_21.log"):
+for fn in ("tuning_10.log", "tuning_12.log", "tuning_13.log", "tuning_16.log", "tuning_17.log", "tuning_18.log", "tuning_19.log", "tuning_20.log", "tuning_21.log", "tuning_22.log"):
     p = os.path.join(R2, fn)
     if os.path.exists(p):
         w(f"`r02/{fn}`:\n```")
@@ -200,6 +200,7 @@ w("""
 * one CTA per hot voxel with a producer / consumer shared-memory ring (`k_voxel_apply_hot`, `KSG_HOT_KERNEL=1`) and a warp-wide ray walk for the `merged` emit (`KSG_EMIT_WARP=1`): 100 and 132 frames/s against 148 (`r02/tuning_10.log`) - kept as opt-in.
 * exact parallel scan of the hot voxels' float chains (`hot_voxel_mode` 1 / 2, `csrc/ksg_hot.cuh`, parity green): slower than the per-voxel kernels it feeds (`r02/bench_merged2_hot*.json`) - off by default.
 * what DID pay for `merged`, in order: per-voxel work items instead of per-tile CTAs (62 -> 141 frames/s), capping the short kernel's residency so that the long one runs beside it (148 -> 166), the thread-per-voxel short kernel (-> 178), a separate deep-pipeline instance for the hot voxels' chains (-> 194), the bare-addition weight chain (-> 200), loop unrolling instead of register rotation in those pipelines and running the small long-segment kernel behind the short one (-> 209), and issuing a batch's 32 shuffles ahead of the weight chain (final number above).  The lesson of the last three: a software pipeline written as `a = b; b = load()` waits for the load it has just issued, and a chain whose every link waits for its own shuffle runs at the shuffle's latency, not the adder's.
+* an L2 persistence window (`cudaAccessPropertyPersisting`) for the `L·freq` rows (`KSG_L2_PERSIST=1`): no effect (217.2 vs 216.5 frames/s, `r02/tuning_22.log`) - the rows are L2 resident anyway.
 * thread-per-voxel kernel for the short segments: 20x fewer warp instructions than the warp-per-voxel kernel (ncu: 1.6 G -> see above) but no faster standalone (dependent gathers at low occupancy); it wins by leaving the SMs to the long-segment kernel (1 CTA/SM: 178 frames/s against 170).
 """)
 
