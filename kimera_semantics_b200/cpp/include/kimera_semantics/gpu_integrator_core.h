@@ -33,6 +33,9 @@ class GpuIntegratorCore {
   // The other direction: replace the device map by the contents of the host layers (ksg_reset + ksg_import_blocks), e.g. after
   // map_io::loadLayers.  The fast integrator's two approximate sets start empty, as in a freshly constructed reference integrator.
   void uploadLayers();
+  // Semantic mesh of the device map (ksg_extract_mesh): triangle soup, per-vertex TsdfVoxel.color and semantic label, blocks in (z, y, x) order
+  bool extractMesh(float min_weight, std::vector<float>* vertices, std::vector<uint8_t>* rgba, std::vector<uint8_t>* labels,
+                   std::vector<int32_t>* block_index, std::vector<int64_t>* block_first);
   int64_t lastVoxelUpdates() const { return last_voxel_updates_; }
   ksg_integrator* handle() { return handle_; }
 

@@ -88,6 +88,19 @@ class SemanticTsdfServer {
     return vxblx_io::saveTsdfLayer(path, *tsdf_layer_);
   }
 
+  // What the reference's server publishes for display: the voxblox mesh coloured by TsdfVoxel.color (launch/kimera_semantics.launch:130-132),
+  // here extracted from the device map (ksg_extract_mesh, csrc/ksg_mesh.cuh): a triangle soup (3 consecutive vertices per triangle) with
+  // the voxel colour and the semantic label per vertex; blocks in (z, y, x) order, block_first[i] = first vertex of block i.
+  struct SemanticMesh {
+    std::vector<float> vertices;          // 3 per vertex
+    std::vector<uint8_t> rgba, labels;    // 4 / 1 per vertex
+    std::vector<int32_t> block_index;     // 3 per block
+    std::vector<int64_t> block_first;     // blocks + 1
+  };
+  bool extractMesh(SemanticMesh* mesh, float min_weight = 1e-4f) {
+    return gpu().extractMesh(min_weight, &mesh->vertices, &mesh->rgba, &mesh->labels, &mesh->block_index, &mesh->block_first);
+  }
+
   vxb::Layer<vxb::TsdfVoxel>* getTsdfLayerPtr() { return tsdf_layer_.get(); }
   vxb::Layer<SemanticVoxel>* getSemanticLayerPtr() { return semantic_layer_.get(); }
   vxb::TsdfIntegratorBase* getIntegratorPtr() { return tsdf_integrator_.get(); }

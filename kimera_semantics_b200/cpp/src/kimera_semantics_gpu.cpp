@@ -295,6 +295,19 @@ void GpuIntegratorCore::syncUpdatedBlocks() {
   if (n) ksg_last_updated_blocks(handle_, n, idx.data());
   copyBlocks(idx);
 }
+bool GpuIntegratorCore::extractMesh(float min_weight, std::vector<float>* vertices, std::vector<uint8_t>* rgba, std::vector<uint8_t>* labels,
+                                    std::vector<int32_t>* block_index, std::vector<int64_t>* block_first) {
+  int64_t nv = 0, nb = 0;
+  if (ksg_extract_mesh(handle_, min_weight, 0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, &nv, &nb) != KSG_OK) return false;
+  vertices->assign((size_t)nv * 3, 0.0f);
+  rgba->assign((size_t)nv * 4, 0);
+  labels->assign((size_t)nv, 0);
+  block_index->assign((size_t)nb * 3, 0);
+  block_first->assign((size_t)nb + 1, 0);
+  return ksg_extract_mesh(handle_, min_weight, nv, vertices->data(), rgba->data(), labels->data(), nb, block_index->data(), block_first->data(),
+                          &nv, &nb) == KSG_OK;
+}
+
 void GpuIntegratorCore::uploadLayers() {
   vxb::BlockIndexList blocks;
   tsdf_layer_->getAllAllocatedBlocks(&blocks);

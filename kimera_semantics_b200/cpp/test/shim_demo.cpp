@@ -88,6 +88,12 @@ int main(int argc, char** argv) {
     }
   }
   if (lazy) server.updateLayers();
+  {
+    SemanticTsdfServer::SemanticMesh mesh;
+    KSG_CHECK(server.extractMesh(&mesh)) << "mesh extraction failed";
+    KSG_CHECK(mesh.vertices.size() % 9 == 0 && mesh.block_first.back() == (int64_t)mesh.labels.size());
+    std::printf("semantic mesh: %zu triangles over %zu blocks\n", mesh.vertices.size() / 9, mesh.block_index.size() / 3);
+  }
   if (save_path) KSG_CHECK(server.saveMap(save_path)) << "cannot save " << save_path;
   vxb::BlockIndexList blocks;
   tsdf_layer.getAllAllocatedBlocks(&blocks);
