@@ -239,7 +239,7 @@ if rows:
     w("| GPUs | mode | frames/s (resident) | frames/s (e2e) | scaling | notes | file |")
     w("|---|---|---|---|---|---|---|")
     out.extend(rows)
-w("\nReading: replicas scale with the number of sequences (0.92 at N = 8 when every rank follows its own trajectory - the slowest stream sets the time; the default is now the same stream on every rank).  The frame-per-GPU mode, with voxel-granular deltas, is 2.2x (`fast5`) to 2.9x (configs[3]) faster on 8 GPUs than ONE GPU running the frames sequentially - its own-frame integration carries the clearing of the delta layers and one host synchronisation per batch, and gather + merge grow with N.  Spatial sharding divides only the per-voxel update: `merged2` 175 -> 244 frames/s on 8 GPUs (ray casting, bundling and the record sort are replicated on every rank: Amdahl), configs[4] is sort / emit bound at N = 8 (its 2 timed steps also allocate thousands of new 725 KB blocks, which is why `value` is below the profiled frame time).")
+w("\nReading: replicas scale with the number of sequences: the N = 2 row is the final commit (same synthetic stream on every rank: 2 x 2470 = 1.00 x the 1-GPU rate); the N = 8 row was taken earlier with one trajectory per rank, where the slowest stream sets the time (0.92).  The frame-per-GPU mode, with voxel-granular deltas, is 2.2x (`fast5`) to 2.9x (configs[3]) faster on 8 GPUs than ONE GPU running the frames sequentially - its own-frame integration carries the clearing of the delta layers and one host synchronisation per batch, and gather + merge grow with N.  Spatial sharding divides only the per-voxel update: `merged2` 175 -> 244 frames/s on 8 GPUs (ray casting, bundling and the record sort are replicated on every rank: Amdahl), configs[4] is sort / emit bound at N = 8 (its 2 timed steps also allocate thousands of new 725 KB blocks, which is why `value` is below the profiled frame time).")
 w("\nReal-NCCL parity: `tests/test_gpu_multi.py` (the sharded map assembled from the ranks' exports equals the unsharded map, bit for bit) — `r02/gpu_multi_n*.log`.")
 
 w("\n## GPU test logs\n")
