@@ -2101,6 +2101,7 @@ int32_t ksg_merge_voxels_device(ksg_integrator* h, int32_t n_deltas, const int64
   { const int rcp = finish_frame(h, nullptr); if (rcp) return rcp; }
   cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
   const int64_t total = (int64_t)n_deltas * stride;
+  if (total > 0x7fffffff) return fail(KSG_ERR_INVALID_ARGUMENT, "merge: n_deltas * stride_entries exceeds 2^31 - 1");
   if (h->exp_slots_cap < total) {
     KSG_CUDA(cudaStreamSynchronize(s));
     if (h->d_exp_slots) cudaFree(h->d_exp_slots);
